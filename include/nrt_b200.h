@@ -1,0 +1,204 @@
+/* nrt_b200.h -- C ABI of libnrt_b200.so, the B200 (sm_100a) native per-ray hot path of
+ * prashantraina/neural_raytracing.
+ *
+ * The reference has NO native/FFI boundary on this path: it is eager PyTorch
+ * (SURVEY.md section 8b).  The boundary a maintainer binds is therefore the set of
+ * Python call sites listed next to each entry point below; INTEGRATION.md shows the
+ * ctypes / torch.library stub for each.  Conventions:
+ *
+ *   - plain C: pointers + sizes, no torch types.  Every pointer is a DEVICE pointer
+ *     (fp32 unless stated) except `nrt_*_host` entry points, which take HOST buffers and do
+ *     the H2D/D2H copies themselves (used for the end-to-end benchmark leg).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  All work
+ *     is enqueued on it; no entry point synchronises the host unless documented.
+ *   - return value: 0 on success, a negative NRT_E_* code otherwise;
+ *     nrt_last_error() returns a human readable message for the calling thread.
+ *   - no CPU fallback exists: without a CUDA device every compute entry point returns
+ *     NRT_E_CUDA.
+ *
+ * Layouts
+ *   rays      [R,6]  (origin xyz, direction xyz), row-major, as the reference's
+ *                    rays[N,W,H,B,6] flattened (cameras.py:53, renderer/cameras.py:575).
+ *   MLP weights: one flat fp32 blob per SkipConnMLP ("packed f32"), see nrt_mlp_t.
+ */
+#ifndef NRT_B200_H_
+#define NRT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRT_ABI_VERSION 1
+
+/* error codes */
+#define NRT_OK 0
+#define NRT_E_INVALID (-1)  /* bad argument / unsupported shape */
+#define NRT_E_CUDA (-2)     /* CUDA runtime error (message has the cudaError string) */
+#define NRT_E_UNSUPPORTED (-3)
+
+/* hidden activation (neural_blocks.py:26 default leaky_relu; sdfs.py:29 softplus) */
+#define NRT_ACT_LEAKY_RELU 0
+#define NRT_ACT_SOFTPLUS 1
+/* output activation applied by the caller sites (bsdfs.py:536,635; scene.py:315;
+ * nerf.py:203,60) -- fused into the epilogue */
+#define NRT_OUT_NONE 0
+#define NRT_OUT_SIGMOID 1
+#define NRT_OUT_SOFTPLUS 2
+#define NRT_OUT_TANH 3
+
+/* arithmetic mode of the MLP contraction */
+#define NRT_PREC_F32 0  /* fp32 FMA, fixed k-sequential order: bit-exact vs oracle/c */
+#define NRT_PREC_F16 1  /* tcgen05 kind::f16, fp16 operands, fp32 accumulate in TMEM   */
+#define NRT_PREC_BF16 2 /* tcgen05 kind::f16, bf16 operands, fp32 accumulate in TMEM   */
+
+#define NRT_MAX_LAYERS 20
+
+/* One SkipConnMLP (pytorch3d/pathtracer/neural_blocks.py:12-86).
+ *
+ * dim_p = in_size + 2*freqs + latent_size.  Linear layers in evaluation order:
+ *   index 0          init   : K = dim_p,                       N = hidden
+ *   index 1..L       layers : K = hidden (+dim_p if (i%skip)==0 && i!=L-1), N = hidden
+ *   index L+1        out    : K = hidden,                      N = out_size
+ * `params` is the packed-f32 blob: for each linear layer in that order, W^T stored
+ * row-major as [K][N] (so element (k,n) = torch weight[n][k]) followed by bias[N].
+ * For skip layers k runs over [hidden activations | encoding] exactly as
+ * torch.cat([x, init], -1) does (neural_blocks.py:83).
+ * `basis` is basis_p [in_size][freqs] row-major (utils.py:33-36).
+ * `params_tc` is the optional tensor-core blob produced by nrt_mlp_pack_tc (NULL when
+ * only NRT_PREC_F32 is used). */
+typedef struct nrt_mlp {
+  int32_t in_size;
+  int32_t latent_size;
+  int32_t freqs;
+  int32_t hidden;
+  int32_t num_layers;
+  int32_t skip;
+  int32_t out_size;
+  int32_t act;
+  const float* basis;
+  const float* params;
+  const void* params_tc;
+} nrt_mlp_t;
+
+/* SphereSDF (pytorch3d/pathtracer/shapes/sdfs.py:16-46): smooth-min (k=32, clamp 1e-4,
+ * utils.py:385-387) of n affine-warped spheres plus the residual MLP `shift`. */
+typedef struct nrt_sphere_sdf {
+  int32_t n;
+  const float* centers; /* [n,3]   */
+  const float* radii;   /* [n]     */
+  const float* tfs;     /* [n,3,3] (identity is added inside, sdfs.py:39) */
+  nrt_mlp_t shift;
+} nrt_sphere_sdf_t;
+
+/* ---- library ------------------------------------------------------------------------ */
+int nrt_abi_version(void);
+const char* nrt_last_error(void);
+/* number of SMs / compute capability of the current device; NRT_E_CUDA if none. */
+int nrt_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- packed parameter sizes --------------------------------------------------------- */
+/* number of floats in the packed-f32 blob of `m` (pointers in m may be NULL). */
+int64_t nrt_mlp_param_count(const nrt_mlp_t* m);
+/* bytes of the tensor-core blob for `prec` (NRT_PREC_F16 / NRT_PREC_BF16). */
+int64_t nrt_mlp_tc_blob_bytes(const nrt_mlp_t* m, int prec);
+/* builds the tensor-core blob (UMMA canonical K-major fp16/bf16 tiles + fp32 biases) from
+ * m->params on the device. */
+int nrt_mlp_pack_tc(const nrt_mlp_t* m, int prec, void* blob_out, void* stream);
+
+/* ---- a2: SkipConnMLP.forward (neural_blocks.py:75-86; fourier2 utils.py:37-40) ---- */
+/* x [M,in_size], latent [M,latent_size] or NULL, out [M,out_size].  out_act is applied to
+ * the result.  If `acts` is non-NULL it receives the post-activation layer inputs needed by
+ * nrt_mlp_backward ([M, hidden*(num_layers+1)] floats). */
+int nrt_mlp_forward(const nrt_mlp_t* m, int prec, int out_act, const float* x,
+                    const float* latent, int64_t M, float* out, float* acts, void* stream);
+/* reverse mode of the above.  g_out [M,out_size] is the gradient w.r.t. the *activated*
+ * output `out` (which must be passed back); g_params (packed-f32 layout, ACCUMULATED
+ * into with atomics: zero it first) ; g_x [M,in_size] / g_latent [M,latent] may be NULL. */
+int nrt_mlp_backward(const nrt_mlp_t* m, int out_act, const float* x, const float* latent,
+                     int64_t M, const float* out, const float* acts, const float* g_out,
+                     float* g_params, float* g_x, float* g_latent, void* stream);
+
+/* ---- a3: SphereSDF.forward (sdfs.py:41-46) ------------------------------------------- */
+int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M, float* out,
+                 void* stream);
+/* a6: value and analytic d(sdf)/dp (replaces SDF.autograd_diff, sdfs.py:184-197). */
+int nrt_sdf_value_grad(const nrt_sphere_sdf_t* s, const float* p, int64_t M, float* value,
+                       float* grad, void* stream);
+
+/* ---- a4: SDF.intersect march loop (sdfs.py:111-131) ---------------------------------- */
+/* depth [R] (final `depths`), hit [R] uint8 (`out_active`).  `active` (optional, [R]
+ * uint8) lets the caller skip rays whose result it will mask anyway (skipped rays report
+ * depth 0 / hit 0, resp. not_blocked 1).  steps_done (optional, device
+ * uint64) accumulates the number of SDF samples actually evaluated (compaction skips
+ * finished rays; the reference evaluates R*max_steps). */
+int nrt_sdf_sphere_trace(const nrt_sphere_sdf_t* s, int prec, const float* rays,
+                         const uint8_t* active, int64_t R, float epsilon, int max_steps,
+                         float max_t, float* depth, uint8_t* hit,
+                         unsigned long long* steps_done, void* stream);
+/* ---- a7: SDF.intersect_test shadow march (sdfs.py:162-181) -------------------------- */
+/* max_t [R] per ray; not_blocked [R] uint8. */
+int nrt_sdf_shadow_test(const nrt_sphere_sdf_t* s, int prec, const float* rays,
+                        const float* max_t, const uint8_t* active, int64_t R, float epsilon,
+                        int max_steps, uint8_t* not_blocked, unsigned long long* steps_done,
+                        void* stream);
+/* ---- a5: SDF.throughput min-along-ray scan (sdfs.py:232-249) ------------------------- */
+/* Scans t_i = fl32(step*(i)) for i = 0..n_steps (step given in double like the python
+ * float), strict-< running argmin.  Outputs best_idx [R] int32, best_pos [R,3]
+ * (= o + fl32(fl32(idx)*fl32(step)) * d, sdfs.py:247-248) and min_val [R]. */
+int nrt_sdf_min_scan(const nrt_sphere_sdf_t* s, int prec, const float* rays, int64_t R,
+                     double step, int n_steps, int32_t* best_idx, float* best_pos,
+                     float* min_val, void* stream);
+
+/* ---- a19: NeRF alpha compositing (nerf.py:206-213 / :66-74) -------------------------- */
+/* Sample-major like the reference: sigma_raw [S,R] (pre-relu density), rgb [S,R,3],
+ * ts [S]; out [R,3].  Replicates the reference quirks: alpha from absolute t, the
+ * roll-by-one, and the last sample's transmittance forced to 1. */
+int nrt_composite_forward(const float* sigma_raw, const float* rgb, const float* ts, int S,
+                          int64_t R, float* out, void* stream);
+int nrt_composite_backward(const float* sigma_raw, const float* rgb, const float* ts, int S,
+                           int64_t R, const float* g_out, float* g_sigma_raw, float* g_rgb,
+                           void* stream);
+
+/* ---- a18: NeRFLE.forward fused volumetric render (nerf.py:175-214) ------------------- */
+/* rays [R,6]; ts [S] sample distances (the reference uses linspace(0, 2+U*0.1, 64));
+ * light_code [n_views, light_dim] with light_dim = second.in_size - 64 - 3 (3 = light
+ * location, nerf.py:197; 48 = envmap code, :184-195); view_of_ray [R] int32 selects the
+ * row (NULL = row 0 for all).  out rgb [R,3].  Optional stratified/hierarchical sampling
+ * is selected through nrt_nerf_sampling_t (extension; not in the reference). */
+typedef struct nrt_nerf_sampling {
+  int32_t n_coarse;     /* S for the first pass                                      */
+  int32_t n_fine;       /* 0 = reference behaviour (single pass, shared ts)          */
+  float t_near, t_far;  /* used when ts == NULL                                      */
+  uint64_t jitter_seed; /* 0 = no stratified jitter                                  */
+} nrt_nerf_sampling_t;
+int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                      const float* rays, int64_t R, const float* ts,
+                      const nrt_nerf_sampling_t* sampling, const float* light_code,
+                      int light_dim, const int32_t* view_of_ray, float* out_rgb,
+                      void* workspace, size_t workspace_bytes, void* stream);
+size_t nrt_nerfle_render_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                   int64_t R, const nrt_nerf_sampling_t* sampling);
+/* Host-buffer variant: copies rays H2D, renders, copies rgb D2H, synchronises. */
+int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                           const float* rays_host, int64_t R, const float* ts_host, int S,
+                           const nrt_nerf_sampling_t* sampling, const float* light_code,
+                           int light_dim, float* out_rgb_host, void* stream);
+
+/* ---- a8/a9/a12/a14/a15/a16: shading glue as fused elementwise kernels ---------------- */
+/* coordinate_system + to_local(-r_d) (interaction.py:9-27,38-41; sdfs.py:158-159).
+ * normals [R,3] -> frame [R,3,3] (columns s,t,n as torch.stack(dim=-1)), wi [R,3]. */
+int nrt_shading_frame(const float* normals, const float* rays, int64_t R, float* frame,
+                      float* wi, void* stream);
+/* to_local(frame, v) for arbitrary v [R,3]. */
+int nrt_to_local(const float* frame, const float* v, int64_t R, float* out, void* stream);
+/* param_rusin2 (utils.py:233-258): a = first argument (`wo` in the source, called with
+ * it.wi), b = second. out [R,3]. */
+int nrt_param_rusin2(const float* a, const float* b, int64_t R, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRT_B200_H_ */

@@ -1,0 +1,110 @@
+// C-ABI plumbing of libnrt_b200: error reporting, descriptor validation, device queries and
+// the entry points that only orchestrate other kernels.
+#include <stdarg.h>
+
+#include <algorithm>
+
+#include "nrt_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void nrt_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int nrt_check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return NRT_OK;
+  nrt_set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return NRT_E_CUDA;
+}
+
+extern "C" const char* nrt_last_error(void) { return g_err; }
+extern "C" int nrt_abi_version(void) { return NRT_ABI_VERSION; }
+
+int nrt_sm_count() {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+extern "C" int nrt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  NRT_CUDA(cudaGetDevice(&dev));
+  int n = 0, maj = 0, min = 0;
+  NRT_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  NRT_CUDA(cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev));
+  NRT_CUDA(cudaDeviceGetAttribute(&min, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm_count) *sm_count = n;
+  if (cc_major) *cc_major = maj;
+  if (cc_minor) *cc_minor = min;
+  return NRT_OK;
+}
+
+static int mlp_shape(const nrt_mlp_t* m, MlpDev* d) {
+  NRT_REQUIRE(m != nullptr, "mlp descriptor is NULL");
+  NRT_REQUIRE(m->in_size >= 1 && m->in_size <= 256, "mlp.in_size %d out of range", m->in_size);
+  NRT_REQUIRE(m->latent_size >= 0 && m->latent_size <= 256, "mlp.latent_size %d out of range", m->latent_size);
+  NRT_REQUIRE(m->freqs >= 0 && m->freqs <= 256, "mlp.freqs %d out of range", m->freqs);
+  NRT_REQUIRE(m->num_layers >= 1 && m->num_layers <= NRT_MAX_LAYERS, "mlp.num_layers %d out of range [1,%d]",
+              m->num_layers, NRT_MAX_LAYERS);
+  NRT_REQUIRE(m->skip >= 1, "mlp.skip must be >= 1");
+  NRT_REQUIRE(m->out_size >= 1 && m->out_size <= 256, "mlp.out_size %d out of range", m->out_size);
+  NRT_REQUIRE(m->hidden >= 1, "mlp.hidden must be positive");
+  NRT_REQUIRE(m->act == NRT_ACT_LEAKY_RELU || m->act == NRT_ACT_SOFTPLUS, "mlp.act %d unknown", m->act);
+  d->in_size = m->in_size; d->latent = m->latent_size; d->freqs = m->freqs; d->hidden = m->hidden;
+  d->L = m->num_layers; d->skip = m->skip; d->out = m->out_size; d->act = m->act;
+  d->dim_p = m->in_size + 2 * m->freqs + m->latent_size;
+  d->n_lin = m->num_layers + 2;
+  d->skip_mask = 0;
+  int off = 0;
+  for (int li = 0; li < d->n_lin; ++li) {
+    int K, N;
+    if (li == 0) { K = d->dim_p; N = d->hidden; }
+    else if (li == d->n_lin - 1) { K = d->hidden; N = d->out; }
+    else {
+      const int i = li - 1;
+      const bool sk = (i % d->skip) == 0 && i != d->L - 1;   // neural_blocks.py:45-49,82
+      if (sk) d->skip_mask |= (1u << i);
+      K = d->hidden + (sk ? d->dim_p : 0); N = d->hidden;
+    }
+    d->K[li] = K; d->N[li] = N;
+    d->w_off[li] = off; off += K * N;
+    d->b_off[li] = off; off += N;
+  }
+  d->basis = m->basis; d->params = m->params;
+  return off;
+}
+
+extern "C" int64_t nrt_mlp_param_count(const nrt_mlp_t* m) {
+  MlpDev d;
+  int n = mlp_shape(m, &d);
+  return (int64_t)n;
+}
+
+int nrt_build_mlp_dev(const nrt_mlp_t* m, MlpDev* out) {
+  int n = mlp_shape(m, out);
+  if (n < 0) return n;
+  NRT_REQUIRE(m->params != nullptr, "mlp.params is NULL");
+  NRT_REQUIRE(m->freqs == 0 || m->basis != nullptr, "mlp.basis is NULL");
+  NRT_REQUIRE(((uintptr_t)m->params & 15) == 0, "mlp.params must be 16-byte aligned");
+  return NRT_OK;
+}
+
+int nrt_build_sdf_dev(const nrt_sphere_sdf_t* s, SdfDev* out) {
+  NRT_REQUIRE(s != nullptr, "sdf descriptor is NULL");
+  NRT_REQUIRE(s->n >= 1, "sdf.n must be >= 1");
+  NRT_REQUIRE(s->centers && s->radii && s->tfs, "sdf sphere parameters are NULL");
+  out->n = s->n; out->centers = s->centers; out->radii = s->radii; out->tfs = s->tfs;
+  int rc = nrt_build_mlp_dev(&s->shift, &out->mlp);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(out->mlp.in_size == 3 && out->mlp.latent == 0 && out->mlp.out == 1,
+              "sdf.shift must be a 3 -> 1 MLP without latent");
+  return NRT_OK;
+}

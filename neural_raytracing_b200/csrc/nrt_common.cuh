@@ -1,0 +1,55 @@
+// Shared host/device declarations for libnrt_b200 (internal; the public ABI is include/nrt_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "nrt_b200.h"
+#include "nrt_detmath.h"
+
+#define NRT_NLIN (NRT_MAX_LAYERS + 2)
+
+// Device-side description of one SkipConnMLP with the packed-f32 offsets resolved.
+struct MlpDev {
+  int in_size, latent, freqs, hidden, L, skip, out, act;
+  int dim_p;          // in_size + 2*freqs + latent
+  int n_lin;          // L + 2
+  int K[NRT_NLIN];    // fan-in of linear layer i
+  int N[NRT_NLIN];    // fan-out
+  int w_off[NRT_NLIN];  // float offset of W^T [K][N] in params
+  int b_off[NRT_NLIN];  // float offset of bias [N]
+  unsigned skip_mask;   // bit i set: hidden layer i (0-based) consumes [h | enc]
+  const float* basis;   // [in_size][freqs]
+  const float* params;
+};
+
+struct SdfDev {
+  int n;
+  const float* centers;
+  const float* radii;
+  const float* tfs;
+  MlpDev mlp;
+};
+
+// ---- host helpers (nrt_capi.cu) -------------------------------------------------------
+void nrt_set_error(const char* fmt, ...);
+int nrt_check_cuda(cudaError_t e, const char* what);
+#define NRT_CUDA(call)                                  \
+  do {                                                  \
+    int _rc = nrt_check_cuda((call), #call);            \
+    if (_rc != NRT_OK) return _rc;                      \
+  } while (0)
+#define NRT_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      nrt_set_error(__VA_ARGS__);   \
+      return NRT_E_INVALID;         \
+    }                               \
+  } while (0)
+
+int nrt_build_mlp_dev(const nrt_mlp_t* m, MlpDev* out);  // validates + resolves offsets
+int nrt_build_sdf_dev(const nrt_sphere_sdf_t* s, SdfDev* out);
+int nrt_sm_count();
+
+static inline int nrt_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

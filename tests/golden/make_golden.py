@@ -1,0 +1,236 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/pytorch3d/pathtracer, imported through oracle/ref_shim.py) on CPU fp32.
+
+Run in the build container only:   python tests/golden/make_golden.py
+The fixtures pin the oracle (tests/test_oracle_vs_golden.py) and, through it, the CUDA path.
+Every fixture stores the reference file:line of the function that produced it in `src`.
+"""
+import os
+import random
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, HERE)
+from oracle import ref_shim  # noqa: E402
+import synth  # noqa: E402
+
+pt = ref_shim.load()
+import torch  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+from pytorch3d.pathtracer.neural_blocks import SkipConnMLP  # noqa: E402
+from pytorch3d.pathtracer.shapes.sdfs import SDF, SphereSDF  # noqa: E402
+from pytorch3d.pathtracer.shapes.nerf import NeRFLE  # noqa: E402
+from pytorch3d.pathtracer.lights import PointLights, LightField  # noqa: E402
+from pytorch3d.pathtracer.bsdf import Diffuse, Conductor, NeuralBSDF, ComposeSpatialVarying  # noqa: E402
+from pytorch3d.pathtracer.integrators import Direct, NeRFIntegrator, NeRFReproduce  # noqa: E402
+from pytorch3d.pathtracer.interaction import coordinate_system, to_local  # noqa: E402
+from pytorch3d.pathtracer.utils import param_rusin2, dir_to_elev_azim  # noqa: E402
+
+torch.set_num_threads(8)
+FIXED_RANDOM = 0.37  # value returned by the patched random.random (sdfs.py:236, nerf.py:178)
+
+
+def T(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
+def load_mlp(mod, w):
+    """Copies synth weights into a reference SkipConnMLP (attribute assignment only)."""
+    mod.basis_p = T(w["basis"]).clone()
+    lins = [mod.init] + list(mod.layers) + [mod.out]
+    assert len(lins) == len(w["W"])
+    with torch.no_grad():
+        for lin, W, b in zip(lins, w["W"], w["b"]):
+            assert tuple(lin.weight.shape) == W.shape, (lin.weight.shape, W.shape)
+            lin.weight.copy_(T(W))
+            lin.bias.copy_(T(b))
+    return mod
+
+
+def ref_mlp(w, act=None):
+    kw = {}
+    if act == "softplus":
+        kw["activation"] = F.softplus
+    m = SkipConnMLP(num_layers=w["num_layers"], hidden_size=w["hidden"], in_size=w["in_size"],
+                    out=w["out"], skip=w["skip"], freqs=w["freqs"], device="cpu",
+                    latent_size=w["latent"], **kw)
+    return load_mlp(m, w)
+
+
+def ref_sdf(w, max_steps=64):
+    s = SphereSDF(n=w["n"], device="cpu")
+    with torch.no_grad():
+        s.centers.copy_(T(w["centers"]))
+        s.radii.copy_(T(w["radii"]))
+        s.tfs.copy_(T(w["tfs"]))
+    load_mlp(s.shift, w["shift"])
+    return SDF(sdf=s, device="cpu", max_steps=max_steps), s
+
+
+MLP_CASES = {
+    # name: (synth kwargs, activation, M)
+    "sdf_shift": (dict(seed=11, in_size=3, out=1, num_layers=8, hidden=128, freqs=32, sigma=32.0), "softplus", 130),
+    "nerf_first": (dict(seed=12, in_size=3, out=65, num_layers=5, hidden=128, freqs=16, sigma=32.0), None, 257),
+    "nerf_second": (dict(seed=13, in_size=70, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0), None, 200),
+    "neural_bsdf": (dict(seed=14, in_size=3, out=3, num_layers=6, hidden=96, freqs=64, sigma=32.0), None, 100),
+    "latent_small": (dict(seed=15, in_size=3, out=9, num_layers=5, hidden=32, freqs=16, sigma=32.0, latent=8), None, 77),
+    "sp_var_small": (dict(seed=16, in_size=3, out=4, num_layers=7, hidden=256, freqs=128, sigma=128.0), None, 70),
+    "one_layer": (dict(seed=17, in_size=5, out=1, num_layers=1, hidden=64, freqs=16, sigma=32.0), None, 64),
+}
+
+
+def gen_mlp():
+    out = {}
+    for name, (kw, act, M) in MLP_CASES.items():
+        w = synth.mlp_weights(**kw)
+        m = ref_mlp(w, act)
+        rs = np.random.RandomState(kw["seed"] + 100)
+        x = (0.6 * rs.standard_normal((M, kw["in_size"]))).astype(np.float32)
+        lat = (0.5 * rs.standard_normal((M, kw.get("latent", 0)))).astype(np.float32) if kw.get("latent", 0) else None
+        with torch.no_grad():
+            y = m(T(x), T(lat) if lat is not None else None).numpy()
+        out[name + "_x"] = x
+        if lat is not None:
+            out[name + "_latent"] = lat
+        out[name + "_y"] = y
+    out["src"] = np.array("neural_blocks.py:75-86 SkipConnMLP.forward; utils.py:37-40 fourier2")
+    np.savez_compressed(os.path.join(HERE, "mlp.npz"), **out)
+    print("mlp.npz", {k: v.shape for k, v in out.items() if k != "src"})
+
+
+def gen_sdf():
+    w = synth.sdf_weights(seed=21)
+    sdf, sphere = ref_sdf(w, max_steps=64)
+    rays = synth.camera_rays(22, 384)
+    rays[:8, 3:] = -rays[:8, 3:]          # a few rays pointing away: guaranteed misses
+    rs = np.random.RandomState(23)
+    pts = (0.5 * rs.standard_normal((300, 3))).astype(np.float32)
+    random.random = lambda: FIXED_RANDOM
+    out = {}
+    with torch.no_grad():
+        out["pts"] = pts
+        out["sdf_vals"] = sphere(T(pts)).numpy()
+    r5 = T(rays).reshape(1, 384, 1, 1, 6)
+    si, active = sdf.intersect(r5, max_t=10, primary=True)
+    out["rays"] = rays
+    out["hit"] = active.reshape(-1).numpy()
+    out["depth"] = si.t.detach().reshape(-1).numpy()
+    out["throughput"] = si.throughput.detach().reshape(-1).numpy()       # = -1000 * sdf(best_pos)
+    out["p_after"] = si.p.detach().reshape(-1, 3).numpy()                 # hit points pushed along n
+    out["normals"] = si.n.detach().reshape(-1, 3).numpy()
+    out["raw_normals"] = si.raw_normals.detach().numpy()
+    out["frame"] = si.frame.detach().reshape(-1, 3, 3).numpy()
+    out["wi"] = si.wi.detach().reshape(-1, 3).numpy()
+    # the min scan internals (sdfs.py:232-249), re-run to expose idx/best_pos
+    thr, best_pos = sdf.throughput(r5[..., :3], r5[..., 3:])
+    out["best_pos"] = best_pos.detach().reshape(-1, 3).numpy()
+    out["scan_dist"] = np.array(sdf.dist, np.float64)
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    # shadow rays from the hit points towards a point light (scene.py:290-299)
+    light = torch.tensor([[0.3, 1.1, 0.2]])
+    d = light[:, None, None, None, :] - si.p.detach()
+    dist = torch.linalg.norm(d, dim=-1, keepdim=True)
+    d = F.normalize(d, eps=1e-6, dim=-1)
+    srays = torch.cat([si.p.detach(), d], dim=-1)
+    with torch.no_grad():
+        nb = sdf.intersect_test(srays, max_t=dist.reshape_as(active)[..., None])
+    out["shadow_rays"] = srays.reshape(-1, 6).numpy()
+    out["shadow_max_t"] = dist.reshape(-1).numpy()
+    out["not_blocked"] = nb.reshape(-1).numpy()
+    # value + autograd gradient at arbitrary points (sdfs.py:184-197)
+    g = sdf.autograd_diff(T(pts[:96]).clone())
+    out["grad_pts"] = g.detach().numpy()
+    out["src"] = np.array("shapes/sdfs.py:37-46,111-160,162-181,184-197,232-249; interaction.py:9-41")
+    np.savez_compressed(os.path.join(HERE, "sdf.npz"), **out)
+    print("sdf.npz hits", int(out["hit"].sum()), "of", len(out["hit"]), "not_blocked", int(out["not_blocked"].sum()))
+
+
+def gen_nerfle():
+    out = {}
+    random.random = lambda: FIXED_RANDOM
+    for tag, envmap in (("pt", False), ("le", True)):
+        n = NeRFLE(envmap=envmap, device="cpu")
+        w1 = synth.mlp_weights(seed=31, in_size=3, out=65, num_layers=5, hidden=128, freqs=16, sigma=32.0)
+        in2 = 64 + (6 if not envmap else 3 + 16 * 3)
+        w2 = synth.mlp_weights(seed=32 + envmap, in_size=in2, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0)
+        # make densities non-trivial: bias the sigma output channel upwards
+        w1["b"][-1][0] = 0.8
+        load_mlp(n.first, w1)
+        load_mlp(n.second, w2)
+        N, Wd, Hd = 2, 6, 4
+        rays = synth.camera_rays(33, N * Wd * Hd).reshape(N, Wd, Hd, 1, 6)
+        loc = np.array([[0.4, 1.0, 0.3], [-0.8, 0.5, 0.6]], np.float32)
+        lights = PointLights(device="cpu", location=T(loc), scale=10)
+        with torch.no_grad():
+            rgb = n(T(rays), lights)
+        out[tag + "_rays"] = rays
+        out[tag + "_light_loc"] = loc
+        out[tag + "_rgb"] = rgb.numpy()
+        if envmap:
+            # the 48-float light code of nerf.py:184-195
+            from pytorch3d.pathtracer.utils import elev_azim_to_dir
+            points = torch.stack(torch.meshgrid(torch.linspace(0, 180, 4), torch.linspace(0, 45, 4)), dim=-1).reshape(-1, 2)
+            with torch.no_grad():
+                out[tag + "_light_code"] = lights.envmap(elev_azim_to_dir(points)).reshape(N, -1).numpy()
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("shapes/nerf.py:175-214 NeRFLE.forward; lights/lights.py:81-88 envmap")
+    np.savez_compressed(os.path.join(HERE, "nerfle.npz"), **out)
+    print("nerfle.npz rgb mean", float(out["pt_rgb"].mean()), float(out["le_rgb"].mean()))
+
+
+def gen_composite():
+    rs = np.random.RandomState(41)
+    out = {}
+    for tag, S, R in (("s64", 64, 50), ("s5", 5, 7), ("s1", 1, 3)):
+        sigma = (2.0 * rs.standard_normal((S, R))).astype(np.float32)
+        rgb = rs.uniform(size=(S, R, 3)).astype(np.float32)
+        ts = np.linspace(0, 2.037, S).astype(np.float32) if S > 1 else np.array([0.7], np.float32)
+        sg = T(sigma).clone().requires_grad_(True)
+        cg = T(rgb).clone().requires_grad_(True)
+        tt = T(ts)
+        # nerf.py:205-213 verbatim semantics
+        sigma_a = F.relu(sg)
+        alpha = 1 - torch.exp(-sigma_a * tt[:, None].expand_as(sigma_a))
+        cp = torch.cumprod((1 - alpha).clamp(min=1e-10), dim=0)
+        cp = torch.roll(cp, 1, 0)
+        cp[-1, ...] = 1
+        weights = alpha * cp
+        res = (weights[..., None] * cg).sum(dim=0)
+        go = T(rs.standard_normal((R, 3)).astype(np.float32))
+        res.backward(go)
+        out.update({tag + "_sigma": sigma, tag + "_rgb": rgb, tag + "_ts": ts, tag + "_out": res.detach().numpy(),
+                    tag + "_gout": go.numpy(), tag + "_gsigma": sg.grad.numpy(), tag + "_grgb": cg.grad.numpy()})
+    out["src"] = np.array("shapes/nerf.py:205-213")
+    np.savez_compressed(os.path.join(HERE, "composite.npz"), **out)
+    print("composite.npz ok")
+
+
+def gen_shading():
+    rs = np.random.RandomState(51)
+    out = {}
+    n = rs.standard_normal((64, 3)).astype(np.float32)
+    n[:4] = 0.0                      # zero normals (missed rays) go through the same code
+    n[4] = [0, 0, -1]; n[5] = [0, 0, 1]
+    v = rs.standard_normal((64, 3)).astype(np.float32)
+    frame = coordinate_system(T(n))
+    out["n"] = n; out["v"] = v
+    out["frame"] = frame.numpy()
+    out["to_local"] = to_local(frame, T(v)).numpy()
+    a = rs.standard_normal((64, 3)).astype(np.float32); b = rs.standard_normal((64, 3)).astype(np.float32)
+    a[0] = [0, 0, 1]; b[0] = [0, 0, 1]
+    out["rusin_a"] = a; out["rusin_b"] = b
+    out["rusin"] = param_rusin2(T(a), T(b)).numpy()
+    out["elev_azim"] = dir_to_elev_azim(T(v)).numpy()
+    out["src"] = np.array("interaction.py:9-41; utils.py:233-258,490-494")
+    np.savez_compressed(os.path.join(HERE, "shading.npz"), **out)
+    print("shading.npz ok")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "composite", "shading"]
+    for w in which:
+        torch.manual_seed(0); random.seed(0); np.random.seed(0)
+        globals()["gen_" + w]()
