@@ -1,0 +1,268 @@
+// nrt_nerfle_render: orchestration of the volumetric render (single pass, or
+// coarse -> importance resample -> fine -> merged compositing), plus the HBM-bound
+// sampling / compositing kernels of the hierarchical path.
+#include <algorithm>
+
+#include "nrt_common.cuh"
+
+int nrt_nerfle_pass_f32(const nrt_mlp_t* first, const nrt_mlp_t* second, const float* rays, int64_t R,
+                        const float* ts, const float* ts_per_ray, int S, const float* light_code,
+                        int light_dim, const int32_t* view_of_ray, int second_out_act, float* out_rgb,
+                        float* out_sigma, float* out_srgb, cudaStream_t st);
+int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
+                       const float* ts, const float* ts_per_ray, int S, const float* light_code,
+                       int light_dim, const int32_t* view_of_ray, int second_out_act, float* out_rgb,
+                       float* out_sigma, float* out_srgb, void* workspace, size_t workspace_bytes,
+                       cudaStream_t st);
+size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int64_t R, int S);
+
+static int nerf_pass(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
+                     const float* ts, const float* ts_per_ray, int S, const float* light_code, int light_dim,
+                     const int32_t* view_of_ray, float* out_rgb, float* out_sigma, float* out_srgb,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (prec == NRT_PREC_F32)
+    return nrt_nerfle_pass_f32(first, second, rays, R, ts, ts_per_ray, S, light_code, light_dim, view_of_ray,
+                               NRT_OUT_SIGMOID, out_rgb, out_sigma, out_srgb, st);
+  return nrt_nerfle_pass_tc(first, second, prec, rays, R, ts, ts_per_ray, S, light_code, light_dim, view_of_ray,
+                            NRT_OUT_SIGMOID, out_rgb, out_sigma, out_srgb, ws, ws_bytes, st);
+}
+
+// ---- stratified sample distances -------------------------------------------------------------
+// ts[r][s] = near + (s + u)/S * (far-near), u = hash(seed, r, s) in [0,1)  (extension; the
+// reference uses the same ts for every ray, nerf.py:178).
+__device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t a, uint64_t b) {
+  uint64_t x = seed ^ (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full);
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return (float)(x >> 40) * (1.0f / 16777216.0f);
+}
+
+__global__ void k_stratified_ts(int64_t R, int S, float t_near, float t_far, uint64_t seed, float* __restrict__ ts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * S) return;
+  const int64_t r = i / S;
+  const int s = (int)(i - r * S);
+  const float u = seed ? hash_u01(seed, (uint64_t)r, (uint64_t)s) : 0.5f;
+  ts[i] = t_near + ((float)s + u) / (float)S * (t_far - t_near);
+}
+
+// ---- importance resampling (standard NeRF sample_pdf, inverse CDF over the coarse bins) ----------
+// One thread per ray.  weights come from the coarse pass with the reference's compositing formula.
+__global__ void k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_shared,
+                             const float* __restrict__ ts_c_per_ray, int Sc, int Sf, int64_t R, uint64_t seed,
+                             float* __restrict__ ts_f) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* sig = sigma_c + r * Sc;
+  const float* tc = ts_c_per_ray ? ts_c_per_ray + r * Sc : ts_c_shared;
+  // total weight (interior samples 1..Sc-2 define Sc-2 bins between mid points, as in NeRF)
+  float cp = 1.0f, total = 0.0f;
+  for (int s = 0; s < Sc; ++s) {
+    const float a = 1.0f - __expf(-fmaxf(sig[s], 0.0f) * tc[s]);
+    if (s >= 1 && s <= Sc - 2) total += a * cp + 1e-5f;
+    cp *= fmaxf(1.0f - a, 1e-10f);
+  }
+  // walk the CDF once while emitting the Sf sorted samples
+  float* out = ts_f + r * Sf;
+  int s = 1;
+  cp = 1.0f;
+  {
+    const float a0 = 1.0f - __expf(-fmaxf(sig[0], 0.0f) * tc[0]);
+    cp *= fmaxf(1.0f - a0, 1e-10f);
+  }
+  float a = 1.0f - __expf(-fmaxf(sig[1], 0.0f) * tc[1]);
+  float w = (a * cp + 1e-5f) / total;
+  float cdf_lo = 0.0f;
+  for (int j = 0; j < Sf; ++j) {
+    const float jit = seed ? hash_u01(seed ^ 0x5bd1e995u, (uint64_t)r, (uint64_t)j) : 0.5f;
+    const float u = ((float)j + jit) / (float)Sf;
+    while (s < Sc - 2 && u > cdf_lo + w) {
+      cdf_lo += w;
+      cp *= fmaxf(1.0f - a, 1e-10f);
+      ++s;
+      a = 1.0f - __expf(-fmaxf(sig[s], 0.0f) * tc[s]);
+      w = (a * cp + 1e-5f) / total;
+    }
+    const float lo = 0.5f * (tc[s - 1] + tc[s]);
+    const float hi = 0.5f * (tc[s] + tc[s + 1]);
+    const float f = fminf(fmaxf((u - cdf_lo) / w, 0.0f), 1.0f);
+    out[j] = lo + f * (hi - lo);
+  }
+}
+
+// ---- merged compositing over coarse + fine samples (both sorted by t), ray-major ----------
+// Reads 16 B/sample (sigma + rgb) + 4 B/sample (t), writes 12 B/ray.  One warp per ray: lanes
+// merge by rank, then the transmittance product is a warp scan.
+__global__ void k_merge_composite(const float* __restrict__ sig_c, const float* __restrict__ rgb_c,
+                                  const float* __restrict__ ts_c_shared, const float* __restrict__ ts_c_per_ray,
+                                  int Sc, const float* __restrict__ sig_f, const float* __restrict__ rgb_f,
+                                  const float* __restrict__ ts_f, int Sf, int64_t R, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  const int warps = blockDim.x >> 5;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = Sc + Sf;
+  float* m_t = sm + (size_t)wid * 5 * S;
+  float* m_sig = m_t + S;
+  float* m_rgb = m_sig + S;
+  const int64_t r = (int64_t)blockIdx.x * warps + wid;
+  if (r >= R) return;
+  const float* tc = ts_c_per_ray ? ts_c_per_ray + r * Sc : ts_c_shared;
+  const float* tf = ts_f + r * Sf;
+  // rank of each element in the merged order: coarse element i goes to i + #(fine < tc[i]),
+  // fine element j to j + #(coarse <= tf[j])  (stable: coarse first on ties)
+  for (int i = lane; i < Sc; i += 32) {
+    const float t = tc[i];
+    int lo = 0, hi = Sf;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < t) lo = mid + 1; else hi = mid; }
+    const int p = i + lo;
+    m_t[p] = t; m_sig[p] = sig_c[r * Sc + i];
+    m_rgb[p * 3] = rgb_c[(r * Sc + i) * 3]; m_rgb[p * 3 + 1] = rgb_c[(r * Sc + i) * 3 + 1];
+    m_rgb[p * 3 + 2] = rgb_c[(r * Sc + i) * 3 + 2];
+  }
+  for (int j = lane; j < Sf; j += 32) {
+    const float t = tf[j];
+    int lo = 0, hi = Sc;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[mid] <= t) lo = mid + 1; else hi = mid; }
+    const int p = j + lo;
+    m_t[p] = t; m_sig[p] = sig_f[r * Sf + j];
+    m_rgb[p * 3] = rgb_f[(r * Sf + j) * 3]; m_rgb[p * 3 + 1] = rgb_f[(r * Sf + j) * 3 + 1];
+    m_rgb[p * 3 + 2] = rgb_f[(r * Sf + j) * 3 + 2];
+  }
+  __syncwarp();
+  // each lane owns a contiguous run of samples; local product, then an exclusive warp scan
+  const int per = (S + 31) / 32;
+  const int s0 = lane * per, s1 = min(S, s0 + per);
+  float prod = 1.0f;
+  for (int s = s0; s < s1; ++s) {
+    const float a = 1.0f - __expf(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
+    prod *= fmaxf(1.0f - a, 1e-10f);
+  }
+  float incl = prod;
+  for (int o = 1; o < 32; o <<= 1) {
+    const float v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= v;
+  }
+  float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) excl = 1.0f;
+  const float total = __shfl_sync(0xffffffffu, incl, 31);
+  float cp = excl, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  for (int s = s0; s < s1; ++s) {
+    const float a = 1.0f - __expf(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
+    float w;
+    if (s == 0) w = a * (S == 1 ? 1.0f : total);   // roll quirk: sample 0 gets the total product
+    else if (s == S - 1) w = a;                      // last transmittance forced to 1
+    else w = a * cp;
+    acc0 += w * m_rgb[s * 3]; acc1 += w * m_rgb[s * 3 + 1]; acc2 += w * m_rgb[s * 3 + 2];
+    cp *= fmaxf(1.0f - a, 1e-10f);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    acc0 += __shfl_down_sync(0xffffffffu, acc0, o);
+    acc1 += __shfl_down_sync(0xffffffffu, acc1, o);
+    acc2 += __shfl_down_sync(0xffffffffu, acc2, o);
+  }
+  if (lane == 0) { out[r * 3] = acc0; out[r * 3 + 1] = acc1; out[r * 3 + 2] = acc2; }
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t nrt_nerfle_render_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                              int64_t R, const nrt_nerf_sampling_t* sampling) {
+  size_t total = 256;
+  int Sc = sampling ? sampling->n_coarse : 64, Sf = sampling ? sampling->n_fine : 0;
+  const bool jitter = sampling && sampling->jitter_seed != 0;
+  if (Sf > 0 || jitter) total += align256((size_t)R * Sc * 4);                       // ts_c per ray
+  if (Sf > 0) {
+    total += align256((size_t)R * Sc * 4) + align256((size_t)R * Sc * 12);            // sigma_c, rgb_c
+    total += align256((size_t)R * Sf * 4) * 2 + align256((size_t)R * Sf * 12);        // ts_f, sigma_f, rgb_f
+  }
+  if (prec != NRT_PREC_F32) total += align256(nrt_nerfle_pass_tc_workspace(first, second, R, std::max(Sc, Sf)));
+  return total;
+}
+
+extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays,
+                                 int64_t R, const float* ts, const nrt_nerf_sampling_t* sampling,
+                                 const float* light_code, int light_dim, const int32_t* view_of_ray,
+                                 float* out_rgb, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NRT_REQUIRE(rays != nullptr && out_rgb != nullptr && R >= 0, "nrt_nerfle_render: bad arguments");
+  NRT_REQUIRE(sampling != nullptr, "nrt_nerfle_render: sampling descriptor is NULL");
+  const int Sc = sampling->n_coarse, Sf = sampling->n_fine;
+  const bool jitter = sampling->jitter_seed != 0;
+  NRT_REQUIRE(Sc >= 1 && Sf >= 0, "nrt_nerfle_render: bad sample counts %d/%d", Sc, Sf);
+  NRT_REQUIRE(ts != nullptr || sampling->t_far > sampling->t_near, "nrt_nerfle_render: need ts or t_near<t_far");
+  const size_t need = nrt_nerfle_render_workspace(first, second, prec, R, sampling);
+  NRT_REQUIRE(need <= 256 || (workspace != nullptr && workspace_bytes >= need),
+              "nrt_nerfle_render: workspace of %zu bytes required, got %zu", need, workspace_bytes);
+  if (R == 0) return NRT_OK;
+  char* wp = (char*)workspace;
+  auto take = [&](size_t bytes) { char* p = wp; wp += align256(bytes); return (void*)p; };
+  float* ts_c = nullptr;
+  if (Sf > 0 || jitter) ts_c = (float*)take((size_t)R * Sc * 4);
+  float *sig_c = nullptr, *rgb_c = nullptr, *ts_f = nullptr, *sig_f = nullptr, *rgb_f = nullptr;
+  if (Sf > 0) {
+    sig_c = (float*)take((size_t)R * Sc * 4); rgb_c = (float*)take((size_t)R * Sc * 12);
+    ts_f = (float*)take((size_t)R * Sf * 4); sig_f = (float*)take((size_t)R * Sf * 4);
+    rgb_f = (float*)take((size_t)R * Sf * 12);
+  }
+  void* tcws = nullptr; size_t tcws_bytes = 0;
+  if (prec != NRT_PREC_F32) {
+    tcws_bytes = nrt_nerfle_pass_tc_workspace(first, second, R, std::max(Sc, Sf));
+    tcws = take(tcws_bytes);
+  }
+  const float* ts_shared = ts;
+  const float* ts_pr = nullptr;
+  if (jitter || (ts == nullptr)) {
+    // per-ray (stratified) distances; without jitter this is the bin-centre grid
+    if (ts_c == nullptr) { nrt_set_error("internal: ts_c missing"); return NRT_E_INVALID; }
+    k_stratified_ts<<<nrt_cdiv(R * Sc, 256), 256, 0, st>>>(R, Sc, sampling->t_near, sampling->t_far,
+                                                          sampling->jitter_seed, ts_c);
+    NRT_CUDA(cudaGetLastError());
+    ts_shared = nullptr; ts_pr = ts_c;
+  }
+  if (Sf == 0)
+    return nerf_pass(first, second, prec, rays, R, ts_shared, ts_pr, Sc, light_code, light_dim, view_of_ray,
+                     out_rgb, nullptr, nullptr, tcws, tcws_bytes, st);
+  // coarse pass: keep per-sample sigma / rgb
+  int rc = nerf_pass(first, second, prec, rays, R, ts_shared, ts_pr, Sc, light_code, light_dim, view_of_ray,
+                     nullptr, sig_c, rgb_c, tcws, tcws_bytes, st);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(Sc >= 3, "hierarchical sampling needs n_coarse >= 3");
+  k_sample_pdf<<<nrt_cdiv(R, 128), 128, 0, st>>>(sig_c, ts_shared, ts_pr, Sc, Sf, R, sampling->jitter_seed, ts_f);
+  NRT_CUDA(cudaGetLastError());
+  rc = nerf_pass(first, second, prec, rays, R, nullptr, ts_f, Sf, light_code, light_dim, view_of_ray, nullptr,
+                 sig_f, rgb_f, tcws, tcws_bytes, st);
+  if (rc != NRT_OK) return rc;
+  const int warps = 4;
+  const size_t smem = (size_t)warps * 5 * (Sc + Sf) * sizeof(float);
+  NRT_REQUIRE(smem <= 48 * 1024, "too many samples per ray for the merge kernel");
+  k_merge_composite<<<nrt_cdiv(R, warps), warps * 32, smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f, rgb_f,
+                                                                  ts_f, Sf, R, out_rgb);
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+extern "C" int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                      const float* rays_host, int64_t R, const float* ts_host, int S,
+                                      const nrt_nerf_sampling_t* sampling, const float* light_code,
+                                      int light_dim, float* out_rgb_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NRT_REQUIRE(rays_host && out_rgb_host && sampling, "nrt_nerfle_render_host: bad arguments");
+  float *d_rays = nullptr, *d_ts = nullptr, *d_out = nullptr;
+  void* ws = nullptr;
+  const size_t wsb = nrt_nerfle_render_workspace(first, second, prec, R, sampling);
+  NRT_CUDA(cudaMallocAsync(&d_rays, (size_t)R * 24, st));
+  NRT_CUDA(cudaMallocAsync(&d_out, (size_t)R * 12, st));
+  NRT_CUDA(cudaMallocAsync(&ws, wsb, st));
+  if (ts_host) {
+    NRT_CUDA(cudaMallocAsync(&d_ts, (size_t)S * 4, st));
+    NRT_CUDA(cudaMemcpyAsync(d_ts, ts_host, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  }
+  NRT_CUDA(cudaMemcpyAsync(d_rays, rays_host, (size_t)R * 24, cudaMemcpyHostToDevice, st));
+  int rc = nrt_nerfle_render(first, second, prec, d_rays, R, d_ts, sampling, light_code, light_dim, nullptr,
+                             d_out, ws, wsb, st);
+  if (rc == NRT_OK) rc = nrt_check_cuda(cudaMemcpyAsync(out_rgb_host, d_out, (size_t)R * 12, cudaMemcpyDeviceToHost, st), "D2H");
+  cudaFreeAsync(d_rays, st); cudaFreeAsync(d_out, st); cudaFreeAsync(ws, st);
+  if (d_ts) cudaFreeAsync(d_ts, st);
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(cudaStreamSynchronize(st));
+  return NRT_OK;
+}

@@ -1,0 +1,320 @@
+"""Functional ops on CUDA tensors.  Thin marshalling over the C ABI of libnrt_b200.so
+(include/nrt_b200.h): torch only provides device memory and the current stream.
+
+No fallback exists: a non-CUDA / non-fp32 / non-contiguous tensor, a missing library or a failed
+kernel raises."""
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _native as N
+from ._native import (ACT_LEAKY_RELU, ACT_SOFTPLUS, OUT_NONE, OUT_SIGMOID, OUT_SOFTPLUS, OUT_TANH,  # noqa: F401
+                      PREC_BF16, PREC_F16, PREC_F32, NrtError)
+
+_PREC_NAMES = {"f32": PREC_F32, "fp32": PREC_F32, "f16": PREC_F16, "fp16": PREC_F16, "bf16": PREC_BF16}
+
+
+def prec_id(p) -> int:
+    if isinstance(p, str):
+        return _PREC_NAMES[p.lower()]
+    return int(p)
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise NrtError("%s must be a CUDA tensor (there is no CPU path)" % name)
+    if t.dtype != dtype:
+        raise NrtError("%s must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        t = t.contiguous()
+    return t
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def mlp_layer_dims(in_size, latent_size, freqs, hidden, num_layers, skip, out_size):
+    """(K, N) of every Linear in evaluation order [init, layers..., out] (neural_blocks.py:36-55)."""
+    dim_p = in_size + 2 * freqs + latent_size
+    dims = [(dim_p, hidden)]
+    for i in range(num_layers):
+        sk = (i % skip) == 0 and i != num_layers - 1
+        dims.append((hidden + (dim_p if sk else 0), hidden))
+    dims.append((hidden, out_size))
+    return dims
+
+
+class PackedMLP:
+    """Device parameters of one SkipConnMLP in the packed-f32 layout of nrt_mlp_t."""
+
+    def __init__(self, in_size, latent_size, freqs, hidden, num_layers, skip, out_size, act,
+                 basis: torch.Tensor, params: torch.Tensor):
+        self.in_size, self.latent_size, self.freqs, self.hidden = in_size, latent_size, freqs, hidden
+        self.num_layers, self.skip, self.out_size, self.act = num_layers, skip, out_size, act
+        self.basis = _chk(basis, "basis").reshape(in_size, freqs)
+        self.params = _chk(params, "params")
+        self.dims = mlp_layer_dims(in_size, latent_size, freqs, hidden, num_layers, skip, out_size)
+        n = sum(k * n_ + n_ for k, n_ in self.dims)
+        if self.params.numel() != n:
+            raise NrtError("packed params have %d floats, expected %d" % (self.params.numel(), n))
+        self.tc_blobs = {}   # prec -> uint8 tensor (tensor-core layout), built on demand
+
+    @staticmethod
+    def pack(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> torch.Tensor:
+        """torch-layout weights (W [N,K]) in order [init, layers..., out] -> flat packed-f32 blob."""
+        chunks = []
+        for W, b in zip(weights, biases):
+            chunks.append(W.detach().t().contiguous().reshape(-1))
+            chunks.append(b.detach().reshape(-1))
+        return torch.cat(chunks).to(torch.float32).contiguous()
+
+    def unpack(self, flat: torch.Tensor):
+        """Inverse of pack for a gradient blob: returns ([gW [N,K]], [gb [N]])."""
+        gW, gb, off = [], [], 0
+        for (k, n) in self.dims:
+            gW.append(flat[off:off + k * n].reshape(k, n).t())
+            off += k * n
+            gb.append(flat[off:off + n])
+            off += n
+        return gW, gb
+
+    def c_struct(self, prec=PREC_F32) -> N.NrtMlp:
+        tc = None
+        if prec != PREC_F32:
+            tc = self.tc_blob(prec).data_ptr()
+        return N.NrtMlp(self.in_size, self.latent_size, self.freqs, self.hidden, self.num_layers, self.skip,
+                        self.out_size, self.act, self.basis.data_ptr(), self.params.data_ptr(), tc)
+
+    def tc_blob(self, prec) -> torch.Tensor:
+        if prec not in self.tc_blobs:
+            c = N.NrtMlp(self.in_size, self.latent_size, self.freqs, self.hidden, self.num_layers, self.skip,
+                         self.out_size, self.act, self.basis.data_ptr(), self.params.data_ptr(), None)
+            nbytes = N.lib().nrt_mlp_tc_blob_bytes(ctypes.byref(c), prec)
+            if nbytes < 0:
+                N.check(int(nbytes))
+            blob = torch.empty(int(nbytes), dtype=torch.uint8, device=self.params.device)
+            N.check(N.lib().nrt_mlp_pack_tc(ctypes.byref(c), prec, _ptr(blob), _stream()))
+            self.tc_blobs[prec] = blob
+        return self.tc_blobs[prec]
+
+
+class PackedSDF:
+    """Device parameters of a SphereSDF (sdfs.py:16-46)."""
+
+    def __init__(self, centers, radii, tfs, shift: PackedMLP):
+        self.centers = _chk(centers.detach(), "centers")
+        self.radii = _chk(radii.detach(), "radii")
+        self.tfs = _chk(tfs.detach(), "tfs")
+        self.shift = shift
+        self.n = self.radii.shape[0]
+
+    def c_struct(self, prec=PREC_F32) -> N.NrtSphereSdf:
+        return N.NrtSphereSdf(self.n, self.centers.data_ptr(), self.radii.data_ptr(), self.tfs.data_ptr(),
+                              self.shift.c_struct(prec))
+
+
+# ---------------------------------------------------------------------------------------------
+def mlp_forward(m: PackedMLP, x: torch.Tensor, latent: Optional[torch.Tensor] = None, out_act=OUT_NONE,
+                prec=PREC_F32, save_acts=False):
+    """SkipConnMLP.forward (neural_blocks.py:75-86) on [..., in_size] -> [..., out_size]."""
+    prec = prec_id(prec)
+    batch = x.shape[:-1]
+    x2 = _chk(x, "x").reshape(-1, m.in_size)
+    M = x2.shape[0]
+    lat = None
+    if m.latent_size:
+        if latent is None:
+            raise NrtError("this MLP needs a latent of size %d" % m.latent_size)
+        lat = _chk(latent, "latent").reshape(M, m.latent_size)
+    out = torch.empty((M, m.out_size), dtype=torch.float32, device=x.device)
+    acts = None
+    if save_acts:
+        acts = torch.empty(((m.num_layers + 1) * m.hidden, M), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        c = m.c_struct(prec)
+        N.check(N.lib().nrt_mlp_forward(ctypes.byref(c), prec, out_act, _ptr(x2), _ptr(lat), M, _ptr(out),
+                                        _ptr(acts), _stream()))
+    out = out.reshape(batch + (m.out_size,))
+    return (out, acts) if save_acts else out
+
+
+def mlp_backward(m: PackedMLP, x, latent, out, acts, g_out, out_act=OUT_NONE, need_input_grad=False):
+    x2 = _chk(x, "x").reshape(-1, m.in_size)
+    M = x2.shape[0]
+    lat = _chk(latent, "latent").reshape(M, m.latent_size) if m.latent_size else None
+    out2 = _chk(out, "out").reshape(M, m.out_size)
+    g2 = _chk(g_out, "g_out").reshape(M, m.out_size)
+    g_params = torch.zeros_like(m.params)
+    g_x = torch.empty_like(x2) if need_input_grad else None
+    g_lat = torch.empty_like(lat) if (need_input_grad and lat is not None) else None
+    with torch.cuda.device(x.device):
+        c = m.c_struct()
+        N.check(N.lib().nrt_mlp_backward(ctypes.byref(c), out_act, _ptr(x2), _ptr(lat), M, _ptr(out2), _ptr(acts),
+                                         _ptr(g2), _ptr(g_params), _ptr(g_x), _ptr(g_lat), _stream()))
+    return g_params, g_x, g_lat
+
+
+def sdf_eval(s: PackedSDF, p: torch.Tensor, prec=PREC_F32) -> torch.Tensor:
+    prec = prec_id(prec)
+    batch = p.shape[:-1]
+    p2 = _chk(p, "p").reshape(-1, 3)
+    out = torch.empty(p2.shape[0], dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        c = s.c_struct(prec)
+        N.check(N.lib().nrt_sdf_eval(ctypes.byref(c), prec, _ptr(p2), p2.shape[0], _ptr(out), _stream()))
+    return out.reshape(batch)
+
+
+def sdf_value_grad(s: PackedSDF, p: torch.Tensor):
+    batch = p.shape[:-1]
+    p2 = _chk(p, "p").reshape(-1, 3)
+    val = torch.empty(p2.shape[0], dtype=torch.float32, device=p.device)
+    grad = torch.empty((p2.shape[0], 3), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        c = s.c_struct()
+        N.check(N.lib().nrt_sdf_value_grad(ctypes.byref(c), _ptr(p2), p2.shape[0], _ptr(val), _ptr(grad), _stream()))
+    return val.reshape(batch), grad.reshape(batch + (3,))
+
+
+def sphere_trace(s: PackedSDF, rays: torch.Tensor, epsilon=1e-3, max_steps=64, max_t=10.0,
+                 active: Optional[torch.Tensor] = None, prec=PREC_F32, steps_counter: Optional[torch.Tensor] = None):
+    """SDF.intersect march loop (sdfs.py:111-131).  rays [...,6] -> depth [...], hit [...] (bool)."""
+    prec = prec_id(prec)
+    batch = rays.shape[:-1]
+    r2 = _chk(rays, "rays").reshape(-1, 6)
+    R = r2.shape[0]
+    depth = torch.empty(R, dtype=torch.float32, device=rays.device)
+    hit = torch.empty(R, dtype=torch.uint8, device=rays.device)
+    act = _chk(active.reshape(-1).to(torch.uint8), "active", torch.uint8) if active is not None else None
+    with torch.cuda.device(rays.device):
+        c = s.c_struct(prec)
+        N.check(N.lib().nrt_sdf_sphere_trace(ctypes.byref(c), prec, _ptr(r2), _ptr(act), R, float(epsilon),
+                                             int(max_steps), float(max_t), _ptr(depth), _ptr(hit),
+                                             _ptr(steps_counter), _stream()))
+    return depth.reshape(batch), hit.bool().reshape(batch)
+
+
+def shadow_test(s: PackedSDF, rays: torch.Tensor, max_t: torch.Tensor, epsilon=1e-3, max_steps=64,
+                active: Optional[torch.Tensor] = None, prec=PREC_F32, steps_counter: Optional[torch.Tensor] = None):
+    """SDF.intersect_test (sdfs.py:162-181).  Returns not_blocked [...] (bool)."""
+    prec = prec_id(prec)
+    batch = rays.shape[:-1]
+    r2 = _chk(rays, "rays").reshape(-1, 6)
+    R = r2.shape[0]
+    mt = _chk(max_t, "max_t").reshape(-1)
+    if mt.numel() != R:
+        mt = mt.expand(R).contiguous()
+    nb = torch.empty(R, dtype=torch.uint8, device=rays.device)
+    act = _chk(active.reshape(-1).to(torch.uint8), "active", torch.uint8) if active is not None else None
+    with torch.cuda.device(rays.device):
+        c = s.c_struct(prec)
+        N.check(N.lib().nrt_sdf_shadow_test(ctypes.byref(c), prec, _ptr(r2), _ptr(mt), _ptr(act), R, float(epsilon),
+                                            int(max_steps), _ptr(nb), _ptr(steps_counter), _stream()))
+    return nb.bool().reshape(batch)
+
+
+def min_scan(s: PackedSDF, rays: torch.Tensor, step: float, n_steps=128, prec=PREC_F32):
+    """SDF.throughput scan (sdfs.py:232-249).  Returns (best_idx int32 [...], best_pos [...,3], min [...])."""
+    prec = prec_id(prec)
+    batch = rays.shape[:-1]
+    r2 = _chk(rays, "rays").reshape(-1, 6)
+    R = r2.shape[0]
+    idx = torch.empty(R, dtype=torch.int32, device=rays.device)
+    pos = torch.empty((R, 3), dtype=torch.float32, device=rays.device)
+    mv = torch.empty(R, dtype=torch.float32, device=rays.device)
+    with torch.cuda.device(rays.device):
+        c = s.c_struct(prec)
+        N.check(N.lib().nrt_sdf_min_scan(ctypes.byref(c), prec, _ptr(r2), R, float(step), int(n_steps), _ptr(idx),
+                                         _ptr(pos), _ptr(mv), _stream()))
+    return idx.reshape(batch), pos.reshape(batch + (3,)), mv.reshape(batch)
+
+
+def composite_forward(sigma_raw: torch.Tensor, rgb: torch.Tensor, ts: torch.Tensor) -> torch.Tensor:
+    """nerf.py:206-213 on sample-major sigma_raw [S,R], rgb [S,R,3], ts [S] -> [R,3]."""
+    sg = _chk(sigma_raw, "sigma_raw")
+    S, R = sg.shape[0], sg[0].numel()
+    c = _chk(rgb, "rgb").reshape(S, R, 3)
+    t = _chk(ts, "ts").reshape(S)
+    out = torch.empty((R, 3), dtype=torch.float32, device=sg.device)
+    with torch.cuda.device(sg.device):
+        N.check(N.lib().nrt_composite_forward(_ptr(sg), _ptr(c), _ptr(t), S, R, _ptr(out), _stream()))
+    return out.reshape(tuple(sigma_raw.shape[1:]) + (3,))
+
+
+def composite_backward(sigma_raw, rgb, ts, g_out):
+    sg = _chk(sigma_raw, "sigma_raw")
+    S, R = sg.shape[0], sg[0].numel()
+    c = _chk(rgb, "rgb").reshape(S, R, 3)
+    t = _chk(ts, "ts").reshape(S)
+    go = _chk(g_out, "g_out").reshape(R, 3)
+    g_s = torch.empty_like(sg)
+    g_c = torch.empty_like(c)
+    with torch.cuda.device(sg.device):
+        N.check(N.lib().nrt_composite_backward(_ptr(sg), _ptr(c), _ptr(t), S, R, _ptr(go), _ptr(g_s), _ptr(g_c),
+                                               _stream()))
+    return g_s, g_c.reshape(rgb.shape)
+
+
+_ws_cache = {}
+
+
+def nerfle_render(first: PackedMLP, second: PackedMLP, rays: torch.Tensor, ts: Optional[torch.Tensor],
+                  light_code: torch.Tensor, view_of_ray: Optional[torch.Tensor] = None, prec=PREC_F32,
+                  n_coarse: Optional[int] = None, n_fine=0, t_near=0.0, t_far=0.0, jitter_seed=0) -> torch.Tensor:
+    """NeRFLE.forward (nerf.py:175-214): rays [...,6] -> rgb [...,3].
+    With n_fine == 0 and jitter_seed == 0 this is the reference's single uniform pass over `ts`."""
+    prec = prec_id(prec)
+    batch = rays.shape[:-1]
+    r2 = _chk(rays, "rays").reshape(-1, 6)
+    R = r2.shape[0]
+    t = _chk(ts, "ts").reshape(-1) if ts is not None else None
+    if n_coarse is None:
+        if t is None:
+            raise NrtError("either ts or n_coarse must be given")
+        n_coarse = t.numel()
+    lc = _chk(light_code, "light_code")
+    lc = lc.reshape(-1, lc.shape[-1])
+    vor = _chk(view_of_ray.reshape(-1), "view_of_ray", torch.int32) if view_of_ray is not None else None
+    out = torch.empty((R, 3), dtype=torch.float32, device=rays.device)
+    samp = N.NrtNerfSampling(int(n_coarse), int(n_fine), float(t_near), float(t_far), int(jitter_seed))
+    with torch.cuda.device(rays.device):
+        c1, c2 = first.c_struct(prec), second.c_struct(prec)
+        nbytes = N.lib().nrt_nerfle_render_workspace(ctypes.byref(c1), ctypes.byref(c2), prec, R, ctypes.byref(samp))
+        key = (rays.device.index, torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=rays.device)
+            _ws_cache[key] = ws
+        N.check(N.lib().nrt_nerfle_render(ctypes.byref(c1), ctypes.byref(c2), prec, _ptr(r2), R, _ptr(t),
+                                          ctypes.byref(samp), _ptr(lc), lc.shape[-1], _ptr(vor), _ptr(out),
+                                          _ptr(ws), ws.numel(), _stream()))
+    return out.reshape(batch + (3,))
+
+
+def nerfle_render_host(first: PackedMLP, second: PackedMLP, rays_host: torch.Tensor, ts_host: torch.Tensor,
+                       light_code: torch.Tensor, out_host: torch.Tensor, prec=PREC_F32, n_coarse=None, n_fine=0,
+                       t_near=0.0, t_far=0.0, jitter_seed=0):
+    """End-to-end leg: HOST (pinned) rays in, HOST rgb out; H2D/D2H copies happen inside the call."""
+    prec = prec_id(prec)
+    assert not rays_host.is_cuda and not out_host.is_cuda
+    R = rays_host.reshape(-1, 6).shape[0]
+    S = ts_host.numel() if ts_host is not None else 0
+    if n_coarse is None:
+        n_coarse = S
+    lc = _chk(light_code, "light_code")
+    samp = N.NrtNerfSampling(int(n_coarse), int(n_fine), float(t_near), float(t_far), int(jitter_seed))
+    with torch.cuda.device(lc.device):
+        c1, c2 = first.c_struct(prec), second.c_struct(prec)
+        N.check(N.lib().nrt_nerfle_render_host(
+            ctypes.byref(c1), ctypes.byref(c2), prec, ctypes.c_void_p(rays_host.data_ptr()), R,
+            ctypes.c_void_p(ts_host.data_ptr()) if ts_host is not None else None, S, ctypes.byref(samp), _ptr(lc),
+            lc.shape[-1], ctypes.c_void_p(out_host.data_ptr()), _stream()))
+    return out_host

@@ -55,3 +55,22 @@ def nerfle_ts(fixed_random, S=64):
 def psnr(a, b):
     mse = float(np.mean((np.asarray(a, np.float64) - np.asarray(b, np.float64)) ** 2))
     return 200.0 if mse == 0 else -10.0 * np.log10(mse)
+
+
+# ---- CUDA-side objects (import torch lazily so CPU-only collection stays cheap) ----
+def cuda_mlp(w, act=None, device="cuda"):
+    import torch
+    from neural_raytracing_b200 import ops
+    Ws = [torch.from_numpy(x).to(device) for x in w["W"]]
+    bs = [torch.from_numpy(x).to(device) for x in w["b"]]
+    params = ops.PackedMLP.pack(Ws, bs)
+    return ops.PackedMLP(w["in_size"], w["latent"], w["freqs"], w["hidden"], w["num_layers"], w["skip"], w["out"],
+                         ops.ACT_SOFTPLUS if act == "softplus" else ops.ACT_LEAKY_RELU,
+                         torch.from_numpy(w["basis"]).to(device), params)
+
+
+def cuda_sdf(w, device="cuda"):
+    import torch
+    from neural_raytracing_b200 import ops
+    return ops.PackedSDF(torch.from_numpy(w["centers"]).to(device), torch.from_numpy(w["radii"]).to(device),
+                         torch.from_numpy(w["tfs"]).to(device), cuda_mlp(w["shift"], "softplus", device))
