@@ -603,9 +603,10 @@ extern "C" int nrt_mlp_forward(const nrt_mlp_t* m, int prec, int out_act, const 
   MlpDev d;
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(M >= 0 && x != nullptr && out != nullptr, "nrt_mlp_forward: null x/out or negative M");
-  NRT_REQUIRE(d.latent == 0 || latent != nullptr, "nrt_mlp_forward: latent_size=%d but latent is NULL", d.latent);
+  NRT_REQUIRE(M >= 0, "nrt_mlp_forward: negative M");
   if (M == 0) return NRT_OK;
+  NRT_REQUIRE(x != nullptr && out != nullptr, "nrt_mlp_forward: null x/out");
+  NRT_REQUIRE(d.latent == 0 || latent != nullptr, "nrt_mlp_forward: latent_size=%d but latent is NULL", d.latent);
   cudaStream_t st = (cudaStream_t)stream;
   if (prec != NRT_PREC_F32) {
     NRT_REQUIRE(acts == nullptr, "nrt_mlp_forward: saved activations are only produced by NRT_PREC_F32");
@@ -628,8 +629,9 @@ extern "C" int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p,
   SdfDev d;
   int rc = nrt_build_sdf_dev(s, &d);
   if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(M >= 0 && p != nullptr && out != nullptr, "nrt_sdf_eval: null p/out or negative M");
+  NRT_REQUIRE(M >= 0, "nrt_sdf_eval: negative M");
   if (M == 0) return NRT_OK;
+  NRT_REQUIRE(p != nullptr && out != nullptr, "nrt_sdf_eval: null p/out");
   cudaStream_t st = (cudaStream_t)stream;
   if (prec != NRT_PREC_F32) return nrt_sdf_eval_tc(s, prec, p, M, out, st);
   NRT_DISPATCH_H(d.mlp.hidden, {
@@ -653,8 +655,8 @@ static int launch_march(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   if (rc != NRT_OK) return rc;
   NRT_REQUIRE(prec == NRT_PREC_F32, "sphere-trace march: only NRT_PREC_F32 is implemented (got %d)", prec);
   NRT_REQUIRE(R >= 0 && R < 2147483647LL, "march: R out of range");
-  NRT_REQUIRE(rays != nullptr && flag != nullptr && max_steps >= 0, "march: bad arguments");
   if (R == 0) return NRT_OK;
+  NRT_REQUIRE(rays != nullptr && flag != nullptr && max_steps >= 0, "march: bad arguments");
   unsigned long long* counter = nullptr;
   rc = next_counter(st, &counter);
   if (rc != NRT_OK) return rc;
@@ -675,7 +677,7 @@ extern "C" int nrt_sdf_sphere_trace(const nrt_sphere_sdf_t* s, int prec, const f
                                     const uint8_t* active, int64_t R, float epsilon, int max_steps,
                                     float max_t, float* depth, uint8_t* hit,
                                     unsigned long long* steps_done, void* stream) {
-  NRT_REQUIRE(depth != nullptr, "nrt_sdf_sphere_trace: depth is NULL");
+  NRT_REQUIRE(depth != nullptr || R == 0, "nrt_sdf_sphere_trace: depth is NULL");
   return launch_march<MARCH_PRIMARY>(s, prec, rays, nullptr, active, R, epsilon, max_steps, max_t, 0.0f, depth,
                                      hit, steps_done, (cudaStream_t)stream);
 }
@@ -684,7 +686,7 @@ extern "C" int nrt_sdf_shadow_test(const nrt_sphere_sdf_t* s, int prec, const fl
                                    const float* max_t, const uint8_t* active, int64_t R, float epsilon,
                                    int max_steps, uint8_t* not_blocked, unsigned long long* steps_done,
                                    void* stream) {
-  NRT_REQUIRE(max_t != nullptr, "nrt_sdf_shadow_test: max_t is NULL");
+  NRT_REQUIRE(max_t != nullptr || R == 0, "nrt_sdf_shadow_test: max_t is NULL");
   // depths start at 1e2 * epsilon (python float product, then cast to fp32; sdfs.py:165-166)
   const float t0 = (float)(1e2 * (double)epsilon);
   return launch_march<MARCH_SHADOW>(s, prec, rays, max_t, active, R, epsilon, max_steps, 0.0f, t0, nullptr,
@@ -698,8 +700,9 @@ extern "C" int nrt_sdf_min_scan(const nrt_sphere_sdf_t* s, int prec, const float
   int rc = nrt_build_sdf_dev(s, &d);
   if (rc != NRT_OK) return rc;
   NRT_REQUIRE(prec == NRT_PREC_F32, "nrt_sdf_min_scan: only NRT_PREC_F32 is implemented (got %d)", prec);
-  NRT_REQUIRE(R >= 0 && rays && best_idx && best_pos && n_steps >= 0, "nrt_sdf_min_scan: bad arguments");
+  NRT_REQUIRE(R >= 0 && n_steps >= 0, "nrt_sdf_min_scan: bad arguments");
   if (R == 0) return NRT_OK;
+  NRT_REQUIRE(rays && best_idx && best_pos, "nrt_sdf_min_scan: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   NRT_DISPATCH_H(d.mlp.hidden, {
     const size_t bytes = (tile_smem_floats(d.mlp.dim_p, H, d.mlp.out, TM) + 2 * TM) * sizeof(float);
@@ -715,8 +718,9 @@ extern "C" int nrt_sdf_min_scan(const nrt_sphere_sdf_t* s, int prec, const float
 
 extern "C" int nrt_composite_forward(const float* sigma_raw, const float* rgb, const float* ts, int S,
                                      int64_t R, float* out, void* stream) {
-  NRT_REQUIRE(sigma_raw && rgb && ts && out && S >= 1 && R >= 0, "nrt_composite_forward: bad arguments");
+  NRT_REQUIRE(S >= 1 && R >= 0, "nrt_composite_forward: bad arguments");
   if (R == 0) return NRT_OK;
+  NRT_REQUIRE(sigma_raw && rgb && ts && out, "nrt_composite_forward: null pointer");
   k_composite_fwd<<<nrt_cdiv(R, 128), 128, 0, (cudaStream_t)stream>>>(sigma_raw, rgb, ts, S, R, out);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
@@ -725,9 +729,9 @@ extern "C" int nrt_composite_forward(const float* sigma_raw, const float* rgb, c
 extern "C" int nrt_composite_backward(const float* sigma_raw, const float* rgb, const float* ts, int S,
                                       int64_t R, const float* g_out, float* g_sigma_raw, float* g_rgb,
                                       void* stream) {
-  NRT_REQUIRE(sigma_raw && rgb && ts && g_out && g_sigma_raw && g_rgb && S >= 1 && R >= 0,
-              "nrt_composite_backward: bad arguments");
+  NRT_REQUIRE(S >= 1 && R >= 0, "nrt_composite_backward: bad arguments");
   if (R == 0) return NRT_OK;
+  NRT_REQUIRE(sigma_raw && rgb && ts && g_out && g_sigma_raw && g_rgb, "nrt_composite_backward: null pointer");
   k_composite_bwd<<<nrt_cdiv(R, 128), 128, 0, (cudaStream_t)stream>>>(sigma_raw, rgb, ts, S, R, g_out,
                                                                       g_sigma_raw, g_rgb);
   NRT_CUDA(cudaGetLastError());

@@ -183,7 +183,9 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
                                  const float* light_code, int light_dim, const int32_t* view_of_ray,
                                  float* out_rgb, void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  NRT_REQUIRE(rays != nullptr && out_rgb != nullptr && R >= 0, "nrt_nerfle_render: bad arguments");
+  NRT_REQUIRE(R >= 0, "nrt_nerfle_render: negative R");
+  if (R == 0) return NRT_OK;
+  NRT_REQUIRE(rays != nullptr && out_rgb != nullptr, "nrt_nerfle_render: null rays/out");
   NRT_REQUIRE(sampling != nullptr, "nrt_nerfle_render: sampling descriptor is NULL");
   const int Sc = sampling->n_coarse, Sf = sampling->n_fine;
   const bool jitter = sampling->jitter_seed != 0;

@@ -175,7 +175,6 @@ int main() {
   printf("device %s cc %d.%d SMs %d\n", p.name, p.major, p.minor, p.multiProcessorCount);
   int bad = 0;
   bad += run(128, 64, 0, 0, false) > 1e-2;
-  run(128, 64, 0, 0, true);            // informational: the swapped convention should be wrong
   bad += run(128, 64, 1, 0, false) > 1e-2;
   bad += run(128, 176, 0, 0, false) > 1e-2;
   bad += run(128, 176, 1, 1, false) > 1e-1;
