@@ -1,0 +1,21 @@
+"""Process-wide knobs of the native backend."""
+
+# arithmetic of the fused MLP kernels where no gradient is required:
+#   "f32"  : fp32 FMA in a fixed order, bit-exact against the CPU oracle (default)
+#   "f16"  : tcgen05 tensor cores, fp16 operands / fp32 accumulate (networks that fit in smem)
+#   "bf16" : same with bf16 operands
+precision = "f32"
+
+# networks the tensor-core path instantiates: (in, latent, freqs, hidden, layers, skip, out, act)
+TC_NETS = {
+    (3, 0, 16, 128, 5, 3, 65, 0),   # NeRFLE.first
+    (70, 0, 16, 64, 8, 3, 3, 0),    # NeRFLE.second (point light)
+    (3, 0, 64, 96, 6, 3, 3, 0),     # NeuralBSDF.mlp
+    (5, 0, 16, 64, 8, 3, 1, 0),     # occlusion MLP
+}
+
+
+def set_precision(p):
+    global precision
+    assert p in ("f32", "f16", "bf16"), p
+    precision = p

@@ -36,20 +36,21 @@ __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t a, uint64_t b)
   return (float)(x >> 40) * (1.0f / 16777216.0f);
 }
 
-__global__ void k_stratified_ts(int64_t R, int S, float t_near, float t_far, uint64_t seed, float* __restrict__ ts) {
+__global__ void k_stratified_ts(int64_t R, int64_t r_off, int S, float t_near, float t_far, uint64_t seed,
+                                float* __restrict__ ts) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * S) return;
   const int64_t r = i / S;
   const int s = (int)(i - r * S);
-  const float u = seed ? hash_u01(seed, (uint64_t)r, (uint64_t)s) : 0.5f;
+  const float u = seed ? hash_u01(seed, (uint64_t)(r + r_off), (uint64_t)s) : 0.5f;
   ts[i] = t_near + ((float)s + u) / (float)S * (t_far - t_near);
 }
 
 // ---- importance resampling (standard NeRF sample_pdf, inverse CDF over the coarse bins) ----------
 // One thread per ray.  weights come from the coarse pass with the reference's compositing formula.
 __global__ void k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_shared,
-                             const float* __restrict__ ts_c_per_ray, int Sc, int Sf, int64_t R, uint64_t seed,
-                             float* __restrict__ ts_f) {
+                             const float* __restrict__ ts_c_per_ray, int Sc, int Sf, int64_t R, int64_t r_off,
+                             uint64_t seed, float* __restrict__ ts_f) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
   const float* sig = sigma_c + r * Sc;
@@ -73,7 +74,7 @@ __global__ void k_sample_pdf(const float* __restrict__ sigma_c, const float* __r
   float w = (a * cp + 1e-5f) / total;
   float cdf_lo = 0.0f;
   for (int j = 0; j < Sf; ++j) {
-    const float jit = seed ? hash_u01(seed ^ 0x5bd1e995u, (uint64_t)r, (uint64_t)j) : 0.5f;
+    const float jit = seed ? hash_u01(seed ^ 0x5bd1e995u, (uint64_t)(r + r_off), (uint64_t)j) : 0.5f;
     const float u = ((float)j + jit) / (float)Sf;
     while (s < Sc - 2 && u > cdf_lo + w) {
       cdf_lo += w;
@@ -106,7 +107,7 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
   const int64_t r = (int64_t)blockIdx.x * warps + wid;
   if (r >= R) return;
   const float* tc = ts_c_per_ray ? ts_c_per_ray + r * Sc : ts_c_shared;
-  const float* tf = ts_f + r * Sf;
+  const float* tf = Sf > 0 ? ts_f + r * Sf : nullptr;
   // rank of each element in the merged order: coarse element i goes to i + #(fine < tc[i]),
   // fine element j to j + #(coarse <= tf[j])  (stable: coarse first on ties)
   for (int i = lane; i < Sc; i += 32) {
@@ -164,17 +165,22 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// rays are rendered in chunks of this many so that the scratch (per-sample sigma / rgb / latent)
+// stays a few hundred MB regardless of the image size
+static const int64_t kRayChunk = 65536;
+
 extern "C" size_t nrt_nerfle_render_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
                                               int64_t R, const nrt_nerf_sampling_t* sampling) {
+  const int64_t C = std::min<int64_t>(R, kRayChunk);
   size_t total = 256;
-  int Sc = sampling ? sampling->n_coarse : 64, Sf = sampling ? sampling->n_fine : 0;
+  const int Sc = sampling ? sampling->n_coarse : 64, Sf = sampling ? sampling->n_fine : 0;
   const bool jitter = sampling && sampling->jitter_seed != 0;
-  if (Sf > 0 || jitter) total += align256((size_t)R * Sc * 4);                       // ts_c per ray
-  if (Sf > 0) {
-    total += align256((size_t)R * Sc * 4) + align256((size_t)R * Sc * 12);            // sigma_c, rgb_c
-    total += align256((size_t)R * Sf * 4) * 2 + align256((size_t)R * Sf * 12);        // ts_f, sigma_f, rgb_f
-  }
-  if (prec != NRT_PREC_F32) total += align256(nrt_nerfle_pass_tc_workspace(first, second, R, std::max(Sc, Sf)));
+  const bool store_c = Sf > 0 || prec != NRT_PREC_F32;    // the tensor-core pass always stores per-sample values
+  total += align256((size_t)C * Sc * 4);                                              // ts_c per ray (jitter / no ts)
+  (void)jitter;
+  if (store_c) total += align256((size_t)C * Sc * 4) + align256((size_t)C * Sc * 12);  // sigma_c, rgb_c
+  if (Sf > 0) total += align256((size_t)C * Sf * 4) * 2 + align256((size_t)C * Sf * 12);  // ts_f, sigma_f, rgb_f
+  if (prec != NRT_PREC_F32) total += align256(nrt_nerfle_pass_tc_workspace(first, second, C, std::max(Sc, Sf)));
   return total;
 }
 
@@ -191,54 +197,66 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
   const bool jitter = sampling->jitter_seed != 0;
   NRT_REQUIRE(Sc >= 1 && Sf >= 0, "nrt_nerfle_render: bad sample counts %d/%d", Sc, Sf);
   NRT_REQUIRE(ts != nullptr || sampling->t_far > sampling->t_near, "nrt_nerfle_render: need ts or t_near<t_far");
+  NRT_REQUIRE(Sf == 0 || Sc >= 3, "hierarchical sampling needs n_coarse >= 3");
   const size_t need = nrt_nerfle_render_workspace(first, second, prec, R, sampling);
-  NRT_REQUIRE(need <= 256 || (workspace != nullptr && workspace_bytes >= need),
+  NRT_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "nrt_nerfle_render: workspace of %zu bytes required, got %zu", need, workspace_bytes);
-  if (R == 0) return NRT_OK;
+  const int64_t C = std::min<int64_t>(R, kRayChunk);
   char* wp = (char*)workspace;
   auto take = [&](size_t bytes) { char* p = wp; wp += align256(bytes); return (void*)p; };
-  float* ts_c = nullptr;
-  if (Sf > 0 || jitter) ts_c = (float*)take((size_t)R * Sc * 4);
+  const bool store_c = Sf > 0 || prec != NRT_PREC_F32;
+  float* ts_c = (float*)take((size_t)C * Sc * 4);
   float *sig_c = nullptr, *rgb_c = nullptr, *ts_f = nullptr, *sig_f = nullptr, *rgb_f = nullptr;
+  if (store_c) { sig_c = (float*)take((size_t)C * Sc * 4); rgb_c = (float*)take((size_t)C * Sc * 12); }
   if (Sf > 0) {
-    sig_c = (float*)take((size_t)R * Sc * 4); rgb_c = (float*)take((size_t)R * Sc * 12);
-    ts_f = (float*)take((size_t)R * Sf * 4); sig_f = (float*)take((size_t)R * Sf * 4);
-    rgb_f = (float*)take((size_t)R * Sf * 12);
+    ts_f = (float*)take((size_t)C * Sf * 4); sig_f = (float*)take((size_t)C * Sf * 4);
+    rgb_f = (float*)take((size_t)C * Sf * 12);
   }
   void* tcws = nullptr; size_t tcws_bytes = 0;
   if (prec != NRT_PREC_F32) {
-    tcws_bytes = nrt_nerfle_pass_tc_workspace(first, second, R, std::max(Sc, Sf));
+    tcws_bytes = nrt_nerfle_pass_tc_workspace(first, second, C, std::max(Sc, Sf));
     tcws = take(tcws_bytes);
   }
-  const float* ts_shared = ts;
-  const float* ts_pr = nullptr;
-  if (jitter || (ts == nullptr)) {
-    // per-ray (stratified) distances; without jitter this is the bin-centre grid
-    if (ts_c == nullptr) { nrt_set_error("internal: ts_c missing"); return NRT_E_INVALID; }
-    k_stratified_ts<<<nrt_cdiv(R * Sc, 256), 256, 0, st>>>(R, Sc, sampling->t_near, sampling->t_far,
-                                                          sampling->jitter_seed, ts_c);
-    NRT_CUDA(cudaGetLastError());
-    ts_shared = nullptr; ts_pr = ts_c;
-  }
-  if (Sf == 0)
-    return nerf_pass(first, second, prec, rays, R, ts_shared, ts_pr, Sc, light_code, light_dim, view_of_ray,
-                     out_rgb, nullptr, nullptr, tcws, tcws_bytes, st);
-  // coarse pass: keep per-sample sigma / rgb
-  int rc = nerf_pass(first, second, prec, rays, R, ts_shared, ts_pr, Sc, light_code, light_dim, view_of_ray,
-                     nullptr, sig_c, rgb_c, tcws, tcws_bytes, st);
-  if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(Sc >= 3, "hierarchical sampling needs n_coarse >= 3");
-  k_sample_pdf<<<nrt_cdiv(R, 128), 128, 0, st>>>(sig_c, ts_shared, ts_pr, Sc, Sf, R, sampling->jitter_seed, ts_f);
-  NRT_CUDA(cudaGetLastError());
-  rc = nerf_pass(first, second, prec, rays, R, nullptr, ts_f, Sf, light_code, light_dim, view_of_ray, nullptr,
-                 sig_f, rgb_f, tcws, tcws_bytes, st);
-  if (rc != NRT_OK) return rc;
   const int warps = 4;
-  const size_t smem = (size_t)warps * 5 * (Sc + Sf) * sizeof(float);
-  NRT_REQUIRE(smem <= 48 * 1024, "too many samples per ray for the merge kernel");
-  k_merge_composite<<<nrt_cdiv(R, warps), warps * 32, smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f, rgb_f,
-                                                                  ts_f, Sf, R, out_rgb);
-  NRT_CUDA(cudaGetLastError());
+  const size_t merge_smem = (size_t)warps * 5 * (Sc + Sf) * sizeof(float);
+  NRT_REQUIRE(merge_smem <= 48 * 1024, "too many samples per ray for the merge kernel");
+
+  for (int64_t r0 = 0; r0 < R; r0 += C) {
+    const int64_t n = std::min<int64_t>(C, R - r0);
+    const float* c_rays = rays + r0 * 6;
+    const int32_t* c_view = view_of_ray ? view_of_ray + r0 : nullptr;
+    float* c_out = out_rgb + r0 * 3;
+    const float* ts_shared = ts;
+    const float* ts_pr = nullptr;
+    if (jitter || ts == nullptr) {
+      // per-ray (stratified) distances; without jitter this is the bin-centre grid
+      k_stratified_ts<<<nrt_cdiv(n * Sc, 256), 256, 0, st>>>(n, r0, Sc, sampling->t_near, sampling->t_far,
+                                                            sampling->jitter_seed, ts_c);
+      NRT_CUDA(cudaGetLastError());
+      ts_shared = nullptr; ts_pr = ts_c;
+    }
+    int rc;
+    if (!store_c) {
+      rc = nerf_pass(first, second, prec, c_rays, n, ts_shared, ts_pr, Sc, light_code, light_dim, c_view, c_out,
+                     nullptr, nullptr, tcws, tcws_bytes, st);
+      if (rc != NRT_OK) return rc;
+      continue;
+    }
+    // coarse pass keeps per-sample sigma / rgb
+    rc = nerf_pass(first, second, prec, c_rays, n, ts_shared, ts_pr, Sc, light_code, light_dim, c_view, nullptr,
+                   sig_c, rgb_c, tcws, tcws_bytes, st);
+    if (rc != NRT_OK) return rc;
+    if (Sf > 0) {
+      k_sample_pdf<<<nrt_cdiv(n, 128), 128, 0, st>>>(sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f);
+      NRT_CUDA(cudaGetLastError());
+      rc = nerf_pass(first, second, prec, c_rays, n, nullptr, ts_f, Sf, light_code, light_dim, c_view, nullptr,
+                     sig_f, rgb_f, tcws, tcws_bytes, st);
+      if (rc != NRT_OK) return rc;
+    }
+    k_merge_composite<<<nrt_cdiv(n, warps), warps * 32, merge_smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f,
+                                                                          rgb_f, ts_f, Sf, n, c_out);
+    NRT_CUDA(cudaGetLastError());
+  }
   return NRT_OK;
 }
 

@@ -1,28 +1,755 @@
-// tcgen05 / TMEM tensor-core path (placeholder until the fused kernels land in this file).
+// tcgen05 / TMEM fused SkipConnMLP kernels (sm_100a).
+//
+// One persistent CTA per SM keeps ALL weights of the network resident in shared memory
+// (pre-packed fp16/bf16 UMMA tiles, loaded once with cp.async.bulk) and pushes 128-sample tiles
+// through every layer with tcgen05.mma (kind::f16, M=128, fp32 accumulators in TMEM).  The
+// activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, apply
+// bias + activation, and write the next layer's A operand straight back into TMEM with
+// tcgen05.st (the MMA reads A from TMEM, B from shared memory).  Two tiles are in flight per CTA
+// (two epilogue warpgroups, one MMA-issuer warp) so the tensor pipe works on one tile while the
+// other tile's epilogue runs.
+//
+// Reference semantics: pytorch3d/pathtracer/neural_blocks.py:75-86, utils.py:37-40.  The
+// Fourier phases x.B are themselves a tiny MMA with x (and B) split into hi+lo halves so that
+// the arguments of sin/cos keep ~fp32 accuracy (SURVEY.md hard part 2).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
 #include "nrt_common.cuh"
 
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// blob layout, shared by the pack kernel (runtime) and the MMA kernels (compile time)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxOps = NRT_MAX_LAYERS + 3;
+
+struct Layout {
+  int split, XR, KRAW, KE, KX, FP, NOP;
+  int n_ops;            // encB, init, layers[0..L-1], out
+  int opN[kMaxOps], opK[kMaxOps];
+  int op_off[kMaxOps];  // in 16-bit elements
+  int w_elems;
+  int bias_off[kMaxOps];  // float offset inside the bias area (ops 1..n_ops-1)
+  int bias_floats;
+  int bytes;
+};
+
+__host__ __device__ constexpr int c16(int x) { return (x + 15) / 16 * 16; }
+__host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr bool is_skip(int i, int skip, int L) { return (i % skip) == 0 && i != L - 1; }
+
+__host__ __device__ constexpr Layout make_layout(int in, int lat, int f, int h, int L, int skip, int out) {
+  Layout y{};
+  // raw-x segment: [x_hi | x_lo] (split) or [x]; padded to 16 K-elements so that every later
+  // segment (sin, cos, latent) starts on an 8-column TMEM boundary.  The same 16-aligned segment
+  // doubles as the A tile of the phase GEMM ([x_hi | x_lo | x_hi] when split).
+  y.split = in <= 5 ? 1 : 0;
+  y.XR = c16(in * (y.split ? 2 : 1));
+  y.KRAW = y.XR + 2 * f + lat;
+  y.KE = c16(y.KRAW);
+  y.KX = y.XR;
+  y.FP = c16(f);
+  y.NOP = c16(out);
+  y.n_ops = L + 3;
+  int off = 0, boff = 0;
+  for (int o = 0; o < y.n_ops; ++o) {
+    int N = 0, K = 0;
+    if (o == 0) { N = y.FP; K = y.KX; }
+    else if (o == 1) { N = h; K = y.KE; }
+    else if (o == y.n_ops - 1) { N = y.NOP; K = h; }
+    else { N = h; K = h + (is_skip(o - 2, skip, L) ? y.KE : 0); }
+    y.opN[o] = N; y.opK[o] = K; y.op_off[o] = off; off += N * K;
+    y.bias_off[o] = boff;
+    if (o >= 1) boff += N;
+  }
+  y.w_elems = off;
+  y.bias_floats = boff;
+  y.bytes = off * 2 + boff * 4;
+  return y;
+}
+
+// maps a K index of the tensor-core encoding layout to the reference encoding index (-1: padding)
+__host__ __device__ inline int enc_ref_index(const Layout& y, int in, int k) {
+  if (k >= y.KRAW) return -1;
+  if (k >= y.XR) return k - y.XR + in;        // sin | cos | latent follow the padded x segment
+  if (k < in) return k;                        // x (hi part)
+  if (y.split && k < 2 * in) return k - in;    // x_lo columns reuse the x weights
+  return -1;                                   // padding (and the third copy of x_hi used by the phase GEMM)
+}
+
+template <int FMT> struct Elem;   // FMT 0: fp16, 1: bf16 (= tcgen05 a/b_format)
+template <> struct Elem<0> {
+  static __device__ __forceinline__ uint16_t cvt(float v) { return __half_as_ushort(__float2half_rn(v)); }
+  static __device__ __forceinline__ float back(uint16_t u) { return __half2float(__ushort_as_half(u)); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <> struct Elem<1> {
+  static __device__ __forceinline__ uint16_t cvt(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+  static __device__ __forceinline__ float back(uint16_t u) { return __bfloat162float(__ushort_as_bfloat16(u)); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// pack kernel: packed-f32 parameters -> UMMA canonical (no-swizzle, K-major) 16-bit tiles + biases
+// element (n,k) of an [N x K] operand lives at ((k/8)*N + n)*8 + k%8
+// ---------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void k_pack_tc(MlpDev m, Layout y, uint8_t* __restrict__ blob) {
+  uint16_t* w = reinterpret_cast<uint16_t*>(blob);
+  float* bias = reinterpret_cast<float*>(blob + (size_t)y.w_elems * 2);
+  const int total = y.w_elems + y.bias_floats;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    if (idx >= y.w_elems) {
+      // biases: ops 1..n_ops-1
+      int b = idx - y.w_elems, o = 1;
+      while (o + 1 < y.n_ops && b >= y.bias_off[o + 1]) ++o;
+      const int n = b - y.bias_off[o];
+      const int li = o - 1;
+      bias[b] = (n < m.N[li]) ? m.params[m.b_off[li] + n] : 0.0f;
+      continue;
+    }
+    int o = 0;
+    while (o + 1 < y.n_ops && idx >= y.op_off[o + 1]) ++o;
+    const int e = idx - y.op_off[o];
+    const int N = y.opN[o];
+    const int chunk = e / (N * 8), rem = e - chunk * (N * 8);
+    const int n = rem / 8, k = chunk * 8 + (rem & 7);
+    float v = 0.0f;
+    if (o == 0) {
+      if (n < m.freqs) {
+        if (y.split) {
+          const int seg = k / m.in_size, j = k - seg * m.in_size;
+          if (seg < 3) {
+            const float bv = m.basis[j * m.freqs + n];
+            const float hi = Elem<FMT>::back(Elem<FMT>::cvt(bv));
+            v = (seg < 2) ? hi : (bv - hi);
+          }
+        } else if (k < m.in_size) {
+          v = m.basis[k * m.freqs + n];
+        }
+      }
+    } else if (o == y.n_ops - 1) {
+      if (n < m.out) v = m.params[m.w_off[m.n_lin - 1] + k * m.out + n];
+    } else {
+      const int li = o - 1;
+      int kref;
+      if (o == 1) kref = enc_ref_index(y, m.in_size, k);
+      else if (k < m.hidden) kref = k;
+      else { const int r = enc_ref_index(y, m.in_size, k - m.hidden); kref = r < 0 ? -1 : m.hidden + r; }
+      if (kref >= 0) v = m.params[m.w_off[li] + kref * m.hidden + n];
+    }
+    w[idx] = Elem<FMT>::cvt(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); no swizzle; base offset 0
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, K = 16
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// tcgen05.ld / st, shape 32x32b: thread i of the warp <-> TMEM lane (32*(warp%4) + i), N columns
+template <int N> struct TmemIO;
+#define NRT_R4(a, i) "=r"(a[i]), "=r"(a[i + 1]), "=r"(a[i + 2]), "=r"(a[i + 3])
+#define NRT_W4(a, i) "r"(a[i]), "r"(a[i + 1]), "r"(a[i + 2]), "r"(a[i + 3])
+template <> struct TmemIO<1> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(r[0]) : "memory");
+  }
+};
+template <> struct TmemIO<2> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(t), "r"(r[0]), "r"(r[1]) : "memory");
+  }
+};
+template <> struct TmemIO<4> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : NRT_R4(r, 0) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(t), NRT_W4(r, 0) : "memory");
+  }
+};
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : NRT_R4(r, 0), NRT_R4(r, 4) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(t), NRT_W4(r, 0), NRT_W4(r, 4) : "memory");
+  }
+};
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : NRT_R4(r, 0), NRT_R4(r, 4), NRT_R4(r, 8), NRT_R4(r, 12) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(t), NRT_W4(r, 0), NRT_W4(r, 4), NRT_W4(r, 8), NRT_W4(r, 12) : "memory");
+  }
+};
+template <> struct TmemIO<32> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : NRT_R4(r, 0), NRT_R4(r, 4), NRT_R4(r, 8), NRT_R4(r, 12), NRT_R4(r, 16), NRT_R4(r, 20), NRT_R4(r, 24), NRT_R4(r, 28)
+                 : "r"(t));
+  }
+};
+// store NP packed 32-bit columns starting at column address t (compile-time decomposition)
+template <int NP>
+__device__ __forceinline__ void tmem_store(uint32_t t, const uint32_t* r) {
+  if constexpr (NP >= 16) { TmemIO<16>::st(t, r); tmem_store<NP - 16>(t + 16, r + 16); }
+  else if constexpr (NP >= 8) { TmemIO<8>::st(t, r); tmem_store<NP - 8>(t + 8, r + 8); }
+  else if constexpr (NP >= 4) { TmemIO<4>::st(t, r); tmem_store<NP - 4>(t + 4, r + 4); }
+  else if constexpr (NP >= 2) { TmemIO<2>::st(t, r); tmem_store<NP - 2>(t + 2, r + 2); }
+  else if constexpr (NP == 1) { TmemIO<1>::st(t, r); }
+}
+template <int NP>
+__device__ __forceinline__ void tmem_load(uint32_t t, uint32_t* r) {
+  if constexpr (NP >= 32) { TmemIO<32>::ld(t, r); tmem_load<NP - 32>(t + 32, r + 32); }
+  else if constexpr (NP >= 16) { TmemIO<16>::ld(t, r); tmem_load<NP - 16>(t + 16, r + 16); }
+  else if constexpr (NP >= 8) { TmemIO<8>::ld(t, r); tmem_load<NP - 8>(t + 8, r + 8); }
+  else if constexpr (NP >= 4) { TmemIO<4>::ld(t, r); tmem_load<NP - 4>(t + 4, r + 4); }
+  else if constexpr (NP >= 2) { TmemIO<2>::ld(t, r); tmem_load<NP - 2>(t + 2, r + 2); }
+  else if constexpr (NP == 1) { TmemIO<1>::ld(t, r); }
+}
+
+// fast activations for the 16-bit path (results are rounded to 16 bits anyway)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+    return x > 20.0f ? x : __logf(1.0f + __expf(x));
+  } else {
+    return fmaxf(x, 0.01f * x);
+  }
+}
+__device__ __forceinline__ void sincos_fast(float x, float* s, float* c) {
+  // two-constant reduction by 2*pi, then MUFU sin/cos on [-pi, pi]
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);
+  r = fmaf(-k, -1.7484555314695172e-07f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compile-time network description
+// ---------------------------------------------------------------------------------------------
+template <int IN_, int LAT_, int F_, int H_, int L_, int SKIP_, int OUT_, int ACT_>
+struct Net {
+  static constexpr int IN = IN_, LAT = LAT_, F = F_, H = H_, L = L_, SKIP = SKIP_, OUT = OUT_, ACT = ACT_;
+  static constexpr Layout Y = make_layout(IN, LAT, F, H, L, SKIP, OUT);
+  static constexpr bool SPLIT = Y.split != 0;
+  static constexpr int XR = Y.XR, KE = Y.KE, KX = Y.KX, FP = Y.FP, NOP = Y.NOP, KRAW = Y.KRAW;
+  static constexpr int DC = imax(H, imax(NOP, FP));       // fp32 accumulator columns
+  static constexpr int UC = imax(H, imax(KE, KX)) / 2;    // union region: encode A / enc_raw / hidden
+  static constexpr int EC = KE / 2;                       // act(enc) region
+  static constexpr int COLS = DC + UC + EC;
+  static constexpr int NSLOT = (2 * COLS <= 512) ? 2 : 1;
+  static constexpr int STAGES = L + 3;                    // encode, init, L layers, out
+  static_assert(COLS <= 512, "network does not fit in TMEM");
+  static_assert(XR % 16 == 0 && F % 16 == 0 && LAT % 16 == 0 && KRAW == KE, "encoding segments must be multiples of 16");
+  static_assert(!SPLIT || 3 * IN <= 16, "split encoding needs 3*in <= 16");
+  static_assert(SPLIT || IN % 2 == 0, "unsplit inputs must come in pairs");
+  static_assert(H % 16 == 0 && H <= 256, "hidden must be a multiple of 16");
+  static_assert(Y.bytes + 2048 <= 227 * 1024, "weights do not fit in shared memory (streaming path not built)");
+};
+
+constexpr int kEpiThreads = 128;
+
+// IO policy concept:
+//   struct IO { __device__ void load(int64_t m, float* x /*IN+LAT*/) const; __device__ void store(int64_t m, const float* o /*OUT, bias added*/) const; };
+
+template <class NET, class IO, int FMT>
+__global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
+k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
+  using E = Elem<FMT>;
+  constexpr Layout Y = NET::Y;
+  constexpr int H = NET::H, IN = NET::IN, LAT = NET::LAT, F = NET::F, L = NET::L;
+  constexpr int NSLOT = NET::NSLOT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint16_t* sW = reinterpret_cast<uint16_t*>(smem);
+  const float* sBias = reinterpret_cast<const float*>(smem + (size_t)Y.w_elems * 2);
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_ready[2];
+  __shared__ __align__(8) uint64_t bar_done[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const bool is_mma_warp = warp == 8;
+  const int64_t ntiles = (M + 127) / 128;
+
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (is_mma_warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if ((tid & 31) == 0) {
+      // all weights + biases: global (L2) -> shared, once per CTA
+      mbar_expect_tx(&bar_w, (uint32_t)Y.bytes);
+      constexpr uint32_t kChunk = 32768;
+      for (uint32_t off = 0; off < (uint32_t)Y.bytes; off += kChunk) {
+        const uint32_t n = min(kChunk, (uint32_t)Y.bytes - off);
+        bulk_g2s(smem + off, blob + off, n, &bar_w);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  mbar_wait(&bar_w, 0);
+
+  if (is_mma_warp) {
+    // ===================== MMA issuer =====================
+    if ((tid & 31) == 0) {
+      const uint32_t sW_addr = smem_u32(sW);
+      uint32_t n_ready[2] = {0, 0};
+      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
+        for (int st = 0; st < NET::STAGES; ++st) {
+          for (int slot = 0; slot < NSLOT; ++slot) {
+            if (t0 + slot >= ntiles) continue;
+            mbar_wait(&bar_ready[slot], n_ready[slot] & 1);
+            n_ready[slot]++;
+            tc_fence_after();
+            const uint32_t base = tmem + slot * NET::COLS;
+            const uint32_t dD = base, aU = base + NET::DC, aE = base + NET::DC + NET::UC;
+            const int N = Y.opN[st];
+            const uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) |
+                                   ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t b_base = sW_addr + (uint32_t)Y.op_off[st] * 2;
+            const uint32_t lbo = (uint32_t)N * 16, sbo = 128;
+            const int kch = Y.opK[st] / 16;
+            const int k_u = (st >= 2 && st < NET::STAGES - 1) ? H / 16 : kch;  // chunks taken from U
+            for (int kc = 0; kc < kch; ++kc) {
+              const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
+              mma_ts(dD, a, make_desc(b_base + (uint32_t)kc * 2 * lbo, lbo, sbo), idesc, kc > 0 ? 1u : 0u);
+            }
+            tc_commit(&bar_done[slot]);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warpgroups (one per tile slot) =====================
+    const int slot = warp >> 2;
+    const int lane_row = tid & 127;               // TMEM lane == row of the tile == sample
+    if (slot < NSLOT) {
+      const uint32_t lane_off = ((uint32_t)((warp & 3) * 32)) << 16;
+      const uint32_t base = tmem + slot * NET::COLS + lane_off;
+      const uint32_t dD = base, aU = base + NET::DC, aE = base + NET::DC + NET::UC;
+      uint32_t n_done = 0;
+      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
+        const int64_t tile = t0 + slot;
+        if (tile >= ntiles) break;
+        const int64_t m = tile * 128 + lane_row;
+        const bool valid = m < M;
+        // ---- stage 0: inputs -> encode-GEMM A operand (+ x / latent parts of enc_raw, enc_act) ----
+        {
+          float x[IN + LAT];
+          if (valid) io.load(m, x);
+          else {
+#pragma unroll
+            for (int j = 0; j < IN + LAT; ++j) x[j] = 0.0f;
+          }
+          uint32_t ax[NET::KX / 2];
+          uint32_t ex[NET::XR / 2];
+#pragma unroll
+          for (int j = 0; j < NET::KX / 2; ++j) { ax[j] = 0; ex[j] = 0; }
+          if constexpr (NET::SPLIT) {
+            uint16_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0;
+            uint16_t a[2 * IN];
+#pragma unroll
+            for (int j = 0; j < IN; ++j) {
+              const uint16_t hi = E::cvt(x[j]);
+              const uint16_t lo = E::cvt(x[j] - E::back(hi));
+              v[j] = hi; v[IN + j] = lo; v[2 * IN + j] = hi;
+              const float ax_ = act_fast<NET::ACT>(x[j]);
+              const uint16_t ahi = E::cvt(ax_);
+              a[j] = ahi; a[IN + j] = E::cvt(ax_ - E::back(ahi));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ax[j] = (uint32_t)v[2 * j] | ((uint32_t)v[2 * j + 1] << 16);
+#pragma unroll
+            for (int j = 0; j < IN; ++j) ex[j] = (uint32_t)a[2 * j] | ((uint32_t)a[2 * j + 1] << 16);
+          } else {
+#pragma unroll
+            for (int j = 0; j < IN / 2; ++j) {
+              ax[j] = E::pack(x[2 * j], x[2 * j + 1]);
+              ex[j] = E::pack(act_fast<NET::ACT>(x[2 * j]), act_fast<NET::ACT>(x[2 * j + 1]));
+            }
+          }
+          tmem_store<NET::KX / 2>(aU, ax);
+          tmem_store<NET::XR / 2>(aE, ex);
+          if constexpr (LAT > 0) {
+            // latent part of the encoding (raw and activated); sits after sin/cos
+            uint32_t lr[LAT / 2], la[LAT / 2];
+#pragma unroll
+            for (int j = 0; j < LAT / 2; ++j) {
+              lr[j] = E::pack(x[IN + 2 * j], x[IN + 2 * j + 1]);
+              la[j] = E::pack(act_fast<NET::ACT>(x[IN + 2 * j]), act_fast<NET::ACT>(x[IN + 2 * j + 1]));
+            }
+            tmem_store<LAT / 2>(aU + (NET::XR + 2 * F) / 2, lr);
+            tmem_store<LAT / 2>(aE + (NET::XR + 2 * F) / 2, la);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+        }
+        // ---- stage 1: phases -> sin / cos -> rest of enc_raw / enc_act ----
+        {
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          uint32_t ph[F];
+          tmem_load<F>(dD, ph);
+          tc_wait_ld();
+          uint32_t sr[F / 2], cr[F / 2], sa[F / 2], ca[F / 2];
+#pragma unroll
+          for (int j = 0; j < F / 2; ++j) {
+            float s0, c0, s1, c1;
+            sincos_fast(__uint_as_float(ph[2 * j]), &s0, &c0);
+            sincos_fast(__uint_as_float(ph[2 * j + 1]), &s1, &c1);
+            sr[j] = E::pack(s0, s1); cr[j] = E::pack(c0, c1);
+            sa[j] = E::pack(act_fast<NET::ACT>(s0), act_fast<NET::ACT>(s1));
+            ca[j] = E::pack(act_fast<NET::ACT>(c0), act_fast<NET::ACT>(c1));
+          }
+          tmem_store<F / 2>(aU + NET::XR / 2, sr);
+          tmem_store<F / 2>(aU + NET::XR / 2 + F / 2, cr);
+          tmem_store<F / 2>(aE + NET::XR / 2, sa);
+          tmem_store<F / 2>(aE + NET::XR / 2 + F / 2, ca);
+          // (the raw-x segment keeps the phase-GEMM tile [x_hi | x_lo | x_hi | 0]; the init / skip weights
+          //  of the third copy and of the padding are zero, see enc_ref_index)
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+        }
+        // ---- stages 2 .. L+1: hidden activations ----
+#pragma unroll 1
+        for (int st = 0; st <= L; ++st) {
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          const float* bias = sBias + Y.bias_off[1 + st];
+#pragma unroll
+          for (int c0 = 0; c0 < H; c0 += 32) {
+            uint32_t acc[32];
+            tmem_load<32>(dD + c0, acc);
+            tc_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float2 b = *reinterpret_cast<const float2*>(bias + c0 + 2 * j);
+              const float v0 = act_fast<NET::ACT>(__uint_as_float(acc[2 * j]) + b.x);
+              const float v1 = act_fast<NET::ACT>(__uint_as_float(acc[2 * j + 1]) + b.y);
+              pk[j] = E::pack(v0, v1);
+            }
+            tmem_store<16>(aU + c0 / 2, pk);
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+        }
+        // ---- output layer ----
+        {
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          constexpr int OC = (NET::OUT + 7) / 8 * 8;
+          uint32_t acc[OC];
+          tmem_load<OC>(dD, acc);
+          tc_wait_ld();
+          const float* bias = sBias + Y.bias_off[NET::STAGES - 1];
+          float o[NET::OUT];
+#pragma unroll
+          for (int j = 0; j < NET::OUT; ++j) o[j] = __uint_as_float(acc[j]) + bias[j];
+          if (valid) io.store(m, o);
+          // the accumulator / operand regions of this slot may now be reused by the next tile
+          tc_fence_before();
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// IO policies
+// ---------------------------------------------------------------------------------------------
+template <int IN, int LAT, int OUT>
+struct IoPlain {   // materialised x [M,IN] (+ latent [M,LAT]) -> out [M,OUT] with output activation
+  const float* x; const float* latent; float* out; int out_act;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+#pragma unroll
+    for (int j = 0; j < IN; ++j) v[j] = __ldg(x + m * IN + j);
+#pragma unroll
+    for (int j = 0; j < LAT; ++j) v[IN + j] = __ldg(latent + m * LAT + j);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) {
+      float v = o[j];
+      if (out_act == NRT_OUT_SIGMOID) v = 1.0f / (1.0f + __expf(-v));
+      else if (out_act == NRT_OUT_SOFTPLUS) v = v > 20.0f ? v : __logf(1.0f + __expf(v));
+      else if (out_act == NRT_OUT_TANH) v = tanhf(v);
+      out[m * OUT + j] = v;
+    }
+  }
+};
+
+// NeRFLE.first: samples along rays in, (sigma_raw fp32, latent 16-bit) out.  nerf.py:178-183
+template <int NLAT>
+struct IoNerfFirst {
+  const float* rays; const float* ts; const float* ts_per_ray; int S;
+  float* sigma; uint16_t* latent; int fmt;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+    const int64_t ray = m / S;
+    const int s = (int)(m - ray * S);
+    const float t = ts_per_ray ? __ldg(ts_per_ray + m) : __ldg(ts + s);
+    const float* r = rays + ray * 6;
+    v[0] = __ldg(r) + t * __ldg(r + 3);
+    v[1] = __ldg(r + 1) + t * __ldg(r + 4);
+    v[2] = __ldg(r + 2) + t * __ldg(r + 5);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+    sigma[m] = o[0];
+    uint4* dst = reinterpret_cast<uint4*>(latent + m * NLAT);
+#pragma unroll
+    for (int j = 0; j < NLAT / 8; ++j) {
+      uint4 q;
+      if (fmt == 0) {
+        q.x = Elem<0>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<0>::pack(o[3 + 8 * j], o[4 + 8 * j]);
+        q.z = Elem<0>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<0>::pack(o[7 + 8 * j], o[8 + 8 * j]);
+      } else {
+        q.x = Elem<1>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<1>::pack(o[3 + 8 * j], o[4 + 8 * j]);
+        q.z = Elem<1>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<1>::pack(o[7 + 8 * j], o[8 + 8 * j]);
+      }
+      dst[j] = q;
+    }
+  }
+};
+
+// NeRFLE.second: [latent | r_d | light code] in, sigmoid(rgb) out.  nerf.py:199-203
+template <int NLAT, int LD>
+struct IoNerfSecond {
+  const float* rays; const uint16_t* latent; const float* light_code; const int32_t* view_of_ray; int S;
+  float* rgb; int fmt; int out_act;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+    const int64_t ray = m / S;
+    const uint4* src = reinterpret_cast<const uint4*>(latent + m * NLAT);
+#pragma unroll
+    for (int j = 0; j < NLAT / 8; ++j) {
+      const uint4 q = __ldg(src + j);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (fmt == 0) {
+          v[8 * j + 2 * e] = Elem<0>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<0>::back((uint16_t)(w[e] >> 16));
+        } else {
+          v[8 * j + 2 * e] = Elem<1>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<1>::back((uint16_t)(w[e] >> 16));
+        }
+      }
+    }
+    const float* r = rays + ray * 6;
+    v[NLAT] = __ldg(r + 3); v[NLAT + 1] = __ldg(r + 4); v[NLAT + 2] = __ldg(r + 5);
+    const int view = view_of_ray ? __ldg(view_of_ray + ray) : 0;
+#pragma unroll
+    for (int j = 0; j < LD; ++j) v[NLAT + 3 + j] = __ldg(light_code + (int64_t)view * LD + j);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      float v = o[j];
+      if (out_act == NRT_OUT_SIGMOID) v = 1.0f / (1.0f + __expf(-v));
+      else if (out_act == NRT_OUT_TANH) v = tanhf(v);
+      rgb[m * 3 + j] = v;
+    }
+  }
+};
+
+template <class NET, class IO, int FMT>
+static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st) {
+  const size_t bytes = (size_t)NET::Y.bytes + 256;
+  auto kern = k_mlp_tc<NET, IO, FMT>;
+  NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const int64_t ntiles = (M + 127) / 128;
+  const int grid = (int)std::min<int64_t>((ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
+  kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M);
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+// the networks instantiated on the tensor-core path (all weights must fit in 227 KB of smem)
+using NetNerfFirst = Net<3, 0, 16, 128, 5, 3, 65, NRT_ACT_LEAKY_RELU>;      // NeRFLE.first   nerf.py:162-167
+using NetNerfSecondPT = Net<70, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;    // NeRFLE.second  nerf.py:169-172
+using NetNeuralBsdf = Net<3, 0, 64, 96, 6, 3, 3, NRT_ACT_LEAKY_RELU>;       // NeuralBSDF.mlp bsdfs.py:616-621
+using NetOcc = Net<5, 0, 16, 64, 8, 3, 1, NRT_ACT_LEAKY_RELU>;              // occlusion MLP  colocate.py:82-85
+
+template <class NET>
+static bool matches(const MlpDev& d) {
+  return d.in_size == NET::IN && d.latent == NET::LAT && d.freqs == NET::F && d.hidden == NET::H && d.L == NET::L &&
+         d.skip == NET::SKIP && d.out == NET::OUT && d.act == NET::ACT;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+static int fmt_of(int prec) { return prec == NRT_PREC_BF16 ? 1 : 0; }
+
 extern "C" int64_t nrt_mlp_tc_blob_bytes(const nrt_mlp_t* m, int prec) {
-  (void)m; (void)prec;
-  nrt_set_error("tensor-core path not built yet");
-  return NRT_E_UNSUPPORTED;
+  NRT_REQUIRE(m != nullptr, "mlp descriptor is NULL");
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "nrt_mlp_tc_blob_bytes: prec must be F16 or BF16");
+  NRT_REQUIRE(m->num_layers >= 1 && m->num_layers <= NRT_MAX_LAYERS && m->hidden % 16 == 0, "unsupported MLP shape");
+  const Layout y = make_layout(m->in_size, m->latent_size, m->freqs, m->hidden, m->num_layers, m->skip, m->out_size);
+  return (int64_t)y.bytes;
 }
+
 extern "C" int nrt_mlp_pack_tc(const nrt_mlp_t* m, int prec, void* blob_out, void* stream) {
-  (void)m; (void)prec; (void)blob_out; (void)stream;
-  nrt_set_error("tensor-core path not built yet");
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "nrt_mlp_pack_tc: prec must be F16 or BF16");
+  NRT_REQUIRE(blob_out != nullptr && ((uintptr_t)blob_out & 15) == 0, "blob_out must be 16-byte aligned");
+  NRT_REQUIRE(d.hidden % 16 == 0, "hidden must be a multiple of 16");
+  const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
+  const int total = y.w_elems + y.bias_floats;
+  const int grid = std::min(nrt_cdiv(total, 256), 1184);
+  if (fmt_of(prec) == 0) k_pack_tc<0><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, (uint8_t*)blob_out);
+  else k_pack_tc<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, (uint8_t*)blob_out);
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+template <class NET>
+static int forward_plain(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent, int64_t M,
+                         float* out, cudaStream_t st) {
+  IoPlain<NET::IN, NET::LAT, NET::OUT> io{x, latent, out, out_act};
+  if (fmt_of(prec) == 0) return launch<NET, decltype(io), 0>(m->params_tc, io, M, st);
+  return launch<NET, decltype(io), 1>(m->params_tc, io, M, st);
+}
+
+int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent, int64_t M,
+                       float* out, cudaStream_t st) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "unknown precision %d", prec);
+  NRT_REQUIRE(m->params_tc != nullptr, "mlp.params_tc is NULL: call nrt_mlp_pack_tc first");
+  if (matches<NetNerfFirst>(d)) return forward_plain<NetNerfFirst>(m, prec, out_act, x, latent, M, out, st);
+  if (matches<NetNerfSecondPT>(d)) return forward_plain<NetNerfSecondPT>(m, prec, out_act, x, latent, M, out, st);
+  if (matches<NetNeuralBsdf>(d)) return forward_plain<NetNeuralBsdf>(m, prec, out_act, x, latent, M, out, st);
+  if (matches<NetOcc>(d)) return forward_plain<NetOcc>(m, prec, out_act, x, latent, M, out, st);
+  nrt_set_error("tensor-core path: MLP shape (in %d, latent %d, freqs %d, hidden %d, layers %d, out %d, act %d) is not "
+                "instantiated; use NRT_PREC_F32", d.in_size, d.latent, d.freqs, d.hidden, d.L, d.out, d.act);
   return NRT_E_UNSUPPORTED;
 }
-int nrt_mlp_forward_tc(const nrt_mlp_t*, int, int, const float*, const float*, int64_t, float*, cudaStream_t) {
-  nrt_set_error("tensor-core path not built yet");
-  return NRT_E_UNSUPPORTED;
-}
+
 int nrt_sdf_eval_tc(const nrt_sphere_sdf_t*, int, const float*, int64_t, float*, cudaStream_t) {
-  nrt_set_error("tensor-core path not built yet");
+  nrt_set_error("tensor-core SDF evaluation needs the weight-streaming path (8x128 MLP = 333 KB > smem); use NRT_PREC_F32");
   return NRT_E_UNSUPPORTED;
 }
-int nrt_nerfle_pass_tc(const nrt_mlp_t*, const nrt_mlp_t*, int, const float*, int64_t, const float*, const float*,
-                       int, const float*, int, const int32_t*, int, float*, float*, float*, void*, size_t,
-                       cudaStream_t) {
-  nrt_set_error("tensor-core path not built yet");
-  return NRT_E_UNSUPPORTED;
+
+size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t*, int64_t R, int S) {
+  const int nlat = first->out_size - 1;
+  return (size_t)R * S * nlat * 2 + 256;   // 16-bit latent scratch between the two kernels
 }
-size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t*, const nrt_mlp_t*, int64_t, int) { return 0; }
+
+int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
+                       const float* ts, const float* ts_per_ray, int S, const float* light_code, int light_dim,
+                       const int32_t* view_of_ray, int second_out_act, float* out_rgb, float* out_sigma,
+                       float* out_srgb, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  MlpDev d1, d2;
+  int rc = nrt_build_mlp_dev(first, &d1);
+  if (rc != NRT_OK) return rc;
+  rc = nrt_build_mlp_dev(second, &d2);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(first->params_tc && second->params_tc, "params_tc is NULL: call nrt_mlp_pack_tc first");
+  NRT_REQUIRE(matches<NetNerfFirst>(d1), "tensor-core NeRF path: first MLP must be NeRFLE.first (3->65, 5x128)");
+  NRT_REQUIRE(matches<NetNerfSecondPT>(d2) && light_dim == 3,
+              "tensor-core NeRF path: second MLP must be the point-light NeRFLE.second (70->3, 8x64)");
+  NRT_REQUIRE(out_rgb == nullptr && out_sigma != nullptr && out_srgb != nullptr,
+              "tensor-core NeRF pass stores per-sample sigma/rgb (compositing is a separate kernel)");
+  NRT_REQUIRE((ts != nullptr) != (ts_per_ray != nullptr), "exactly one of ts / ts_per_ray must be given");
+  const int64_t M = R * S;
+  NRT_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)M * 64 * 2, "workspace too small");
+  uint16_t* lat = reinterpret_cast<uint16_t*>(workspace);
+  const int fmt = fmt_of(prec);
+  IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt};
+  IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act};
+  if (fmt == 0) {
+    rc = launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st);
+    if (rc != NRT_OK) return rc;
+    return launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st);
+  }
+  rc = launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st);
+  if (rc != NRT_OK) return rc;
+  return launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st);
+}
