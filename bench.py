@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native neural_raytracing hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision f16|bf16|f32]
+
+Workload (BASELINE.json configs[1]): nerf_synthetic-shape NeRF volumetric render, 800x800 rays,
+64 coarse + 128 importance-resampled fine samples per ray, random-init NeRFLE-architecture MLPs
+(pytorch3d/pathtracer/shapes/nerf.py:153-214), forward only.  One "step" = one full frame per GPU
+(weak scaling: every rank renders its own 640,000-ray frame; rays are independent, no collective
+on the data path).
+
+Prints ONE JSON line (rank 0):
+  value      rays/s, whole job, inputs resident in HBM, CUDA-event timed (max over ranks)
+  e2e        same through the public host-buffer entry point (pinned rays H2D + rgb D2H inside)
+  roofline   dominant kernel (tcgen05 fused first MLP): algorithmic FLOP / event-timed duration
+             against the measured bf16 peak in MEASURED_PEAKS.json
+  cpu_baseline  the reference's eager-PyTorch op sequence re-stated in oracle/port.py, timed on
+             the host cores on a bounded sample of the same workload (rank 0, N=1 only)
+
+`--impl reference` times only that CPU restatement (the reference is pure Python/PyTorch and does
+not exist on the GPU box; oracle/ is its pinned restatement) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+IMG = 800
+N_COARSE, N_FINE = 64, 128
+T_NEAR, T_FAR = 0.0, 2.05
+JITTER_SEED = 7
+# algorithmic FLOP per MLP sample = 2 * MAC of the Linear layers
+FLOP_FIRST, FLOP_SECOND = 2 * 103680, 2 * 59072
+CPU_SAMPLE_RAYS = 4096
+
+
+def synthetic_weights(seed):
+    """Random-init weights with nn.Linear's default distribution U(-1/sqrt(K), 1/sqrt(K)) for the
+    NeRFLE architecture (first: 3->65, 5x128; second: 70->3, 8x64; sigma=32, 16 frequencies)."""
+    def mlp(seed, in_size, out, num_layers, hidden, freqs, sigma, skip=3):
+        rs = np.random.RandomState(seed)
+        basis = (sigma * rs.standard_normal((freqs, in_size))).astype(np.float32).T.copy()
+        dim_p = in_size + 2 * freqs
+        shapes = [(hidden, dim_p)]
+        for i in range(num_layers):
+            sk = (i % skip) == 0 and i != num_layers - 1
+            shapes.append((hidden, hidden + (dim_p if sk else 0)))
+        shapes.append((out, hidden))
+        W = [rs.uniform(-1 / np.sqrt(k), 1 / np.sqrt(k), size=(n, k)).astype(np.float32) for n, k in shapes]
+        b = [rs.uniform(-1 / np.sqrt(k), 1 / np.sqrt(k), size=(n,)).astype(np.float32) for n, k in shapes]
+        return dict(in_size=in_size, out=out, num_layers=num_layers, hidden=hidden, freqs=freqs, latent=0,
+                    skip=skip, basis=basis, W=W, b=b)
+    w1 = mlp(seed, 3, 65, 5, 128, 16, 32.0)
+    w2 = mlp(seed + 1, 70, 3, 8, 64, 16, 32.0)
+    w1["b"][-1][0] = 0.5   # non-trivial densities
+    return w1, w2
+
+
+def camera_rays(size, view):
+    """Pinhole camera on the unit sphere looking at the origin (fov 60 deg), one ray per pixel."""
+    az = 0.7 * view + 0.3
+    el = 0.4
+    c = np.array([np.cos(el) * np.sin(az), np.sin(el), np.cos(el) * np.cos(az)], np.float64)
+    fwd = -c / np.linalg.norm(c)
+    right = np.cross(fwd, [0, 1, 0]); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    u = (np.arange(size) + 0.5) / size * 2 - 1
+    xx, yy = np.meshgrid(u, u, indexing="ij")
+    t = np.tan(np.radians(30))
+    d = fwd[None, None] + t * xx[..., None] * right[None, None] + t * yy[..., None] * up[None, None]
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    o = np.broadcast_to(c, d.shape)
+    return np.concatenate([o, d], -1).reshape(-1, 6).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = None
+        self.p = None
+
+    def start(self):
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        try:
+            self.p.terminate(); self.p.wait(timeout=5)
+            self.f.flush(); self.f.seek(0)
+            sm, mx, reasons = [], [], set()
+            for line in self.f.read().strip().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                busy = [s for s in sm if s >= 0.5 * max(sm)] or sm
+                out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                       "samples": len(sm)}
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.f.name)
+            except Exception:
+                pass
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1384.0), d.get("hbm_gbs", 6532.5), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_rate(w1, w2, rays, steps, warmup):
+    """rays/s of the reference's eager op sequence (oracle/port.py) on the host cores."""
+    import torch
+    from oracle import port
+    code = np.array([[0.4, 1.0, 0.3]], np.float32)
+    torch.set_num_threads(os.cpu_count() or 1)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        port.torch_nerfle_render(w1, w2, rays, code, N_COARSE, N_FINE, T_NEAR, T_FAR, seed=JITTER_SEED)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    return rays.shape[0] / (ms / 1e3), ms, torch.get_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    w1, w2 = synthetic_weights(0)
+    rays = camera_rays(IMG, 0)
+    sel = np.linspace(0, rays.shape[0] - 1, CPU_SAMPLE_RAYS).astype(np.int64)
+    rate, ms, threads = cpu_reference_rate(w1, w2, rays[sel], args.steps, args.warmup)
+    sample = "%d of the %d rays of the frame (evenly strided), full 64+128 samples/ray, per step" % (CPU_SAMPLE_RAYS, IMG * IMG)
+    line = {
+        "impl": "reference", "metric": "rays_per_sec", "value": rate, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "mlp_samples_per_sec": rate * (N_COARSE + N_FINE),
+        "config": workload_config("f32 (CPU, eager PyTorch op sequence)"),
+        "cpu_baseline": {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(precision):
+    return {"workload": "cfg2 nerf_synthetic-shape NeRF volumetric render %dx%d, %d coarse + %d fine samples/ray, "
+                        "NeRFLE MLPs (3->65 5x128, 70->3 8x64), random init, forward only" % (IMG, IMG, N_COARSE, N_FINE),
+            "rays_per_step_per_gpu": IMG * IMG, "samples_per_ray": N_COARSE + N_FINE, "precision": precision,
+            "l2": "flushed (256 MiB memset) between timed iterations; per-step intermediates (>1 GB) exceed L2",
+            "sharding": "one frame per rank, no data-path collective"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from neural_raytracing_b200 import ops
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w1, w2 = synthetic_weights(0)
+
+    def to_packed(w):
+        Ws = [torch.from_numpy(x).to(dev) for x in w["W"]]
+        bs = [torch.from_numpy(x).to(dev) for x in w["b"]]
+        return ops.PackedMLP(w["in_size"], 0, w["freqs"], w["hidden"], w["num_layers"], w["skip"], w["out"],
+                             ops.ACT_LEAKY_RELU, torch.from_numpy(w["basis"]).to(dev), ops.PackedMLP.pack(Ws, bs))
+    m1, m2 = to_packed(w1), to_packed(w2)
+    rays_np = camera_rays(IMG, rank)
+    R = rays_np.shape[0]
+    rays = torch.from_numpy(rays_np).to(dev)
+    code = torch.tensor([[0.4, 1.0, 0.3]], device=dev)
+    rays_host = torch.from_numpy(rays_np).pin_memory()
+    out_host = torch.empty(R, 3).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    kw = dict(prec=args.precision, n_coarse=N_COARSE, n_fine=N_FINE, t_near=T_NEAR, t_far=T_FAR, jitter_seed=JITTER_SEED)
+
+    def step():
+        return ops.nerfle_render(m1, m2, rays, None, code, **kw)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- CPU baseline first (rank 0, N=1 only), so it does not overlap the GPU timing ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sel = np.linspace(0, R - 1, CPU_SAMPLE_RAYS).astype(np.int64)
+        rate, ms, threads = cpu_reference_rate(w1, w2, rays_np[sel], 2, 1)
+        cpu = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+               "sample": "%d evenly strided rays of the frame, 64+128 samples/ray, mean of 2 runs after 1 warm-up "
+                         "(oracle/port.py: the reference's eager PyTorch op sequence on the host cores)" % CPU_SAMPLE_RAYS}
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()            # nvidia-smi needs ~1 s to come up: start it before the warm-up
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    ops.profile_collect()
+    ops.profile_enable(True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in evs:
+        flush.zero_()          # L2 flush, outside the event bracket
+        a.record()
+        step()
+        b.record()
+    barrier()
+    clocks = sampler.stop()
+    prof = ops.profile_collect()
+    ops.profile_enable(False)
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * R / (ms_per_step / 1e3)
+
+    # ---- end to end: pinned host rays in, host rgb out, copies inside the timed region ----
+    e2e_steps = max(3, min(args.steps, 10))
+    ops.nerfle_render_host(m1, m2, rays_host, None, code, out_host, **kw)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.nerfle_render_host(m1, m2, rays_host, None, code, out_host, **kw)   # synchronises before returning
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = world * R / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak_tf, peak_gbs, peak_src = measured_peaks()
+        first_ms, first_n = prof.get("mlp_tc_nerf_first", (0.0, 0))
+        launches = sum(n for _, n in prof.values())
+        roof = None
+        if first_n and first_ms > 0:
+            samples_per_launch = R * (N_COARSE + N_FINE) * args.steps / first_n
+            tf = samples_per_launch * FLOP_FIRST / (first_ms / first_n * 1e-3) / 1e12
+            roof = {"bound": "tensor", "kernel": "k_mlp_tc<NeRFLE.first> (tcgen05, %s operands)" % args.precision,
+                    "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                    "peak_source": peak_src, "launches": first_n, "avg_launch_ms": first_ms / first_n,
+                    "algorithmic_flop_per_sample": FLOP_FIRST,
+                    "share_of_step": first_ms / total_ms if total_ms else None}
+        elif args.precision == "f32":
+            fm, fn = prof.get("nerfle_fused_f32", (0.0, 0))
+            if fn and fm > 0:
+                tf = R * (N_COARSE + N_FINE) * args.steps / fn * (FLOP_FIRST + FLOP_SECOND) / (fm / fn * 1e-3) / 1e12
+                roof = {"bound": "tensor", "kernel": "k_nerfle (fp32 FMA, exact path)", "achieved": tf, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None, "peak_source": peak_src}
+        line = {
+            "metric": "rays_per_sec", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+            "mlp_samples_per_sec": value * (N_COARSE + N_FINE),
+            "model_tflops": value * (N_COARSE + N_FINE) * (FLOP_FIRST + FLOP_SECOND) / 1e12,
+            "config": workload_config(args.precision),
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * 24, "d2h_bytes_per_step": R * 12,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
+            "clocks": clocks,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -99,6 +99,15 @@ const char* nrt_last_error(void);
 /* number of SMs / compute capability of the current device; NRT_E_CUDA if none. */
 int nrt_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* ---- launch accounting / per-kernel timing (used by bench.py for `roofline` and `gpu_launches`) -- */
+/* When enabled every kernel launch of the library is bracketed by CUDA events on its stream. */
+int nrt_profile_enable(int on);
+int nrt_profile_num_tags(void);
+const char* nrt_profile_tag_name(int tag);
+/* per tag: summed device ms of the launches recorded since the last collect (needs enable) and the
+ * number of launches since the last collect (always counted).  Synchronises the events; resets. */
+int nrt_profile_collect(int n_tags, double* ms_by_tag, long long* launches_by_tag);
+
 /* ---- packed parameter sizes --------------------------------------------------------- */
 /* number of floats in the packed-f32 blob of `m` (pointers in m may be NULL). */
 int64_t nrt_mlp_param_count(const nrt_mlp_t* m);

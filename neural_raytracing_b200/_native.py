@@ -44,6 +44,10 @@ SIGNATURES = {
     "nrt_abi_version": (c_int, []),
     "nrt_last_error": (ctypes.c_char_p, []),
     "nrt_device_info": (c_int, [ctypes.POINTER(c_int)] * 3),
+    "nrt_profile_enable": (c_int, [c_int]),
+    "nrt_profile_num_tags": (c_int, []),
+    "nrt_profile_tag_name": (ctypes.c_char_p, [c_int]),
+    "nrt_profile_collect": (c_int, [c_int, ctypes.POINTER(c_f64), ctypes.POINTER(ctypes.c_longlong)]),
     "nrt_mlp_param_count": (c_i64, [_PM]),
     "nrt_mlp_tc_blob_bytes": (c_i64, [_PM, c_int]),
     "nrt_mlp_pack_tc": (c_int, [_PM, c_int, c_vp, c_vp]),

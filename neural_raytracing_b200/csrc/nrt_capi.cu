@@ -108,3 +108,62 @@ int nrt_build_sdf_dev(const nrt_sphere_sdf_t* s, SdfDev* out) {
               "sdf.shift must be a 3 -> 1 MLP without latent");
   return NRT_OK;
 }
+
+// ---- launch accounting and optional CUDA-event timing of every kernel launch ----------------
+#include <mutex>
+#include <vector>
+static const char* kTagNames[TAG_COUNT] = {
+    "mlp_fwd_f32", "sdf_eval_f32", "sdf_march_f32", "sdf_shadow_f32", "sdf_min_scan_f32", "nerfle_fused_f32",
+    "composite_fwd", "composite_bwd", "mlp_tc_nerf_first", "mlp_tc_nerf_second", "mlp_tc_generic", "mlp_tc_pack",
+    "stratified_ts", "sample_pdf", "merge_composite", "mlp_bwd_f32", "sdf_value_grad_f32", "shade"};
+static std::mutex g_prof_mu;
+static long long g_launches[TAG_COUNT] = {0};
+static bool g_prof_on = false;
+struct ProfRec { cudaEvent_t a, b; int tag; };
+static std::vector<ProfRec> g_prof_recs;
+static std::vector<cudaEvent_t> g_prof_pool;
+
+static cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void nrt_prof_begin(int tag, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_launches[tag]++;
+  if (!g_prof_on) return;
+  ProfRec r; r.a = prof_event(); r.b = prof_event(); r.tag = tag;
+  cudaEventRecord(r.a, st);
+  g_prof_recs.push_back(r);
+}
+void nrt_prof_end(int tag, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof_on) return;
+  for (size_t i = g_prof_recs.size(); i-- > 0;)
+    if (g_prof_recs[i].tag == tag) { cudaEventRecord(g_prof_recs[i].b, st); break; }
+}
+extern "C" int nrt_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return NRT_OK;
+}
+extern "C" int nrt_profile_num_tags(void) { return TAG_COUNT; }
+extern "C" const char* nrt_profile_tag_name(int tag) { return (tag >= 0 && tag < TAG_COUNT) ? kTagNames[tag] : ""; }
+// Synchronises the recorded events and returns, per tag, the summed device time (ms) of the launches
+// recorded since the last collect and the number of launches since the last collect.  Resets both.
+extern "C" int nrt_profile_collect(int n_tags, double* ms_by_tag, long long* launches_by_tag) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int t = 0; t < n_tags && t < TAG_COUNT; ++t) {
+    if (ms_by_tag) ms_by_tag[t] = 0.0;
+    if (launches_by_tag) { launches_by_tag[t] = g_launches[t]; }
+    g_launches[t] = 0;
+  }
+  for (auto& r : g_prof_recs) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      if (ms_by_tag && r.tag < n_tags) ms_by_tag[r.tag] += ms;
+    }
+    g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+  }
+  g_prof_recs.clear();
+  return NRT_OK;
+}

@@ -52,4 +52,18 @@ int nrt_build_mlp_dev(const nrt_mlp_t* m, MlpDev* out);  // validates + resolves
 int nrt_build_sdf_dev(const nrt_sphere_sdf_t* s, SdfDev* out);
 int nrt_sm_count();
 
+// launch accounting / optional per-kernel event timing (nrt_profile_* in the C ABI)
+enum NrtTag {
+  TAG_MLP_F32 = 0, TAG_SDF_EVAL_F32, TAG_MARCH_F32, TAG_SHADOW_F32, TAG_MIN_SCAN_F32, TAG_NERFLE_F32,
+  TAG_COMPOSITE_FWD, TAG_COMPOSITE_BWD, TAG_TC_NERF_FIRST, TAG_TC_NERF_SECOND, TAG_TC_MLP, TAG_TC_PACK,
+  TAG_STRATIFIED_TS, TAG_SAMPLE_PDF, TAG_MERGE_COMPOSITE, TAG_MLP_BWD_F32, TAG_SDF_GRAD_F32, TAG_SHADE, TAG_COUNT
+};
+void nrt_prof_begin(int tag, cudaStream_t st);
+void nrt_prof_end(int tag, cudaStream_t st);
+struct NrtProfScope {
+  int tag; cudaStream_t st;
+  NrtProfScope(int t, cudaStream_t s) : tag(t), st(s) { nrt_prof_begin(tag, st); }
+  ~NrtProfScope() { nrt_prof_end(tag, st); }
+};
+
 static inline int nrt_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -618,6 +618,7 @@ extern "C" int nrt_mlp_forward(const nrt_mlp_t* m, int prec, int out_act, const 
     if (rc != NRT_OK) return rc;
     const int64_t ntiles = (M + TM - 1) / TM;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count() * 8);
+    NrtProfScope _ps(TAG_MLP_F32, st);
     k_mlp_fwd<H, TM><<<grid, kThreads, bytes, st>>>(d, x, latent, M, out, acts, out_act);
   })
   NRT_CUDA(cudaGetLastError());
@@ -640,6 +641,7 @@ extern "C" int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p,
     if (rc != NRT_OK) return rc;
     const int64_t ntiles = (M + TM - 1) / TM;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count() * 8);
+    NrtProfScope _ps(TAG_SDF_EVAL_F32, st);
     k_sdf_eval<H, TM><<<grid, kThreads, bytes, st>>>(d, p, M, out);
   })
   NRT_CUDA(cudaGetLastError());
@@ -666,6 +668,7 @@ static int launch_march(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
     if (rc != NRT_OK) return rc;
     const int64_t ntiles = (R + TM - 1) / TM;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count());
+    NrtProfScope _ps(MODE == MARCH_PRIMARY ? TAG_MARCH_F32 : TAG_SHADOW_F32, st);
     k_sdf_march<H, TM, MODE><<<grid, kThreads, bytes, st>>>(d, rays, max_t_per_ray, active, R, eps, max_steps,
                                                             max_t, t_start, depth, flag, counter, steps_done);
   })
@@ -710,6 +713,7 @@ extern "C" int nrt_sdf_min_scan(const nrt_sphere_sdf_t* s, int prec, const float
     if (rc != NRT_OK) return rc;
     const int64_t ntiles = (R + TM - 1) / TM;
     const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count() * 4);
+    NrtProfScope _ps(TAG_MIN_SCAN_F32, st);
     k_sdf_min_scan<H, TM><<<grid, kThreads, bytes, st>>>(d, rays, R, step, n_steps, best_idx, best_pos, min_val);
   })
   NRT_CUDA(cudaGetLastError());
@@ -721,6 +725,7 @@ extern "C" int nrt_composite_forward(const float* sigma_raw, const float* rgb, c
   NRT_REQUIRE(S >= 1 && R >= 0, "nrt_composite_forward: bad arguments");
   if (R == 0) return NRT_OK;
   NRT_REQUIRE(sigma_raw && rgb && ts && out, "nrt_composite_forward: null pointer");
+  NrtProfScope _ps(TAG_COMPOSITE_FWD, (cudaStream_t)stream);
   k_composite_fwd<<<nrt_cdiv(R, 128), 128, 0, (cudaStream_t)stream>>>(sigma_raw, rgb, ts, S, R, out);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
@@ -732,6 +737,7 @@ extern "C" int nrt_composite_backward(const float* sigma_raw, const float* rgb, 
   NRT_REQUIRE(S >= 1 && R >= 0, "nrt_composite_backward: bad arguments");
   if (R == 0) return NRT_OK;
   NRT_REQUIRE(sigma_raw && rgb && ts && g_out && g_sigma_raw && g_rgb, "nrt_composite_backward: null pointer");
+  NrtProfScope _ps(TAG_COMPOSITE_BWD, (cudaStream_t)stream);
   k_composite_bwd<<<nrt_cdiv(R, 128), 128, 0, (cudaStream_t)stream>>>(sigma_raw, rgb, ts, S, R, g_out,
                                                                       g_sigma_raw, g_rgb);
   NRT_CUDA(cudaGetLastError());
@@ -772,7 +778,8 @@ int nrt_nerfle_pass_f32(const nrt_mlp_t* first, const nrt_mlp_t* second, const f
   if (m1.hidden == H1 && m2.hidden == H2) {                                          \
     rc = set_smem(k_nerfle<H1, H2, TM>, bytes);                                      \
     if (rc != NRT_OK) return rc;                                                     \
-    k_nerfle<H1, H2, TM><<<grid, kThreads, bytes, st>>>(m1, m2, a);                  \
+    { NrtProfScope _ps(TAG_NERFLE_F32, st);                                          \
+    k_nerfle<H1, H2, TM><<<grid, kThreads, bytes, st>>>(m1, m2, a); }                \
     NRT_CUDA(cudaGetLastError());                                                    \
     return NRT_OK;                                                                   \
   }

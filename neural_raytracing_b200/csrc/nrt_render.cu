@@ -230,6 +230,7 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
     const float* ts_pr = nullptr;
     if (jitter || ts == nullptr) {
       // per-ray (stratified) distances; without jitter this is the bin-centre grid
+      NrtProfScope _ps(TAG_STRATIFIED_TS, st);
       k_stratified_ts<<<nrt_cdiv(n * Sc, 256), 256, 0, st>>>(n, r0, Sc, sampling->t_near, sampling->t_far,
                                                             sampling->jitter_seed, ts_c);
       NRT_CUDA(cudaGetLastError());
@@ -247,14 +248,16 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
                    sig_c, rgb_c, tcws, tcws_bytes, st);
     if (rc != NRT_OK) return rc;
     if (Sf > 0) {
-      k_sample_pdf<<<nrt_cdiv(n, 128), 128, 0, st>>>(sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f);
+      { NrtProfScope _ps(TAG_SAMPLE_PDF, st);
+      k_sample_pdf<<<nrt_cdiv(n, 128), 128, 0, st>>>(sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f); }
       NRT_CUDA(cudaGetLastError());
       rc = nerf_pass(first, second, prec, c_rays, n, nullptr, ts_f, Sf, light_code, light_dim, c_view, nullptr,
                      sig_f, rgb_f, tcws, tcws_bytes, st);
       if (rc != NRT_OK) return rc;
     }
+    { NrtProfScope _ps(TAG_MERGE_COMPOSITE, st);
     k_merge_composite<<<nrt_cdiv(n, warps), warps * 32, merge_smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f,
-                                                                          rgb_f, ts_f, Sf, n, c_out);
+                                                                          rgb_f, ts_f, Sf, n, c_out); }
     NRT_CUDA(cudaGetLastError());
   }
   return NRT_OK;

@@ -635,12 +635,13 @@ struct IoNerfSecond {
 };
 
 template <class NET, class IO, int FMT>
-static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st) {
+static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP) {
   const size_t bytes = (size_t)NET::Y.bytes + 256;
   auto kern = k_mlp_tc<NET, IO, FMT>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int64_t ntiles = (M + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
+  NrtProfScope _ps(tag, st);
   kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
@@ -682,6 +683,7 @@ extern "C" int nrt_mlp_pack_tc(const nrt_mlp_t* m, int prec, void* blob_out, voi
   const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
   const int total = y.w_elems + y.bias_floats;
   const int grid = std::min(nrt_cdiv(total, 256), 1184);
+  NrtProfScope _ps(TAG_TC_PACK, (cudaStream_t)stream);
   if (fmt_of(prec) == 0) k_pack_tc<0><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, (uint8_t*)blob_out);
   else k_pack_tc<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, (uint8_t*)blob_out);
   NRT_CUDA(cudaGetLastError());
@@ -745,11 +747,11 @@ int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
   IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt};
   IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act};
   if (fmt == 0) {
-    rc = launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st);
+    rc = launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);
     if (rc != NRT_OK) return rc;
-    return launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st);
+    return launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
   }
-  rc = launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st);
+  rc = launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);
   if (rc != NRT_OK) return rc;
-  return launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st);
+  return launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
 }

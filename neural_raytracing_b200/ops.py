@@ -12,6 +12,9 @@ from . import _native as N
 from ._native import (ACT_LEAKY_RELU, ACT_SOFTPLUS, OUT_NONE, OUT_SIGMOID, OUT_SOFTPLUS, OUT_TANH,  # noqa: F401
                       PREC_BF16, PREC_F16, PREC_F32, NrtError)
 
+# set once the analytic-Jacobian kernel is part of the library
+HAS_SDF_VALUE_GRAD = False
+
 _PREC_NAMES = {"f32": PREC_F32, "fp32": PREC_F32, "f16": PREC_F16, "fp16": PREC_F16, "bf16": PREC_BF16}
 
 
@@ -318,3 +321,17 @@ def nerfle_render_host(first: PackedMLP, second: PackedMLP, rays_host: torch.Ten
             ctypes.c_void_p(ts_host.data_ptr()) if ts_host is not None else None, S, ctypes.byref(samp), _ptr(lc),
             lc.shape[-1], ctypes.c_void_p(out_host.data_ptr()), _stream()))
     return out_host
+
+
+# ---- launch accounting / per-kernel timing ----------------------------------------------------
+def profile_enable(on: bool):
+    N.check(N.lib().nrt_profile_enable(1 if on else 0))
+
+
+def profile_collect():
+    """{kernel tag: (summed device ms [needs profile_enable], launches)} since the last collect."""
+    n = N.lib().nrt_profile_num_tags()
+    ms = (ctypes.c_double * n)()
+    cnt = (ctypes.c_longlong * n)()
+    N.check(N.lib().nrt_profile_collect(n, ms, cnt))
+    return {N.lib().nrt_profile_tag_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}

@@ -1,0 +1,127 @@
+"""Integrators on the hot path (pytorch3d/pathtracer/integrators/integrators.py): Direct,
+NeRFIntegrator, NeRFReproduce, plus the trivial debug views built on the same protocol."""
+import torch
+import torch.nn as nn
+
+from ..neural_blocks import SkipConnMLP
+from ..scene import sample_emitter_dir_w_isect, sample_emitter_dir_w_learned_occ, sample_emitter_dir_wo_isect
+
+
+class Integrator(nn.Module):
+    def __init__(self, max_depth=2, russian_roulette_depth=5, sampler=None, lights=None):
+        super().__init__()
+        self.max_depth = max_depth
+        self.rr_depth = russian_roulette_depth
+        self.sampler = sampler
+        self.lights = lights
+
+    def dims(self):
+        raise NotImplementedError()
+
+    def sample(self, shapes, rays, bsdf, **kwargs):
+        raise NotImplementedError()
+
+
+class Debug(Integrator):
+    def dims(self):
+        return 3
+
+    def sample(self, shapes, rays, bsdf, **kwargs):
+        si, active = shapes.intersect(rays)
+        return torch.where(active.unsqueeze(-1), (si.n + 1) / 2, torch.zeros_like(si.n)), active, si
+
+
+class Silhouette(Integrator):
+    def dims(self):
+        return 1
+
+    def sample(self, shapes, rays, bsdf, **kwargs):
+        si, active = shapes.intersect(rays)
+        return 1 - active.unsqueeze(-1).float(), active, si
+
+
+class Mask(Integrator):
+    def __init__(self, sub_integrator, **kwargs):
+        super().__init__(**kwargs)
+        self.sub_integrator = sub_integrator
+
+    def dims(self):
+        return self.sub_integrator.dims() + 1
+
+    def sample(self, density_field, rays, bsdf, **kwargs):
+        result, active, si = self.sub_integrator.sample(density_field, rays, bsdf, **kwargs)
+        result = torch.cat([result, active.float().unsqueeze(-1)], dim=-1)
+        return result, torch.ones_like(active), si
+
+
+class Direct(Integrator):
+    """Direct lighting: intersect, sample the emitter (optionally shadow-tested / with learned
+    occlusion), evaluate the BSDF, accumulate on the hits (integrators.py:139-206)."""
+    DEFAULT_EMITTER_SAMPLES = 1
+    DEFAULT_BSDF_SAMPLES = 0
+
+    def dims(self):
+        return 3
+
+    def __init__(self, emitter_samples=DEFAULT_EMITTER_SAMPLES, bsdf_samples=DEFAULT_BSDF_SAMPLES, training=True,
+                 **kwargs):
+        self.emitter_samples = emitter_samples
+        self.bsdf_samples = bsdf_samples
+        self.training = training
+        super().__init__(**kwargs)
+
+    def sample(self, shapes, rays, bsdf, **kwargs):
+        sampler = kwargs.get("sampler", self.sampler)
+        lights = kwargs.get("lights", self.lights)
+        w_isect = kwargs.get("w_isect")
+        emit = sample_emitter_dir_wo_isect
+        if w_isect is True:
+            emit = sample_emitter_dir_w_isect
+        if isinstance(w_isect, SkipConnMLP):
+            def emit(it, s, lights, sampler, active):
+                return sample_emitter_dir_w_learned_occ(it, s, lights, sampler, w_isect, active)
+        result = torch.zeros(*rays.shape[:-1], 3, device=rays.device)
+        it, active = shapes.intersect(rays, primary=self.training)
+        if not active.any():
+            return result, active, it
+        for _ in range(self.emitter_samples):
+            ds, emitter_val = emit(it, shapes, lights=lights, sampler=sampler, active=active)
+            lit = active & (ds.pdf > 0)
+            wo = it.to_local(ds.d)
+            bsdf_val, _pdf = bsdf.eval_and_pdf(it, wo, active=lit)
+            result[lit] = result[lit] + bsdf_val[lit] * emitter_val[lit] / self.emitter_samples
+        if self.bsdf_samples:
+            raise NotImplementedError("BSDF sampling is not implemented in the reference either (integrators.py:198)")
+        return result, active, it
+
+
+class NeRFIntegrator(Integrator):
+    """Appends sigmoid(throughput) as an alpha channel and marks every pixel valid (integrators.py:243-257)."""
+
+    def __init__(self, sub_integrator, **kwargs):
+        super().__init__(**kwargs)
+        self.sub_integrator = sub_integrator
+
+    def dims(self):
+        return self.sub_integrator.dims() + 1
+
+    def sample(self, density_field, rays, bsdf, **kwargs):
+        result, active, mi = self.sub_integrator.sample(density_field, rays, bsdf, **kwargs)
+        alpha = mi.throughput.unsqueeze(-1)
+        if mi.with_logits:
+            alpha = alpha.sigmoid()
+        return torch.cat([result, alpha], dim=-1), torch.tensor(True, device=result.device), mi
+
+
+class NeRFReproduce(Integrator):
+    """Uses a volumetric NeRF module in place of surface integration (integrators.py:260-267)."""
+
+    def dims(self):
+        return 3
+
+    def sample(self, nerf, rays, lights, **kwargs):
+        result = nerf(rays, lights)
+
+        class Dummy:
+            ...
+        return result, torch.tensor(True, device=result.device), Dummy()

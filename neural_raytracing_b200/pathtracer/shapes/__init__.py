@@ -1,0 +1,2 @@
+from .sdfs import SDF, SPHERE_SDF, SphereSDF
+from .nerf import NeRFLE, PlainNeRF

@@ -1,0 +1,124 @@
+"""Volumetric NeRF models (pytorch3d/pathtracer/shapes/nerf.py): NeRFLE and PlainNeRF."""
+import random
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import config, ops
+from ..neural_blocks import SkipConnMLP
+from ..utils import dir_to_elev_azim, elev_azim_to_dir
+
+
+def composite_reference_ops(sigma_raw, rgb, ts):
+    """nerf.py:205-213 on sample-major tensors with torch ops (differentiable)."""
+    sigma_a = F.relu(sigma_raw)
+    shape = (-1,) + (1,) * (sigma_a.dim() - 1)
+    alpha = 1 - torch.exp(-sigma_a * ts.reshape(shape))
+    cp = torch.cumprod((1 - alpha).clamp(min=1e-10), dim=0)
+    cp = torch.roll(cp, 1, 0)
+    cp[-1, ...] = 1
+    return ((alpha * cp)[..., None] * rgb).sum(dim=0)
+
+
+class _Composite(torch.autograd.Function):
+    """Compositing through the HBM-bound CUDA kernels (forward + backward)."""
+
+    @staticmethod
+    def forward(ctx, sigma_raw, rgb, ts):
+        s, c, t = sigma_raw.contiguous().float(), rgb.contiguous().float(), ts.contiguous().float()
+        ctx.save_for_backward(s, c, t)
+        return ops.composite_forward(s, c, t)
+
+    @staticmethod
+    def backward(ctx, g):
+        s, c, t = ctx.saved_tensors
+        gs, gc = ops.composite_backward(s, c, t, g.contiguous().float())
+        return gs, gc, None
+
+
+def composite(sigma_raw, rgb, ts):
+    if sigma_raw.is_cuda:
+        return _Composite.apply(sigma_raw, rgb, ts)
+    return composite_reference_ops(sigma_raw, rgb, ts)
+
+
+class NeRFLE(nn.Module):
+    """NeRF with a point light / environment-light code (nerf.py:153-214)."""
+
+    def __init__(self, envmap=False, bins=4, device="cuda"):
+        super().__init__()
+        self.latent_size = 64
+        self.first = SkipConnMLP(num_layers=5, hidden_size=128, in_size=3, out=1 + self.latent_size,
+                                 device=device).to(device)
+        self.bins = bins
+        self.second = SkipConnMLP(in_size=self.latent_size + (6 if not envmap else 3 + bins * bins * 3), out=3,
+                                  device=device).to(device)
+        self.envmap = envmap
+
+    def _light_code(self, lights, device):
+        """[n_views, 3] light location, or the [n_views, 3*bins^2] environment code (nerf.py:184-197)."""
+        if getattr(self, "envmap", False):
+            grid = torch.stack(torch.meshgrid(torch.linspace(0, 180, self.bins, device=device),
+                                              torch.linspace(0, 45, self.bins, device=device), indexing="ij"),
+                               dim=-1).reshape(-1, 2)
+            code = lights.envmap(elev_azim_to_dir(grid))
+            return code.reshape(code.shape[0], -1)
+        return lights.location
+
+    def _needs_grad(self, rays):
+        return torch.is_grad_enabled() and (rays.requires_grad or any(p.requires_grad for p in self.parameters()))
+
+    def forward(self, rays, lights):
+        r_o, r_d = rays.split([3, 3], dim=-1)
+        device = r_o.device
+        ts = torch.linspace(0, 2 + random.random() * 0.1, 64, device=device)
+        code = self._light_code(lights, device)
+        if rays.is_cuda and not self._needs_grad(rays):
+            # fused render: rays in, rgb out
+            N = rays.shape[0]
+            per_view = rays[0].numel() // 6
+            view = torch.arange(N, device=device, dtype=torch.int32).repeat_interleave(per_view)
+            prec = config.precision if (config.precision != "f32" and not self.envmap) else "f32"
+            return ops.nerfle_render(self.first.packed(), self.second.packed(), rays.detach().float(), ts,
+                                     code.detach().float(), view, prec=prec)
+        # differentiable path: fused MLP kernels where available + CUDA compositing
+        pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
+        first_out = self.first(pts)
+        latent, alpha = first_out[..., 1:], first_out[..., 0]
+        lead = latent.shape[:-1]
+        light = code.reshape((1, code.shape[0]) + (1,) * (len(lead) - 2) + (-1,)).expand(lead + (-1,))
+        rgb = self.second(torch.cat([latent, r_d[None, ...].expand(lead + (3,)), light], dim=-1)).sigmoid()
+        return composite(alpha, rgb, ts)
+
+
+class PlainNeRF(nn.Module):
+    """Per-image-latent NeRF (nerf.py:9-74)."""
+
+    def __init__(self, latent_size: int = 32, intermediate_size: int = 32, steps=32, device="cuda"):
+        super().__init__()
+        self.latent = None
+        self.latent_size = latent_size
+        self.steps = steps
+        self.first = SkipConnMLP(in_size=3, out=1 + intermediate_size, latent_size=latent_size, num_layers=5,
+                                 hidden_size=32, device=device).to(device)
+        self.second = SkipConnMLP(in_size=2, out=3, latent_size=latent_size + intermediate_size, num_layers=5,
+                                  hidden_size=32, device=device).to(device)
+
+    def assign_latent(self, latent):
+        assert latent.shape[-1] == self.latent_size
+        assert len(latent.shape) == 2, "expected latent in [B, L]"
+        self.latent = latent
+
+    def forward(self, rays, lights):
+        assert self.latent is not None
+        r_o, r_d = rays.split([3, 3], dim=-1)
+        ts = torch.linspace(0.4, 2 + random.random() * 0.1, self.steps, device=r_o.device)
+        pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
+        latent = self.latent[None, :, None, None, None, :].expand(pts.shape[:-1] + (-1,))
+        first_out = self.first(pts, latent)
+        alpha, inter = first_out[..., 0], first_out[..., 1:]
+        view = dir_to_elev_azim(r_d)[None, ...].expand(latent.shape[:-1] + (2,))
+        rgb = self.second(view, torch.cat([inter, latent], dim=-1)).tanh()
+        alpha = alpha + torch.randn_like(alpha) * 1e-3      # nerf.py:66
+        return (composite(alpha, rgb, ts) + 1) / 2

@@ -1,0 +1,176 @@
+"""SphereSDF and the sphere-tracing SDF shape (pytorch3d/pathtracer/shapes/sdfs.py).
+
+The three gradient-free scan loops that are >95 % of a reference step (march :119-131, min scan
+:232-249, shadow march :169-180) run in the fused CUDA kernels of libnrt_b200 (persistent,
+slot-compacted).  Everything autograd has to see (sdf(best_pos), normals) follows the reference's
+own differentiable definition."""
+import random
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import utils as U
+from ... import ops
+from ..interaction import MixedInteraction
+from ..neural_blocks import SkipConnMLP
+
+
+def SPHERE_SDF(p):
+    return torch.norm(p, dim=-1) - 1
+
+
+class SphereSDF(nn.Module):
+    """Smooth-min of n affinely warped spheres plus a residual MLP (sdfs.py:16-46)."""
+
+    def __init__(self, n=2 << 6, device="cuda"):
+        super().__init__()
+        self.centers = nn.Parameter(0.3 * torch.rand(n, 3, device=device) - 0.15)
+        self.radii = nn.Parameter(0.2 * torch.rand(n, device=device) - 0.1)
+        self.tfs = nn.Parameter(torch.zeros(n, 3, 3, device=device))
+        self.shift = SkipConnMLP(num_layers=8, hidden_size=128, in_size=3, out=1, device=device, freqs=32,
+                                 activation=F.softplus, zero_init=True).to(device)
+
+    def set_center(self, at):
+        self.centers = nn.Parameter(at.expand_as(self.centers).clone().detach())
+
+    def transform(self, p):
+        tfs = self.tfs + torch.eye(3, device=p.device).unsqueeze(0)
+        return torch.einsum("ijk,ibk->ibj", tfs, p.expand(tfs.shape[0], -1, -1))
+
+    def packed(self) -> "ops.PackedSDF":
+        return ops.PackedSDF(self.centers, self.radii, self.tfs, self.shift.packed())
+
+    def _needs_grad(self, p):
+        return torch.is_grad_enabled() and (p.requires_grad or any(q.requires_grad for q in self.parameters()))
+
+    def forward_reference_ops(self, p):
+        q = self.transform(p.reshape(-1, 3).unsqueeze(0)) - self.centers.unsqueeze(1)
+        sd = q.norm(p=2, dim=-1) - self.radii.unsqueeze(-1)
+        out = U.smooth_min(sd, k=32.).reshape(p.shape[:-1])
+        return out + self.shift.forward_reference_ops(p).reshape_as(out)
+
+    def forward(self, p):
+        if p.is_cuda and not self._needs_grad(p):
+            return ops.sdf_eval(self.packed(), p.detach().float())
+        return self.forward_reference_ops(p)
+
+
+class SDF:
+    """General SDF shape: ray marching, soft-silhouette throughput, normals (sdfs.py:89-249)."""
+
+    def __init__(self, device="cuda", sdf=SPHERE_SDF, epsilon=1e-3, max_steps=32, dist=2.2, **kwargs):
+        self.device = torch.device(device)
+        self.sdf = sdf
+        self.epsilon = epsilon
+        self.max_steps = max_steps
+        self.dist = dist
+
+    def __len__(self):
+        return 1
+
+    def parameters(self):
+        return self.sdf.parameters()
+
+    # ---- fused / unfused dispatch -----------------------------------------------------------
+    def _fused(self):
+        """PackedSDF if self.sdf is (or wraps) a SphereSDF the kernels can evaluate, else None."""
+        s = self.sdf
+        if isinstance(s, SphereSDF) and s.centers.is_cuda:
+            return s.packed()
+        return None
+
+    def _march_generic(self, r_o, r_d, max_t):
+        # arbitrary callables (edit scripts: SDF(sdf=bend)) cannot be fused: the reference's own loop
+        depths = torch.zeros(r_o.shape[:-1] + (1,), device=r_o.device)
+        remaining = torch.ones(depths.shape[:-1], dtype=torch.bool, device=r_o.device)
+        hit_any = torch.zeros_like(remaining)
+        with torch.no_grad():
+            for _ in range(self.max_steps):
+                remaining = remaining & (depths < max_t).squeeze(-1)
+                d = self.sdf(r_o + r_d * depths)
+                hits = remaining & (d <= self.epsilon)
+                hit_any = hit_any | hits
+                remaining = remaining & ~hits
+                depths = torch.where(remaining.unsqueeze(-1), depths + d.unsqueeze(-1), depths)
+        return depths, hit_any
+
+    def intersect(self, rays, max_t=10, active=True, primary: bool = True):
+        r_o, r_d = rays.split(3, dim=-1)
+        packed = self._fused()
+        if packed is not None:
+            d, out_active = ops.sphere_trace(packed, rays.detach(), self.epsilon, self.max_steps, float(max_t))
+            depths = d.unsqueeze(-1)
+        else:
+            depths, out_active = self._march_generic(r_o, r_d, max_t)
+        p = r_o + depths * r_d
+        throughput = 0
+        if primary:
+            throughput, _best = self.throughput(r_o, r_d)
+            throughput = -1000 * throughput
+        si = MixedInteraction(p=p, t=depths.squeeze(), obj=self, throughput=throughput)
+        normals = torch.zeros_like(p)
+        if out_active.any():          # host sync, as in the reference: raw_normals is [K,3], K = #hits
+            raw = self.autograd_diff(p[out_active])
+            setattr(si, "raw_normals", raw)
+            normals[out_active] = F.normalize(raw, eps=1e-6, dim=-1)
+            p[out_active] = p[out_active] + normals[out_active] * self.epsilon * 5
+        si.set_normals(normals)
+        si.wi = si.to_local(-r_d)
+        return si, out_active
+
+    def intersect_test(self, rays, max_t=10, active=True):
+        packed = self._fused()
+        if packed is not None:
+            mt = max_t if torch.is_tensor(max_t) else torch.full(rays.shape[:-1], float(max_t), device=rays.device)
+            act = active if torch.is_tensor(active) else None
+            return ops.shadow_test(packed, rays.detach(), mt.detach().float().reshape(rays.shape[:-1]), self.epsilon,
+                                   self.max_steps, active=act)
+        r_o, r_d = rays.split(3, dim=-1)
+        depths = torch.zeros(r_o.shape[:-1] + (1,), device=rays.device) + 1e2 * self.epsilon
+        remaining = torch.ones(depths.shape[:-1], dtype=torch.bool, device=rays.device)
+        with torch.no_grad():
+            for _ in range(self.max_steps):
+                d = self.sdf(r_o + r_d * depths)
+                hits = remaining & (d < self.epsilon)
+                depths = torch.where(remaining.unsqueeze(-1), depths + d.unsqueeze(-1), depths)
+                remaining = remaining & ~hits
+        return (depths >= max_t).squeeze(-1) | remaining
+
+    def autograd_diff(self, p):
+        """d sdf / d p at p (sdfs.py:184-197).  With gradients enabled this is the reference's
+        create_graph autograd (so eikonal / shading losses reach the SDF weights); without, the
+        fused analytic-Jacobian kernel."""
+        s = self.sdf
+        wants_graph = torch.is_grad_enabled() and (not isinstance(s, SphereSDF) or
+                                                   any(q.requires_grad for q in s.parameters()))
+        if isinstance(s, SphereSDF) and p.is_cuda and not wants_graph and ops.HAS_SDF_VALUE_GRAD:
+            return ops.sdf_value_grad(s.packed(), p.detach())[1]
+        with torch.enable_grad():
+            if not p.requires_grad:
+                p = p.requires_grad_()
+            out = s.forward_reference_ops(p) if isinstance(s, SphereSDF) else s(p)
+            n, = torch.autograd.grad(inputs=p, outputs=out, grad_outputs=torch.ones_like(out), create_graph=True,
+                                     retain_graph=True, only_inputs=True)
+        return n
+
+    def throughput(self, r_o_local, d):
+        """Minimum of the SDF along the ray (sdfs.py:232-249): scan without grad, then one
+        differentiable evaluation at the argmin."""
+        n = 128
+        max_t = getattr(self, "dist", 2.2) + random.random() * (2 / n)
+        step = max_t / n
+        packed = self._fused()
+        if packed is not None:
+            rays = torch.cat([r_o_local.expand_as(d), d], dim=-1).detach()
+            _idx, best_pos, _mv = ops.min_scan(packed, rays, step, n)
+        else:
+            with torch.no_grad():
+                sd = self.sdf(r_o_local).squeeze(-1)
+                cur, idxs = sd, torch.zeros_like(sd, dtype=torch.long)
+                for i in range(n):
+                    sd = self.sdf(r_o_local + (step * (i + 1)) * d).squeeze(-1)
+                    idxs = torch.where(sd < cur, i + 1, idxs)
+                    cur = torch.minimum(cur, sd)
+            best_pos = r_o_local + idxs.unsqueeze(-1).unsqueeze(-1) * step * d
+        return self.sdf(best_pos), best_pos
