@@ -229,8 +229,93 @@ def gen_shading():
     print("shading.npz ok")
 
 
+def build_pipeline(P, kind, device="cpu"):
+    """Builds the colocate-style ('colocate') or DTU-style ('dtu') scene out of the package `P`
+    (either the reference `pytorch3d.pathtracer` or the drop-in mirror): identical code for both."""
+    import torch.nn as nn
+    sdfs, bsdfm, lightsm, integ = P.shapes.sdfs, P.bsdf, P.lights, P.integrators
+    sphere = sdfs.SphereSDF(n=64, device=device)
+    synth.fill_module(sphere, 61, shift_std=0.02)
+    shape = sdfs.SDF(sdf=sphere, device=device, max_steps=64)
+    if kind == "colocate":
+        # colocate.py:63-85: 2 neural + diffuse + conductor bases, point light, learned occlusion MLP
+        kids = [bsdfm.NeuralBSDF(device=device), bsdfm.NeuralBSDF(device=device),
+                bsdfm.Diffuse(preprocess=nn.Softplus(), device=device), bsdfm.Conductor(activation=nn.Softplus(), device=device)]
+        kids[2].reflectance = torch.tensor([0.3, 0.6, 0.2], device=device, requires_grad=True)
+        kids[3].specular = torch.tensor([0.7, 0.4, 0.9], device=device, requires_grad=True)
+        lights = lightsm.PointLights(device=device, location=[[0.9, 0.5, 0.7]], scale=5)
+        occ = P.neural_blocks.SkipConnMLP(in_size=5, out=1, device=device)
+        synth.fill_module(occ, 65)
+        integrator, w_isect = integ.Direct(), occ
+    else:
+        # dtu.py:95-106: neural + diffuse(sigmoid) bases, learned light field, NeRFIntegrator(Direct())
+        kids = [bsdfm.NeuralBSDF(activation=nn.Sigmoid(), device=device), bsdfm.NeuralBSDF(activation=nn.Sigmoid(), device=device),
+                bsdfm.Diffuse(preprocess=torch.sigmoid, device=device)]
+        kids[2].reflectance = torch.tensor([0.2, -0.4, 0.5], device=device, requires_grad=True)
+        lights = lightsm.LightField(device=device)
+        synth.fill_module(lights, 66)
+        integrator, w_isect = integ.NeRFIntegrator(integ.Direct()), False
+    for i, k in enumerate(kids[:2]):
+        synth.fill_module(k, 62 + i)
+    bsdf = bsdfm.ComposeSpatialVarying(kids, device=device)
+    bsdf.sp_var_fn._synth_sigma = 128.0
+    synth.fill_module(bsdf, 64)
+    return shape, sphere, bsdf, lights, integrator, w_isect
+
+
+def gen_pipeline():
+    """Full reference renders: colocate-style pathtrace (main.py:13-93 + integrators.py:156-206 + scene.py:301-318)
+    and a DTU-style pathtrace_sample with LightField + eikonal/BCE-style gradients."""
+    import pytorch3d.pathtracer as P
+    import pytorch3d.pathtracer.shapes.sdfs, pytorch3d.pathtracer.bsdf, pytorch3d.pathtracer.lights  # noqa: F401
+    import pytorch3d.pathtracer.integrators, pytorch3d.pathtracer.neural_blocks, pytorch3d.pathtracer.cameras  # noqa: F401
+    from pytorch3d.pathtracer.cameras import NeRFCamera
+    from pytorch3d.pathtracer.utils import eikonal_loss
+    out = {}
+    random.random = lambda: FIXED_RANDOM
+    size = 16
+    c2w, focal = synth.nerf_cameras(1, size)
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cpu")
+    # ---- colocate-style forward
+    shape, sphere, bsdf, lights, integrator, w_isect = build_pipeline(P, "colocate")
+    with torch.no_grad():
+        img, mi = P.pathtrace(shape, size=size, chunk_size=size, bundle_size=1, bsdf=bsdf, integrator=integrator,
+                              lights=lights, cameras=cam, device="cpu", silent=True, background=0, w_isect=w_isect,
+                              with_noise=False, addition=lambda it: it)
+    out["colocate_img"] = img.numpy()
+    out["colocate_throughput"] = mi.throughput.reshape(-1).numpy()
+    out["colocate_weights"] = mi.normalized_weights.reshape(-1, 4).numpy()
+    out["colocate_raw_normals"] = mi.raw_normals.detach().numpy()
+    # ---- DTU-style forward + backward
+    shape, sphere, bsdf, lights, integrator, w_isect = build_pipeline(P, "dtu")
+    c2w2, focal2 = synth.nerf_cameras(2, size)
+    cam2 = NeRFCamera(cam_to_world=c2w2, focal=focal2, device="cpu")
+    got, mi = P.pathtrace_sample(shape, size=size, chunk_size=size, bundle_size=1, crop_size=8, uv=(3, 5), bsdf=bsdf,
+                                 integrator=integrator, lights=lights, cameras=cam2, device="cpu", silent=True,
+                                 background=0, w_isect=w_isect, with_noise=False, addition=lambda it: it,
+                                 squeeze_first=False)
+    out["dtu_img"] = got.detach().numpy()
+    out["dtu_throughput"] = mi.throughput.detach().reshape(-1).numpy()
+    loss = (got[..., :3] - 0.5).square().mean() + 0.1 * eikonal_loss(mi.raw_normals) + \
+        torch.nn.functional.binary_cross_entropy_with_logits(mi.throughput.reshape(-1), torch.ones(mi.throughput.numel()) * 0.5)
+    loss.backward()
+    out["dtu_loss"] = np.array(loss.item(), np.float64)
+    out["dtu_g_sdf_out_w"] = sphere.shift.out.weight.grad.numpy()
+    out["dtu_g_sdf_l3_w"] = sphere.shift.layers[3].weight.grad.numpy()
+    out["dtu_g_centers"] = sphere.centers.grad.numpy()
+    out["dtu_g_bsdf0_init_w"] = bsdf.bsdfs[0].mlp.init.weight.grad.numpy()
+    out["dtu_g_spvar_out_w"] = bsdf.sp_var_fn.out.weight.grad.numpy()
+    out["dtu_g_light_out_w"] = lights.light_field_approx.out.weight.grad.numpy()
+    out["dtu_g_light_color"] = lights.color.grad.numpy()
+    out["dtu_g_reflectance"] = bsdf.bsdfs[2].reflectance.grad.numpy()
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("main.py:13-179; integrators/integrators.py:156-257; scene.py:290-324; bsdf/bsdfs.py; lights/lights.py")
+    np.savez_compressed(os.path.join(HERE, "pipeline.npz"), **out)
+    print("pipeline.npz: colocate img mean %.4f hits %d; dtu loss %.5f" % (out["colocate_img"].mean(), len(out["colocate_raw_normals"]), loss.item()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "composite", "shading"]
+    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "composite", "shading", "pipeline"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()

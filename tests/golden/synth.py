@@ -50,3 +50,59 @@ def camera_rays(seed, n_rays, dist=1.0, jitter=0.35):
     d = -o + jitter * rs.standard_normal((n_rays, 3))
     d = d / np.linalg.norm(d, axis=-1, keepdims=True)
     return np.concatenate([o, d], -1).astype(np.float32)
+
+
+def _name_seed(name, seed):
+    h = 2166136261
+    for ch in (name + "#%d" % seed).encode():
+        h = ((h ^ ch) * 16777619) & 0xFFFFFFFF
+    return h
+
+
+def fill_module(mod, seed, shift_std=None):
+    """Deterministically (re)initialises every nn.Parameter and every SkipConnMLP.basis_p of `mod`
+    from the parameter NAME, so a reference module and its drop-in mirror (same attribute names)
+    receive identical weights.  Linear weights ~ U(+-1/sqrt(fan_in)); if shift_std is given every
+    parameter whose name contains 'shift.' is N(0, shift_std) instead (SphereSDF residual MLP)."""
+    import torch
+    with torch.no_grad():
+        for name, p in sorted(mod.named_parameters(), key=lambda kv: kv[0]):
+            rs = np.random.RandomState(_name_seed(name, seed))
+            if shift_std is not None and "shift." in name:
+                v = shift_std * rs.standard_normal(tuple(p.shape))
+            elif name.endswith("centers"):
+                v = 0.3 * rs.uniform(size=tuple(p.shape)) - 0.15
+            elif name.endswith("radii"):
+                v = 0.2 * rs.uniform(size=tuple(p.shape)) - 0.1
+            elif name.endswith("tfs"):
+                v = 0.05 * rs.standard_normal(tuple(p.shape))
+            elif name.endswith("color"):
+                v = rs.uniform(-0.5, 0.5, size=tuple(p.shape))
+            else:
+                fan_in = p.shape[1] if p.dim() >= 2 else max(1, p.shape[0])
+                b = 1.0 / np.sqrt(fan_in)
+                v = rs.uniform(-b, b, size=tuple(p.shape))
+            p.copy_(torch.from_numpy(np.asarray(v, np.float32)).to(p.device))
+        for name, m in sorted(mod.named_modules(), key=lambda kv: kv[0]):
+            if hasattr(m, "basis_p") and hasattr(m, "dim_p"):
+                rs = np.random.RandomState(_name_seed(name + ".basis_p", seed))
+                shape = tuple(m.basis_p.shape)            # [in, freqs]
+                sigma = float(getattr(m, "_synth_sigma", 32.0))
+                m.basis_p = torch.from_numpy((sigma * rs.standard_normal(shape)).astype(np.float32)).to(m.basis_p.device)
+    return mod
+
+
+def nerf_cameras(n_views, size, device="cpu"):
+    """cam_to_world [N,4,4] on the unit sphere looking at the origin (NeRF convention: -z forward) + focal."""
+    import torch
+    mats = []
+    for i in range(n_views):
+        az, el = 0.5 + 0.9 * i, 0.35 + 0.1 * i
+        c = np.array([np.cos(el) * np.sin(az), np.sin(el), np.cos(el) * np.cos(az)])
+        fwd = -c / np.linalg.norm(c)
+        right = np.cross(fwd, [0, 1, 0]); right /= np.linalg.norm(right)
+        up = np.cross(right, fwd)
+        m = np.eye(4)
+        m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, c
+        mats.append(m)
+    return torch.tensor(np.stack(mats), dtype=torch.float, device=device), 0.5 * size / np.tan(np.radians(25))
