@@ -263,29 +263,43 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
   return NRT_OK;
 }
 
+// grow-only device scratch of the host-buffer entry point (a stream-ordered pool would hand the memory
+// back at every synchronisation and re-allocate >1 GB per call)
+static void* g_host_ws[4] = {nullptr, nullptr, nullptr, nullptr};
+static size_t g_host_ws_bytes[4] = {0, 0, 0, 0};
+static int host_scratch(int slot, size_t bytes, void** out) {
+  if (g_host_ws_bytes[slot] < bytes) {
+    if (g_host_ws[slot]) NRT_CUDA(cudaFree(g_host_ws[slot]));
+    g_host_ws[slot] = nullptr; g_host_ws_bytes[slot] = 0;
+    NRT_CUDA(cudaMalloc(&g_host_ws[slot], bytes));
+    g_host_ws_bytes[slot] = bytes;
+  }
+  *out = g_host_ws[slot];
+  return NRT_OK;
+}
+
 extern "C" int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
                                       const float* rays_host, int64_t R, const float* ts_host, int S,
                                       const nrt_nerf_sampling_t* sampling, const float* light_code,
                                       int light_dim, float* out_rgb_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   NRT_REQUIRE(rays_host && out_rgb_host && sampling, "nrt_nerfle_render_host: bad arguments");
-  float *d_rays = nullptr, *d_ts = nullptr, *d_out = nullptr;
-  void* ws = nullptr;
+  NRT_REQUIRE(R >= 0, "nrt_nerfle_render_host: negative R");
+  if (R == 0) return NRT_OK;
+  void *d_rays = nullptr, *d_ts = nullptr, *d_out = nullptr, *ws = nullptr;
   const size_t wsb = nrt_nerfle_render_workspace(first, second, prec, R, sampling);
-  NRT_CUDA(cudaMallocAsync(&d_rays, (size_t)R * 24, st));
-  NRT_CUDA(cudaMallocAsync(&d_out, (size_t)R * 12, st));
-  NRT_CUDA(cudaMallocAsync(&ws, wsb, st));
+  int rc = host_scratch(0, (size_t)R * 24, &d_rays); if (rc != NRT_OK) return rc;
+  rc = host_scratch(1, (size_t)R * 12, &d_out); if (rc != NRT_OK) return rc;
+  rc = host_scratch(2, wsb, &ws); if (rc != NRT_OK) return rc;
   if (ts_host) {
-    NRT_CUDA(cudaMallocAsync(&d_ts, (size_t)S * 4, st));
+    rc = host_scratch(3, (size_t)S * 4, &d_ts); if (rc != NRT_OK) return rc;
     NRT_CUDA(cudaMemcpyAsync(d_ts, ts_host, (size_t)S * 4, cudaMemcpyHostToDevice, st));
   }
   NRT_CUDA(cudaMemcpyAsync(d_rays, rays_host, (size_t)R * 24, cudaMemcpyHostToDevice, st));
-  int rc = nrt_nerfle_render(first, second, prec, d_rays, R, d_ts, sampling, light_code, light_dim, nullptr,
-                             d_out, ws, wsb, st);
-  if (rc == NRT_OK) rc = nrt_check_cuda(cudaMemcpyAsync(out_rgb_host, d_out, (size_t)R * 12, cudaMemcpyDeviceToHost, st), "D2H");
-  cudaFreeAsync(d_rays, st); cudaFreeAsync(d_out, st); cudaFreeAsync(ws, st);
-  if (d_ts) cudaFreeAsync(d_ts, st);
+  rc = nrt_nerfle_render(first, second, prec, (const float*)d_rays, R, (const float*)d_ts, sampling, light_code, light_dim,
+                         nullptr, (float*)d_out, ws, wsb, st);
   if (rc != NRT_OK) return rc;
+  NRT_CUDA(cudaMemcpyAsync(out_rgb_host, d_out, (size_t)R * 12, cudaMemcpyDeviceToHost, st));
   NRT_CUDA(cudaStreamSynchronize(st));
   return NRT_OK;
 }

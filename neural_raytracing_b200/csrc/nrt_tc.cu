@@ -173,6 +173,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
   }
 }
+// non-blocking phase test (all lanes of the warp call it; the result is warp-uniform)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
@@ -256,10 +268,28 @@ template <> struct TmemIO<32> {
                  : "r"(t));
   }
 };
+#define NRT_R16(a, i) NRT_R4(a, i), NRT_R4(a, i + 4), NRT_R4(a, i + 8), NRT_R4(a, i + 12)
+#define NRT_W16(a, i) NRT_W4(a, i), NRT_W4(a, i + 4), NRT_W4(a, i + 8), NRT_W4(a, i + 12)
+template <> struct TmemIO<64> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                 "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+                 "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                 : NRT_R16(r, 0), NRT_R16(r, 16), NRT_R16(r, 32), NRT_R16(r, 48) : "r"(t));
+  }
+};
+// x32 store lives outside TmemIO<32> (which only loads)
+__device__ __forceinline__ void tmem_st32(uint32_t t, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+               "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+               ::"r"(t), NRT_W16(r, 0), NRT_W16(r, 16) : "memory");
+}
 // store NP packed 32-bit columns starting at column address t (compile-time decomposition)
 template <int NP>
 __device__ __forceinline__ void tmem_store(uint32_t t, const uint32_t* r) {
-  if constexpr (NP >= 16) { TmemIO<16>::st(t, r); tmem_store<NP - 16>(t + 16, r + 16); }
+  if constexpr (NP >= 32) { tmem_st32(t, r); tmem_store<NP - 32>(t + 32, r + 32); }
+  else if constexpr (NP >= 16) { TmemIO<16>::st(t, r); tmem_store<NP - 16>(t + 16, r + 16); }
   else if constexpr (NP >= 8) { TmemIO<8>::st(t, r); tmem_store<NP - 8>(t + 8, r + 8); }
   else if constexpr (NP >= 4) { TmemIO<4>::st(t, r); tmem_store<NP - 4>(t + 4, r + 4); }
   else if constexpr (NP >= 2) { TmemIO<2>::st(t, r); tmem_store<NP - 2>(t + 2, r + 2); }
@@ -267,7 +297,8 @@ __device__ __forceinline__ void tmem_store(uint32_t t, const uint32_t* r) {
 }
 template <int NP>
 __device__ __forceinline__ void tmem_load(uint32_t t, uint32_t* r) {
-  if constexpr (NP >= 32) { TmemIO<32>::ld(t, r); tmem_load<NP - 32>(t + 32, r + 32); }
+  if constexpr (NP >= 64) { TmemIO<64>::ld(t, r); tmem_load<NP - 64>(t + 64, r + 64); }
+  else if constexpr (NP >= 32) { TmemIO<32>::ld(t, r); tmem_load<NP - 32>(t + 32, r + 32); }
   else if constexpr (NP >= 16) { TmemIO<16>::ld(t, r); tmem_load<NP - 16>(t + 16, r + 16); }
   else if constexpr (NP >= 8) { TmemIO<8>::ld(t, r); tmem_load<NP - 8>(t + 8, r + 8); }
   else if constexpr (NP >= 4) { TmemIO<4>::ld(t, r); tmem_load<NP - 4>(t + 4, r + 4); }
@@ -283,6 +314,34 @@ __device__ __forceinline__ float act_fast(float x) {
   } else {
     return fmaxf(x, 0.01f * x);
   }
+}
+// act(a), act(b) rounded to the operand format and packed; the leaky ReLU runs on the packed pair
+template <int ACT, int FMT>
+__device__ __forceinline__ uint32_t act_pack(float a, float b) {
+  if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+    return Elem<FMT>::pack(act_fast<ACT>(a), act_fast<ACT>(b));
+  } else if constexpr (FMT == 0) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const __half2 r = __hmax2(h, __hmul2(h, __floats2half2_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 r = __hmax2(h, __hmul2(h, __floats2bfloat162_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+// D[lane][0..N) = bias[0..N): the next layer's MMA then only accumulates (no bias add in its epilogue)
+template <int N>
+__device__ __forceinline__ void preload_bias(uint32_t dD, const float* __restrict__ bias) {
+  static_assert(N % 8 == 0, "bias pieces are multiples of 8 columns");
+  uint32_t r[N];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j);
+    r[4 * j] = __float_as_uint(b.x); r[4 * j + 1] = __float_as_uint(b.y);
+    r[4 * j + 2] = __float_as_uint(b.z); r[4 * j + 3] = __float_as_uint(b.w);
+  }
+  tmem_store<N>(dD, r);
 }
 __device__ __forceinline__ void sincos_fast(float x, float* s, float* c) {
   // two-constant reduction by 2*pi, then MUFU sin/cos on [-pi, pi]
@@ -318,12 +377,53 @@ struct Net {
 
 constexpr int kEpiThreads = 128;
 
+// Issues the MMAs of stage ST of one tile slot.  Called by the WHOLE MMA warp (convergent); one elected lane
+// issues.  (Issuing from a divergent single lane makes the compiler wrap every UTCHMMA in an
+// ELECT / R2UR / BRA.U.ANY serialisation loop: ~135 cycles per MMA instead of ~72, see profiles/.)
+template <class NET, int FMT, int ST>
+__device__ __forceinline__ void issue_stage(uint32_t sW_addr, uint32_t dD, uint32_t aU, uint32_t aE, uint64_t* done_bar) {
+  constexpr Layout Y = NET::Y;
+  constexpr uint32_t N = (uint32_t)Y.opN[ST];
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((N >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t lbo = N * 16, sbo = 128;
+  constexpr int kch = Y.opK[ST] / 16;
+  constexpr int k_u = (ST >= 2 && ST < NET::STAGES - 1) ? NET::H / 16 : kch;   // K chunks taken from U
+  constexpr uint32_t b_off = (uint32_t)Y.op_off[ST] * 2;
+  if (elect_one()) {
+    const uint64_t bd0 = make_desc(sW_addr + b_off, lbo, sbo);
+#pragma unroll
+    for (int kc = 0; kc < kch; ++kc) {
+      const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
+      // every layer's accumulator was pre-loaded with its bias by the previous epilogue; only the
+      // phase GEMM (stage 0) starts from zero
+      mma_ts(dD, a, bd0 + (uint64_t)((kc * 2 * lbo) >> 4), idesc, (ST > 0 || kc > 0) ? 1u : 0u);
+    }
+    tc_commit(done_bar);
+  }
+  __syncwarp();
+}
+template <class NET, int FMT, int ST = 0>
+__device__ __forceinline__ void issue_stage_dyn(int st, uint32_t sW_addr, uint32_t dD, uint32_t aU, uint32_t aE,
+                                                uint64_t* done_bar) {
+  if constexpr (ST < NET::STAGES) {
+    if (st == ST) issue_stage<NET, FMT, ST>(sW_addr, dD, aU, aE, done_bar);
+    else issue_stage_dyn<NET, FMT, ST + 1>(st, sW_addr, dD, aU, aE, done_bar);
+  }
+}
+
 // IO policy concept:
 //   struct IO { __device__ void load(int64_t m, float* x /*IN+LAT*/) const; __device__ void store(int64_t m, const float* o /*OUT, bias added*/) const; };
 
 template <class NET, class IO, int FMT>
 __global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
-k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
+k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg) {
+  // dbg (development only, tools/tc_timeline.py): clock64 stamps of CTA 0 for a few tile iterations
+  constexpr int kDbgIt0 = 4, kDbgIts = 4;
+  auto stamp = [&](int it, int st, int slot, int k) {
+    if (dbg != nullptr && blockIdx.x == 0 && it >= kDbgIt0 && it < kDbgIt0 + kDbgIts)
+      dbg[(((it - kDbgIt0) * NET::STAGES + st) * 2 + slot) * 8 + k] = clock64();
+  };
   using E = Elem<FMT>;
   constexpr Layout Y = NET::Y;
   constexpr int H = NET::H, IN = NET::IN, LAT = NET::LAT, F = NET::F, L = NET::L;
@@ -335,11 +435,13 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
   __shared__ __align__(8) uint64_t bar_ready[2];
   __shared__ __align__(8) uint64_t bar_done[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_bias[NET::STAGES];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const bool is_mma_warp = warp == 8;
   const int64_t ntiles = (M + 127) / 128;
+  if (tid < NET::STAGES) s_bias[tid] = (uint32_t)Y.bias_off[tid];
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
@@ -368,33 +470,37 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
 
   if (is_mma_warp) {
     // ===================== MMA issuer =====================
-    if ((tid & 31) == 0) {
-      const uint32_t sW_addr = smem_u32(sW);
-      uint32_t n_ready[2] = {0, 0};
-      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
-        for (int st = 0; st < NET::STAGES; ++st) {
-          for (int slot = 0; slot < NSLOT; ++slot) {
-            if (t0 + slot >= ntiles) continue;
-            mbar_wait(&bar_ready[slot], n_ready[slot] & 1);
-            n_ready[slot]++;
-            tc_fence_after();
-            const uint32_t base = tmem + slot * NET::COLS;
-            const uint32_t dD = base, aU = base + NET::DC, aE = base + NET::DC + NET::UC;
-            const int N = Y.opN[st];
-            const uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) |
-                                   ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t b_base = sW_addr + (uint32_t)Y.op_off[st] * 2;
-            const uint32_t lbo = (uint32_t)N * 16, sbo = 128;
-            const int kch = Y.opK[st] / 16;
-            const int k_u = (st >= 2 && st < NET::STAGES - 1) ? H / 16 : kch;  // chunks taken from U
-            for (int kc = 0; kc < kch; ++kc) {
-              const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
-              mma_ts(dD, a, make_desc(b_base + (uint32_t)kc * 2 * lbo, lbo, sbo), idesc, kc > 0 ? 1u : 0u);
-            }
-            tc_commit(&bar_done[slot]);
-          }
+    // The whole warp runs this loop convergently (one elected lane issues).  Slots are served in
+    // whatever order they become ready, so the two tiles drift into anti-phase: the tensor pipe works
+    // on one tile while the other tile's epilogue (or prologue / output store) runs.
+    const uint32_t sW_addr = smem_u32(sW);
+    int st[2] = {0, 0};
+    uint32_t n_ready[2] = {0, 0};
+    int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
+    bool live[2] = {tile[0] < ntiles, NSLOT > 1 && tile[1] < ntiles};
+    int it_dbg[2] = {0, 0};
+    while (live[0] || live[1]) {
+      bool progressed = false;
+#pragma unroll
+      for (int slot = 0; slot < NSLOT; ++slot) {
+        if (!live[slot]) continue;
+        if (!mbar_test(&bar_ready[slot], n_ready[slot] & 1)) continue;
+        progressed = true;
+        n_ready[slot]++;
+        tc_fence_after();
+        if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 1);
+        const uint32_t base = tmem + slot * NET::COLS;
+        issue_stage_dyn<NET, FMT>(st[slot], sW_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+        if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 2);
+        if (++st[slot] == NET::STAGES) {
+          st[slot] = 0;
+          it_dbg[slot]++;
+          tile[slot] += (int64_t)gridDim.x * NSLOT;
+          live[slot] = tile[slot] < ntiles;
         }
       }
+      // this warp shares an SM sub-partition with two epilogue warps: do not burn their issue slots
+      if (!progressed) __nanosleep(32);
     }
   } else {
     // ===================== epilogue warpgroups (one per tile slot) =====================
@@ -405,7 +511,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
       const uint32_t base = tmem + slot * NET::COLS + lane_off;
       const uint32_t dD = base, aU = base + NET::DC, aE = base + NET::DC + NET::UC;
       uint32_t n_done = 0;
-      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
+      int it_dbg = 0;
+      auto estamp = [&](int st, int k) { if (lane_row == 0) stamp(it_dbg, st, slot, k); };
+      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT, ++it_dbg) {
         const int64_t tile = t0 + slot;
         if (tile >= ntiles) break;
         const int64_t m = tile * 128 + lane_row;
@@ -471,6 +579,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
           uint32_t ph[F];
           tmem_load<F>(dD, ph);
           tc_wait_ld();
+          preload_bias<H>(dD, sBias + s_bias[1]);
           uint32_t sr[F / 2], cr[F / 2], sa[F / 2], ca[F / 2];
 #pragma unroll
           for (int j = 0; j < F / 2; ++j) {
@@ -494,27 +603,28 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
         // ---- stages 2 .. L+1: hidden activations ----
 #pragma unroll 1
         for (int st = 0; st <= L; ++st) {
+          estamp(2 + st, 3);
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
-          const float* bias = sBias + Y.bias_off[1 + st];
+          estamp(2 + st, 4);
+          uint32_t acc[H];
+          tmem_load<H>(dD, acc);          // the whole accumulator row, one wait
+          tc_wait_ld();
+          estamp(2 + st, 5);
+          uint32_t pk[H / 2];
 #pragma unroll
-          for (int c0 = 0; c0 < H; c0 += 32) {
-            uint32_t acc[32];
-            tmem_load<32>(dD + c0, acc);
-            tc_wait_ld();
-            uint32_t pk[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float2 b = *reinterpret_cast<const float2*>(bias + c0 + 2 * j);
-              const float v0 = act_fast<NET::ACT>(__uint_as_float(acc[2 * j]) + b.x);
-              const float v1 = act_fast<NET::ACT>(__uint_as_float(acc[2 * j + 1]) + b.y);
-              pk[j] = E::pack(v0, v1);
-            }
-            tmem_store<16>(aU + c0 / 2, pk);
-          }
+          for (int j = 0; j < H / 2; ++j)
+            pk[j] = act_pack<NET::ACT, FMT>(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+          tmem_store<H / 2>(aU, pk);
+          // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
+          // the conversion so the accumulator registers are dead and all 32 LDS.128 can be in flight
+          if (st < L) preload_bias<H>(dD, sBias + s_bias[2 + st]);
+          else preload_bias<NET::NOP>(dD, sBias + s_bias[NET::STAGES - 1]);
+          estamp(2 + st, 6);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&bar_ready[slot]);
+          estamp(2 + st, 7);
         }
         // ---- output layer ----
         {
@@ -524,10 +634,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
           uint32_t acc[OC];
           tmem_load<OC>(dD, acc);
           tc_wait_ld();
-          const float* bias = sBias + Y.bias_off[NET::STAGES - 1];
-          float o[NET::OUT];
+          float o[NET::OUT];   // bias already accumulated (pre-loaded into the accumulator)
 #pragma unroll
-          for (int j = 0; j < NET::OUT; ++j) o[j] = __uint_as_float(acc[j]) + bias[j];
+          for (int j = 0; j < NET::OUT; ++j) o[j] = __uint_as_float(acc[j]);
           if (valid) io.store(m, o);
           // the accumulator / operand regions of this slot may now be reused by the next tile
           tc_fence_before();
@@ -634,6 +743,9 @@ struct IoNerfSecond {
   }
 };
 
+static long long* g_dbg_timeline = nullptr;   // development only, see tools/tc_timeline.py
+extern "C" void nrtdbg_set_timeline(long long* dev_buf) { g_dbg_timeline = dev_buf; }
+
 template <class NET, class IO, int FMT>
 static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP) {
   const size_t bytes = (size_t)NET::Y.bytes + 256;
@@ -642,7 +754,7 @@ static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, in
   const int64_t ntiles = (M + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
   NrtProfScope _ps(tag, st);
-  kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M);
+  kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M, g_dbg_timeline);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
 }
