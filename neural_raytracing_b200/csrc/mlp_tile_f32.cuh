@@ -66,6 +66,12 @@ __device__ __forceinline__ float act_grad_from_out(int act, float a) {
   }
   return a > 0.0f ? 1.0f : 0.01f;
 }
+// derivative of the activation expressed through its INPUT z (torch semantics: softplus' = sigmoid,
+// 1 beyond the threshold; leaky_relu' = 1 for z > 0 else the slope)
+__device__ __forceinline__ float act_grad_from_in(int act, float z) {
+  if (act == NRT_ACT_SOFTPLUS) return z > 20.0f ? 1.0f : nrt_sigmoidf(z);
+  return z > 0.0f ? 1.0f : 0.01f;
+}
 __device__ __forceinline__ float out_act_apply(int out_act, float x) {
   switch (out_act) {
     case NRT_OUT_SIGMOID: return nrt_sigmoidf(x);
@@ -88,27 +94,55 @@ __device__ __forceinline__ void cp_async_wait() {
 // Fourier features of the in_size raw inputs already sitting in enc_raw rows [0,in_size):
 // rows [in, in+f) = sin(x.B), rows [in+f, in+2f) = cos(x.B)  (utils.py:37-40).
 // Then enc_act = act(enc_raw) for all dim_p rows.  Ends with __syncthreads().
-template <int TM>
+// JAC = true: forward-mode Jacobian.  Tile columns come in groups of four [value, d/dp0, d/dp1, d/dp2] of the
+// same point; the caller wrote the point into the value column of rows [0,3) (tangent columns are filled here).
+template <int TM, bool JAC = false>
 __device__ void encode_tile(const MlpDev& m, const TileSmem& s) {
   const int tid = threadIdx.x;
   const int F = m.freqs, I = m.in_size;
+  if (JAC) {
+    for (int idx = tid; idx < I * TM; idx += kThreads) {
+      const int j = idx / TM, mm = idx - j * TM;
+      if (mm & 3) s.enc_raw[idx] = ((mm & 3) - 1 == j) ? 1.0f : 0.0f;     // d p_j / d p_c
+    }
+    __syncthreads();
+  }
   for (int idx = tid; idx < F * TM; idx += kThreads) {
     const int f = idx / TM, mm = idx - f * TM;
+    if (JAC && (mm & 3)) continue;
     float arg = 0.0f;
     for (int j = 0; j < I; ++j) arg = nrt_fma(s.enc_raw[j * TM + mm], __ldg(m.basis + j * F + f), arg);
     float sn, cs;
     nrt_sincosf(arg, &sn, &cs);
     s.enc_raw[(I + f) * TM + mm] = sn;
     s.enc_raw[(I + F + f) * TM + mm] = cs;
+    if (JAC) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float b = __ldg(m.basis + c * F + f);
+        s.enc_raw[(I + f) * TM + mm + 1 + c] = cs * b;        // d sin = cos * B
+        s.enc_raw[(I + F + f) * TM + mm + 1 + c] = -sn * b;   // d cos = -sin * B
+      }
+    }
   }
   __syncthreads();
-  for (int idx = tid; idx < m.dim_p * TM; idx += kThreads) s.enc_act[idx] = act_apply(m.act, s.enc_raw[idx]);
+  for (int idx = tid; idx < m.dim_p * TM; idx += kThreads) {
+    if (!JAC) { s.enc_act[idx] = act_apply(m.act, s.enc_raw[idx]); continue; }
+    const int mm = idx % TM;
+    if (mm & 3) continue;
+    const float z = s.enc_raw[idx];
+    const float g = act_grad_from_in(m.act, z);
+    s.enc_act[idx] = act_apply(m.act, z);
+    s.enc_act[idx + 1] = g * s.enc_raw[idx + 1];
+    s.enc_act[idx + 2] = g * s.enc_raw[idx + 2];
+    s.enc_act[idx + 3] = g * s.enc_raw[idx + 3];
+  }
   __syncthreads();
 }
 
 // One Linear(K0+K1 -> H) over the tile: input rows come from in0 ([K0][TM]) followed by
 // in1 ([K1][TM]); writes act(z) (or z if !apply_act) to outp [H][TM].  Ends with a barrier.
-template <int H, int TM>
+template <int H, int TM, bool JAC = false>
 __device__ void hidden_layer(const MlpDev& m, int li, const float* __restrict__ in0, int K0,
                              const float* __restrict__ in1, int K1, float* __restrict__ outp,
                              float* __restrict__ wbuf, bool apply_act) {
@@ -127,7 +161,7 @@ __device__ void hidden_layer(const MlpDev& m, int li, const float* __restrict__ 
     for (int e = 0; e < C::VEC; ++e) {
       const float b = __ldg(bg + v * (C::NG * C::VEC) + tn * C::VEC + e);
 #pragma unroll
-      for (int r = 0; r < C::RM; ++r) acc[r][v * C::VEC + e] = b;
+      for (int r = 0; r < C::RM; ++r) acc[r][v * C::VEC + e] = (JAC && r > 0) ? 0.0f : b;   // tangents carry no bias
     }
 
   const int nchunks = (K + kKC - 1) / kKC;
@@ -184,7 +218,11 @@ __device__ void hidden_layer(const MlpDev& m, int li, const float* __restrict__ 
       const int n = v * (C::NG * C::VEC) + tn * C::VEC + e;
       float4 o;
       const int j = v * C::VEC + e;
-      if (apply_act) {
+      if (apply_act && JAC) {
+        // the four columns of this thread are (value, three tangents) of one point
+        const float g = act_grad_from_in(m.act, acc[0][j]);
+        o.x = act_apply(m.act, acc[0][j]); o.y = g * acc[1][j]; o.z = g * acc[2][j]; o.w = g * acc[3][j];
+      } else if (apply_act) {
         o.x = act_apply(m.act, acc[0][j]); o.y = act_apply(m.act, acc[1][j]);
         o.z = act_apply(m.act, acc[2][j]); o.w = act_apply(m.act, acc[3][j]);
       } else {
@@ -197,7 +235,7 @@ __device__ void hidden_layer(const MlpDev& m, int li, const float* __restrict__ 
 
 // Final Linear(H -> out) (small fan-out): one (n, m) output per thread iteration, weights
 // through the read-only path.  Writes raw (pre output-activation) values to outb [out][TM].
-template <int TM>
+template <int TM, bool JAC = false>
 __device__ void out_layer(const MlpDev& m, const float* __restrict__ hin, float* __restrict__ outb) {
   const int li = m.n_lin - 1;
   const float* __restrict__ Wg = m.params + m.w_off[li];
@@ -205,7 +243,7 @@ __device__ void out_layer(const MlpDev& m, const float* __restrict__ hin, float*
   const int NO = m.out, K = m.hidden;
   for (int idx = threadIdx.x; idx < NO * TM; idx += kThreads) {
     const int n = idx / TM, mm = idx - n * TM;
-    float acc = __ldg(bg + n);
+    float acc = (JAC && (mm & 3)) ? 0.0f : __ldg(bg + n);
     for (int k = 0; k < K; ++k) acc = nrt_fma(hin[k * TM + mm], __ldg(Wg + k * NO + n), acc);
     outb[n * TM + mm] = acc;
   }
@@ -217,10 +255,10 @@ __device__ void out_layer(const MlpDev& m, const float* __restrict__ hin, float*
 // Postcondition: outb [out][TM] holds the pre-output-activation result.
 // If acts_g != nullptr the post-activation hidden states are stored for the backward pass:
 // acts_g[(l*H + k)*M_total + m_base + mm], l = 0..L.
-template <int H, int TM>
+template <int H, int TM, bool JAC = false>
 __device__ void mlp_tile_forward(const MlpDev& m, const TileSmem& s, float* acts_g, int64_t M_total,
                                  int64_t m_base, int valid) {
-  encode_tile<TM>(m, s);
+  encode_tile<TM, JAC>(m, s);
   float* cur = s.h0;
   float* nxt = s.h1;
   auto save = [&](int l, const float* h) {
@@ -230,15 +268,15 @@ __device__ void mlp_tile_forward(const MlpDev& m, const TileSmem& s, float* acts
       if (mm < valid) acts_g[((size_t)l * H + k) * M_total + m_base + mm] = h[idx];
     }
   };
-  hidden_layer<H, TM>(m, 0, s.enc_raw, m.dim_p, nullptr, 0, cur, s.wbuf, true);
+  hidden_layer<H, TM, JAC>(m, 0, s.enc_raw, m.dim_p, nullptr, 0, cur, s.wbuf, true);
   save(0, cur);
   for (int i = 0; i < m.L; ++i) {
     const bool sk = (m.skip_mask >> i) & 1u;
-    hidden_layer<H, TM>(m, 1 + i, cur, H, s.enc_act, sk ? m.dim_p : 0, nxt, s.wbuf, true);
+    hidden_layer<H, TM, JAC>(m, 1 + i, cur, H, s.enc_act, sk ? m.dim_p : 0, nxt, s.wbuf, true);
     save(1 + i, nxt);
     float* t = cur; cur = nxt; nxt = t;
   }
-  out_layer<TM>(m, cur, s.outb);
+  out_layer<TM, JAC>(m, cur, s.outb);
 }
 
 }  // namespace nrt

@@ -13,7 +13,7 @@ from ._native import (ACT_LEAKY_RELU, ACT_SOFTPLUS, OUT_NONE, OUT_SIGMOID, OUT_S
                       PREC_BF16, PREC_F16, PREC_F32, NrtError)
 
 # set once the analytic-Jacobian kernel is part of the library
-HAS_SDF_VALUE_GRAD = False
+HAS_SDF_VALUE_GRAD = True
 
 _PREC_NAMES = {"f32": PREC_F32, "fp32": PREC_F32, "f16": PREC_F16, "fp16": PREC_F16, "bf16": PREC_BF16}
 
@@ -264,6 +264,44 @@ def composite_backward(sigma_raw, rgb, ts, g_out):
         N.check(N.lib().nrt_composite_backward(_ptr(sg), _ptr(c), _ptr(t), S, R, _ptr(go), _ptr(g_s), _ptr(g_c),
                                                _stream()))
     return g_s, g_c.reshape(rgb.shape)
+
+
+def shading_frame(normals: torch.Tensor, rays: Optional[torch.Tensor] = None):
+    """coordinate_system(normals) [..,3,3] and, if rays are given, wi = to_local(frame, -r_d)
+    (interaction.py:9-27, 38-41; sdfs.py:158-159)."""
+    batch = normals.shape[:-1]
+    n2 = _chk(normals, "normals").reshape(-1, 3)
+    R = n2.shape[0]
+    frame = torch.empty((R, 3, 3), dtype=torch.float32, device=normals.device)
+    wi = r2 = None
+    if rays is not None:
+        r2 = _chk(rays, "rays").reshape(-1, 6)
+        wi = torch.empty((R, 3), dtype=torch.float32, device=normals.device)
+    with torch.cuda.device(normals.device):
+        N.check(N.lib().nrt_shading_frame(_ptr(n2), _ptr(r2), R, _ptr(frame), _ptr(wi), _stream()))
+    frame = frame.reshape(batch + (3, 3))
+    return (frame, wi.reshape(batch + (3,))) if rays is not None else frame
+
+
+def to_local(frame: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    batch = v.shape[:-1]
+    f2 = _chk(frame, "frame").reshape(-1, 9)
+    v2 = _chk(v, "v").expand(batch + (3,)).reshape(-1, 3).contiguous()
+    out = torch.empty_like(v2)
+    with torch.cuda.device(v.device):
+        N.check(N.lib().nrt_to_local(_ptr(f2), _ptr(v2), v2.shape[0], _ptr(out), _stream()))
+    return out.reshape(batch + (3,))
+
+
+def param_rusin2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """utils.py:233-258 on [...,3] x [...,3]."""
+    batch = a.shape[:-1]
+    a2 = _chk(a, "a").reshape(-1, 3)
+    b2 = _chk(b, "b").reshape(-1, 3)
+    out = torch.empty_like(a2)
+    with torch.cuda.device(a.device):
+        N.check(N.lib().nrt_param_rusin2(_ptr(a2), _ptr(b2), a2.shape[0], _ptr(out), _stream()))
+    return out.reshape(batch + (3,))
 
 
 _ws_cache = {}

@@ -4,11 +4,22 @@ from dataclasses import dataclass
 import torch
 import torch.nn.functional as F
 
+from .. import ops
+
+
+def _fused_ok(*ts):
+    """CUDA fp32 tensors and no autograd graph needed -> the elementwise CUDA kernels can be used."""
+    if not all(t.is_cuda and t.dtype == torch.float32 for t in ts):
+        return False
+    return not (torch.is_grad_enabled() and any(t.requires_grad for t in ts))
+
 
 def coordinate_system(n):
     """Branch-free orthonormal frame around n (interaction.py:9-27), returned as columns
     [s, t, n] of a [...,3,3] tensor.  Keeps the reference's 1e-6 / 1e-7 guards and the three
     re-normalisations."""
+    if _fused_ok(n):
+        return ops.shading_frame(n)
     n = F.normalize(n, eps=1e-7, dim=-1)
     x, y, z = n[..., 0:1], n[..., 1:2], n[..., 2:3]
     sign = torch.where(z >= 0, 1., -1.)
@@ -28,6 +39,8 @@ def partial_frame(n, wi):
 
 def to_local(frame, wo):
     """interaction.py:38-41: normalize(mean over xyz of frame * wo) -- i.e. frame^T wo / 3, renormalised."""
+    if _fused_ok(frame, wo) and wo.shape[:-1] == frame.shape[:-2]:
+        return ops.to_local(frame, wo)
     w = wo.unsqueeze(-1).expand_as(frame)
     return F.normalize((frame * w).mean(dim=-2), eps=1e-7, dim=-1)
 

@@ -34,6 +34,10 @@ def rotate_vector(v, axis, c, s):
 def param_rusin2(wo, wi):
     """utils.py:233-258: (cos phi_d, cos theta_h, cos theta_d) from two local directions,
     including the reference's s = -sqrt(clamp(1 - H_z, 1e-6)) quirk."""
+    if wo.is_cuda and wi.is_cuda and wo.shape == wi.shape and wo.dtype == torch.float32 and \
+            not (torch.is_grad_enabled() and (wo.requires_grad or wi.requires_grad)):
+        from .. import ops
+        return ops.param_rusin2(wo, wi)
     wo = F.normalize(wo, dim=-1)
     wi = F.normalize(wi, dim=-1)
     y_axis = torch.tensor([0., 1., 0.], device=wo.device).expand_as(wo)
