@@ -124,11 +124,14 @@ int nrt_mlp_pack_tc(const nrt_mlp_t* m, int prec, void* blob_out, void* stream);
 int nrt_mlp_forward(const nrt_mlp_t* m, int prec, int out_act, const float* x,
                     const float* latent, int64_t M, float* out, float* acts, void* stream);
 /* reverse mode of the above.  g_out [M,out_size] is the gradient w.r.t. the *activated*
- * output `out` (which must be passed back); g_params (packed-f32 layout, ACCUMULATED
- * into with atomics: zero it first) ; g_x [M,in_size] / g_latent [M,latent] may be NULL. */
+ * output `out` (which must be passed back); params_nk holds the same weights in nn.Linear's
+ * native layout (per layer W [N][K], evaluation order, no biases) so the data-gradient GEMM
+ * streams rows over n; g_params (packed-f32 layout, ACCUMULATED into with atomics: zero it
+ * first); g_x [M,in_size] / g_latent [M,latent] may be NULL. */
 int nrt_mlp_backward(const nrt_mlp_t* m, int out_act, const float* x, const float* latent,
                      int64_t M, const float* out, const float* acts, const float* g_out,
-                     float* g_params, float* g_x, float* g_latent, void* stream);
+                     const float* params_nk, float* g_params, float* g_x, float* g_latent,
+                     void* stream);
 
 /* ---- a3: SphereSDF.forward (sdfs.py:41-46) ------------------------------------------- */
 int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M, float* out,

@@ -69,6 +69,7 @@ class PackedMLP:
         if self.params.numel() != n:
             raise NrtError("packed params have %d floats, expected %d" % (self.params.numel(), n))
         self.tc_blobs = {}   # prec -> uint8 tensor (tensor-core layout), built on demand
+        self._params_nk = None
 
     @staticmethod
     def pack(weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor]) -> torch.Tensor:
@@ -88,6 +89,16 @@ class PackedMLP:
             gb.append(flat[off:off + n])
             off += n
         return gW, gb
+
+    def params_nk(self) -> torch.Tensor:
+        """The weights in nn.Linear's [N][K] layout (per layer, no biases) for the backward's data-gradient GEMM."""
+        if self._params_nk is None:
+            chunks, off = [], 0
+            for (k, n) in self.dims:
+                chunks.append(self.params[off:off + k * n].reshape(k, n).t().contiguous().reshape(-1))
+                off += k * n + n
+            self._params_nk = torch.cat(chunks).contiguous()
+        return self._params_nk
 
     def c_struct(self, prec=PREC_F32) -> N.NrtMlp:
         tc = None
@@ -161,7 +172,8 @@ def mlp_backward(m: PackedMLP, x, latent, out, acts, g_out, out_act=OUT_NONE, ne
     with torch.cuda.device(x.device):
         c = m.c_struct()
         N.check(N.lib().nrt_mlp_backward(ctypes.byref(c), out_act, _ptr(x2), _ptr(lat), M, _ptr(out2), _ptr(acts),
-                                         _ptr(g2), _ptr(g_params), _ptr(g_x), _ptr(g_lat), _stream()))
+                                         _ptr(g2), _ptr(m.params_nk()), _ptr(g_params), _ptr(g_x), _ptr(g_lat),
+                                         _stream()))
     return g_params, g_x, g_lat
 
 

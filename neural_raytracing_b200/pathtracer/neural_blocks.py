@@ -127,7 +127,8 @@ class SkipConnMLP(nn.Module):
         if p.is_cuda and not self._needs_grad(p, latent):
             return ops.mlp_forward(self.packed(), p.detach().float(), None if latent is None else latent.detach().float(),
                                    out_act=out_act, prec=self.precision())
-        if p.is_cuda and _FUSED_BACKWARD[0] and not getattr(self, "_higher_order", False):
+        if p.is_cuda and _FUSED_BACKWARD[0] and not getattr(self, "_higher_order", False) and \
+                _activation_id(self.activation) is not None:
             return _FusedMLP.apply(self, p, latent, out_act, *self._flat_params())
         y = self.forward_reference_ops(p, latent)
         if out_act == ops.OUT_SIGMOID:
@@ -140,7 +141,7 @@ class SkipConnMLP(nn.Module):
 
 
 # first-order autograd through the fused forward/backward kernels (enabled once nrt_mlp_backward exists)
-_FUSED_BACKWARD = [False]
+_FUSED_BACKWARD = [True]
 
 
 class _FusedMLP(torch.autograd.Function):
