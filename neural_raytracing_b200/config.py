@@ -12,6 +12,7 @@ TC_NETS = {
     (70, 0, 16, 64, 8, 3, 3, 0),    # NeRFLE.second (point light)
     (3, 0, 64, 96, 6, 3, 3, 0),     # NeuralBSDF.mlp
     (5, 0, 16, 64, 8, 3, 1, 0),     # occlusion MLP
+    (3, 0, 32, 128, 8, 3, 1, 1),    # SphereSDF.shift (softplus; weights streamed through shared memory)
 }
 
 

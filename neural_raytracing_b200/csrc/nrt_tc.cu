@@ -307,10 +307,15 @@ __device__ __forceinline__ void tmem_load(uint32_t t, uint32_t* r) {
 }
 
 // fast activations for the 16-bit path (results are rounded to 16 bits anyway)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 template <int ACT>
 __device__ __forceinline__ float act_fast(float x) {
   if constexpr (ACT == NRT_ACT_SOFTPLUS) {
-    return x > 20.0f ? x : __logf(1.0f + __expf(x));
+    // branch-free softplus: max(x,0) + log(1 + exp(-|x|)); beyond torch's threshold (20) the log term is < 3e-9,
+    // i.e. the result is x like F.softplus.  Two MUFU ops, no divergence (a `x > 20 ? x : ...` form compiles to a
+    // per-element branch that cost ~100 cycles per element).
+    return fmaf(0.6931471805599453f, lg2_approx(1.0f + ex2_approx(-1.4426950408889634f * fabsf(x))), fmaxf(x, 0.0f));
   } else {
     return fmaxf(x, 0.01f * x);
   }
@@ -372,7 +377,19 @@ struct Net {
   static_assert(!SPLIT || 3 * IN <= 16, "split encoding needs 3*in <= 16");
   static_assert(SPLIT || IN % 2 == 0, "unsplit inputs must come in pairs");
   static_assert(H % 16 == 0 && H <= 256, "hidden must be a multiple of 16");
-  static_assert(Y.bytes + 2048 <= 227 * 1024, "weights do not fit in shared memory (streaming path not built)");
+  // Weights that do not fit in shared memory are STREAMED: each tile slot owns two stage buffers and the MMA warp
+  // prefetches the next stage's operand (cp.async.bulk from L2) while the current stage computes.
+  static constexpr int kSmemBudget = 227 * 1024 - 2048;
+  static constexpr bool STREAM = Y.bytes > kSmemBudget;
+  static constexpr int max_op_bytes() {
+    int m = 0;
+    for (int o = 0; o < Y.n_ops; ++o) m = imax(m, Y.opN[o] * Y.opK[o] * 2);
+    return m;
+  }
+  static constexpr int MAXOP = max_op_bytes();
+  static constexpr int BIAS_BYTES = Y.bias_floats * 4;
+  static constexpr int SMEM_BYTES = STREAM ? NSLOT * 2 * MAXOP + BIAS_BYTES : Y.bytes;
+  static_assert(SMEM_BYTES <= kSmemBudget, "stage buffers do not fit in shared memory");
 };
 
 constexpr int kEpiThreads = 128;
@@ -381,7 +398,7 @@ constexpr int kEpiThreads = 128;
 // issues.  (Issuing from a divergent single lane makes the compiler wrap every UTCHMMA in an
 // ELECT / R2UR / BRA.U.ANY serialisation loop: ~135 cycles per MMA instead of ~72, see profiles/.)
 template <class NET, int FMT, int ST>
-__device__ __forceinline__ void issue_stage(uint32_t sW_addr, uint32_t dD, uint32_t aU, uint32_t aE, uint64_t* done_bar) {
+__device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE, uint64_t* done_bar) {
   constexpr Layout Y = NET::Y;
   constexpr uint32_t N = (uint32_t)Y.opN[ST];
   constexpr uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((N >> 3) << 17) |
@@ -389,9 +406,8 @@ __device__ __forceinline__ void issue_stage(uint32_t sW_addr, uint32_t dD, uint3
   constexpr uint32_t lbo = N * 16, sbo = 128;
   constexpr int kch = Y.opK[ST] / 16;
   constexpr int k_u = (ST >= 2 && ST < NET::STAGES - 1) ? NET::H / 16 : kch;   // K chunks taken from U
-  constexpr uint32_t b_off = (uint32_t)Y.op_off[ST] * 2;
   if (elect_one()) {
-    const uint64_t bd0 = make_desc(sW_addr + b_off, lbo, sbo);
+    const uint64_t bd0 = make_desc(b_addr, lbo, sbo);
 #pragma unroll
     for (int kc = 0; kc < kch; ++kc) {
       const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
@@ -404,12 +420,17 @@ __device__ __forceinline__ void issue_stage(uint32_t sW_addr, uint32_t dD, uint3
   __syncwarp();
 }
 template <class NET, int FMT, int ST = 0>
-__device__ __forceinline__ void issue_stage_dyn(int st, uint32_t sW_addr, uint32_t dD, uint32_t aU, uint32_t aE,
+__device__ __forceinline__ void issue_stage_dyn(int st, uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE,
                                                 uint64_t* done_bar) {
   if constexpr (ST < NET::STAGES) {
-    if (st == ST) issue_stage<NET, FMT, ST>(sW_addr, dD, aU, aE, done_bar);
-    else issue_stage_dyn<NET, FMT, ST + 1>(st, sW_addr, dD, aU, aE, done_bar);
+    if (st == ST) issue_stage<NET, FMT, ST>(b_addr, dD, aU, aE, done_bar);
+    else issue_stage_dyn<NET, FMT, ST + 1>(st, b_addr, dD, aU, aE, done_bar);
   }
+}
+// bulk copy of one stage operand (<= 32 KB pieces) from the blob into a stage buffer; completes on `bar`
+__device__ __forceinline__ void stream_op(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+  mbar_expect_tx(bar, bytes);
+  for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
 }
 
 // IO policy concept:
@@ -429,9 +450,12 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   constexpr int H = NET::H, IN = NET::IN, LAT = NET::LAT, F = NET::F, L = NET::L;
   constexpr int NSLOT = NET::NSLOT;
   extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool STREAM = NET::STREAM;
   uint16_t* sW = reinterpret_cast<uint16_t*>(smem);
-  const float* sBias = reinterpret_cast<const float*>(smem + (size_t)Y.w_elems * 2);
+  const float* sBias = reinterpret_cast<const float*>(smem + (STREAM ? (size_t)NSLOT * 2 * NET::MAXOP : (size_t)Y.w_elems * 2));
   __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_wfull[2][2];   // streaming: stage buffer b of slot s has landed
+  __shared__ uint32_t s_opoff[NET::STAGES], s_opbytes[NET::STAGES];
   __shared__ __align__(8) uint64_t bar_ready[2];
   __shared__ __align__(8) uint64_t bar_done[2];
   __shared__ uint32_t tmem_base_s;
@@ -441,11 +465,18 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   const int warp = tid >> 5;
   const bool is_mma_warp = warp == 8;
   const int64_t ntiles = (M + 127) / 128;
-  if (tid < NET::STAGES) s_bias[tid] = (uint32_t)Y.bias_off[tid];
+  if (tid < NET::STAGES) {
+    s_bias[tid] = (uint32_t)Y.bias_off[tid];
+    s_opoff[tid] = (uint32_t)Y.op_off[tid] * 2;
+    s_opbytes[tid] = (uint32_t)(Y.opN[tid] * Y.opK[tid] * 2);
+  }
 
   if (tid == 0) {
     mbar_init(&bar_w, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1);
+      mbar_init(&bar_wfull[s][0], 1); mbar_init(&bar_wfull[s][1], 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -453,12 +484,18 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     if ((tid & 31) == 0) {
-      // all weights + biases: global (L2) -> shared, once per CTA
-      mbar_expect_tx(&bar_w, (uint32_t)Y.bytes);
-      constexpr uint32_t kChunk = 32768;
-      for (uint32_t off = 0; off < (uint32_t)Y.bytes; off += kChunk) {
-        const uint32_t n = min(kChunk, (uint32_t)Y.bytes - off);
-        bulk_g2s(smem + off, blob + off, n, &bar_w);
+      if (STREAM) {
+        // only the biases are resident; stage operands are streamed by the MMA loop
+        mbar_expect_tx(&bar_w, (uint32_t)NET::BIAS_BYTES);
+        bulk_g2s(smem + (size_t)NSLOT * 2 * NET::MAXOP, blob + (size_t)Y.w_elems * 2, (uint32_t)NET::BIAS_BYTES, &bar_w);
+      } else {
+        // all weights + biases: global (L2) -> shared, once per CTA
+        mbar_expect_tx(&bar_w, (uint32_t)Y.bytes);
+        constexpr uint32_t kChunk = 32768;
+        for (uint32_t off = 0; off < (uint32_t)Y.bytes; off += kChunk) {
+          const uint32_t n = min(kChunk, (uint32_t)Y.bytes - off);
+          bulk_g2s(smem + off, blob + off, n, &bar_w);
+        }
       }
     }
   }
@@ -479,6 +516,14 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
     bool live[2] = {tile[0] < ntiles, NSLOT > 1 && tile[1] < ntiles};
     int it_dbg[2] = {0, 0};
+    uint32_t n_issued[2] = {0, 0};      // streaming: stages issued per slot (selects the stage buffer)
+    if (STREAM) {
+#pragma unroll
+      for (int slot = 0; slot < NSLOT; ++slot)
+        if (live[slot] && elect_one())
+          stream_op(smem + (size_t)(slot * 2) * NET::MAXOP, blob + s_opoff[0], s_opbytes[0], &bar_wfull[slot][0]);
+      __syncwarp();
+    }
     while (live[0] || live[1]) {
       bool progressed = false;
 #pragma unroll
@@ -490,13 +535,30 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         tc_fence_after();
         if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 1);
         const uint32_t base = tmem + slot * NET::COLS;
-        issue_stage_dyn<NET, FMT>(st[slot], sW_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+        uint32_t b_addr = sW_addr + s_opoff[st[slot]];
+        if (STREAM) {
+          const uint32_t b = n_issued[slot] & 1;
+          mbar_wait(&bar_wfull[slot][b], (n_issued[slot] >> 1) & 1);
+          b_addr = sW_addr + (uint32_t)((slot * 2 + b) * NET::MAXOP);
+        }
+        issue_stage_dyn<NET, FMT>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
         if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 2);
         if (++st[slot] == NET::STAGES) {
           st[slot] = 0;
           it_dbg[slot]++;
           tile[slot] += (int64_t)gridDim.x * NSLOT;
           live[slot] = tile[slot] < ntiles;
+        }
+        if (STREAM) {
+          // prefetch the operand of this slot's next stage into its other buffer.  That buffer held the operand
+          // of the previous stage, whose MMAs completed before the epilogue that made this stage ready.
+          n_issued[slot]++;
+          if (live[slot] && elect_one()) {
+            const uint32_t nb = n_issued[slot] & 1;
+            stream_op(smem + (size_t)(slot * 2 + nb) * NET::MAXOP, blob + s_opoff[st[slot]], s_opbytes[st[slot]],
+                      &bar_wfull[slot][nb]);
+          }
+          __syncwarp();
         }
       }
       // this warp shares an SM sub-partition with two epilogue warps: do not burn their issue slots
@@ -746,9 +808,39 @@ struct IoNerfSecond {
 static long long* g_dbg_timeline = nullptr;   // development only, see tools/tc_timeline.py
 extern "C" void nrtdbg_set_timeline(long long* dev_buf) { g_dbg_timeline = dev_buf; }
 
+// smooth-min of the warped spheres (sdfs.py:37-46, utils.py:385-387), fast-math version for the 16-bit path
+__device__ __forceinline__ float sphere_smin_fast(const SdfDev& sd, float px, float py, float pz) {
+  float sum = 0.0f;
+  for (int i = 0; i < sd.n; ++i) {
+    const float* T = sd.tfs + i * 9;
+    float q[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float t0 = __ldg(T + j * 3 + 0) + (j == 0 ? 1.0f : 0.0f);
+      const float t1 = __ldg(T + j * 3 + 1) + (j == 1 ? 1.0f : 0.0f);
+      const float t2 = __ldg(T + j * 3 + 2) + (j == 2 ? 1.0f : 0.0f);
+      q[j] = fmaf(t2, pz, fmaf(t1, py, t0 * px)) - __ldg(sd.centers + i * 3 + j);
+    }
+    const float d = sqrtf(fmaf(q[2], q[2], fmaf(q[1], q[1], q[0] * q[0]))) - __ldg(sd.radii + i);
+    sum += __expf(-32.0f * d);
+  }
+  return -__logf(fmaxf(sum, 1e-4f)) * (1.0f / 32.0f);
+}
+
+struct IoSdfEval {   // points [M,3] in, sdf value (sphere set + residual MLP) out
+  static constexpr int kSplitOut = 1;
+  SdfDev sd; const float* p; float* out;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+    v[0] = __ldg(p + m * 3); v[1] = __ldg(p + m * 3 + 1); v[2] = __ldg(p + m * 3 + 2);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+    out[m] = sphere_smin_fast(sd, __ldg(p + m * 3), __ldg(p + m * 3 + 1), __ldg(p + m * 3 + 2)) + o[0];
+  }
+};
+
 template <class NET, class IO, int FMT>
 static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP) {
-  const size_t bytes = (size_t)NET::Y.bytes + 256;
+  const size_t bytes = (size_t)NET::SMEM_BYTES + 256;
   auto kern = k_mlp_tc<NET, IO, FMT>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int64_t ntiles = (M + 127) / 128;
@@ -764,6 +856,7 @@ using NetNerfFirst = Net<3, 0, 16, 128, 5, 3, 65, NRT_ACT_LEAKY_RELU>;      // N
 using NetNerfSecondPT = Net<70, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;    // NeRFLE.second  nerf.py:169-172
 using NetNeuralBsdf = Net<3, 0, 64, 96, 6, 3, 3, NRT_ACT_LEAKY_RELU>;       // NeuralBSDF.mlp bsdfs.py:616-621
 using NetOcc = Net<5, 0, 16, 64, 8, 3, 1, NRT_ACT_LEAKY_RELU>;              // occlusion MLP  colocate.py:82-85
+using NetSdfShift = Net<3, 0, 32, 128, 8, 3, 1, NRT_ACT_SOFTPLUS>;         // SphereSDF.shift sdfs.py:23-31 (streamed)
 
 template <class NET>
 static bool matches(const MlpDev& d) {
@@ -821,14 +914,22 @@ int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x
   if (matches<NetNerfSecondPT>(d)) return forward_plain<NetNerfSecondPT>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetNeuralBsdf>(d)) return forward_plain<NetNeuralBsdf>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetOcc>(d)) return forward_plain<NetOcc>(m, prec, out_act, x, latent, M, out, st);
+  if (matches<NetSdfShift>(d)) return forward_plain<NetSdfShift>(m, prec, out_act, x, latent, M, out, st);
   nrt_set_error("tensor-core path: MLP shape (in %d, latent %d, freqs %d, hidden %d, layers %d, out %d, act %d) is not "
                 "instantiated; use NRT_PREC_F32", d.in_size, d.latent, d.freqs, d.hidden, d.L, d.out, d.act);
   return NRT_E_UNSUPPORTED;
 }
 
-int nrt_sdf_eval_tc(const nrt_sphere_sdf_t*, int, const float*, int64_t, float*, cudaStream_t) {
-  nrt_set_error("tensor-core SDF evaluation needs the weight-streaming path (8x128 MLP = 333 KB > smem); use NRT_PREC_F32");
-  return NRT_E_UNSUPPORTED;
+int nrt_sdf_eval_tc(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M, float* out, cudaStream_t st) {
+  SdfDev d;
+  int rc = nrt_build_sdf_dev(s, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "unknown precision %d", prec);
+  NRT_REQUIRE(s->shift.params_tc != nullptr, "sdf.shift.params_tc is NULL: call nrt_mlp_pack_tc first");
+  NRT_REQUIRE(matches<NetSdfShift>(d.mlp), "tensor-core SDF path: shift must be the 8x128 softplus MLP with 32 frequencies");
+  IoSdfEval io{d, p, out};
+  if (fmt_of(prec) == 0) return launch<NetSdfShift, IoSdfEval, 0>(s->shift.params_tc, io, M, st);
+  return launch<NetSdfShift, IoSdfEval, 1>(s->shift.params_tc, io, M, st);
 }
 
 size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t*, int64_t R, int S) {

@@ -24,6 +24,23 @@ for name in ("nerf_first", "nerf_second", "neural_bsdf", "occ"):
                 print("%-12s M=%4d %-4s max_abs_err %.3e (|y| max %.3f) finite=%s" % (name, M, prec, np.abs(y - yo).max(), np.abs(yo).max(), np.isfinite(y).all()))
             except Exception as e:
                 print(name, M, prec, "FAILED", e)
+# SDF residual MLP (softplus, weights streamed) and the full SDF on the tensor cores
+wsdf = helpers.golden_sdf_weights()
+rs = np.random.RandomState(5)
+pts = (0.5 * rs.standard_normal((3000, 3))).astype(np.float32)
+yo = c_oracle.mlp_forward(helpers.oracle_mlp(wsdf["shift"], "softplus"), pts)
+vo = c_oracle.sdf_eval(helpers.oracle_sdf(wsdf), pts)
+for prec in ("f16", "bf16"):
+    y = ops.mlp_forward(helpers.cuda_mlp(wsdf["shift"], "softplus"), T(pts), prec=prec).cpu().numpy()
+    v = ops.sdf_eval(helpers.cuda_sdf(wsdf), T(pts), prec=prec).cpu().numpy()
+    print("sdf_shift %-4s max_abs_err %.3e (|y| max %.3f) | sdf_eval max_abs_err %.3e (|v| max %.3f)" % (prec, np.abs(y - yo).max(), np.abs(yo).max(), np.abs(v - vo).max(), np.abs(vo).max()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+big = T((0.5 * rs.standard_normal((148 * 256 * 16, 3))).astype(np.float32)); sdf_c = helpers.cuda_sdf(wsdf)
+ops.sdf_eval(sdf_c, big, prec="f16"); torch.cuda.synchronize()
+e0.record(); ops.sdf_eval(sdf_c, big, prec="f16"); e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1); print("sdf_eval f16 %d pts: %.3f ms -> %.1f Msamples/s, %.1f TFLOP/s" % (big.shape[0], ms, big.shape[0] / ms / 1e3, big.shape[0] * 331008 / ms / 1e9))
+e0.record(); ops.sdf_eval(sdf_c, big, prec="f32"); e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1); print("sdf_eval f32 %d pts: %.3f ms -> %.1f Msamples/s, %.1f TFLOP/s" % (big.shape[0], ms, big.shape[0] / ms / 1e3, big.shape[0] * 331008 / ms / 1e9))
 g = helpers.golden("nerfle")
 w1, w2 = helpers.nerfle_weights(False)
 rays = synth.camera_rays(33, 500)
