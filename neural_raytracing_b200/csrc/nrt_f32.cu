@@ -597,6 +597,13 @@ int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x
                        int64_t M, float* out, cudaStream_t st);  // nrt_tc.cu
 int nrt_sdf_eval_tc(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M, float* out,
                     cudaStream_t st);
+int nrt_sdf_march_tc(int shadow, const nrt_sphere_sdf_t* s, int prec, const float* rays, const float* max_t_per_ray,
+                     const uint8_t* active, int64_t R, float eps, int max_steps, float max_t, float t_start,
+                     float* depth, uint8_t* flag, unsigned long long* counter, unsigned long long* steps_done,
+                     cudaStream_t st);
+int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, int64_t R, double step, int n_steps,
+                        int32_t* best_idx, float* best_pos, float* min_val, unsigned long long* counter,
+                        cudaStream_t st);
 
 extern "C" int nrt_mlp_forward(const nrt_mlp_t* m, int prec, int out_act, const float* x,
                                const float* latent, int64_t M, float* out, float* acts, void* stream) {
@@ -655,13 +662,15 @@ static int launch_march(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   SdfDev d;
   int rc = nrt_build_sdf_dev(s, &d);
   if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(prec == NRT_PREC_F32, "sphere-trace march: only NRT_PREC_F32 is implemented (got %d)", prec);
   NRT_REQUIRE(R >= 0 && R < 2147483647LL, "march: R out of range");
   if (R == 0) return NRT_OK;
   NRT_REQUIRE(rays != nullptr && flag != nullptr && max_steps >= 0, "march: bad arguments");
   unsigned long long* counter = nullptr;
   rc = next_counter(st, &counter);
   if (rc != NRT_OK) return rc;
+  if (prec != NRT_PREC_F32)
+    return nrt_sdf_march_tc(MODE == MARCH_SHADOW, s, prec, rays, max_t_per_ray, active, R, eps, max_steps, max_t,
+                            t_start, depth, flag, counter, steps_done, st);
   NRT_DISPATCH_H(d.mlp.hidden, {
     const size_t bytes = (tile_smem_floats(d.mlp.dim_p, H, d.mlp.out, TM) + 12 * TM) * sizeof(float);
     rc = set_smem(k_sdf_march<H, TM, MODE>, bytes);
@@ -702,11 +711,16 @@ extern "C" int nrt_sdf_min_scan(const nrt_sphere_sdf_t* s, int prec, const float
   SdfDev d;
   int rc = nrt_build_sdf_dev(s, &d);
   if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(prec == NRT_PREC_F32, "nrt_sdf_min_scan: only NRT_PREC_F32 is implemented (got %d)", prec);
   NRT_REQUIRE(R >= 0 && n_steps >= 0, "nrt_sdf_min_scan: bad arguments");
   if (R == 0) return NRT_OK;
   NRT_REQUIRE(rays && best_idx && best_pos, "nrt_sdf_min_scan: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
+  if (prec != NRT_PREC_F32) {
+    unsigned long long* counter = nullptr;
+    rc = next_counter(st, &counter);
+    if (rc != NRT_OK) return rc;
+    return nrt_sdf_min_scan_tc(s, prec, rays, R, step, n_steps, best_idx, best_pos, min_val, counter, st);
+  }
   NRT_DISPATCH_H(d.mlp.hidden, {
     const size_t bytes = (tile_smem_floats(d.mlp.dim_p, H, d.mlp.out, TM) + 2 * TM) * sizeof(float);
     rc = set_smem(k_sdf_min_scan<H, TM>, bytes);

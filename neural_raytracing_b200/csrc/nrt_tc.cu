@@ -16,6 +16,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "nrt_common.cuh"
 
@@ -314,7 +315,8 @@ __device__ __forceinline__ float act_fast(float x) {
   if constexpr (ACT == NRT_ACT_SOFTPLUS) {
     // branch-free softplus: max(x,0) + log(1 + exp(-|x|)); beyond torch's threshold (20) the log term is < 3e-9,
     // i.e. the result is x like F.softplus.  Two MUFU ops, no divergence (a `x > 20 ? x : ...` form compiles to a
-    // per-element branch that cost ~100 cycles per element).
+    // per-element branch that cost ~100 cycles per element).  A one-MUFU variant (ex2 + degree-5 polynomial for
+    // log1p) measured the same throughput in isolation (tools/softplus_bw.cu) and is less accurate.
     return fmaf(0.6931471805599453f, lg2_approx(1.0f + ex2_approx(-1.4426950408889634f * fabsf(x))), fmaxf(x, 0.0f));
   } else {
     return fmaxf(x, 0.01f * x);
@@ -335,6 +337,76 @@ __device__ __forceinline__ uint32_t act_pack(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&r);
   }
 }
+// 32 accumulator columns -> act -> 16 packed operand columns.  Written structure-of-arrays over groups of 8
+// elements so that every step is 8 independent instructions: a single epilogue warp has its SM sub-partition
+// (almost) to itself, so the conversion runs at the speed of its dependent chains unless the ILP is explicit
+// (the straight per-pair loop over a whole 128-column row measured ~4 cycles per instruction).
+template <int ACT, int FMT>
+__device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint32_t* __restrict__ pk) {
+  if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float x[8], u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[8 * g + i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = ex2_approx(-1.4426950408889634f * fabsf(x[i]));
+      // (a one-MUFU variant, ex2 + degree-5 polynomial for log1p on the FMA pipe, measured the same row time here
+      //  and is slightly less accurate: tools/softplus_bw.cu, profiles/r01_kernel_optimisation_log.md)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = fmaf(0.6931471805599453f, u[i], fmaxf(x[i], 0.0f));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(u[2 * i], u[2 * i + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = Elem<FMT>::pack(__uint_as_float(acc[16 * g + 2 * i]), __uint_as_float(acc[16 * g + 2 * i + 1]));
+      if constexpr (FMT == 0) {
+        __half2 m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = __hmul2(*reinterpret_cast<__half2*>(&h[i]), __floats2half2_rn(0.01f, 0.01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&h[i]), m[i]);
+          pk[8 * g + i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+      } else {
+        __nv_bfloat162 m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&h[i]), __floats2bfloat162_rn(0.01f, 0.01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&h[i]), m[i]);
+          pk[8 * g + i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+      }
+    }
+  }
+}
+// One accumulator row (H fp32 columns at dD) -> activated 16-bit operand columns at aU, in 32-column chunks:
+// the tcgen05.ld of chunk c+1 is in flight while chunk c is converted (64 + 16 live registers instead of 192).
+template <int ACT, int FMT, int H>
+__device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU) {
+  static_assert(H % 32 == 0, "hidden width must be a multiple of 32");
+  constexpr int NC = H / 32;
+  uint32_t buf[2][32];
+  TmemIO<32>::ld(dD, buf[0]);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) TmemIO<32>::ld(dD + 32 * (c + 1), buf[(c + 1) & 1]);
+    uint32_t pk[16];
+    convert32<ACT, FMT>(buf[c & 1], pk);
+    TmemIO<16>::st(aU + 16 * c, pk);
+    if (c + 1 < NC) tc_wait_ld();
+  }
+}
+
 // D[lane][0..N) = bias[0..N): the next layer's MMA then only accumulates (no bias add in its epilogue)
 template <int N>
 __device__ __forceinline__ void preload_bias(uint32_t dD, const float* __restrict__ bias) {
@@ -433,8 +505,25 @@ __device__ __forceinline__ void stream_op(uint8_t* dst, const uint8_t* src, uint
   for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
 }
 
-// IO policy concept:
-//   struct IO { __device__ void load(int64_t m, float* x /*IN+LAT*/) const; __device__ void store(int64_t m, const float* o /*OUT, bias added*/) const; };
+// IO policy concepts.
+//   tile policy:       struct IO { __device__ void load(int64_t m, float* x /*IN+LAT*/) const;
+//                                  __device__ void store(int64_t m, const float* o /*OUT, bias added*/) const; };
+//     sample m of the flat batch <-> row m % 128 of tile m / 128; tiles are dealt round-robin to the CTAs.
+//   iterative policy:  struct IO { struct State; void init(State&); bool next(State&, float* x); void consume(State&, const float* o);
+//                                  void finish(State&); };
+//     every epilogue thread owns one *trajectory* (a marching ray): next() retires a finished trajectory, pulls a
+//     new one from a global queue (warp-aggregated atomic) and produces the next evaluation point; consume()
+//     takes the network output.  The tile slot keeps cycling while any of its 128 threads is live, so every MMA
+//     row is (up to the queue tail) spent on a live ray: this is the compaction of the sphere-trace march.
+template <class T, class = void> struct IsIterative : std::false_type {};
+template <class T> struct IsIterative<T, std::void_t<typename T::State>> : std::true_type {};
+struct NoState {};
+template <class T, class = void> struct StateOf { using type = NoState; };
+template <class T> struct StateOf<T, std::void_t<typename T::State>> { using type = typename T::State; };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <class NET, class IO, int FMT>
 __global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
@@ -460,6 +549,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   __shared__ __align__(8) uint64_t bar_done[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_bias[NET::STAGES];
+  constexpr bool ITER = IsIterative<IO>::value;
+  __shared__ volatile uint32_t s_slot_live[2];   // iterative policies: 0 once the slot's queue has run dry
+  __shared__ uint32_t s_warp_live[2][4];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -472,6 +564,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   }
 
   if (tid == 0) {
+    s_slot_live[0] = 1; s_slot_live[1] = 1;
     mbar_init(&bar_w, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1);
@@ -514,7 +607,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     int st[2] = {0, 0};
     uint32_t n_ready[2] = {0, 0};
     int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
-    bool live[2] = {tile[0] < ntiles, NSLOT > 1 && tile[1] < ntiles};
+    bool live[2] = {ITER || tile[0] < ntiles, NSLOT > 1 && (ITER || tile[1] < ntiles)};
     int it_dbg[2] = {0, 0};
     uint32_t n_issued[2] = {0, 0};      // streaming: stages issued per slot (selects the stage buffer)
     if (STREAM) {
@@ -533,6 +626,15 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         progressed = true;
         n_ready[slot]++;
         tc_fence_after();
+        if constexpr (ITER) {
+          if (st[slot] == 0 && s_slot_live[slot] == 0) {
+            // the slot's epilogue found no live trajectory and the queue is empty: retire the slot (after draining
+            // the operand prefetch that was issued for the iteration that will not happen)
+            live[slot] = false;
+            if (STREAM) mbar_wait(&bar_wfull[slot][n_issued[slot] & 1], (n_issued[slot] >> 1) & 1);
+            continue;
+          }
+        }
         if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 1);
         const uint32_t base = tmem + slot * NET::COLS;
         uint32_t b_addr = sW_addr + s_opoff[st[slot]];
@@ -546,8 +648,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         if (++st[slot] == NET::STAGES) {
           st[slot] = 0;
           it_dbg[slot]++;
-          tile[slot] += (int64_t)gridDim.x * NSLOT;
-          live[slot] = tile[slot] < ntiles;
+          if constexpr (!ITER) {
+            tile[slot] += (int64_t)gridDim.x * NSLOT;
+            live[slot] = tile[slot] < ntiles;
+          }
         }
         if (STREAM) {
           // prefetch the operand of this slot's next stage into its other buffer.  That buffer held the operand
@@ -575,16 +679,33 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
       uint32_t n_done = 0;
       int it_dbg = 0;
       auto estamp = [&](int st, int k) { if (lane_row == 0) stamp(it_dbg, st, slot, k); };
-      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT, ++it_dbg) {
-        const int64_t tile = t0 + slot;
-        if (tile >= ntiles) break;
-        const int64_t m = tile * 128 + lane_row;
-        const bool valid = m < M;
+      typename StateOf<IO>::type state;
+      if constexpr (ITER) io.init(state);
+      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT;; t0 += (int64_t)gridDim.x * NSLOT, ++it_dbg) {
+        int64_t m = 0;
+        bool valid;
+        float x[IN + LAT];
+        if constexpr (ITER) {
+          valid = io.next(state, x);
+          const unsigned bal = __ballot_sync(0xffffffffu, valid);
+          if ((tid & 31) == 0) s_warp_live[slot][warp & 3] = bal;
+          named_bar_sync(1 + slot, kEpiThreads);
+          const bool any = (s_warp_live[slot][0] | s_warp_live[slot][1] | s_warp_live[slot][2] | s_warp_live[slot][3]) != 0;
+          if (!any) {
+            if (lane_row == 0) s_slot_live[slot] = 0;
+            mbar_arrive(&bar_ready[slot]);   // release: the MMA warp reads s_slot_live after its acquire
+            break;
+          }
+        } else {
+          const int64_t tile = t0 + slot;
+          if (tile >= ntiles) break;
+          m = tile * 128 + lane_row;
+          valid = m < M;
+          if (valid) io.load(m, x);
+        }
         // ---- stage 0: inputs -> encode-GEMM A operand (+ x / latent parts of enc_raw, enc_act) ----
         {
-          float x[IN + LAT];
-          if (valid) io.load(m, x);
-          else {
+          if (!valid) {
 #pragma unroll
             for (int j = 0; j < IN + LAT; ++j) x[j] = 0.0f;
           }
@@ -669,15 +790,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
           estamp(2 + st, 4);
-          uint32_t acc[H];
-          tmem_load<H>(dD, acc);          // the whole accumulator row, one wait
-          tc_wait_ld();
           estamp(2 + st, 5);
-          uint32_t pk[H / 2];
-#pragma unroll
-          for (int j = 0; j < H / 2; ++j)
-            pk[j] = act_pack<NET::ACT, FMT>(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
-          tmem_store<H / 2>(aU, pk);
+          convert_row<NET::ACT, FMT, H>(dD, aU);
           // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
           // the conversion so the accumulator registers are dead and all 32 LDS.128 can be in flight
           if (st < L) preload_bias<H>(dD, sBias + s_bias[2 + st]);
@@ -699,11 +813,13 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           float o[NET::OUT];   // bias already accumulated (pre-loaded into the accumulator)
 #pragma unroll
           for (int j = 0; j < NET::OUT; ++j) o[j] = __uint_as_float(acc[j]);
-          if (valid) io.store(m, o);
+          if constexpr (ITER) { if (valid) io.consume(state, o); }
+          else { if (valid) io.store(m, o); }
           // the accumulator / operand regions of this slot may now be reused by the next tile
           tc_fence_before();
         }
       }
+      if constexpr (ITER) io.finish(state);
     }
   }
   tc_fence_before();
@@ -838,6 +954,127 @@ struct IoSdfEval {   // points [M,3] in, sdf value (sphere set + residual MLP) o
   }
 };
 
+// ---- iterative policies: thread = ray --------------------------------------------------------------------
+// Pulls one ray index per needing lane from the global queue with ONE atomic per warp.  Returns -1 when the
+// queue is exhausted.  Must be called by the whole warp.
+__device__ __forceinline__ long long grab_ray(unsigned long long* counter, int64_t R, bool need) {
+  const unsigned bal = __ballot_sync(0xffffffffu, need);
+  if (bal == 0) return -1;
+  const int lane = threadIdx.x & 31;
+  unsigned long long base = 0;
+  if (lane == __ffs(bal) - 1) base = atomicAdd(counter, (unsigned long long)__popc(bal));
+  base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+  const long long r = (long long)base + __popc(bal & ((1u << lane) - 1u));
+  return (need && r < R) ? r : -1;
+}
+
+enum { TC_MARCH_PRIMARY = 0, TC_MARCH_SHADOW = 1 };
+
+// a4 / a7: sphere-trace march and shadow march on the tensor cores (sdfs.py:111-131, 162-181).  Same per-ray
+// state machine as k_sdf_march (nrt_f32.cu); the SDF value comes from the 16-bit tensor-core evaluation.
+template <int MODE>
+struct IoMarch {
+  SdfDev sd;
+  const float* rays; const float* max_t_per_ray; const uint8_t* active; int64_t R;
+  float eps; int max_steps; float max_t; float t_start;
+  float* depth; uint8_t* flag; unsigned long long* counter; unsigned long long* steps_done;
+  struct State { float o[3], d[3], p[3], t, tmax; int it; long long r; bool dry; unsigned steps; };
+  __device__ __forceinline__ void init(State& s) const { s.r = -1; s.dry = false; s.steps = 0; s.it = 0; s.t = 0.0f; s.tmax = 0.0f; }
+  __device__ __forceinline__ bool next(State& s, float* x) const {
+    for (;;) {
+      if (s.r >= 0) {
+        // pre-evaluation checks: max_steps reached, or (primary) `remaining &= depth < max_t`
+        bool done = s.it >= max_steps;
+        if (MODE == TC_MARCH_PRIMARY) done = done || !(s.t < max_t);
+        if (done) {
+          if (MODE == TC_MARCH_PRIMARY) { depth[s.r] = s.t; flag[s.r] = 0; }
+          else flag[s.r] = 1;   // never hit: `remaining` stays true => not blocked
+          s.r = -1;
+        }
+      }
+      const bool need = s.r < 0 && !s.dry;
+      if (__ballot_sync(0xffffffffu, need) == 0) break;
+      const long long r = grab_ray(counter, R, need);
+      if (need) {
+        if (r < 0) { s.dry = true; }
+        else if (active != nullptr && active[r] == 0) {
+          // inactive rays are skipped (their shading is masked to 0 by the caller)
+          if (MODE == TC_MARCH_PRIMARY) { depth[r] = t_start; flag[r] = 0; } else flag[r] = 1;
+        } else {
+          const float* rp = rays + r * 6;
+          s.o[0] = __ldg(rp); s.o[1] = __ldg(rp + 1); s.o[2] = __ldg(rp + 2);
+          s.d[0] = __ldg(rp + 3); s.d[1] = __ldg(rp + 4); s.d[2] = __ldg(rp + 5);
+          s.t = t_start; s.it = 0; s.r = r;
+          s.tmax = (MODE == TC_MARCH_SHADOW) ? __ldg(max_t_per_ray + r) : max_t;
+        }
+      }
+    }
+    if (s.r < 0) return false;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { s.p[j] = __fadd_rn(s.o[j], __fmul_rn(s.d[j], s.t)); x[j] = s.p[j]; }
+    return true;
+  }
+  __device__ __forceinline__ void consume(State& s, const float* o) const {
+    const float d = sphere_smin_fast(sd, s.p[0], s.p[1], s.p[2]) + o[0];
+    s.steps++;
+    if (MODE == TC_MARCH_PRIMARY) {
+      if (d <= eps) { depth[s.r] = s.t; flag[s.r] = 1; s.r = -1; }   // depth is NOT advanced on the hit step
+      else { s.t += d; s.it++; }
+    } else {
+      s.t += d; s.it++;
+      if (d < eps) { flag[s.r] = (s.t >= s.tmax) ? 1 : 0; s.r = -1; }
+    }
+  }
+  __device__ __forceinline__ void finish(State& s) const {
+    if (steps_done == nullptr) return;
+    unsigned v = s.steps;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(steps_done, (unsigned long long)v);
+  }
+};
+
+// a5: SDF.throughput min-along-ray scan (sdfs.py:232-249): n_steps+1 evaluations per ray, strict-< running argmin.
+struct IoMinScan {
+  SdfDev sd;
+  const float* rays; int64_t R; double step; int n_steps;
+  int32_t* best_idx; float* best_pos; float* min_val; unsigned long long* counter;
+  struct State { float o[3], d[3], p[3], cur_min; int j, idx; long long r; bool dry; };
+  __device__ __forceinline__ void init(State& s) const { s.r = -1; s.dry = false; s.j = 0; s.idx = 0; s.cur_min = 0.0f; }
+  __device__ __forceinline__ bool next(State& s, float* x) const {
+    if (s.r >= 0 && s.j > n_steps) {
+      best_idx[s.r] = s.idx;
+      if (min_val) min_val[s.r] = s.cur_min;
+      const float tb = __fmul_rn((float)s.idx, (float)step);   // best_pos = r_o + (idx.float() * fl32(step)) * d
+#pragma unroll
+      for (int j = 0; j < 3; ++j) best_pos[s.r * 3 + j] = __fadd_rn(s.o[j], __fmul_rn(tb, s.d[j]));
+      s.r = -1;
+    }
+    const bool need = s.r < 0 && !s.dry;
+    const long long r = grab_ray(counter, R, need);
+    if (need) {
+      if (r < 0) s.dry = true;
+      else {
+        const float* rp = rays + r * 6;
+        s.o[0] = __ldg(rp); s.o[1] = __ldg(rp + 1); s.o[2] = __ldg(rp + 2);
+        s.d[0] = __ldg(rp + 3); s.d[1] = __ldg(rp + 4); s.d[2] = __ldg(rp + 5);
+        s.j = 0; s.r = r;
+      }
+    }
+    if (s.r < 0) return false;
+    const float t = (float)(step * (double)s.j);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { s.p[j] = (s.j == 0) ? s.o[j] : __fadd_rn(s.o[j], __fmul_rn(t, s.d[j])); x[j] = s.p[j]; }
+    return true;
+  }
+  __device__ __forceinline__ void consume(State& s, const float* o) const {
+    const float v = sphere_smin_fast(sd, s.p[0], s.p[1], s.p[2]) + o[0];
+    if (s.j == 0) { s.cur_min = v; s.idx = 0; }
+    else { if (v < s.cur_min) s.idx = s.j; s.cur_min = fminf(s.cur_min, v); }
+    s.j++;
+  }
+  __device__ __forceinline__ void finish(State&) const {}
+};
+
 template <class NET, class IO, int FMT>
 static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP) {
   const size_t bytes = (size_t)NET::SMEM_BYTES + 256;
@@ -928,8 +1165,47 @@ int nrt_sdf_eval_tc(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t
   NRT_REQUIRE(s->shift.params_tc != nullptr, "sdf.shift.params_tc is NULL: call nrt_mlp_pack_tc first");
   NRT_REQUIRE(matches<NetSdfShift>(d.mlp), "tensor-core SDF path: shift must be the 8x128 softplus MLP with 32 frequencies");
   IoSdfEval io{d, p, out};
-  if (fmt_of(prec) == 0) return launch<NetSdfShift, IoSdfEval, 0>(s->shift.params_tc, io, M, st);
-  return launch<NetSdfShift, IoSdfEval, 1>(s->shift.params_tc, io, M, st);
+  if (fmt_of(prec) == 0) return launch<NetSdfShift, IoSdfEval, 0>(s->shift.params_tc, io, M, st, TAG_TC_SDF_EVAL);
+  return launch<NetSdfShift, IoSdfEval, 1>(s->shift.params_tc, io, M, st, TAG_TC_SDF_EVAL);
+}
+
+template <int MODE>
+static int march_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, const float* max_t_per_ray,
+                    const uint8_t* active, int64_t R, float eps, int max_steps, float max_t, float t_start,
+                    float* depth, uint8_t* flag, unsigned long long* counter, unsigned long long* steps_done,
+                    cudaStream_t st) {
+  SdfDev d;
+  int rc = nrt_build_sdf_dev(s, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "unknown precision %d", prec);
+  NRT_REQUIRE(s->shift.params_tc != nullptr, "sdf.shift.params_tc is NULL: call nrt_mlp_pack_tc first");
+  NRT_REQUIRE(matches<NetSdfShift>(d.mlp), "tensor-core SDF path: shift must be the 8x128 softplus MLP with 32 frequencies");
+  IoMarch<MODE> io{d, rays, max_t_per_ray, active, R, eps, max_steps, max_t, t_start, depth, flag, counter, steps_done};
+  const int tag = MODE == TC_MARCH_PRIMARY ? TAG_TC_MARCH : TAG_TC_SHADOW;
+  if (fmt_of(prec) == 0) return launch<NetSdfShift, IoMarch<MODE>, 0>(s->shift.params_tc, io, R, st, tag);
+  return launch<NetSdfShift, IoMarch<MODE>, 1>(s->shift.params_tc, io, R, st, tag);
+}
+int nrt_sdf_march_tc(int shadow, const nrt_sphere_sdf_t* s, int prec, const float* rays, const float* max_t_per_ray,
+                     const uint8_t* active, int64_t R, float eps, int max_steps, float max_t, float t_start,
+                     float* depth, uint8_t* flag, unsigned long long* counter, unsigned long long* steps_done,
+                     cudaStream_t st) {
+  if (shadow) return march_tc<TC_MARCH_SHADOW>(s, prec, rays, max_t_per_ray, active, R, eps, max_steps, max_t, t_start,
+                                               depth, flag, counter, steps_done, st);
+  return march_tc<TC_MARCH_PRIMARY>(s, prec, rays, max_t_per_ray, active, R, eps, max_steps, max_t, t_start, depth,
+                                    flag, counter, steps_done, st);
+}
+int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, int64_t R, double step, int n_steps,
+                        int32_t* best_idx, float* best_pos, float* min_val, unsigned long long* counter,
+                        cudaStream_t st) {
+  SdfDev d;
+  int rc = nrt_build_sdf_dev(s, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "unknown precision %d", prec);
+  NRT_REQUIRE(s->shift.params_tc != nullptr, "sdf.shift.params_tc is NULL: call nrt_mlp_pack_tc first");
+  NRT_REQUIRE(matches<NetSdfShift>(d.mlp), "tensor-core SDF path: shift must be the 8x128 softplus MLP with 32 frequencies");
+  IoMinScan io{d, rays, R, step, n_steps, best_idx, best_pos, min_val, counter};
+  if (fmt_of(prec) == 0) return launch<NetSdfShift, IoMinScan, 0>(s->shift.params_tc, io, R, st, TAG_TC_MIN_SCAN);
+  return launch<NetSdfShift, IoMinScan, 1>(s->shift.params_tc, io, R, st, TAG_TC_MIN_SCAN);
 }
 
 size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t*, int64_t R, int S) {

@@ -50,9 +50,14 @@ class SphereSDF(nn.Module):
         out = U.smooth_min(sd, k=32.).reshape(p.shape[:-1])
         return out + self.shift.forward_reference_ops(p).reshape_as(out)
 
+    def precision(self):
+        """Arithmetic of the gradient-free SDF evaluations: config.precision when the residual MLP has the shape
+        the tensor-core path instantiates (the default 8x128 softplus net), else fp32."""
+        return self.shift.precision()
+
     def forward(self, p):
         if p.is_cuda and not self._needs_grad(p):
-            return ops.sdf_eval(self.packed(), p.detach().float())
+            return ops.sdf_eval(self.packed(), p.detach().float(), prec=self.precision())
         return self.forward_reference_ops(p)
 
 
@@ -99,7 +104,8 @@ class SDF:
         r_o, r_d = rays.split(3, dim=-1)
         packed = self._fused()
         if packed is not None:
-            d, out_active = ops.sphere_trace(packed, rays.detach(), self.epsilon, self.max_steps, float(max_t))
+            d, out_active = ops.sphere_trace(packed, rays.detach(), self.epsilon, self.max_steps, float(max_t),
+                                             prec=self.sdf.precision())
             depths = d.unsqueeze(-1)
         else:
             depths, out_active = self._march_generic(r_o, r_d, max_t)
@@ -125,7 +131,7 @@ class SDF:
             mt = max_t if torch.is_tensor(max_t) else torch.full(rays.shape[:-1], float(max_t), device=rays.device)
             act = active if torch.is_tensor(active) else None
             return ops.shadow_test(packed, rays.detach(), mt.detach().float().reshape(rays.shape[:-1]), self.epsilon,
-                                   self.max_steps, active=act)
+                                   self.max_steps, active=act, prec=self.sdf.precision())
         r_o, r_d = rays.split(3, dim=-1)
         depths = torch.zeros(r_o.shape[:-1] + (1,), device=rays.device) + 1e2 * self.epsilon
         remaining = torch.ones(depths.shape[:-1], dtype=torch.bool, device=rays.device)
@@ -163,7 +169,7 @@ class SDF:
         packed = self._fused()
         if packed is not None:
             rays = torch.cat([r_o_local.expand_as(d), d], dim=-1).detach()
-            _idx, best_pos, _mv = ops.min_scan(packed, rays, step, n)
+            _idx, best_pos, _mv = ops.min_scan(packed, rays, step, n, prec=self.sdf.precision())
         else:
             with torch.no_grad():
                 sd = self.sdf(r_o_local).squeeze(-1)

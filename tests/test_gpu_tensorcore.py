@@ -133,3 +133,84 @@ def test_render_is_chunk_invariant():
     h2 = ops.nerfle_render(m1, m2, rays[70001:].contiguous(), ts, code, prec="f16")
     assert torch.equal(full, torch.cat([h1, h2]))
     assert torch.isfinite(full).all() and full.min() >= 0
+
+
+# ---------------------------------------------------------------------------------------------
+# Sphere-trace march / shadow march / min scan on the tensor cores (SDF residual MLP streamed).
+# The fp32 kernels are bit-identical to the oracle (test_gpu_parity.py); the 16-bit evaluation moves the
+# SDF value by ~1e-4 (fp16) / ~1e-3 (bf16), so a ray whose trajectory passes within that distance of the
+# epsilon = 1e-3 threshold may flip (grazing rays).  Gates: hit-mask disagreement <= 0.1 % (fp16) / 0.5 % (bf16)
+# of the rays.  Depth of rays that hit in both: the march stops at the first step with sdf <= epsilon, so a 1e-4
+# change of the SDF value can end a trajectory one step earlier or later, i.e. move the reported depth by one
+# step of length <= epsilon = 1e-3: the distribution is bimodal (~3e-5, or ~1e-3).  Gate: median < 0.2 * tol and
+# >= 99 % of the rays within tol = epsilon + 3e-4 (fp16) / 5e-3 (bf16); the remaining < 1 % are grazing rays
+# that converge on a different surface point.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R", [1, 130, 5000, 60000])
+@pytest.mark.parametrize("prec,max_xor,tol", [("f16", 1e-3, 1.3e-3), ("bf16", 5e-3, 5e-3)])
+def test_tc_sphere_trace_vs_oracle(R, prec, max_xor, tol):
+    from neural_raytracing_b200 import ops
+    w = helpers.golden_sdf_weights()
+    rays = synth.camera_rays(3, R)
+    sdf = helpers.cuda_sdf(w)
+    if R <= 5000:
+        do, ho = c_oracle.sphere_trace(helpers.oracle_sdf(w), rays, 1e-3, 64, 10.0)
+    else:   # the fp32 kernel is bit-identical to the oracle (test_gpu_parity.py) and finishes in milliseconds
+        d32, h32 = ops.sphere_trace(sdf, _t(rays), 1e-3, 64, 10.0, prec="f32")
+        do, ho = d32.cpu().numpy(), h32.cpu().numpy()
+    import torch
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d, h = ops.sphere_trace(sdf, _t(rays), 1e-3, 64, 10.0, prec=prec, steps_counter=cnt)
+    d, h = d.cpu().numpy(), h.cpu().numpy()
+    assert np.isfinite(d).all()
+    xor = int((h ^ ho.astype(bool)).sum())
+    assert xor <= max(1, int(max_xor * R)), (xor, R)
+    both = h & ho.astype(bool)
+    if both.any():
+        err = np.abs(d - do)[both]
+        assert int((err > tol).sum()) <= max(2, int(0.01 * err.size)), (np.quantile(err, [0.5, 0.99, 1.0]),)
+        assert np.median(err) < 0.2 * tol
+    # compaction: far fewer SDF evaluations than the reference's R * max_steps lock-step loop
+    assert 0 < int(cnt.item()) <= R * 64
+
+
+@pytest.mark.parametrize("R", [1, 257, 20000])
+def test_tc_shadow_and_min_scan_vs_fp32(R):
+    import torch
+    from neural_raytracing_b200 import ops
+    w = helpers.golden_sdf_weights()
+    sdf = helpers.cuda_sdf(w)
+    rays = _t(synth.camera_rays(5, R))
+    d32, _ = ops.sphere_trace(sdf, rays, 1e-3, 64, 10.0, prec="f32")
+    p = rays[:, :3] + d32[:, None] * rays[:, 3:]
+    dirv = torch.tensor([0.3, 1.2, 0.4], device="cuda") - p
+    dist = dirv.norm(dim=-1)
+    srays = torch.cat([p, dirv / dist[:, None]], -1).contiguous()
+    nb32 = ops.shadow_test(sdf, srays, dist, 1e-3, 64, prec="f32")
+    nb16 = ops.shadow_test(sdf, srays, dist, 1e-3, 64, prec="f16")
+    assert int((nb32 ^ nb16).sum()) <= max(1, int(2e-3 * R))
+    step = (2.2 + 0.37 * 2 / 128) / 128
+    i32, p32, m32 = ops.min_scan(sdf, rays, step, 128, prec="f32")
+    i16, p16, m16 = ops.min_scan(sdf, rays, step, 128, prec="f16")
+    # the minimum VALUE is what the silhouette loss consumes (via sdf(best_pos)); the argmin index itself is
+    # ill-conditioned wherever the SDF is flat (smooth_min clamps at 0.288 far from all spheres)
+    assert float((m16 - m32).abs().max()) < 1e-3
+    assert int(i16.min()) >= 0 and int(i16.max()) <= 128
+    v_at_16 = ops.sdf_eval(sdf, p16.contiguous(), prec="f32")
+    assert float((v_at_16 - m32).abs().max()) < 1e-3   # the position found is (within tolerance) a minimiser
+
+
+def test_tc_march_is_order_invariant():
+    """Compaction on the tensor-core path: a ray's result depends only on its own state."""
+    import torch
+    from neural_raytracing_b200 import ops
+    sdf = helpers.cuda_sdf(helpers.golden_sdf_weights())
+    rays = _t(synth.camera_rays(9, 30000))
+    perm = torch.randperm(rays.shape[0], device="cuda", generator=torch.Generator(device="cuda").manual_seed(1))
+    d1, h1 = ops.sphere_trace(sdf, rays, 1e-3, 64, 10.0, prec="f16")
+    d2, h2 = ops.sphere_trace(sdf, rays[perm].contiguous(), 1e-3, 64, 10.0, prec="f16")
+    assert torch.equal(h1[perm], h2) and torch.equal(d1[perm], d2)
+    act = (torch.arange(rays.shape[0], device="cuda") % 3 != 0)
+    d3, h3 = ops.sphere_trace(sdf, rays, 1e-3, 64, 10.0, prec="f16", active=act)
+    assert torch.equal(h3[act], h1[act]) and torch.equal(d3[act], d1[act])
+    assert not h3[~act].any() and float(d3[~act].abs().max()) == 0.0
