@@ -133,6 +133,27 @@ int nrt_mlp_backward(const nrt_mlp_t* m, int out_act, const float* x, const floa
                      const float* params_nk, float* g_params, float* g_x, float* g_latent,
                      void* stream);
 
+/* ---- a2 (training): SkipConnMLP forward + backward on the tensor cores ---------------- */
+/* What torch.autograd does for neural_blocks.py:75-86 in the reference's training loops (nerfle.py:113-116,
+ * training_utils.py:211-260), as three tcgen05 kernels: a forward that saves its activations as 16-bit tiles,
+ * the fused data-gradient chain, and the weight-gradient kernel.  prec = NRT_PREC_F16 (default; gradients are
+ * loss-scaled on the device by a power of two taken from max|g_out|) or NRT_PREC_BF16; fp32 accumulation.
+ * Instantiated for NeRFLE.first (3->65, 5x128) and the point-light NeRFLE.second (70->3, 8x64).
+ *   workspace: nrt_mlp_train_tc_workspace_bytes(m, M) bytes, 256-byte aligned, must stay untouched between the
+ *              forward and the backward call of the same batch;
+ *   m->params_tc: the nrt_mlp_pack_tc blob of the same prec;
+ *   dgrad_blob: transposed weights, nrt_mlp_pack_tc_dgrad (need_x = 1 adds the rows needed for g_x);
+ *   out [M,out_size]: the ACTIVATED output of the forward; g_out: gradient w.r.t. it;
+ *   g_params: packed-f32 layout, ACCUMULATED into (zero it first); g_x [M,in_size] or NULL. */
+int64_t nrt_mlp_train_tc_workspace_bytes(const nrt_mlp_t* m, int64_t M);
+int64_t nrt_mlp_tc_dgrad_blob_bytes(const nrt_mlp_t* m, int need_x);
+int nrt_mlp_pack_tc_dgrad(const nrt_mlp_t* m, int prec, int need_x, void* blob_out, void* stream);
+int nrt_mlp_forward_train_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, int64_t M, float* out,
+                             void* workspace, size_t workspace_bytes, void* stream);
+int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, int64_t M, const float* out, const float* g_out,
+                        const void* dgrad_blob, void* workspace, size_t workspace_bytes, float* g_params,
+                        float* g_x, void* stream);
+
 /* ---- a3: SphereSDF.forward (sdfs.py:41-46) ------------------------------------------- */
 int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M, float* out,
                  void* stream);

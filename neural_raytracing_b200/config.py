@@ -15,6 +15,23 @@ TC_NETS = {
     (3, 0, 32, 128, 8, 3, 1, 1),    # SphereSDF.shift (softplus; weights streamed through shared memory)
 }
 
+# arithmetic of the differentiable (training) MLP evaluations:
+#   "f32"  : fused fp32 forward/backward kernels (default; gradients agree with float64 autograd to ~1e-6)
+#   "f16"  : tcgen05 forward-with-saved-tiles + fused dgrad chain + wgrad kernel, fp16 operands with an automatic
+#            power-of-two loss scale; "bf16": same with bf16 operands
+train_precision = "f32"
+# networks the tensor-core TRAINING path instantiates
+TRAIN_TC_NETS = {
+    (3, 0, 16, 128, 5, 3, 65, 0),   # NeRFLE.first
+    (70, 0, 16, 64, 8, 3, 3, 0),    # NeRFLE.second (point light)
+}
+
+
+def set_train_precision(p):
+    global train_precision
+    assert p in ("f32", "f16", "bf16"), p
+    train_precision = p
+
 
 def set_precision(p):
     global precision

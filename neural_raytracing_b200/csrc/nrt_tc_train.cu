@@ -1,0 +1,810 @@
+// Tensor-core TRAINING path of the fused SkipConnMLP (sm_100a): forward that saves its activations, the fused
+// data-gradient chain and the weight-gradient kernel.  fp16 operands by default (the forward's rounding decides
+// which leaky_relu kinks flip, and fp16 is 8x finer than bf16), fp32 accumulation in TMEM; the gradients are
+// loss-scaled by a power of two derived from max|g_out| on the device so that they stay in fp16's normal range,
+// and un-scaled when the weight gradients leave TMEM.  NRT_PREC_BF16 selects bf16 operands (scale still applied).
+//
+//   forward  (k_mlp_tc<.., SaveTiles>, tc_core.cuh): as inference, plus per 128-sample tile the activations a_l
+//            (l = 0..L), the raw and the activated encoding as UMMA-canonical tiles (k = sample), and the sign
+//            masks of a_l (what leaky_relu' needs).
+//   dgrad    (k_mlp_dgrad_tc): g_out -> dZ_L -> ... -> dZ_0 (-> dEnc -> g_x) with the TRANSPOSED weights resident
+//            in shared memory; dZ_l never leaves the SM on its way to the next layer (TMEM operand), and is
+//            saved once as a tile for the weight gradients.
+//   wgrad    (k_mlp_wgrad_tc): per linear layer dW^T = dZ^T . [input | 1]: both operands are saved tiles pulled
+//            into shared memory with one bulk copy each (2-stage ring), K' = samples, the accumulator
+//            [N_out x (K_in + 16)] stays in TMEM over the CTA's whole sample range and is flushed once with
+//            coalesced float atomics.  The "1" row of the activation tiles makes the bias gradient one more
+//            accumulator column.
+//
+// Reference semantics: what torch.autograd computes for neural_blocks.py:75-86 (+ utils.py:37-40 for g_x).
+#include "tc_core.cuh"
+
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// dgrad blob: the weights with the roles of K and N swapped, UMMA canonical K-major, backward op order
+//   op 0        : output layer   B'[n' = hidden unit][k' = output]
+//   op 1+j      : hidden layer l = L-1-j   B'[n' = input of the layer (h | enc if NEEDX and skip)][k' = unit]
+//   op L+1 (X)  : init layer     B'[n' = encoding column][k' = unit]
+//   op L+2 (X)  : Fourier basis  B'[n' = input j][k' = frequency f] = basis[j][f]
+// ---------------------------------------------------------------------------------------------
+struct DLayout {
+  int n_ops;
+  int opN[kMaxOps], opK[kMaxOps], op_off[kMaxOps];
+  int w_elems, bytes;
+};
+__host__ __device__ constexpr DLayout make_dlayout(int in, int lat, int f, int h, int L, int skip, int out, bool needx) {
+  const Layout y = make_layout(in, lat, f, h, L, skip, out);
+  DLayout d{};
+  d.n_ops = 1 + L + (needx ? 2 : 0);
+  int off = 0;
+  for (int o = 0; o < d.n_ops; ++o) {
+    int N = 0, K = 0;
+    if (o == 0) { N = h; K = y.NOP; }
+    else if (o <= L) { const int l = L - o; N = h + ((needx && is_skip(l, skip, L)) ? y.KE : 0); K = h; }
+    else if (o == L + 1) { N = y.KE; K = h; }
+    else { N = y.XR; K = y.FP; }
+    d.opN[o] = N; d.opK[o] = K; d.op_off[o] = off; off += N * K;
+  }
+  d.w_elems = off;
+  d.bytes = off * 2;
+  return d;
+}
+
+template <int FMT>
+__global__ void k_pack_dgrad(MlpDev m, Layout y, DLayout d, int needx, uint8_t* __restrict__ blob) {
+  uint16_t* w = reinterpret_cast<uint16_t*>(blob);
+  const int L = m.L, h = m.hidden;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < d.w_elems; idx += gridDim.x * blockDim.x) {
+    int o = 0;
+    while (o + 1 < d.n_ops && idx >= d.op_off[o + 1]) ++o;
+    const int e = idx - d.op_off[o];
+    const int N = d.opN[o];
+    const int chunk = e / (N * 8), rem = e - chunk * (N * 8);
+    const int n = rem / 8, k = chunk * 8 + (rem & 7);
+    float v = 0.0f;
+    if (o == 0) {
+      if (k < m.out) v = m.params[m.w_off[m.n_lin - 1] + n * m.out + k];
+    } else if (o <= L) {
+      const int li = 1 + (L - o);
+      if (n < h) v = m.params[m.w_off[li] + n * h + k];
+      else { const int r = enc_ref_index(y, m.in_size, n - h); if (r >= 0) v = m.params[m.w_off[li] + (h + r) * h + k]; }
+    } else if (o == L + 1) {
+      const int r = enc_ref_index(y, m.in_size, n);
+      if (r >= 0) v = m.params[m.w_off[0] + r * h + k];
+    } else {
+      if (n < m.in_size && k < m.freqs) v = m.basis[n * m.freqs + k];
+    }
+    (void)needx;
+    w[idx] = Elem<FMT>::cvt(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// training workspace (one per MLP and batch): all sections 256-byte aligned
+// ---------------------------------------------------------------------------------------------
+struct TrainWs {
+  uint16_t* acts;      // [L+1][ntiles][(H+16) x 128]
+  uint16_t* enc_raw;   // [ntiles][(KE+16) x 128]
+  uint16_t* enc_act;   // [ntiles][(KE+16) x 128]
+  uint16_t* dz;        // [L+1][ntiles][H x 128]
+  uint16_t* gout;      // [ntiles][NOP x 128]
+  uint32_t* masks;     // [L+1][H/32][ntiles*128] sign bits of a_l
+  float* scale;        // [0]: max |g_out * out_act'| as float bits (atomicMax), [1]: loss scale S, [2]: 1/S
+  int64_t ntiles;
+  size_t bytes;
+};
+static TrainWs carve_ws(const Layout& y, int h, int L, int64_t M, void* base) {
+  TrainWs w{};
+  w.ntiles = (M + 127) / 128;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 255) / 256 * 256; return o; };
+  const size_t nt = (size_t)w.ntiles;
+  const size_t o_acts = take((size_t)(L + 1) * nt * (h + kTileRowsExtra) * 128 * 2);
+  const size_t o_er = take(nt * (y.KE + kTileRowsExtra) * 128 * 2);
+  const size_t o_ea = take(nt * (y.KE + kTileRowsExtra) * 128 * 2);
+  const size_t o_dz = take((size_t)(L + 1) * nt * h * 128 * 2);
+  const size_t o_go = take(nt * y.NOP * 128 * 2);
+  const size_t o_mk = take((size_t)(L + 1) * (h / 32) * nt * 128 * 4);
+  const size_t o_sc = take(256);
+  w.bytes = off;
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  if (b) {
+    w.acts = (uint16_t*)(b + o_acts); w.enc_raw = (uint16_t*)(b + o_er); w.enc_act = (uint16_t*)(b + o_ea);
+    w.dz = (uint16_t*)(b + o_dz); w.gout = (uint16_t*)(b + o_go); w.masks = (uint32_t*)(b + o_mk);
+    w.scale = (float*)(b + o_sc);
+  }
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward IO that also records the sign masks is not needed: the masks come from the packed activations inside
+// the kernel.  Here: the plain IO (x in, activated output out) and the mask writer hook.
+// ---------------------------------------------------------------------------------------------
+template <int IN, int OUT>
+struct IoTrainFwd {
+  const float* x; float* out; int out_act;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+#pragma unroll
+    for (int j = 0; j < IN; ++j) v[j] = __ldg(x + m * IN + j);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) {
+      float v = o[j];
+      if (out_act == NRT_OUT_SIGMOID) v = 1.0f / (1.0f + __expf(-v));
+      else if (out_act == NRT_OUT_SOFTPLUS) v = v > 20.0f ? v : __logf(1.0f + __expf(v));
+      else if (out_act == NRT_OUT_TANH) v = tanhf(v);
+      out[m * OUT + j] = v;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// dgrad chain
+// ---------------------------------------------------------------------------------------------
+template <class NET, bool NEEDX>
+struct DNet {
+  static constexpr DLayout DY = make_dlayout(NET::IN, NET::LAT, NET::F, NET::H, NET::L, NET::SKIP, NET::OUT, NEEDX);
+  static constexpr int H = NET::H, L = NET::L, KE = NET::KE, XR = NET::XR, FP = NET::FP, NOP = NET::NOP;
+  static constexpr int MC = imax(H, NEEDX ? XR : 0);          // main fp32 accumulator columns
+  static constexpr int EC = NEEDX ? KE : 0;                   // dEnc accumulator columns
+  static constexpr int AC = imax(H, imax(NOP, FP)) / 2;       // 16-bit A operand columns
+  static constexpr int COLS = MC + EC + AC;
+  static constexpr int NSLOT = (2 * COLS <= 512) ? 2 : 1;
+  static constexpr int STAGES = DY.n_ops;
+  static constexpr int first_skip_op() {   // backward-order index of the first op that adds into dEnc (-1: none)
+    for (int o = 1; o <= L; ++o) if (is_skip(L - o, NET::SKIP, L)) return o;
+    return -1;
+  }
+  static constexpr int FIRST_E = first_skip_op();
+  static_assert(COLS <= 512, "dgrad tile does not fit in TMEM");
+  static_assert(!NEEDX || (!NET::SPLIT && NET::LAT == 0), "input gradients: unsplit inputs, no latent");
+  static_assert(NET::ACT == NRT_ACT_LEAKY_RELU, "tensor-core backward: leaky_relu networks");
+  static_assert(DY.bytes + 1024 <= 227 * 1024, "transposed weights do not fit in shared memory");
+};
+
+template <class NET, class DN, int FMT, int ST>
+__device__ __forceinline__ void issue_dstage(uint32_t sW_addr, uint32_t dM, uint32_t dE, uint32_t aA, uint64_t* done_bar) {
+  constexpr DLayout D = DN::DY;
+  constexpr int L = NET::L, H = NET::H;
+  constexpr uint32_t N = (uint32_t)D.opN[ST];
+  constexpr int kch = D.opK[ST] / 16;
+  constexpr uint32_t lbo = N * 16;
+  constexpr bool has_enc = (ST >= 1 && ST <= L) && (N > (uint32_t)H);   // skip layer with NEEDX
+  constexpr bool to_e = (ST == L + 1);                                   // init layer: accumulate into dEnc
+  constexpr uint32_t n_main = has_enc ? (uint32_t)H : N;
+  constexpr uint32_t idesc_main = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((n_main >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t n_enc = has_enc ? (N - (uint32_t)H) : 16u;
+  constexpr uint32_t idesc_enc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((n_enc >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (elect_one()) {
+    const uint64_t bd0 = make_desc(sW_addr + (uint32_t)D.op_off[ST] * 2, lbo, 128);
+#pragma unroll
+    for (int kc = 0; kc < kch; ++kc) {
+      const uint64_t bd = bd0 + (uint64_t)((kc * 2 * lbo) >> 4);
+      if constexpr (to_e) {
+        mma_ts(dE, aA + kc * 8, bd, idesc_main, (DN::FIRST_E >= 0 || kc > 0) ? 1u : 0u);
+      } else {
+        mma_ts(dM, aA + kc * 8, bd, idesc_main, kc > 0 ? 1u : 0u);
+        if constexpr (has_enc)
+          mma_ts(dE, aA + kc * 8, bd + (uint64_t)((H * 16) >> 4), idesc_enc, (ST != DN::FIRST_E || kc > 0) ? 1u : 0u);
+      }
+    }
+    tc_commit(done_bar);
+  }
+  __syncwarp();
+}
+template <class NET, class DN, int FMT, int ST = 0>
+__device__ __forceinline__ void issue_dstage_dyn(int st, uint32_t sW_addr, uint32_t dM, uint32_t dE, uint32_t aA, uint64_t* done_bar) {
+  if constexpr (ST < DN::STAGES) {
+    if (st == ST) issue_dstage<NET, DN, FMT, ST>(sW_addr, dM, dE, aA, done_bar);
+    else issue_dstage_dyn<NET, DN, FMT, ST + 1>(st, sW_addr, dM, dE, aA, done_bar);
+  }
+}
+
+// gradient IO: g_out (w.r.t. the ACTIVATED output `out`) in, g_x out
+template <int IN, int OUT>
+struct IoGrad {
+  const float* out; const float* g_out; float* g_x; int out_act; const float* scale;
+  // raw gradient w.r.t. the pre-activation output (no loss scale)
+  __device__ __forceinline__ float g_pre(int64_t m, int j) const {
+    float v = __ldg(g_out + m * OUT + j);
+    if (out_act != NRT_OUT_NONE) {
+      const float y = __ldg(out + m * OUT + j);
+      if (out_act == NRT_OUT_SIGMOID) v *= y * (1.0f - y);
+      else if (out_act == NRT_OUT_SOFTPLUS) v *= 1.0f - __expf(-y);
+      else if (out_act == NRT_OUT_TANH) v *= 1.0f - y * y;
+    }
+    return v;
+  }
+  __device__ __forceinline__ void load_g(int64_t m, float* g) const {
+    const float S = scale[1];
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) g[j] = g_pre(m, j) * S;
+  }
+  __device__ __forceinline__ void store_gx1(int64_t m, int j, float v) const { g_x[m * IN + j] = v * scale[2]; }
+};
+
+// loss scale: S = 2^(8 - ceil(log2(max|g|))) so that the largest scaled gradient entering the chain is in [128, 256]
+template <class IO, int OUT>
+__global__ void k_grad_absmax(IO io, int64_t M, float* __restrict__ scale) {
+  float mx = 0.0f;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M * OUT; idx += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(io.g_pre(idx / OUT, (int)(idx % OUT)));
+    if (v < 3.0e38f) mx = fmaxf(mx, v);   // ignores inf / nan
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(scale), __float_as_uint(mx));
+}
+__global__ void k_grad_scale(float* __restrict__ scale) {
+  const float mx = scale[0];
+  int e = 0;
+  if (mx > 0.0f) { frexpf(mx, &e); }          // mx = f * 2^e, f in [0.5, 1)
+  const int k = mx > 0.0f ? 8 - e : 0;
+  scale[1] = ldexpf(1.0f, k);
+  scale[2] = ldexpf(1.0f, -k);
+}
+
+// 32 fp32 gradient columns x leaky_relu'(sign bits in `mask`) -> 16 packed 16-bit pairs
+template <int FMT>
+__device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uint32_t mask, uint32_t* __restrict__ pk) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float d = __uint_as_float(acc[8 * g + i]);
+      v[i] = ((mask >> (8 * g + i)) & 1u) ? 0.01f * d : d;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(v[2 * i], v[2 * i + 1]);
+  }
+}
+
+template <class NET, class DN, class IO, int FMT>
+__global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
+k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
+  using E = Elem<FMT>;
+  constexpr DLayout D = DN::DY;
+  constexpr int H = NET::H, L = NET::L, IN = NET::IN, F = NET::F, KE = NET::KE, NOP = NET::NOP, XR = NET::XR;
+  constexpr int NSLOT = DN::NSLOT;
+  constexpr bool NEEDX = DN::EC > 0;
+  constexpr int NC = H / 32;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_ready[2];
+  __shared__ __align__(8) uint64_t bar_done[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const bool is_mma_warp = warp == 8;
+  const int64_t ntiles = (M + 127) / 128;
+  if (tid == 0) {
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (is_mma_warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if ((tid & 31) == 0) {
+      mbar_expect_tx(&bar_w, (uint32_t)D.bytes);
+      for (uint32_t off = 0; off < (uint32_t)D.bytes; off += 32768u)
+        bulk_g2s(smem + off, blob + off, min(32768u, (uint32_t)D.bytes - off), &bar_w);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  mbar_wait(&bar_w, 0);
+
+  if (is_mma_warp) {
+    const uint32_t sW_addr = smem_u32(smem);
+    int st[2] = {0, 0};
+    uint32_t n_ready[2] = {0, 0};
+    int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
+    bool live[2] = {tile[0] < ntiles, NSLOT > 1 && tile[1] < ntiles};
+    while (live[0] || live[1]) {
+      bool progressed = false;
+#pragma unroll
+      for (int slot = 0; slot < NSLOT; ++slot) {
+        if (!live[slot]) continue;
+        if (!mbar_test(&bar_ready[slot], n_ready[slot] & 1)) continue;
+        progressed = true;
+        n_ready[slot]++;
+        tc_fence_after();
+        const uint32_t base = tmem + slot * DN::COLS;
+        issue_dstage_dyn<NET, DN, FMT>(st[slot], sW_addr, base, base + DN::MC, base + DN::MC + DN::EC, &bar_done[slot]);
+        if (++st[slot] == DN::STAGES) {
+          st[slot] = 0;
+          tile[slot] += (int64_t)gridDim.x * NSLOT;
+          live[slot] = tile[slot] < ntiles;
+        }
+      }
+      if (!progressed) __nanosleep(32);
+    }
+  } else {
+    const int slot = warp >> 2;
+    const int lane_row = tid & 127;
+    if (slot < NSLOT) {
+      const uint32_t lane_off = ((uint32_t)((warp & 3) * 32)) << 16;
+      const uint32_t base = tmem + slot * DN::COLS + lane_off;
+      const uint32_t dM = base, dE = base + DN::MC, aA = base + DN::MC + DN::EC;
+      uint32_t n_done = 0;
+      const int64_t mpad = ntiles * 128;
+      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
+        const int64_t tile = t0 + slot;
+        if (tile >= ntiles) break;
+        const int64_t m = tile * 128 + lane_row;
+        const bool valid = m < M;
+        // ---- g_out -> A operand of the output layer's transposed GEMM (+ saved as a tile for wgrad) ----
+        {
+          float g[NET::OUT];
+          if (valid) io.load_g(m, g);
+          else {
+#pragma unroll
+            for (int j = 0; j < NET::OUT; ++j) g[j] = 0.0f;
+          }
+          uint32_t pk[NOP / 2];
+#pragma unroll
+          for (int j = 0; j < NOP / 2; ++j)
+            pk[j] = E::pack(2 * j < NET::OUT ? g[2 * j] : 0.0f, 2 * j + 1 < NET::OUT ? g[2 * j + 1] : 0.0f);
+          tmem_store<NOP / 2>(aA, pk);
+          save_cols<NOP / 2>(tile_row_ptr(ws.gout, tile, NOP, lane_row), 0, pk);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+        }
+        // ---- dA_l -> dZ_l = dA_l * act'(z_l), l = L .. 0 ----
+#pragma unroll 1
+        for (int i = 0; i <= L; ++i) {
+          const int l = L - i;
+          uint32_t mask[NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) mask[c] = __ldg(ws.masks + ((int64_t)(l * NC + c)) * mpad + m);
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          uint16_t* zrow = tile_row_ptr(ws.dz, (int64_t)l * ntiles + tile, H, lane_row);
+          uint32_t buf[2][32];
+          TmemIO<32>::ld(dM, buf[0]);
+          tc_wait_ld();
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (c + 1 < NC) TmemIO<32>::ld(dM + 32 * (c + 1), buf[(c + 1) & 1]);
+            uint32_t pk[16];
+            dconvert32<FMT>(buf[c & 1], mask[c], pk);
+            TmemIO<16>::st(aA + 16 * c, pk);
+            save_cols<16>(zrow, 32 * c, pk);
+            if (c + 1 < NC) tc_wait_ld();
+          }
+          if constexpr (NEEDX) {
+            if (i == L) {
+              // dEnc so far = sum over skip layers of d act(enc): through act' (sign of the raw encoding) in place
+              const uint16_t* er = tile_row_ptr(ws.enc_raw, tile, KE + kTileRowsExtra, lane_row);
+#pragma unroll
+              for (int c = 0; c < KE / 16; ++c) {
+                uint32_t e[16];
+                TmemIO<16>::ld(dE + 16 * c, e);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  const uint16_t r = er[(16 * c + j) * 8];
+                  if (DN::FIRST_E < 0) e[j] = 0u;
+                  else if (r & 0x8000u) e[j] = __float_as_uint(0.01f * __uint_as_float(e[j]));
+                }
+                TmemIO<16>::st(dE + 16 * c, e);
+              }
+            }
+          }
+          if (i < L || NEEDX) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bar_ready[slot]);
+          } else {
+            tc_fence_before();
+          }
+        }
+        if constexpr (NEEDX) {
+          const uint16_t* er = tile_row_ptr(ws.enc_raw, tile, KE + kTileRowsExtra, lane_row);
+          // ---- dEnc complete (init layer added): q_f = cos_f * dsin_f - sin_f * dcos_f -> A operand of the basis GEMM ----
+          {
+            mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+            tc_fence_after();
+            uint32_t ds[F], dc[F];
+            tmem_load<F>(dE + XR, ds);
+            tmem_load<F>(dE + XR + F, dc);
+            tc_wait_ld();
+            uint32_t q[NET::FP / 2];
+#pragma unroll
+            for (int j = 0; j < F / 2; ++j) {
+              float qq[2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int f = 2 * j + e;
+                const float sn = E::back(er[(XR + f) * 8]), cs = E::back(er[(XR + F + f) * 8]);
+                qq[e] = cs * __uint_as_float(ds[f]) - sn * __uint_as_float(dc[f]);
+              }
+              q[j] = E::pack(qq[0], qq[1]);
+            }
+            tmem_store<NET::FP / 2>(aA, q);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bar_ready[slot]);
+          }
+          // ---- g_x = dEnc[x] + q . basis^T ----
+          {
+            mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+            tc_fence_after();
+            constexpr int XC = (IN + 7) / 8 * 8;
+#pragma unroll
+            for (int c = 0; c < XC / 8; ++c) {
+              uint32_t a[8], b[8];
+              TmemIO<8>::ld(dE + 8 * c, a);
+              TmemIO<8>::ld(dM + 8 * c, b);
+              tc_wait_ld();
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (8 * c + j < IN) io.store_gx1(m, 8 * c + j, __uint_as_float(a[j]) + __uint_as_float(b[j]));
+              }
+            }
+            tc_fence_before();
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: D'[n_out (lanes)][cols] = sum over samples dZ[s][n_out] * src[s][col]
+// ---------------------------------------------------------------------------------------------
+struct WgradJob {
+  const uint16_t* a_tiles; int a_rows;     // dZ (or g_out) tiles: the M = 128 operand
+  const uint16_t* s0_tiles; int s0_rows;   // first source (activation tile or raw encoding), with the ones row
+  const uint16_t* s1_tiles; int s1_rows;   // second source (activated encoding of a skip layer) or null
+  int n_valid;                              // valid output units (lanes)
+  int N;                                    // fan-out of the linear layer (row stride of W^T [K][N])
+  int w_off, b_off;                         // float offsets in the packed-f32 gradient blob
+  int s0_kind;                              // 0: hidden activations (col c -> k = c), 1: encoding (col c -> enc_ref_index)
+  int s0_valid;                             // columns of source 0 before the ones row
+  int k_base1;                              // k offset of source 1 rows (hidden width)
+};
+constexpr int kMaxJobs = NRT_MAX_LAYERS + 2;
+struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; };
+
+template <int FMT>
+__global__ void __launch_bounds__(160, 1)
+k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_bytes, float* __restrict__ g_params,
+               const float* __restrict__ scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[2];
+  __shared__ __align__(8) uint64_t bar_empty[2];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ WgradJob job;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    job = jobs_g->j[blockIdx.y];
+    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const int n = (int)(t_end - t_begin);
+  const uint32_t a_bytes = (uint32_t)job.a_rows * 256u, s0_bytes = (uint32_t)job.s0_rows * 256u;
+  const uint32_t s1_bytes = job.s1_tiles ? (uint32_t)job.s1_rows * 256u : 0u;
+
+  if (warp == 4) {
+    // producer + MMA issuer (whole warp convergent, one elected lane acts)
+    const uint32_t idesc0 = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | (((uint32_t)job.s0_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | (((uint32_t)job.s1_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    for (int i = 0; i <= n; ++i) {
+      if (i < n) {
+        const int slot = i & 1;
+        if (i >= 2) mbar_wait(&bar_empty[slot], ((i >> 1) - 1) & 1);
+        if (elect_one()) {
+          uint8_t* sb = smem + (size_t)slot * stage_bytes;
+          const int64_t t = t_begin + i;
+          mbar_expect_tx(&bar_full[slot], a_bytes + s0_bytes + s1_bytes);
+          bulk_g2s(sb, job.a_tiles + t * (int64_t)(job.a_rows * 128), a_bytes, &bar_full[slot]);
+          for (uint32_t off = 0; off < s0_bytes; off += 32768u)
+            bulk_g2s(sb + 32768 + off, reinterpret_cast<const uint8_t*>(job.s0_tiles + t * (int64_t)(job.s0_rows * 128)) + off,
+                     min(32768u, s0_bytes - off), &bar_full[slot]);
+          if (s1_bytes)
+            bulk_g2s(sb + 32768 + 40960, job.s1_tiles + t * (int64_t)(job.s1_rows * 128), s1_bytes, &bar_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (i >= 1) {
+        const int j = i - 1, slot = j & 1;
+        mbar_wait(&bar_full[slot], (j >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sb = smem_u32(smem + (size_t)slot * stage_bytes);
+          const uint32_t lbo_a = (uint32_t)job.a_rows * 16u, lbo0 = (uint32_t)job.s0_rows * 16u, lbo1 = (uint32_t)job.s1_rows * 16u;
+          const uint64_t ad = make_desc(sb, lbo_a, 128), b0 = make_desc(sb + 32768, lbo0, 128), b1 = make_desc(sb + 32768 + 40960, lbo1, 128);
+          for (int kc = 0; kc < 8; ++kc) {
+            const uint32_t acc = (j > 0 || kc > 0) ? 1u : 0u;
+            // D'[tmem] (+)= A''[smem] * B''[smem]^T
+            asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                         ::"r"(tmem), "l"(ad + (uint64_t)((kc * 2 * lbo_a) >> 4)), "l"(b0 + (uint64_t)((kc * 2 * lbo0) >> 4)), "r"(idesc0), "r"(acc) : "memory");
+            if (s1_bytes)
+              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                           ::"r"(tmem + (uint32_t)job.s0_rows), "l"(ad + (uint64_t)((kc * 2 * lbo_a) >> 4)), "l"(b1 + (uint64_t)((kc * 2 * lbo1) >> 4)), "r"(idesc1), "r"(acc) : "memory");
+          }
+          tc_commit(&bar_empty[slot]);
+          if (j == n - 1) tc_commit(&bar_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (n > 0) {
+    // epilogue: lane = output unit; coalesced float atomics into the packed-f32 gradient blob
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int unit = tid;   // 0..127
+    const uint32_t trow = tmem + (((uint32_t)(warp * 32)) << 16);
+    const Layout y = jobs_g->y;
+    const int in_size = jobs_g->in_size;
+    const int ncols = job.s0_rows + (job.s1_tiles ? job.s1_rows : 0);
+    const float inv_s = scale[2];
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      uint32_t v[16];
+      TmemIO<16>::ld(trow + c0, v);
+      tc_wait_ld();
+      if (unit < job.n_valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = c0 + j;
+          int dst = -1;
+          if (c < job.s0_rows) {
+            if (c < job.s0_valid) {
+              const int k = job.s0_kind == 0 ? c : enc_ref_index(y, in_size, c);
+              if (k >= 0) dst = job.w_off + k * job.N + unit;
+            } else if (c == job.s0_valid) {
+              dst = job.b_off + unit;
+            }
+          } else {
+            const int k = enc_ref_index(y, in_size, c - job.s0_rows);
+            if (k >= 0 && c - job.s0_rows < y.KE) dst = job.w_off + (job.k_base1 + k) * job.N + unit;
+          }
+          if (dst >= 0) atomicAdd(g_params + dst, __uint_as_float(v[j]) * inv_s);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// mask writer: sign bits of the saved activation tiles -> [L+1][H/32][mpad] words (one thread per sample and word)
+__global__ void k_act_masks(const uint16_t* __restrict__ acts, int H, int L, int64_t ntiles, uint32_t* __restrict__ masks) {
+  const int64_t mpad = ntiles * 128;
+  const int NC = H / 32;
+  const int64_t total = (int64_t)(L + 1) * NC * mpad;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = idx % mpad;
+    const int c = (int)((idx / mpad) % NC);
+    const int l = (int)(idx / (mpad * NC));
+    const int FR = H + kTileRowsExtra;
+    const int s = (int)(m & 127);
+    const uint16_t* row = acts + ((int64_t)l * ntiles + (m >> 7)) * (int64_t)(FR * 128) + (s >> 3) * (FR * 8) + (s & 7);
+    uint32_t w = 0;
+    for (int j = 0; j < 32; ++j) w |= (uint32_t)((row[(32 * c + j) * 8] >> 15) & 1u) << j;
+    masks[idx] = w;
+  }
+}
+
+using NetNerfFirst = Net<3, 0, 16, 128, 5, 3, 65, NRT_ACT_LEAKY_RELU>;
+using NetNerfSecondPT = Net<70, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;
+
+template <class NET>
+static bool matches(const MlpDev& d) {
+  return d.in_size == NET::IN && d.latent == NET::LAT && d.freqs == NET::F && d.hidden == NET::H && d.L == NET::L &&
+         d.skip == NET::SKIP && d.out == NET::OUT && d.act == NET::ACT;
+}
+
+template <class NET, int FMT>
+static int train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_t M, float* out, const TrainWs& ws, cudaStream_t st) {
+  IoTrainFwd<NET::IN, NET::OUT> io{x, out, out_act};
+  SaveTiles sv{ws.acts, ws.enc_raw, ws.enc_act, ws.ntiles};
+  const size_t bytes = (size_t)NET::SMEM_BYTES + 256;
+  auto kern = k_mlp_tc<NET, decltype(io), FMT, SaveTiles>;
+  NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const int grid = (int)std::min<int64_t>((ws.ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
+  {
+    NrtProfScope _ps(TAG_TC_TRAIN_FWD, st);
+    kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, nullptr, sv);
+  }
+  NRT_CUDA(cudaGetLastError());
+  {
+    NrtProfScope _ps(TAG_TC_TRAIN_FWD, st);
+    const int64_t total = (int64_t)(NET::L + 1) * (NET::H / 32) * ws.ntiles * 128;
+    k_act_masks<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(ws.acts, NET::H, NET::L, ws.ntiles, ws.masks);
+  }
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+template <class NET, bool NEEDX, int FMT>
+static int train_backward(const nrt_mlp_t* m, const MlpDev& d, int out_act, int64_t M, const float* out, const float* g_out,
+                          const void* dblob, const TrainWs& ws, float* g_params, float* g_x, cudaStream_t st) {
+  using DN = DNet<NET, NEEDX>;
+  IoGrad<NET::IN, NET::OUT> io{out, g_out, g_x, out_act, ws.scale};
+  {
+    NrtProfScope _ps(TAG_TC_DGRAD, st);
+    NRT_CUDA(cudaMemsetAsync(ws.scale, 0, 16, st));
+    k_grad_absmax<decltype(io), NET::OUT><<<(int)std::min<int64_t>((M * NET::OUT + 255) / 256, 148 * 8), 256, 0, st>>>(io, M, ws.scale);
+    k_grad_scale<<<1, 1, 0, st>>>(ws.scale);
+    NRT_CUDA(cudaGetLastError());
+  }
+  {
+    const size_t bytes = (size_t)DN::DY.bytes + 256;
+    auto kern = k_mlp_dgrad_tc<NET, DN, decltype(io), FMT>;
+    NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    const int grid = (int)std::min<int64_t>((ws.ntiles + DN::NSLOT - 1) / DN::NSLOT, (int64_t)nrt_sm_count());
+    NrtProfScope _ps(TAG_TC_DGRAD, st);
+    kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(dblob), io, M, ws);
+    NRT_CUDA(cudaGetLastError());
+  }
+  // ---- weight gradients: one job per linear layer ----
+  constexpr int H = NET::H, L = NET::L, KE = NET::KE, NOP = NET::NOP;
+  constexpr int FRA = H + kTileRowsExtra, FRE = KE + kTileRowsExtra;
+  WgradJobs jobs{};
+  jobs.y = NET::Y; jobs.in_size = NET::IN; jobs.n = L + 2;
+  const int64_t nt = ws.ntiles;
+  for (int li = 0; li <= L + 1; ++li) {
+    WgradJob& j = jobs.j[li];
+    j.N = d.N[li]; j.w_off = d.w_off[li]; j.b_off = d.b_off[li]; j.k_base1 = H;
+    if (li == L + 1) {
+      j.a_tiles = ws.gout; j.a_rows = NOP; j.n_valid = NET::OUT;
+      j.s0_tiles = ws.acts + (int64_t)L * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
+    } else if (li == 0) {
+      j.a_tiles = ws.dz; j.a_rows = H; j.n_valid = H;
+      j.s0_tiles = ws.enc_raw; j.s0_rows = FRE; j.s0_kind = 1; j.s0_valid = KE;
+    } else {
+      j.a_tiles = ws.dz + (int64_t)li * nt * H * 128; j.a_rows = H; j.n_valid = H;
+      j.s0_tiles = ws.acts + (int64_t)(li - 1) * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
+      if (is_skip(li - 1, NET::SKIP, L)) { j.s1_tiles = ws.enc_act; j.s1_rows = FRE; }
+    }
+  }
+  static WgradJobs* d_jobs[64] = {nullptr};
+  static unsigned d_jobs_next = 0;
+  const unsigned slot = __atomic_fetch_add(&d_jobs_next, 1u, __ATOMIC_RELAXED) % 64;
+  if (d_jobs[slot] == nullptr) NRT_CUDA(cudaMalloc(&d_jobs[slot], sizeof(WgradJobs)));
+  NRT_CUDA(cudaMemcpyAsync(d_jobs[slot], &jobs, sizeof(WgradJobs), cudaMemcpyHostToDevice, st));
+  // stage: [A'' 32 KB][source 0 <= 40 KB][source 1 <= 32 KB] ; + 32 KB tail so that the M = 128 operand may over-read
+  static_assert(FRA * 256 <= 40960 && FRE * 256 <= 32768 && H * 256 <= 32768, "wgrad stage layout");
+  const int stage_bytes = 32768 + 40960 + 32768;
+  const size_t bytes = 2 * (size_t)stage_bytes + 16384;
+  auto kern = k_mlp_wgrad_tc<FMT>;
+  NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jobs.n - 1) / jobs.n));
+  {
+    NrtProfScope _ps(TAG_TC_WGRAD, st);
+    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(d_jobs[slot], nt, stage_bytes, g_params, ws.scale);
+  }
+  NRT_CUDA(cudaGetLastError());
+  (void)m;
+  return NRT_OK;
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// which networks the training path instantiates, and whether their input gradient is available
+static int train_net_id(const MlpDev& d) {
+  if (matches<NetNerfFirst>(d)) return 1;
+  if (matches<NetNerfSecondPT>(d)) return 2;
+  return 0;
+}
+
+extern "C" int64_t nrt_mlp_train_tc_workspace_bytes(const nrt_mlp_t* m, int64_t M) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(train_net_id(d) != 0, "tensor-core training path: this MLP shape is not instantiated");
+  const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
+  return (int64_t)carve_ws(y, d.hidden, d.L, M, nullptr).bytes;
+}
+
+extern "C" int64_t nrt_mlp_tc_dgrad_blob_bytes(const nrt_mlp_t* m, int need_x) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  return (int64_t)make_dlayout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out, need_x != 0).bytes;
+}
+
+extern "C" int nrt_mlp_pack_tc_dgrad(const nrt_mlp_t* m, int prec, int need_x, void* blob_out, void* stream) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(blob_out != nullptr && ((uintptr_t)blob_out & 15) == 0, "blob_out must be 16-byte aligned");
+  const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
+  const DLayout dl = make_dlayout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out, need_x != 0);
+  NrtProfScope _ps(TAG_TC_PACK, (cudaStream_t)stream);
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "nrt_mlp_pack_tc_dgrad: prec must be F16 or BF16");
+  const int grid = std::min(nrt_cdiv(dl.w_elems, 256), 1184);
+  if (prec == NRT_PREC_F16) k_pack_dgrad<0><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, dl, need_x, (uint8_t*)blob_out);
+  else k_pack_dgrad<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, dl, need_x, (uint8_t*)blob_out);
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
+}
+
+extern "C" int nrt_mlp_forward_train_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, int64_t M, float* out,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(M >= 0, "negative M");
+  if (M == 0) return NRT_OK;
+  NRT_REQUIRE(x && out && workspace, "nrt_mlp_forward_train_tc: null pointer");
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "tensor-core training path: prec must be F16 or BF16");
+  NRT_REQUIRE(m->params_tc != nullptr, "mlp.params_tc is NULL: call nrt_mlp_pack_tc (same prec) first");
+  const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
+  const TrainWs ws = carve_ws(y, d.hidden, d.L, M, workspace);
+  NRT_REQUIRE(workspace_bytes >= ws.bytes && ((uintptr_t)workspace & 255) == 0, "training workspace too small or not 256-byte aligned");
+  switch (train_net_id(d)) {
+    case 1:
+      if (prec == NRT_PREC_F16) return train_forward<NetNerfFirst, 0>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
+      return train_forward<NetNerfFirst, 1>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
+    case 2:
+      if (prec == NRT_PREC_F16) return train_forward<NetNerfSecondPT, 0>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
+      return train_forward<NetNerfSecondPT, 1>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
+  }
+  nrt_set_error("tensor-core training path: this MLP shape is not instantiated (NeRFLE.first / NeRFLE.second are)");
+  return NRT_E_UNSUPPORTED;
+}
+
+extern "C" int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, int64_t M, const float* out, const float* g_out,
+                                   const void* dgrad_blob, void* workspace, size_t workspace_bytes, float* g_params,
+                                   float* g_x, void* stream) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(m, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(M >= 0, "negative M");
+  if (M == 0) return NRT_OK;
+  NRT_REQUIRE(out && g_out && dgrad_blob && workspace && g_params, "nrt_mlp_backward_tc: null pointer");
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "tensor-core training path: prec must be F16 or BF16");
+  const bool f16 = prec == NRT_PREC_F16;
+  const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
+  const TrainWs ws = carve_ws(y, d.hidden, d.L, M, workspace);
+  NRT_REQUIRE(workspace_bytes >= ws.bytes, "training workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (train_net_id(d)) {
+    case 1:
+      NRT_REQUIRE(g_x == nullptr, "NeRFLE.first on the tensor-core path has no input gradient (split-precision inputs)");
+      if (f16) return train_backward<NetNerfFirst, false, 0>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
+      return train_backward<NetNerfFirst, false, 1>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
+    case 2:
+      if (g_x) {
+        if (f16) return train_backward<NetNerfSecondPT, true, 0>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, g_x, st);
+        return train_backward<NetNerfSecondPT, true, 1>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, g_x, st);
+      }
+      if (f16) return train_backward<NetNerfSecondPT, false, 0>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
+      return train_backward<NetNerfSecondPT, false, 1>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
+  }
+  nrt_set_error("tensor-core training path: this MLP shape is not instantiated");
+  return NRT_E_UNSUPPORTED;
+}

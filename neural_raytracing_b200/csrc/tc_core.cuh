@@ -1,0 +1,877 @@
+// tcgen05 / TMEM building blocks shared by the forward kernels (nrt_tc.cu) and the training kernels
+// (nrt_tc_train.cu): blob layout, PTX wrappers, TMEM load/store helpers, the compile-time network description
+// and the fused forward kernel template k_mlp_tc.  Internal header of libnrt_b200.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "nrt_common.cuh"
+
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// blob layout, shared by the pack kernel (runtime) and the MMA kernels (compile time)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxOps = NRT_MAX_LAYERS + 3;
+
+struct Layout {
+  int split, XR, KRAW, KE, KX, FP, NOP;
+  int n_ops;            // encB, init, layers[0..L-1], out
+  int opN[kMaxOps], opK[kMaxOps];
+  int op_off[kMaxOps];  // in 16-bit elements
+  int w_elems;
+  int bias_off[kMaxOps];  // float offset inside the bias area (ops 1..n_ops-1)
+  int bias_floats;
+  int bytes;
+};
+
+__host__ __device__ constexpr int c16(int x) { return (x + 15) / 16 * 16; }
+__host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr bool is_skip(int i, int skip, int L) { return (i % skip) == 0 && i != L - 1; }
+
+__host__ __device__ constexpr Layout make_layout(int in, int lat, int f, int h, int L, int skip, int out) {
+  Layout y{};
+  // raw-x segment: [x_hi | x_lo] (split) or [x]; padded to 16 K-elements so that every later
+  // segment (sin, cos, latent) starts on an 8-column TMEM boundary.  The same 16-aligned segment
+  // doubles as the A tile of the phase GEMM ([x_hi | x_lo | x_hi] when split).
+  y.split = in <= 5 ? 1 : 0;
+  y.XR = c16(in * (y.split ? 2 : 1));
+  y.KRAW = y.XR + 2 * f + lat;
+  y.KE = c16(y.KRAW);
+  y.KX = y.XR;
+  y.FP = c16(f);
+  y.NOP = c16(out);
+  y.n_ops = L + 3;
+  int off = 0, boff = 0;
+  for (int o = 0; o < y.n_ops; ++o) {
+    int N = 0, K = 0;
+    if (o == 0) { N = y.FP; K = y.KX; }
+    else if (o == 1) { N = h; K = y.KE; }
+    else if (o == y.n_ops - 1) { N = y.NOP; K = h; }
+    else { N = h; K = h + (is_skip(o - 2, skip, L) ? y.KE : 0); }
+    y.opN[o] = N; y.opK[o] = K; y.op_off[o] = off; off += N * K;
+    y.bias_off[o] = boff;
+    if (o >= 1) boff += N;
+  }
+  y.w_elems = off;
+  y.bias_floats = boff;
+  y.bytes = off * 2 + boff * 4;
+  return y;
+}
+
+// maps a K index of the tensor-core encoding layout to the reference encoding index (-1: padding)
+__host__ __device__ inline int enc_ref_index(const Layout& y, int in, int k) {
+  if (k >= y.KRAW) return -1;
+  if (k >= y.XR) return k - y.XR + in;        // sin | cos | latent follow the padded x segment
+  if (k < in) return k;                        // x (hi part)
+  if (y.split && k < 2 * in) return k - in;    // x_lo columns reuse the x weights
+  return -1;                                   // padding (and the third copy of x_hi used by the phase GEMM)
+}
+
+template <int FMT> struct Elem;   // FMT 0: fp16, 1: bf16 (= tcgen05 a/b_format)
+template <> struct Elem<0> {
+  static __device__ __forceinline__ uint16_t cvt(float v) { return __half_as_ushort(__float2half_rn(v)); }
+  static __device__ __forceinline__ float back(uint16_t u) { return __half2float(__ushort_as_half(u)); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+template <> struct Elem<1> {
+  static __device__ __forceinline__ uint16_t cvt(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+  static __device__ __forceinline__ float back(uint16_t u) { return __bfloat162float(__ushort_as_bfloat16(u)); }
+  static __device__ __forceinline__ uint32_t pack(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// pack kernel: packed-f32 parameters -> UMMA canonical (no-swizzle, K-major) 16-bit tiles + biases
+// element (n,k) of an [N x K] operand lives at ((k/8)*N + n)*8 + k%8
+// ---------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void k_pack_tc(MlpDev m, Layout y, uint8_t* __restrict__ blob) {
+  uint16_t* w = reinterpret_cast<uint16_t*>(blob);
+  float* bias = reinterpret_cast<float*>(blob + (size_t)y.w_elems * 2);
+  const int total = y.w_elems + y.bias_floats;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    if (idx >= y.w_elems) {
+      // biases: ops 1..n_ops-1
+      int b = idx - y.w_elems, o = 1;
+      while (o + 1 < y.n_ops && b >= y.bias_off[o + 1]) ++o;
+      const int n = b - y.bias_off[o];
+      const int li = o - 1;
+      bias[b] = (n < m.N[li]) ? m.params[m.b_off[li] + n] : 0.0f;
+      continue;
+    }
+    int o = 0;
+    while (o + 1 < y.n_ops && idx >= y.op_off[o + 1]) ++o;
+    const int e = idx - y.op_off[o];
+    const int N = y.opN[o];
+    const int chunk = e / (N * 8), rem = e - chunk * (N * 8);
+    const int n = rem / 8, k = chunk * 8 + (rem & 7);
+    float v = 0.0f;
+    if (o == 0) {
+      if (n < m.freqs) {
+        if (y.split) {
+          const int seg = k / m.in_size, j = k - seg * m.in_size;
+          if (seg < 3) {
+            const float bv = m.basis[j * m.freqs + n];
+            const float hi = Elem<FMT>::back(Elem<FMT>::cvt(bv));
+            v = (seg < 2) ? hi : (bv - hi);
+          }
+        } else if (k < m.in_size) {
+          v = m.basis[k * m.freqs + n];
+        }
+      }
+    } else if (o == y.n_ops - 1) {
+      if (n < m.out) v = m.params[m.w_off[m.n_lin - 1] + k * m.out + n];
+    } else {
+      const int li = o - 1;
+      int kref;
+      if (o == 1) kref = enc_ref_index(y, m.in_size, k);
+      else if (k < m.hidden) kref = k;
+      else { const int r = enc_ref_index(y, m.in_size, k - m.hidden); kref = r < 0 ? -1 : m.hidden + r; }
+      if (kref >= 0) v = m.params[m.w_off[li] + kref * m.hidden + n];
+    }
+    w[idx] = Elem<FMT>::cvt(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  }
+}
+// non-blocking phase test (all lanes of the warp call it; the result is warp-uniform)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (sm_100); no swizzle; base offset 0
+  return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, M = 128, K = 16
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+
+// tcgen05.ld / st, shape 32x32b: thread i of the warp <-> TMEM lane (32*(warp%4) + i), N columns
+template <int N> struct TmemIO;
+#define NRT_R4(a, i) "=r"(a[i]), "=r"(a[i + 1]), "=r"(a[i + 2]), "=r"(a[i + 3])
+#define NRT_W4(a, i) "r"(a[i]), "r"(a[i + 1]), "r"(a[i + 2]), "r"(a[i + 3])
+template <> struct TmemIO<1> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[0]) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(t), "r"(r[0]) : "memory");
+  }
+};
+template <> struct TmemIO<2> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(t), "r"(r[0]), "r"(r[1]) : "memory");
+  }
+};
+template <> struct TmemIO<4> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : NRT_R4(r, 0) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(t), NRT_W4(r, 0) : "memory");
+  }
+};
+template <> struct TmemIO<8> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : NRT_R4(r, 0), NRT_R4(r, 4) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(t), NRT_W4(r, 0), NRT_W4(r, 4) : "memory");
+  }
+};
+template <> struct TmemIO<16> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : NRT_R4(r, 0), NRT_R4(r, 4), NRT_R4(r, 8), NRT_R4(r, 12) : "r"(t));
+  }
+  static __device__ __forceinline__ void st(uint32_t t, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(t), NRT_W4(r, 0), NRT_W4(r, 4), NRT_W4(r, 8), NRT_W4(r, 12) : "memory");
+  }
+};
+template <> struct TmemIO<32> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : NRT_R4(r, 0), NRT_R4(r, 4), NRT_R4(r, 8), NRT_R4(r, 12), NRT_R4(r, 16), NRT_R4(r, 20), NRT_R4(r, 24), NRT_R4(r, 28)
+                 : "r"(t));
+  }
+};
+#define NRT_R16(a, i) NRT_R4(a, i), NRT_R4(a, i + 4), NRT_R4(a, i + 8), NRT_R4(a, i + 12)
+#define NRT_W16(a, i) NRT_W4(a, i), NRT_W4(a, i + 4), NRT_W4(a, i + 8), NRT_W4(a, i + 12)
+template <> struct TmemIO<64> {
+  static __device__ __forceinline__ void ld(uint32_t t, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                 "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,"
+                 "%32,%33,%34,%35,%36,%37,%38,%39,%40,%41,%42,%43,%44,%45,%46,%47,"
+                 "%48,%49,%50,%51,%52,%53,%54,%55,%56,%57,%58,%59,%60,%61,%62,%63}, [%64];"
+                 : NRT_R16(r, 0), NRT_R16(r, 16), NRT_R16(r, 32), NRT_R16(r, 48) : "r"(t));
+  }
+};
+// x32 store lives outside TmemIO<32> (which only loads)
+__device__ __forceinline__ void tmem_st32(uint32_t t, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+               "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+               ::"r"(t), NRT_W16(r, 0), NRT_W16(r, 16) : "memory");
+}
+// store NP packed 32-bit columns starting at column address t (compile-time decomposition)
+template <int NP>
+__device__ __forceinline__ void tmem_store(uint32_t t, const uint32_t* r) {
+  if constexpr (NP >= 32) { tmem_st32(t, r); tmem_store<NP - 32>(t + 32, r + 32); }
+  else if constexpr (NP >= 16) { TmemIO<16>::st(t, r); tmem_store<NP - 16>(t + 16, r + 16); }
+  else if constexpr (NP >= 8) { TmemIO<8>::st(t, r); tmem_store<NP - 8>(t + 8, r + 8); }
+  else if constexpr (NP >= 4) { TmemIO<4>::st(t, r); tmem_store<NP - 4>(t + 4, r + 4); }
+  else if constexpr (NP >= 2) { TmemIO<2>::st(t, r); tmem_store<NP - 2>(t + 2, r + 2); }
+  else if constexpr (NP == 1) { TmemIO<1>::st(t, r); }
+}
+template <int NP>
+__device__ __forceinline__ void tmem_load(uint32_t t, uint32_t* r) {
+  if constexpr (NP >= 64) { TmemIO<64>::ld(t, r); tmem_load<NP - 64>(t + 64, r + 64); }
+  else if constexpr (NP >= 32) { TmemIO<32>::ld(t, r); tmem_load<NP - 32>(t + 32, r + 32); }
+  else if constexpr (NP >= 16) { TmemIO<16>::ld(t, r); tmem_load<NP - 16>(t + 16, r + 16); }
+  else if constexpr (NP >= 8) { TmemIO<8>::ld(t, r); tmem_load<NP - 8>(t + 8, r + 8); }
+  else if constexpr (NP >= 4) { TmemIO<4>::ld(t, r); tmem_load<NP - 4>(t + 4, r + 4); }
+  else if constexpr (NP >= 2) { TmemIO<2>::ld(t, r); tmem_load<NP - 2>(t + 2, r + 2); }
+  else if constexpr (NP == 1) { TmemIO<1>::ld(t, r); }
+}
+
+// fast activations for the 16-bit path (results are rounded to 16 bits anyway)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+    // branch-free softplus: max(x,0) + log(1 + exp(-|x|)); beyond torch's threshold (20) the log term is < 3e-9,
+    // i.e. the result is x like F.softplus.  Two MUFU ops, no divergence (a `x > 20 ? x : ...` form compiles to a
+    // per-element branch that cost ~100 cycles per element).  A one-MUFU variant (ex2 + degree-5 polynomial for
+    // log1p) measured the same throughput in isolation (tools/softplus_bw.cu) and is less accurate.
+    return fmaf(0.6931471805599453f, lg2_approx(1.0f + ex2_approx(-1.4426950408889634f * fabsf(x))), fmaxf(x, 0.0f));
+  } else {
+    return fmaxf(x, 0.01f * x);
+  }
+}
+// act(a), act(b) rounded to the operand format and packed; the leaky ReLU runs on the packed pair
+template <int ACT, int FMT>
+__device__ __forceinline__ uint32_t act_pack(float a, float b) {
+  if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+    return Elem<FMT>::pack(act_fast<ACT>(a), act_fast<ACT>(b));
+  } else if constexpr (FMT == 0) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const __half2 r = __hmax2(h, __hmul2(h, __floats2half2_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 r = __hmax2(h, __hmul2(h, __floats2bfloat162_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+// 32 accumulator columns -> act -> 16 packed operand columns.  Written structure-of-arrays over groups of 8
+// elements so that every step is 8 independent instructions: a single epilogue warp has its SM sub-partition
+// (almost) to itself, so the conversion runs at the speed of its dependent chains unless the ILP is explicit
+// (the straight per-pair loop over a whole 128-column row measured ~4 cycles per instruction).
+template <int ACT, int FMT>
+__device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint32_t* __restrict__ pk) {
+  if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float x[8], u[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[8 * g + i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = ex2_approx(-1.4426950408889634f * fabsf(x[i]));
+      // (a one-MUFU variant, ex2 + degree-5 polynomial for log1p on the FMA pipe, measured the same row time here
+      //  and is slightly less accurate: tools/softplus_bw.cu, profiles/r01_kernel_optimisation_log.md)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = fmaf(0.6931471805599453f, u[i], fmaxf(x[i], 0.0f));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(u[2 * i], u[2 * i + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      uint32_t h[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) h[i] = Elem<FMT>::pack(__uint_as_float(acc[16 * g + 2 * i]), __uint_as_float(acc[16 * g + 2 * i + 1]));
+      if constexpr (FMT == 0) {
+        __half2 m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = __hmul2(*reinterpret_cast<__half2*>(&h[i]), __floats2half2_rn(0.01f, 0.01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&h[i]), m[i]);
+          pk[8 * g + i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+      } else {
+        __nv_bfloat162 m[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m[i] = __hmul2(*reinterpret_cast<__nv_bfloat162*>(&h[i]), __floats2bfloat162_rn(0.01f, 0.01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&h[i]), m[i]);
+          pk[8 * g + i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+      }
+    }
+  }
+}
+// ---- saved-activation tiles (training) -------------------------------------------------------------------
+// A saved tensor [M x F] is stored as one block per 128-sample tile, in the SAME canonical K-major UMMA layout
+// as the weights but with k = sample: element (feature f, sample s) of a tile with FR rows sits at
+// ((s/8)*FR + f)*8 + s%8.  The weight-gradient kernel can then pull a whole tile into shared memory with one
+// bulk copy and feed it to tcgen05.mma as is (K' = samples).  Activation tiles carry 16 extra rows; row F is the
+// constant 1 (its product with dZ is the bias gradient), rows F+1..F+15 are never written nor used.
+constexpr int kTileRowsExtra = 16;
+struct NoSave { static constexpr bool kOn = false; };
+struct SaveTiles {
+  static constexpr bool kOn = true;
+  uint16_t* acts;      // [L+1][ntiles] tiles of (H+16) x 128: a_l = act(z) feeding hidden layer l (l = L: output layer)
+  uint16_t* enc_raw;   // [ntiles] tiles of (KE+16) x 128: the encoding as the init layer sees it
+  uint16_t* enc_act;   // [ntiles] tiles of (KE+16) x 128: act(encoding) as the skip layers see it
+  int64_t ntiles;
+};
+// thread-private view of one tile: pointer to (feature 0, this thread's sample)
+__device__ __forceinline__ uint16_t* tile_row_ptr(uint16_t* tiles, int64_t tile, int FR, int s) {
+  return tiles + tile * (int64_t)(FR * 128) + (s >> 3) * (FR * 8) + (s & 7);
+}
+// stores NP packed pairs = features col0 .. col0+2NP-1 of this thread's sample
+template <int NP>
+__device__ __forceinline__ void save_cols(uint16_t* row, int col0, const uint32_t* pk) {
+#pragma unroll
+  for (int j = 0; j < NP; ++j) {
+    row[(col0 + 2 * j) * 8] = (uint16_t)(pk[j] & 0xffffu);
+    row[(col0 + 2 * j + 1) * 8] = (uint16_t)(pk[j] >> 16);
+  }
+}
+template <int FMT> __device__ __forceinline__ uint16_t one16() { return FMT == 0 ? (uint16_t)0x3C00 : (uint16_t)0x3F80; }
+
+// One accumulator row (H fp32 columns at dD) -> activated 16-bit operand columns at aU, in 32-column chunks:
+// the tcgen05.ld of chunk c+1 is in flight while chunk c is converted (64 + 16 live registers instead of 192).
+template <int ACT, int FMT, int H, bool SAVE = false>
+__device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* save_row = nullptr) {
+  static_assert(H % 32 == 0, "hidden width must be a multiple of 32");
+  constexpr int NC = H / 32;
+  uint32_t buf[2][32];
+  TmemIO<32>::ld(dD, buf[0]);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) TmemIO<32>::ld(dD + 32 * (c + 1), buf[(c + 1) & 1]);
+    uint32_t pk[16];
+    convert32<ACT, FMT>(buf[c & 1], pk);
+    TmemIO<16>::st(aU + 16 * c, pk);
+    if constexpr (SAVE) save_cols<16>(save_row, 32 * c, pk);
+    if (c + 1 < NC) tc_wait_ld();
+  }
+  if constexpr (SAVE) save_row[H * 8] = one16<FMT>();
+}
+
+// D[lane][0..N) = bias[0..N): the next layer's MMA then only accumulates (no bias add in its epilogue)
+template <int N>
+__device__ __forceinline__ void preload_bias(uint32_t dD, const float* __restrict__ bias) {
+  static_assert(N % 8 == 0, "bias pieces are multiples of 8 columns");
+  uint32_t r[N];
+#pragma unroll
+  for (int j = 0; j < N / 4; ++j) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + 4 * j);
+    r[4 * j] = __float_as_uint(b.x); r[4 * j + 1] = __float_as_uint(b.y);
+    r[4 * j + 2] = __float_as_uint(b.z); r[4 * j + 3] = __float_as_uint(b.w);
+  }
+  tmem_store<N>(dD, r);
+}
+__device__ __forceinline__ void sincos_fast(float x, float* s, float* c) {
+  // two-constant reduction by 2*pi, then MUFU sin/cos on [-pi, pi]
+  const float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);
+  r = fmaf(-k, -1.7484555314695172e-07f, r);
+  *s = __sinf(r);
+  *c = __cosf(r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compile-time network description
+// ---------------------------------------------------------------------------------------------
+template <int IN_, int LAT_, int F_, int H_, int L_, int SKIP_, int OUT_, int ACT_>
+struct Net {
+  static constexpr int IN = IN_, LAT = LAT_, F = F_, H = H_, L = L_, SKIP = SKIP_, OUT = OUT_, ACT = ACT_;
+  static constexpr Layout Y = make_layout(IN, LAT, F, H, L, SKIP, OUT);
+  static constexpr bool SPLIT = Y.split != 0;
+  static constexpr int XR = Y.XR, KE = Y.KE, KX = Y.KX, FP = Y.FP, NOP = Y.NOP, KRAW = Y.KRAW;
+  static constexpr int DC = imax(H, imax(NOP, FP));       // fp32 accumulator columns
+  static constexpr int UC = imax(H, imax(KE, KX)) / 2;    // union region: encode A / enc_raw / hidden
+  static constexpr int EC = KE / 2;                       // act(enc) region
+  static constexpr int COLS = DC + UC + EC;
+  static constexpr int NSLOT = (2 * COLS <= 512) ? 2 : 1;
+  static constexpr int STAGES = L + 3;                    // encode, init, L layers, out
+  static_assert(COLS <= 512, "network does not fit in TMEM");
+  static_assert(XR % 16 == 0 && F % 16 == 0 && LAT % 16 == 0 && KRAW == KE, "encoding segments must be multiples of 16");
+  static_assert(!SPLIT || 3 * IN <= 16, "split encoding needs 3*in <= 16");
+  static_assert(SPLIT || IN % 2 == 0, "unsplit inputs must come in pairs");
+  static_assert(H % 16 == 0 && H <= 256, "hidden must be a multiple of 16");
+  // Weights that do not fit in shared memory are STREAMED: each tile slot owns two stage buffers and the MMA warp
+  // prefetches the next stage's operand (cp.async.bulk from L2) while the current stage computes.
+  static constexpr int kSmemBudget = 227 * 1024 - 2048;
+  static constexpr bool STREAM = Y.bytes > kSmemBudget;
+  static constexpr int max_op_bytes() {
+    int m = 0;
+    for (int o = 0; o < Y.n_ops; ++o) m = imax(m, Y.opN[o] * Y.opK[o] * 2);
+    return m;
+  }
+  static constexpr int MAXOP = max_op_bytes();
+  static constexpr int BIAS_BYTES = Y.bias_floats * 4;
+  static constexpr int SMEM_BYTES = STREAM ? NSLOT * 2 * MAXOP + BIAS_BYTES : Y.bytes;
+  static_assert(SMEM_BYTES <= kSmemBudget, "stage buffers do not fit in shared memory");
+};
+
+constexpr int kEpiThreads = 128;
+
+// Issues the MMAs of stage ST of one tile slot.  Called by the WHOLE MMA warp (convergent); one elected lane
+// issues.  (Issuing from a divergent single lane makes the compiler wrap every UTCHMMA in an
+// ELECT / R2UR / BRA.U.ANY serialisation loop: ~135 cycles per MMA instead of ~72, see profiles/.)
+template <class NET, int FMT, int ST>
+__device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE, uint64_t* done_bar) {
+  constexpr Layout Y = NET::Y;
+  constexpr uint32_t N = (uint32_t)Y.opN[ST];
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((N >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+  constexpr uint32_t lbo = N * 16, sbo = 128;
+  constexpr int kch = Y.opK[ST] / 16;
+  constexpr int k_u = (ST >= 2 && ST < NET::STAGES - 1) ? NET::H / 16 : kch;   // K chunks taken from U
+  if (elect_one()) {
+    const uint64_t bd0 = make_desc(b_addr, lbo, sbo);
+#pragma unroll
+    for (int kc = 0; kc < kch; ++kc) {
+      const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
+      // every layer's accumulator was pre-loaded with its bias by the previous epilogue; only the
+      // phase GEMM (stage 0) starts from zero
+      mma_ts(dD, a, bd0 + (uint64_t)((kc * 2 * lbo) >> 4), idesc, (ST > 0 || kc > 0) ? 1u : 0u);
+    }
+    tc_commit(done_bar);
+  }
+  __syncwarp();
+}
+template <class NET, int FMT, int ST = 0>
+__device__ __forceinline__ void issue_stage_dyn(int st, uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE,
+                                                uint64_t* done_bar) {
+  if constexpr (ST < NET::STAGES) {
+    if (st == ST) issue_stage<NET, FMT, ST>(b_addr, dD, aU, aE, done_bar);
+    else issue_stage_dyn<NET, FMT, ST + 1>(st, b_addr, dD, aU, aE, done_bar);
+  }
+}
+// bulk copy of one stage operand (<= 32 KB pieces) from the blob into a stage buffer; completes on `bar`
+__device__ __forceinline__ void stream_op(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
+  mbar_expect_tx(bar, bytes);
+  for (uint32_t off = 0; off < bytes; off += 32768u) bulk_g2s(dst + off, src + off, min(32768u, bytes - off), bar);
+}
+
+// IO policy concepts.
+//   tile policy:       struct IO { __device__ void load(int64_t m, float* x /*IN+LAT*/) const;
+//                                  __device__ void store(int64_t m, const float* o /*OUT, bias added*/) const; };
+//     sample m of the flat batch <-> row m % 128 of tile m / 128; tiles are dealt round-robin to the CTAs.
+//   iterative policy:  struct IO { struct State; void init(State&); bool next(State&, float* x); void consume(State&, const float* o);
+//                                  void finish(State&); };
+//     every epilogue thread owns one *trajectory* (a marching ray): next() retires a finished trajectory, pulls a
+//     new one from a global queue (warp-aggregated atomic) and produces the next evaluation point; consume()
+//     takes the network output.  The tile slot keeps cycling while any of its 128 threads is live, so every MMA
+//     row is (up to the queue tail) spent on a live ray: this is the compaction of the sphere-trace march.
+template <class T, class = void> struct IsIterative : std::false_type {};
+template <class T> struct IsIterative<T, std::void_t<typename T::State>> : std::true_type {};
+struct NoState {};
+template <class T, class = void> struct StateOf { using type = NoState; };
+template <class T> struct StateOf<T, std::void_t<typename T::State>> { using type = typename T::State; };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <class NET, class IO, int FMT, class SV = NoSave>
+__global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
+k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg, SV sv = SV{}) {
+  // dbg (development only, tools/tc_timeline.py): clock64 stamps of CTA 0 for a few tile iterations
+  constexpr int kDbgIt0 = 4, kDbgIts = 4;
+  auto stamp = [&](int it, int st, int slot, int k) {
+    if (dbg != nullptr && blockIdx.x == 0 && it >= kDbgIt0 && it < kDbgIt0 + kDbgIts)
+      dbg[(((it - kDbgIt0) * NET::STAGES + st) * 2 + slot) * 8 + k] = clock64();
+  };
+  using E = Elem<FMT>;
+  constexpr Layout Y = NET::Y;
+  constexpr int H = NET::H, IN = NET::IN, LAT = NET::LAT, F = NET::F, L = NET::L;
+  constexpr int NSLOT = NET::NSLOT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr bool STREAM = NET::STREAM;
+  uint16_t* sW = reinterpret_cast<uint16_t*>(smem);
+  const float* sBias = reinterpret_cast<const float*>(smem + (STREAM ? (size_t)NSLOT * 2 * NET::MAXOP : (size_t)Y.w_elems * 2));
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_wfull[2][2];   // streaming: stage buffer b of slot s has landed
+  __shared__ uint32_t s_opoff[NET::STAGES], s_opbytes[NET::STAGES];
+  __shared__ __align__(8) uint64_t bar_ready[2];
+  __shared__ __align__(8) uint64_t bar_done[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_bias[NET::STAGES];
+  constexpr bool ITER = IsIterative<IO>::value;
+  __shared__ volatile uint32_t s_slot_live[2];   // iterative policies: 0 once the slot's queue has run dry
+  __shared__ uint32_t s_warp_live[2][4];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const bool is_mma_warp = warp == 8;
+  const int64_t ntiles = (M + 127) / 128;
+  if (tid < NET::STAGES) {
+    s_bias[tid] = (uint32_t)Y.bias_off[tid];
+    s_opoff[tid] = (uint32_t)Y.op_off[tid] * 2;
+    s_opbytes[tid] = (uint32_t)(Y.opN[tid] * Y.opK[tid] * 2);
+  }
+
+  if (tid == 0) {
+    s_slot_live[0] = 1; s_slot_live[1] = 1;
+    mbar_init(&bar_w, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1);
+      mbar_init(&bar_wfull[s][0], 1); mbar_init(&bar_wfull[s][1], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (is_mma_warp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if ((tid & 31) == 0) {
+      if (STREAM) {
+        // only the biases are resident; stage operands are streamed by the MMA loop
+        mbar_expect_tx(&bar_w, (uint32_t)NET::BIAS_BYTES);
+        bulk_g2s(smem + (size_t)NSLOT * 2 * NET::MAXOP, blob + (size_t)Y.w_elems * 2, (uint32_t)NET::BIAS_BYTES, &bar_w);
+      } else {
+        // all weights + biases: global (L2) -> shared, once per CTA
+        mbar_expect_tx(&bar_w, (uint32_t)Y.bytes);
+        constexpr uint32_t kChunk = 32768;
+        for (uint32_t off = 0; off < (uint32_t)Y.bytes; off += kChunk) {
+          const uint32_t n = min(kChunk, (uint32_t)Y.bytes - off);
+          bulk_g2s(smem + off, blob + off, n, &bar_w);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  mbar_wait(&bar_w, 0);
+
+  if (is_mma_warp) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs this loop convergently (one elected lane issues).  Slots are served in
+    // whatever order they become ready, so the two tiles drift into anti-phase: the tensor pipe works
+    // on one tile while the other tile's epilogue (or prologue / output store) runs.
+    const uint32_t sW_addr = smem_u32(sW);
+    int st[2] = {0, 0};
+    uint32_t n_ready[2] = {0, 0};
+    int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
+    bool live[2] = {ITER || tile[0] < ntiles, NSLOT > 1 && (ITER || tile[1] < ntiles)};
+    int it_dbg[2] = {0, 0};
+    uint32_t n_issued[2] = {0, 0};      // streaming: stages issued per slot (selects the stage buffer)
+    if (STREAM) {
+#pragma unroll
+      for (int slot = 0; slot < NSLOT; ++slot)
+        if (live[slot] && elect_one())
+          stream_op(smem + (size_t)(slot * 2) * NET::MAXOP, blob + s_opoff[0], s_opbytes[0], &bar_wfull[slot][0]);
+      __syncwarp();
+    }
+    while (live[0] || live[1]) {
+      bool progressed = false;
+#pragma unroll
+      for (int slot = 0; slot < NSLOT; ++slot) {
+        if (!live[slot]) continue;
+        if (!mbar_test(&bar_ready[slot], n_ready[slot] & 1)) continue;
+        progressed = true;
+        n_ready[slot]++;
+        tc_fence_after();
+        if constexpr (ITER) {
+          if (st[slot] == 0 && s_slot_live[slot] == 0) {
+            // the slot's epilogue found no live trajectory and the queue is empty: retire the slot (after draining
+            // the operand prefetch that was issued for the iteration that will not happen)
+            live[slot] = false;
+            if (STREAM) mbar_wait(&bar_wfull[slot][n_issued[slot] & 1], (n_issued[slot] >> 1) & 1);
+            continue;
+          }
+        }
+        if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 1);
+        const uint32_t base = tmem + slot * NET::COLS;
+        uint32_t b_addr = sW_addr + s_opoff[st[slot]];
+        if (STREAM) {
+          const uint32_t b = n_issued[slot] & 1;
+          mbar_wait(&bar_wfull[slot][b], (n_issued[slot] >> 1) & 1);
+          b_addr = sW_addr + (uint32_t)((slot * 2 + b) * NET::MAXOP);
+        }
+        issue_stage_dyn<NET, FMT>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+        if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 2);
+        if (++st[slot] == NET::STAGES) {
+          st[slot] = 0;
+          it_dbg[slot]++;
+          if constexpr (!ITER) {
+            tile[slot] += (int64_t)gridDim.x * NSLOT;
+            live[slot] = tile[slot] < ntiles;
+          }
+        }
+        if (STREAM) {
+          // prefetch the operand of this slot's next stage into its other buffer.  That buffer held the operand
+          // of the previous stage, whose MMAs completed before the epilogue that made this stage ready.
+          n_issued[slot]++;
+          if (live[slot] && elect_one()) {
+            const uint32_t nb = n_issued[slot] & 1;
+            stream_op(smem + (size_t)(slot * 2 + nb) * NET::MAXOP, blob + s_opoff[st[slot]], s_opbytes[st[slot]],
+                      &bar_wfull[slot][nb]);
+          }
+          __syncwarp();
+        }
+      }
+      // this warp shares an SM sub-partition with two epilogue warps: do not burn their issue slots
+      if (!progressed) __nanosleep(32);
+    }
+  } else {
+    // ===================== epilogue warpgroups (one per tile slot) =====================
+    const int slot = warp >> 2;
+    const int lane_row = tid & 127;               // TMEM lane == row of the tile == sample
+    if (slot < NSLOT) {
+      const uint32_t lane_off = ((uint32_t)((warp & 3) * 32)) << 16;
+      const uint32_t base = tmem + slot * NET::COLS + lane_off;
+      const uint32_t dD = base, aU = base + NET::DC, aE = base + NET::DC + NET::UC;
+      uint32_t n_done = 0;
+      int it_dbg = 0;
+      auto estamp = [&](int st, int k) { if (lane_row == 0) stamp(it_dbg, st, slot, k); };
+      typename StateOf<IO>::type state;
+      if constexpr (ITER) io.init(state);
+      for (int64_t t0 = (int64_t)blockIdx.x * NSLOT;; t0 += (int64_t)gridDim.x * NSLOT, ++it_dbg) {
+        int64_t m = 0;
+        bool valid;
+        float x[IN + LAT];
+        if constexpr (ITER) {
+          valid = io.next(state, x);
+          const unsigned bal = __ballot_sync(0xffffffffu, valid);
+          if ((tid & 31) == 0) s_warp_live[slot][warp & 3] = bal;
+          named_bar_sync(1 + slot, kEpiThreads);
+          const bool any = (s_warp_live[slot][0] | s_warp_live[slot][1] | s_warp_live[slot][2] | s_warp_live[slot][3]) != 0;
+          if (!any) {
+            if (lane_row == 0) s_slot_live[slot] = 0;
+            mbar_arrive(&bar_ready[slot]);   // release: the MMA warp reads s_slot_live after its acquire
+            break;
+          }
+        } else {
+          const int64_t tile = t0 + slot;
+          if (tile >= ntiles) break;
+          m = tile * 128 + lane_row;
+          valid = m < M;
+          if (valid) io.load(m, x);
+        }
+        // ---- stage 0: inputs -> encode-GEMM A operand (+ x / latent parts of enc_raw, enc_act) ----
+        {
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < IN + LAT; ++j) x[j] = 0.0f;
+          }
+          uint32_t ax[NET::KX / 2];
+          uint32_t ex[NET::XR / 2];
+#pragma unroll
+          for (int j = 0; j < NET::KX / 2; ++j) { ax[j] = 0; ex[j] = 0; }
+          if constexpr (NET::SPLIT) {
+            uint16_t v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = 0;
+            uint16_t a[2 * IN];
+#pragma unroll
+            for (int j = 0; j < IN; ++j) {
+              const uint16_t hi = E::cvt(x[j]);
+              const uint16_t lo = E::cvt(x[j] - E::back(hi));
+              v[j] = hi; v[IN + j] = lo; v[2 * IN + j] = hi;
+              const float ax_ = act_fast<NET::ACT>(x[j]);
+              const uint16_t ahi = E::cvt(ax_);
+              a[j] = ahi; a[IN + j] = E::cvt(ax_ - E::back(ahi));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ax[j] = (uint32_t)v[2 * j] | ((uint32_t)v[2 * j + 1] << 16);
+#pragma unroll
+            for (int j = 0; j < IN; ++j) ex[j] = (uint32_t)a[2 * j] | ((uint32_t)a[2 * j + 1] << 16);
+          } else {
+#pragma unroll
+            for (int j = 0; j < IN / 2; ++j) {
+              ax[j] = E::pack(x[2 * j], x[2 * j + 1]);
+              ex[j] = E::pack(act_fast<NET::ACT>(x[2 * j]), act_fast<NET::ACT>(x[2 * j + 1]));
+            }
+          }
+          tmem_store<NET::KX / 2>(aU, ax);
+          tmem_store<NET::XR / 2>(aE, ex);
+          if constexpr (SV::kOn) {
+            static_assert(!ITER, "activation tiles are saved by the tile policies only");
+            uint16_t* rr = tile_row_ptr(sv.enc_raw, m >> 7, NET::KE + kTileRowsExtra, lane_row);
+            uint16_t* ra = tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row);
+            save_cols<NET::KX / 2>(rr, 0, ax);
+            save_cols<NET::XR / 2>(ra, 0, ex);
+            rr[NET::KE * 8] = one16<FMT>();
+            ra[NET::KE * 8] = one16<FMT>();
+          }
+          if constexpr (LAT > 0) {
+            // latent part of the encoding (raw and activated); sits after sin/cos
+            uint32_t lr[LAT / 2], la[LAT / 2];
+#pragma unroll
+            for (int j = 0; j < LAT / 2; ++j) {
+              lr[j] = E::pack(x[IN + 2 * j], x[IN + 2 * j + 1]);
+              la[j] = E::pack(act_fast<NET::ACT>(x[IN + 2 * j]), act_fast<NET::ACT>(x[IN + 2 * j + 1]));
+            }
+            tmem_store<LAT / 2>(aU + (NET::XR + 2 * F) / 2, lr);
+            tmem_store<LAT / 2>(aE + (NET::XR + 2 * F) / 2, la);
+            if constexpr (SV::kOn) {
+              save_cols<LAT / 2>(tile_row_ptr(sv.enc_raw, m >> 7, NET::KE + kTileRowsExtra, lane_row), NET::XR + 2 * F, lr);
+              save_cols<LAT / 2>(tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row), NET::XR + 2 * F, la);
+            }
+          }
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+        }
+        // ---- stage 1: phases -> sin / cos -> rest of enc_raw / enc_act ----
+        {
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          uint32_t ph[F];
+          tmem_load<F>(dD, ph);
+          tc_wait_ld();
+          preload_bias<H>(dD, sBias + s_bias[1]);
+          uint32_t sr[F / 2], cr[F / 2], sa[F / 2], ca[F / 2];
+#pragma unroll
+          for (int j = 0; j < F / 2; ++j) {
+            float s0, c0, s1, c1;
+            sincos_fast(__uint_as_float(ph[2 * j]), &s0, &c0);
+            sincos_fast(__uint_as_float(ph[2 * j + 1]), &s1, &c1);
+            sr[j] = E::pack(s0, s1); cr[j] = E::pack(c0, c1);
+            sa[j] = E::pack(act_fast<NET::ACT>(s0), act_fast<NET::ACT>(s1));
+            ca[j] = E::pack(act_fast<NET::ACT>(c0), act_fast<NET::ACT>(c1));
+          }
+          tmem_store<F / 2>(aU + NET::XR / 2, sr);
+          tmem_store<F / 2>(aU + NET::XR / 2 + F / 2, cr);
+          tmem_store<F / 2>(aE + NET::XR / 2, sa);
+          tmem_store<F / 2>(aE + NET::XR / 2 + F / 2, ca);
+          if constexpr (SV::kOn) {
+            uint16_t* rr = tile_row_ptr(sv.enc_raw, m >> 7, NET::KE + kTileRowsExtra, lane_row);
+            uint16_t* ra = tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row);
+            save_cols<F / 2>(rr, NET::XR, sr);
+            save_cols<F / 2>(rr, NET::XR + F, cr);
+            save_cols<F / 2>(ra, NET::XR, sa);
+            save_cols<F / 2>(ra, NET::XR + F, ca);
+          }
+          // (the raw-x segment keeps the phase-GEMM tile [x_hi | x_lo | x_hi | 0]; the init / skip weights
+          //  of the third copy and of the padding are zero, see enc_ref_index)
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+        }
+        // ---- stages 2 .. L+1: hidden activations ----
+#pragma unroll 1
+        for (int st = 0; st <= L; ++st) {
+          estamp(2 + st, 3);
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          estamp(2 + st, 4);
+          estamp(2 + st, 5);
+          if constexpr (SV::kOn)
+            convert_row<NET::ACT, FMT, H, true>(dD, aU, tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row));
+          else
+            convert_row<NET::ACT, FMT, H>(dD, aU);
+          // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
+          // the conversion so the accumulator registers are dead and all 32 LDS.128 can be in flight
+          if (st < L) preload_bias<H>(dD, sBias + s_bias[2 + st]);
+          else preload_bias<NET::NOP>(dD, sBias + s_bias[NET::STAGES - 1]);
+          estamp(2 + st, 6);
+          tc_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar_ready[slot]);
+          estamp(2 + st, 7);
+        }
+        // ---- output layer ----
+        {
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          constexpr int OC = (NET::OUT + 7) / 8 * 8;
+          uint32_t acc[OC];
+          tmem_load<OC>(dD, acc);
+          tc_wait_ld();
+          float o[NET::OUT];   // bias already accumulated (pre-loaded into the accumulator)
+#pragma unroll
+          for (int j = 0; j < NET::OUT; ++j) o[j] = __uint_as_float(acc[j]);
+          if constexpr (ITER) { if (valid) io.consume(state, o); }
+          else { if (valid) io.store(m, o); }
+          // the accumulator / operand regions of this slot may now be reused by the next tile
+          tc_fence_before();
+        }
+      }
+      if constexpr (ITER) io.finish(state);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_mma_warp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+
+}  // namespace tc

@@ -69,6 +69,7 @@ class PackedMLP:
         if self.params.numel() != n:
             raise NrtError("packed params have %d floats, expected %d" % (self.params.numel(), n))
         self.tc_blobs = {}   # prec -> uint8 tensor (tensor-core layout), built on demand
+        self.dgrad_blobs = {}   # need_x -> uint8 tensor (transposed weights for the tensor-core backward)
         self._params_nk = None
 
     @staticmethod
@@ -118,6 +119,19 @@ class PackedMLP:
             N.check(N.lib().nrt_mlp_pack_tc(ctypes.byref(c), prec, _ptr(blob), _stream()))
             self.tc_blobs[prec] = blob
         return self.tc_blobs[prec]
+
+
+    def dgrad_blob(self, need_x: bool, prec=PREC_F16) -> torch.Tensor:
+        key = (bool(need_x), prec)
+        if key not in self.dgrad_blobs:
+            c = self.c_struct()
+            nbytes = N.lib().nrt_mlp_tc_dgrad_blob_bytes(ctypes.byref(c), int(key[0]))
+            if nbytes < 0:
+                N.check(int(nbytes))
+            blob = torch.empty(int(nbytes), dtype=torch.uint8, device=self.params.device)
+            N.check(N.lib().nrt_mlp_pack_tc_dgrad(ctypes.byref(c), prec, int(key[0]), _ptr(blob), _stream()))
+            self.dgrad_blobs[key] = blob
+        return self.dgrad_blobs[key]
 
 
 class PackedSDF:
@@ -175,6 +189,40 @@ def mlp_backward(m: PackedMLP, x, latent, out, acts, g_out, out_act=OUT_NONE, ne
                                          _ptr(g2), _ptr(m.params_nk()), _ptr(g_params), _ptr(g_x), _ptr(g_lat),
                                          _stream()))
     return g_params, g_x, g_lat
+
+
+def mlp_forward_train_tc(m: PackedMLP, x: torch.Tensor, out_act=OUT_NONE, prec=PREC_F16):
+    """Tensor-core training forward: returns (out [M,out], workspace) -- the workspace holds the saved
+    activation tiles and must be handed to mlp_backward_tc unchanged."""
+    prec = prec_id(prec)
+    x2 = _chk(x, "x").reshape(-1, m.in_size)
+    M = x2.shape[0]
+    out = torch.empty((M, m.out_size), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        c = m.c_struct(prec)
+        nbytes = N.lib().nrt_mlp_train_tc_workspace_bytes(ctypes.byref(c), M)
+        if nbytes < 0:
+            N.check(int(nbytes))
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=x.device)
+        N.check(N.lib().nrt_mlp_forward_train_tc(ctypes.byref(c), prec, out_act, _ptr(x2), M, _ptr(out), _ptr(ws),
+                                                 ws.numel(), _stream()))
+    return out, ws
+
+
+def mlp_backward_tc(m: PackedMLP, M: int, out: torch.Tensor, g_out: torch.Tensor, ws: torch.Tensor, out_act=OUT_NONE,
+                    need_input_grad=False, prec=PREC_F16):
+    """Tensor-core backward of mlp_forward_train_tc: (g_params packed-f32, g_x or None)."""
+    prec = prec_id(prec)
+    out2 = _chk(out, "out").reshape(M, m.out_size)
+    g2 = _chk(g_out, "g_out").reshape(M, m.out_size)
+    g_params = torch.zeros_like(m.params)
+    g_x = torch.empty((M, m.in_size), dtype=torch.float32, device=out.device) if need_input_grad else None
+    with torch.cuda.device(out.device):
+        c = m.c_struct(prec)
+        blob = m.dgrad_blob(need_input_grad, prec)
+        N.check(N.lib().nrt_mlp_backward_tc(ctypes.byref(c), prec, out_act, M, _ptr(out2), _ptr(g2), _ptr(blob), _ptr(ws),
+                                            ws.numel(), _ptr(g_params), _ptr(g_x), _stream()))
+    return g_params, g_x
 
 
 def sdf_eval(s: PackedSDF, p: torch.Tensor, prec=PREC_F32) -> torch.Tensor:

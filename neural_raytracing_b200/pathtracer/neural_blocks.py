@@ -100,6 +100,16 @@ class SkipConnMLP(nn.Module):
                m.out.out_features, _activation_id(m.activation))
         return config.precision if key in config.TC_NETS else "f32"
 
+    def train_precision(self):
+        """Arithmetic of the differentiable evaluation (config.train_precision where the tensor-core training
+        kernels are instantiated for this shape, else fp32)."""
+        if config.train_precision == "f32" or self.latent_size:
+            return "f32"
+        m = self
+        key = (m.in_size, m.latent_size, m.basis_p.shape[-1], m.init.out_features, len(m.layers), m.skip,
+               m.out.out_features, _activation_id(m.activation))
+        return config.train_precision if key in config.TRAIN_TC_NETS else "f32"
+
     def _needs_grad(self, *tensors):
         if not torch.is_grad_enabled():
             return False
@@ -150,15 +160,34 @@ class _FusedMLP(torch.autograd.Function):
         pk = module.packed()
         x = p.detach().float().contiguous()
         lat = None if latent is None else latent.detach().float().contiguous()
-        out, acts = ops.mlp_forward(pk, x, lat, out_act=out_act, prec="f32", save_acts=True)
         ctx.pk, ctx.out_act = pk, out_act
-        ctx.save_for_backward(x, lat if lat is not None else x.new_empty(0), out, acts)
         ctx.has_latent = latent is not None
         ctx.need_in = p.requires_grad or (latent is not None and latent.requires_grad)
+        ctx.tc_prec = module.train_precision()
+        if ctx.tc_prec != "f32" and (not ctx.need_in or pk.in_size > 5):
+            # tensor-core training path: the workspace holds the saved activation tiles
+            out, ws = ops.mlp_forward_train_tc(pk, x, out_act=out_act, prec=ctx.tc_prec)
+            ctx.lead = p.shape[:-1]
+            ctx.save_for_backward(out, ws)
+            return out.reshape(p.shape[:-1] + (pk.out_size,))
+        ctx.tc_prec = "f32"
+        out, acts = ops.mlp_forward(pk, x, lat, out_act=out_act, prec="f32", save_acts=True)
+        ctx.save_for_backward(x, lat if lat is not None else x.new_empty(0), out, acts)
         return out
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.tc_prec != "f32":
+            out, ws = ctx.saved_tensors
+            M = out.shape[0]
+            g_params, g_x = ops.mlp_backward_tc(ctx.pk, M, out, g.contiguous().float().reshape(M, -1), ws,
+                                                out_act=ctx.out_act, need_input_grad=ctx.need_in, prec=ctx.tc_prec)
+            gW, gb = ctx.pk.unpack(g_params)
+            flat = []
+            for w, b in zip(gW, gb):
+                flat += [w, b]
+            gx = None if g_x is None else g_x.reshape(ctx.lead + (ctx.pk.in_size,))
+            return (None, gx, None, None) + tuple(flat)
         x, lat, out, acts = ctx.saved_tensors
         lat = lat if ctx.has_latent else None
         g_params, g_x, g_lat = ops.mlp_backward(ctx.pk, x, lat, out, acts, g.contiguous().float(), out_act=ctx.out_act,

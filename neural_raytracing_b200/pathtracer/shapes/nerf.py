@@ -88,7 +88,7 @@ class NeRFLE(nn.Module):
         latent, alpha = first_out[..., 1:], first_out[..., 0]
         lead = latent.shape[:-1]
         light = code.reshape((1, code.shape[0]) + (1,) * (len(lead) - 2) + (-1,)).expand(lead + (-1,))
-        rgb = self.second(torch.cat([latent, r_d[None, ...].expand(lead + (3,)), light], dim=-1)).sigmoid()
+        rgb = self.second(torch.cat([latent, r_d[None, ...].expand(lead + (3,)), light], dim=-1), out_act=ops.OUT_SIGMOID)
         return composite(alpha, rgb, ts)
 
 

@@ -46,10 +46,12 @@ for size, chunk in ((64, 64), (512, 128)):
             "ms_per_frame": ms, "rays_per_sec": R / ms * 1e3,
             "reference_executed_sdf_samples_per_sec": R * (64 + 130 + 64) / ms * 1e3,
             "kernel_ms_per_frame": {k: round(v[0] / 5, 3) for k, v in prof.items() if v[1]},
-            "note": "march/scan/shadow on the fp32 exact kernels; MLPs that fit smem (NeuralBSDF, occ) on tcgen05 when prec=f16"}
+            "note": "prec=f32: everything on the fp32 exact kernels; prec=f16: march/scan/shadow + NeuralBSDF + occ MLPs on tcgen05, sp_var (16x256) still fp32"}
 config.set_precision("f32")
 # ---- cfg3: nerfle.py training step, 4 views x 32x32 crop = 4096 rays, S = 64, fwd + bwd + AdamW ----
 n = NeRFLE(device="cuda"); synth.fill_module(n, 3)
+with torch.no_grad():
+    n.first.out.bias[0] = 0.8     # positive density: non-trivial gradients
 opt = torch.optim.AdamW(n.parameters(), lr=8e-5, weight_decay=0)
 rays = torch.from_numpy(synth.camera_rays(5, 4 * 32 * 32).reshape(4, 32, 32, 1, 6)).cuda()
 lights = PointLights(device="cuda", location=torch.randn(4, 3, device="cuda"), scale=10)
@@ -58,13 +60,16 @@ def step():
     opt.zero_grad()
     loss = torch.nn.functional.mse_loss(n(rays, lights), target)
     loss.backward(); opt.step()
-ops.profile_collect(); ops.profile_enable(True)
-ms = timed(step)
-prof = ops.profile_collect(); ops.profile_enable(False)
-out["cfg3_nerfle_train_4096rays"] = {"ms_per_step": ms, "rays_per_sec": 4096 / ms * 1e3, "mlp_samples_per_sec": 4096 * 64 / ms * 1e3,
-                                     "model_tflops_fwd_bwd": 4096 * 64 * 325504 * 3 / ms / 1e9,
-                                     "kernel_ms_per_step": {k: round(v[0] / 8, 3) for k, v in prof.items() if v[1]},
-                                     "note": "fused fp32 forward (saves activations) + fused fp32 backward + CUDA compositing fwd/bwd + torch AdamW"}
+for tprec in ("f32", "f16"):
+    config.set_train_precision(tprec)
+    ops.profile_collect(); ops.profile_enable(True)
+    ms = timed(step)
+    prof = ops.profile_collect(); ops.profile_enable(False)
+    out["cfg3_nerfle_train_4096rays_" + tprec] = {
+        "ms_per_step": ms, "rays_per_sec": 4096 / ms * 1e3, "mlp_samples_per_sec": 4096 * 64 / ms * 1e3,
+        "model_tflops_fwd_bwd": 4096 * 64 * 325504 * 3 / ms / 1e9,
+        "kernel_ms_per_step": {k: round(v[0] / 8, 3) for k, v in prof.items() if v[1]},
+        "note": "train_precision=%s: fused MLP forward (saves activations) + fused backward + CUDA compositing fwd/bwd + torch AdamW" % tprec}
 # same at the 65,536-ray batch of cfg5
 rays2 = torch.from_numpy(synth.camera_rays(6, 4 * 128 * 128).reshape(4, 128, 128, 1, 6)).cuda()
 target2 = torch.full((4, 128, 128, 1, 3), 0.5, device="cuda")
@@ -72,9 +77,15 @@ def step2():
     opt.zero_grad()
     loss = torch.nn.functional.mse_loss(n(rays2, lights), target2)
     loss.backward(); opt.step()
-ms = timed(step2, n=3, warm=2)
-out["cfg5_nerfle_train_65536rays_1gpu"] = {"ms_per_step": ms, "rays_per_sec": 65536 / ms * 1e3,
-                                           "model_tflops_fwd_bwd": 65536 * 64 * 325504 * 3 / ms / 1e9}
+for tprec in ("f32", "f16"):
+    config.set_train_precision(tprec)
+    ops.profile_collect(); ops.profile_enable(True)
+    ms = timed(step2, n=3, warm=2)
+    prof = ops.profile_collect(); ops.profile_enable(False)
+    out["cfg5_nerfle_train_65536rays_1gpu_" + tprec] = {
+        "ms_per_step": ms, "rays_per_sec": 65536 / ms * 1e3, "model_tflops_fwd_bwd": 65536 * 64 * 325504 * 3 / ms / 1e9,
+        "kernel_ms_per_step": {k: round(v[0] / 5, 3) for k, v in prof.items() if v[1]}}
+config.set_train_precision("f32")
 # ---- cfg4: DTU-style training step on a crop (SDF + 3-basis BSDF + LightField, eikonal + BCE) ----
 shape, sphere, bsdf, lights, integrator, w_isect = scenes.build_pipeline(P, "dtu", device="cuda")
 params = list(sphere.parameters()) + list(bsdf.parameters()) + list(lights.parameters())
@@ -89,10 +100,13 @@ def dtu_step():
                                  w_isect=w_isect, with_noise=False, addition=lambda it: it, squeeze_first=False)
     loss = (got[..., :3] - 0.5).square().mean() + 0.1 * eikonal_loss(mi.raw_normals)
     loss.backward(); opt2.step()
-ops.profile_collect(); ops.profile_enable(True)
-ms = timed(dtu_step, n=3, warm=2)
-prof = ops.profile_collect(); ops.profile_enable(False)
-out["cfg4_dtu_style_step_128x128crop"] = {"ms_per_step": ms, "rays_per_sec": crop * crop / ms * 1e3,
-                                          "kernel_ms_per_step": {k: round(v[0] / 5, 3) for k, v in prof.items() if v[1]},
-                                          "note": "16,384-ray crop; march + min-scan on the fp32 kernels; differentiable parts as described in DESIGN.md"}
+for prec in ("f32", "f16"):
+    config.set_precision(prec)
+    ops.profile_collect(); ops.profile_enable(True)
+    ms = timed(dtu_step, n=3, warm=2)
+    prof = ops.profile_collect(); ops.profile_enable(False)
+    out["cfg4_dtu_style_step_128x128crop_" + prec] = {"ms_per_step": ms, "rays_per_sec": crop * crop / ms * 1e3,
+                                              "kernel_ms_per_step": {k: round(v[0] / 5, 3) for k, v in prof.items() if v[1]},
+                                              "note": "16,384-ray crop; gradient-free march + min-scan in `prec`; differentiable parts as described in DESIGN.md"}
+config.set_precision("f32")
 print(json.dumps(out, indent=1))
