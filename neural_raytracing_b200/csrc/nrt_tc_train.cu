@@ -5,8 +5,8 @@
 // and un-scaled when the weight gradients leave TMEM.  NRT_PREC_BF16 selects bf16 operands (scale still applied).
 //
 //   forward  (k_mlp_tc<.., SaveTiles>, tc_core.cuh): as inference, plus per 128-sample tile the activations a_l
-//            (l = 0..L), the raw and the activated encoding as UMMA-canonical tiles (k = sample), and the sign
-//            masks of a_l (what leaky_relu' needs).
+//            (l = 0..L), the raw and the activated encoding as UMMA-canonical MN-major tiles (MN = feature,
+//            K = sample; 16-byte vector stores per thread).
 //   dgrad    (k_mlp_dgrad_tc): g_out -> dZ_L -> ... -> dZ_0 (-> dEnc -> g_x) with the TRANSPOSED weights resident
 //            in shared memory; dZ_l never leaves the SM on its way to the next layer (TMEM operand), and is
 //            saved once as a tile for the weight gradients.
@@ -89,7 +89,6 @@ struct TrainWs {
   uint16_t* enc_act;   // [ntiles][(KE+16) x 128]
   uint16_t* dz;        // [L+1][ntiles][H x 128]
   uint16_t* gout;      // [ntiles][NOP x 128]
-  uint32_t* masks;     // [L+1][H/32][ntiles*128] sign bits of a_l
   float* scale;        // [0]: max |g_out * out_act'| as float bits (atomicMax), [1]: loss scale S, [2]: 1/S
   int64_t ntiles;
   size_t bytes;
@@ -105,21 +104,19 @@ static TrainWs carve_ws(const Layout& y, int h, int L, int64_t M, void* base) {
   const size_t o_ea = take(nt * (y.KE + kTileRowsExtra) * 128 * 2);
   const size_t o_dz = take((size_t)(L + 1) * nt * h * 128 * 2);
   const size_t o_go = take(nt * y.NOP * 128 * 2);
-  const size_t o_mk = take((size_t)(L + 1) * (h / 32) * nt * 128 * 4);
   const size_t o_sc = take(256);
   w.bytes = off;
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   if (b) {
     w.acts = (uint16_t*)(b + o_acts); w.enc_raw = (uint16_t*)(b + o_er); w.enc_act = (uint16_t*)(b + o_ea);
-    w.dz = (uint16_t*)(b + o_dz); w.gout = (uint16_t*)(b + o_go); w.masks = (uint32_t*)(b + o_mk);
+    w.dz = (uint16_t*)(b + o_dz); w.gout = (uint16_t*)(b + o_go);
     w.scale = (float*)(b + o_sc);
   }
   return w;
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward IO that also records the sign masks is not needed: the masks come from the packed activations inside
-// the kernel.  Here: the plain IO (x in, activated output out) and the mask writer hook.
+// training-forward IO: materialised x in, activated output out
 // ---------------------------------------------------------------------------------------------
 template <int IN, int OUT>
 struct IoTrainFwd {
@@ -334,7 +331,6 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
       const uint32_t base = tmem + slot * DN::COLS + lane_off;
       const uint32_t dM = base, dE = base + DN::MC, aA = base + DN::MC + DN::EC;
       uint32_t n_done = 0;
-      const int64_t mpad = ntiles * 128;
       for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
         const int64_t tile = t0 + slot;
         if (tile >= ntiles) break;
@@ -362,9 +358,27 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
 #pragma unroll 1
         for (int i = 0; i <= L; ++i) {
           const int l = L - i;
+          // leaky_relu'(z_l): the sign bits of the saved a_l row of this sample (16-byte loads, packed into one word
+          // per 32 features while the layer's MMA is still in flight)
           uint32_t mask[NC];
+          {
+            const uint16_t* arow = tile_row_ptr(ws.acts, (int64_t)l * ntiles + tile, H + kTileRowsExtra, lane_row);
 #pragma unroll
-          for (int c = 0; c < NC; ++c) mask[c] = __ldg(ws.masks + ((int64_t)(l * NC + c)) * mpad + m);
+            for (int c = 0; c < NC; ++c) {
+              uint32_t w = 0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint4 q = __ldg(reinterpret_cast<const uint4*>(arow + (4 * c + g) * 64));
+                const uint32_t r[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  w |= ((r[e] >> 15) & 1u) << (8 * g + 2 * e);
+                  w |= (r[e] >> 31) << (8 * g + 2 * e + 1);
+                }
+              }
+              mask[c] = w;
+            }
+          }
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
           uint16_t* zrow = tile_row_ptr(ws.dz, (int64_t)l * ntiles + tile, H, lane_row);
@@ -391,7 +405,7 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
                 tc_wait_ld();
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                  const uint16_t r = er[(16 * c + j) * 8];
+                  const uint16_t r = er[tile_elem(16 * c + j)];
                   if (DN::FIRST_E < 0) e[j] = 0u;
                   else if (r & 0x8000u) e[j] = __float_as_uint(0.01f * __uint_as_float(e[j]));
                 }
@@ -424,7 +438,7 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 const int f = 2 * j + e;
-                const float sn = E::back(er[(XR + f) * 8]), cs = E::back(er[(XR + F + f) * 8]);
+                const float sn = E::back(er[tile_elem(XR + f)]), cs = E::back(er[tile_elem(XR + F + f)]);
                 qq[e] = cs * __uint_as_float(ds[f]) - sn * __uint_as_float(dc[f]);
               }
               q[j] = E::pack(qq[0], qq[1]);
@@ -513,8 +527,10 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
 
   if (warp == 4) {
     // producer + MMA issuer (whole warp convergent, one elected lane acts)
-    const uint32_t idesc0 = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | (((uint32_t)job.s0_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t idesc1 = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | (((uint32_t)job.s1_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // both operands are MN-major tiles (feature-contiguous core-matrix rows): a_major (bit 15) = b_major (bit 16) = 1
+    constexpr uint32_t kMajorMN = (1u << 15) | (1u << 16);
+    const uint32_t idesc0 = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | kMajorMN | (((uint32_t)job.s0_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc1 = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | kMajorMN | (((uint32_t)job.s1_rows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     for (int i = 0; i <= n; ++i) {
       if (i < n) {
         const int slot = i & 1;
@@ -597,24 +613,6 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-// mask writer: sign bits of the saved activation tiles -> [L+1][H/32][mpad] words (one thread per sample and word)
-__global__ void k_act_masks(const uint16_t* __restrict__ acts, int H, int L, int64_t ntiles, uint32_t* __restrict__ masks) {
-  const int64_t mpad = ntiles * 128;
-  const int NC = H / 32;
-  const int64_t total = (int64_t)(L + 1) * NC * mpad;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = idx % mpad;
-    const int c = (int)((idx / mpad) % NC);
-    const int l = (int)(idx / (mpad * NC));
-    const int FR = H + kTileRowsExtra;
-    const int s = (int)(m & 127);
-    const uint16_t* row = acts + ((int64_t)l * ntiles + (m >> 7)) * (int64_t)(FR * 128) + (s >> 3) * (FR * 8) + (s & 7);
-    uint32_t w = 0;
-    for (int j = 0; j < 32; ++j) w |= (uint32_t)((row[(32 * c + j) * 8] >> 15) & 1u) << j;
-    masks[idx] = w;
-  }
-}
-
 using NetNerfFirst = Net<3, 0, 16, 128, 5, 3, 65, NRT_ACT_LEAKY_RELU>;
 using NetNerfSecondPT = Net<70, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;
 
@@ -637,11 +635,6 @@ static int train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_
     kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, nullptr, sv);
   }
   NRT_CUDA(cudaGetLastError());
-  {
-    NrtProfScope _ps(TAG_TC_TRAIN_FWD, st);
-    const int64_t total = (int64_t)(NET::L + 1) * (NET::H / 32) * ws.ntiles * 128;
-    k_act_masks<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(ws.acts, NET::H, NET::L, ws.ntiles, ws.masks);
-  }
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
 }

@@ -379,11 +379,14 @@ __device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint
   }
 }
 // ---- saved-activation tiles (training) -------------------------------------------------------------------
-// A saved tensor [M x F] is stored as one block per 128-sample tile, in the SAME canonical K-major UMMA layout
-// as the weights but with k = sample: element (feature f, sample s) of a tile with FR rows sits at
-// ((s/8)*FR + f)*8 + s%8.  The weight-gradient kernel can then pull a whole tile into shared memory with one
-// bulk copy and feed it to tcgen05.mma as is (K' = samples).  Activation tiles carry 16 extra rows; row F is the
-// constant 1 (its product with dZ is the bias gradient), rows F+1..F+15 are never written nor used.
+// A saved tensor [M x F] is stored as one block per 128-sample tile in the UMMA canonical MN-major (no swizzle)
+// layout with MN = feature, K = sample: 8x8 core matrices whose rows are 8 consecutive FEATURES (16 bytes) of one
+// sample, 8 samples per core matrix, feature groups 128 bytes apart, sample groups FR*16 bytes apart:
+//     element (feature f, sample s) of a tile with FR rows  ->  ((s/8)*(FR/8) + f/8)*64 + (s%8)*8 + f%8.
+// The epilogue thread that owns sample s therefore writes its row with 16-byte vector stores (8 lanes = 128
+// contiguous bytes), and the weight-gradient kernel pulls a whole tile into shared memory with one bulk copy and
+// feeds it to tcgen05.mma as is (K' = samples, a_major = b_major = MN).  Activation tiles carry 16 extra rows;
+// row F is the constant 1 (its product with dZ is the bias gradient), rows F+1..F+15 are never written nor used.
 constexpr int kTileRowsExtra = 16;
 struct NoSave { static constexpr bool kOn = false; };
 struct SaveTiles {
@@ -395,16 +398,16 @@ struct SaveTiles {
 };
 // thread-private view of one tile: pointer to (feature 0, this thread's sample)
 __device__ __forceinline__ uint16_t* tile_row_ptr(uint16_t* tiles, int64_t tile, int FR, int s) {
-  return tiles + tile * (int64_t)(FR * 128) + (s >> 3) * (FR * 8) + (s & 7);
+  return tiles + tile * (int64_t)(FR * 128) + (s >> 3) * (FR * 8) + (s & 7) * 8;
 }
-// stores NP packed pairs = features col0 .. col0+2NP-1 of this thread's sample
+__device__ __forceinline__ int tile_elem(int f) { return (f >> 3) * 64 + (f & 7); }   // offset of feature f in a row view
+// stores NP packed pairs = features col0 .. col0+2NP-1 of this thread's sample (col0 % 8 == 0, NP % 4 == 0)
 template <int NP>
 __device__ __forceinline__ void save_cols(uint16_t* row, int col0, const uint32_t* pk) {
+  static_assert(NP % 4 == 0, "whole 8-feature groups");
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    row[(col0 + 2 * j) * 8] = (uint16_t)(pk[j] & 0xffffu);
-    row[(col0 + 2 * j + 1) * 8] = (uint16_t)(pk[j] >> 16);
-  }
+  for (int g = 0; g < NP / 4; ++g)
+    *reinterpret_cast<uint4*>(row + ((col0 >> 3) + g) * 64) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
 }
 template <int FMT> __device__ __forceinline__ uint16_t one16() { return FMT == 0 ? (uint16_t)0x3C00 : (uint16_t)0x3F80; }
 
@@ -426,7 +429,7 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
     if constexpr (SAVE) save_cols<16>(save_row, 32 * c, pk);
     if (c + 1 < NC) tc_wait_ld();
   }
-  if constexpr (SAVE) save_row[H * 8] = one16<FMT>();
+  if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
 }
 
 // D[lane][0..N) = bias[0..N): the next layer's MMA then only accumulates (no bias add in its epilogue)
@@ -768,8 +771,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             uint16_t* ra = tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row);
             save_cols<NET::KX / 2>(rr, 0, ax);
             save_cols<NET::XR / 2>(ra, 0, ex);
-            rr[NET::KE * 8] = one16<FMT>();
-            ra[NET::KE * 8] = one16<FMT>();
+            rr[tile_elem(NET::KE)] = one16<FMT>();
+            ra[tile_elem(NET::KE)] = one16<FMT>();
           }
           if constexpr (LAT > 0) {
             // latent part of the encoding (raw and activated); sits after sin/cos
