@@ -189,6 +189,130 @@ def workload_config(precision):
             "sharding": "one frame per rank, no data-path collective"}
 
 
+def supplementary(dev, rank, world, steps=5, warmup=3):
+    """Other BASELINE.json configs, measured after the headline run (reported under "also"; never part of `value`).
+      cfg5_train: nerfle.py-style training step on 65,536 rays IN TOTAL (strong scaling: rank g takes 65,536/N rays),
+                  S = 64, mse, AdamW, tensor-core training kernels (fp16 operands), ONE flat NCCL all-reduce of the
+                  164,164 MLP gradients per step;
+      cfg3_train: the same step at 4,096 rays (N = 1 only);
+      cfg1_sdf_march: sphere-trace + min-along-ray scan of a random-init SphereSDF (64 spheres + 8x128 softplus MLP),
+                  512x512 rays, max_steps 64, tensor-core march (N = 1 only)."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from neural_raytracing_b200 import config, distributed as D, ops
+    from neural_raytracing_b200.pathtracer.lights import PointLights
+    from neural_raytracing_b200.pathtracer.shapes.nerf import NeRFLE
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    out = {}
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def train_bench(total_rays, side):
+        torch.manual_seed(1)
+        net = NeRFLE(device=dev)
+        with torch.no_grad():
+            net.first.out.bias[0] = 0.5
+        opt = torch.optim.AdamW(net.parameters(), lr=8e-5, weight_decay=0)
+        rays_all = torch.from_numpy(camera_rays(side, 0)).to(dev)
+        lo, hi = D.shard_range(total_rays, rank, world)
+        rays = rays_all[lo:hi].reshape(1, hi - lo, 1, 1, 6).contiguous()
+        lights = PointLights(device=dev, location=torch.tensor([[0.4, 1.0, 0.3]], device=dev), scale=10)
+        target = torch.full((1, hi - lo, 1, 1, 3), 0.5, device=dev)
+        ar = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+
+        def one(i=None):
+            random.seed(0)
+            opt.zero_grad(set_to_none=True)
+            loss = (net(rays, lights) - target).square().sum() / (total_rays * 3)
+            loss.backward()
+            if i is not None:
+                ar[i][0].record()
+            D.allreduce_gradients(net.parameters(), average=False)
+            if i is not None:
+                ar[i][1].record()
+            opt.step()
+            return loss
+        for _ in range(warmup):
+            one()
+        sync()
+        for i, (a, b) in enumerate(ev):
+            a.record(); loss = one(i); b.record()
+        sync()
+        ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / steps)
+        ar_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ar) / steps)
+        return {"ms_per_step": ms, "rays_per_sec": total_rays / ms * 1e3, "mlp_samples_per_sec": total_rays * 64 / ms * 1e3,
+                "model_tflops_fwd_bwd": total_rays * 64 * (FLOP_FIRST + FLOP_SECOND) * 3 / ms / 1e9,
+                "grad_allreduce_ms": ar_ms, "grad_bucket_bytes": 4 * sum(p.numel() for p in net.parameters()),
+                "loss": float(loss.detach()), "scaling": "strong", "train_precision": config.train_precision}
+
+    prev = config.train_precision
+    try:
+        config.set_train_precision("f16")
+        try:
+            out["cfg5_train_65536rays"] = train_bench(65536, 256)
+        except Exception as e:   # noqa: BLE001 -- supplementary numbers must never break the headline line
+            out["cfg5_train_65536rays"] = {"error": repr(e)[:300]}
+        if world == 1:
+            try:
+                out["cfg3_train_4096rays"] = train_bench(4096, 64)
+            except Exception as e:   # noqa: BLE001
+                out["cfg3_train_4096rays"] = {"error": repr(e)[:300]}
+    finally:
+        config.set_train_precision(prev)
+    if world == 1:
+        try:
+            torch.manual_seed(2)
+            sphere = SphereSDF(n=64, device=dev)
+            with torch.no_grad():
+                for q in sphere.shift.parameters():
+                    q.normal_(0, 0.02)   # the reference zero-initialises the residual MLP (sdfs.py:30): perturb it
+                sphere.radii.abs_().add_(0.05)   # sdfs.py:20 draws radii in [-0.1, 0.1]: make the object visible
+            shape = SDF(device=dev, sdf=sphere, max_steps=64)
+            packed = sphere.packed()
+            rays = torch.from_numpy(camera_rays(512, 0)).to(dev)
+            R = rays.shape[0]
+            res = {}
+            for prec in ("f16", "f32"):
+                cnt = torch.zeros(1, dtype=torch.int64, device=dev)
+                def fn():
+                    d, h = ops.sphere_trace(packed, rays, shape.epsilon, 64, 10.0, prec=prec, steps_counter=cnt)
+                    ops.min_scan(packed, rays, 2.2 / 128, 128, prec=prec)
+                    return h
+                fn(); torch.cuda.synchronize(); cnt.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); h = fn(); b.record(); torch.cuda.synchronize()
+                ms = a.elapsed_time(b)
+                evals = int(cnt.item()) + R * 129
+                res[prec] = {"ms": ms, "rays_per_sec": R / ms * 1e3, "sdf_samples_per_sec": evals / ms * 1e3,
+                             "tflops": evals * 331008 / ms / 1e9, "hit_fraction": float(h.float().mean())}
+            out["cfg1_sdf_march_512x512"] = res
+        except Exception as e:   # noqa: BLE001
+            out["cfg1_sdf_march_512x512"] = {"error": repr(e)[:300]}
+    return out
+
+
+def ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("mlp_tc_nerf_first_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,6 +321,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="f16", choices=["f16", "bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the supplementary configs reported under `also`")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -294,6 +419,12 @@ def main():
     e2e_ms = float(t.item())
     e2e_value = world * R / (e2e_ms / 1e3)
 
+    also = None
+    if not args.no_also:
+        del flush
+        torch.cuda.empty_cache()
+        also = supplementary(dev, rank, world)
+
     if rank == 0:
         peak_tf, peak_gbs, peak_src = measured_peaks()
         first_ms, first_n = prof.get("mlp_tc_nerf_first", (0.0, 0))
@@ -303,7 +434,7 @@ def main():
             samples_per_launch = R * (N_COARSE + N_FINE) * args.steps / first_n
             tf = samples_per_launch * FLOP_FIRST / (first_ms / first_n * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": "k_mlp_tc<NeRFLE.first> (tcgen05, %s operands)" % args.precision,
-                    "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": None,
+                    "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf, "traffic": ncu_traffic(),
                     "peak_source": peak_src, "launches": first_n, "avg_launch_ms": first_ms / first_n,
                     "algorithmic_flop_per_sample": FLOP_FIRST,
                     "share_of_step": first_ms / total_ms if total_ms else None}
@@ -327,6 +458,7 @@ def main():
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "also": also,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
