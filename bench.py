@@ -246,14 +246,18 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
         for _ in range(warmup):
             one()
         sync()
+        ops.profile_collect(); ops.profile_enable(True)
         for i, (a, b) in enumerate(ev):
             a.record(); loss = one(i); b.record()
         sync()
+        prof = ops.profile_collect(); ops.profile_enable(False)
         ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / steps)
         ar_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ar) / steps)
         return {"ms_per_step": ms, "rays_per_sec": total_rays / ms * 1e3, "mlp_samples_per_sec": total_rays * 64 / ms * 1e3,
                 "model_tflops_fwd_bwd": total_rays * 64 * (FLOP_FIRST + FLOP_SECOND) * 3 / ms / 1e9,
                 "grad_allreduce_ms": ar_ms, "grad_bucket_bytes": 4 * sum(p.numel() for p in net.parameters()),
+                "kernel_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]},
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
                 "loss": float(loss.detach()), "scaling": "strong", "train_precision": config.train_precision}
 
     prev = config.train_precision
@@ -277,6 +281,7 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             with torch.no_grad():
                 for q in sphere.shift.parameters():
                     q.normal_(0, 0.02)   # the reference zero-initialises the residual MLP (sdfs.py:30): perturb it
+                sphere.shift.out.weight.mul_(0.1); sphere.shift.out.bias.zero_()   # residual of a few mm, like a trained SDF
                 sphere.radii.abs_().add_(0.05)   # sdfs.py:20 draws radii in [-0.1, 0.1]: make the object visible
             shape = SDF(device=dev, sdf=sphere, max_steps=64)
             packed = sphere.packed()
@@ -369,15 +374,6 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- CPU baseline first (rank 0, N=1 only), so it does not overlap the GPU timing ----
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sel = np.linspace(0, R - 1, CPU_SAMPLE_RAYS).astype(np.int64)
-        rate, ms, threads = cpu_reference_rate(w1, w2, rays_np[sel], 2, 1)
-        cpu = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
-               "sample": "%d evenly strided rays of the frame, 64+128 samples/ray, mean of 2 runs after 1 warm-up "
-                         "(oracle/port.py: the reference's eager PyTorch op sequence on the host cores)" % CPU_SAMPLE_RAYS}
-
     sampler = ClockSampler(local_rank)
     sampler.start()            # nvidia-smi needs ~1 s to come up: start it before the warm-up
     for _ in range(args.warmup):
@@ -424,6 +420,16 @@ def main():
         del flush
         torch.cuda.empty_cache()
         also = supplementary(dev, rank, world)
+
+    # ---- CPU baseline last (rank 0, N=1 only): it must not overlap the GPU timing, and running it first leaves the
+    # host's OpenMP pool spinning under the launch-bound training steps of `also` ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sel = np.linspace(0, R - 1, CPU_SAMPLE_RAYS).astype(np.int64)
+        rate, ms, threads = cpu_reference_rate(w1, w2, rays_np[sel], 2, 1)
+        cpu = {"value": rate, "unit": "rays/s", "cores": threads, "kind": "port",
+               "sample": "%d evenly strided rays of the frame, 64+128 samples/ray, mean of 2 runs after 1 warm-up "
+                         "(oracle/port.py: the reference's eager PyTorch op sequence on the host cores)" % CPU_SAMPLE_RAYS}
 
     if rank == 0:
         peak_tf, peak_gbs, peak_src = measured_peaks()
