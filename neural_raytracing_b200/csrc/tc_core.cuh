@@ -24,7 +24,9 @@ struct Layout {
   int op_off[kMaxOps];  // in 16-bit elements
   int w_elems;
   int bias_off[kMaxOps];  // float offset inside the bias area (ops 1..n_ops-1)
-  int bias_floats;
+  int bias_floats;        // floats of the fp32 area: biases, then the two optional tables below
+  int wout_f32_off;       // [H][4] fp32 output weights (out <= 4: the output layer runs in the last epilogue), or -1
+  int basis_f32_off;      // [in][FP] fp32 Fourier basis (split-precision inputs: phases on the CUDA cores), or -1
   int bytes;
 };
 
@@ -57,6 +59,10 @@ __host__ __device__ constexpr Layout make_layout(int in, int lat, int f, int h, 
     if (o >= 1) boff += N;
   }
   y.w_elems = off;
+  y.wout_f32_off = -1;
+  y.basis_f32_off = -1;
+  if (out <= 4) { y.wout_f32_off = boff; boff += h * 4; }
+  if (y.split) { y.basis_f32_off = boff; boff += in * y.FP; }
   y.bias_floats = boff;
   y.bytes = off * 2 + boff * 4;
   return y;
@@ -100,8 +106,19 @@ __global__ void k_pack_tc(MlpDev m, Layout y, uint8_t* __restrict__ blob) {
   const int total = y.w_elems + y.bias_floats;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     if (idx >= y.w_elems) {
+      int b = idx - y.w_elems;
+      if (y.basis_f32_off >= 0 && b >= y.basis_f32_off) {
+        const int e = b - y.basis_f32_off, j = e / y.FP, f = e - j * y.FP;
+        bias[b] = f < m.freqs ? m.basis[j * m.freqs + f] : 0.0f;
+        continue;
+      }
+      if (y.wout_f32_off >= 0 && b >= y.wout_f32_off) {
+        const int e = b - y.wout_f32_off, k = e >> 2, j = e & 3;
+        bias[b] = j < m.out ? m.params[m.w_off[m.n_lin - 1] + k * m.out + j] : 0.0f;
+        continue;
+      }
       // biases: ops 1..n_ops-1
-      int b = idx - y.w_elems, o = 1;
+      int o = 1;
       while (o + 1 < y.n_ops && b >= y.bias_off[o + 1]) ++o;
       const int n = b - y.bias_off[o];
       const int li = o - 1;
@@ -432,6 +449,56 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
   if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
 }
 
+// Last hidden layer of a network with a tiny output layer: act(accumulator row) . W_out (fp32, [H][4] in shared
+// memory, broadcast reads) accumulated on the fly; o[] must hold the output bias on entry.
+template <int ACT, int FMT, int H, int OUT, bool SAVE>
+__device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __restrict__ wout, float* __restrict__ o,
+                                                uint16_t* save_row = nullptr) {
+  static_assert(H % 32 == 0 && OUT <= 4, "fused output layer");
+  constexpr int NC = H / 32;
+  uint32_t buf[2][32];
+  TmemIO<32>::ld(dD, buf[0]);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) TmemIO<32>::ld(dD + 32 * (c + 1), buf[(c + 1) & 1]);
+    uint32_t pk[16];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float a[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(buf[c & 1][8 * g + i]);
+      if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+        float u[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = ex2_approx(-1.4426950408889634f * fabsf(a[i]));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaf(0.6931471805599453f, u[i], fmaxf(a[i], 0.0f));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], 0.01f * a[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 w = *reinterpret_cast<const float4*>(wout + (32 * c + 8 * g + i) * 4);
+        o[0] = fmaf(a[i], w.x, o[0]);
+        if constexpr (OUT > 1) o[1] = fmaf(a[i], w.y, o[1]);
+        if constexpr (OUT > 2) o[2] = fmaf(a[i], w.z, o[2]);
+        if constexpr (OUT > 3) o[3] = fmaf(a[i], w.w, o[3]);
+      }
+      if constexpr (SAVE) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(a[2 * i], a[2 * i + 1]);
+      }
+    }
+    if constexpr (SAVE) save_cols<16>(save_row, 32 * c, pk);
+    if (c + 1 < NC) tc_wait_ld();
+  }
+  if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
+}
+
 // D[lane][0..N) = bias[0..N): the next layer's MMA then only accumulates (no bias add in its epilogue)
 template <int N>
 __device__ __forceinline__ void preload_bias(uint32_t dD, const float* __restrict__ bias) {
@@ -469,6 +536,15 @@ struct Net {
   static constexpr int COLS = DC + UC + EC;
   static constexpr int NSLOT = (2 * COLS <= 512) ? 2 : 1;
   static constexpr int STAGES = L + 3;                    // encode, init, L layers, out
+  // Two of those stages need no tensor core and cost a full MMA -> commit -> wait round trip each:
+  //  * split-precision inputs (in <= 5): the Fourier phases are in*F FMAs per sample -> computed in fp32 by the
+  //    epilogue thread that owns the sample, together with sin / cos, BEFORE the first MMA (stage 0 disappears);
+  //  * out <= 4: the output layer is H*out FMAs per sample -> accumulated in fp32 while the last hidden
+  //    activations are produced (the last stage disappears, and that layer no longer rounds to 16 bits).
+  static constexpr bool ENC_CUDA = Y.basis_f32_off >= 0;
+  static constexpr bool FUSE_OUT = Y.wout_f32_off >= 0;
+  static constexpr int FIRST_STAGE = ENC_CUDA ? 1 : 0;
+  static constexpr int END_STAGE = FUSE_OUT ? STAGES - 1 : STAGES;   // one past the last MMA stage
   static_assert(COLS <= 512, "network does not fit in TMEM");
   static_assert(XR % 16 == 0 && F % 16 == 0 && LAT % 16 == 0 && KRAW == KE, "encoding segments must be multiples of 16");
   static_assert(!SPLIT || 3 * IN <= 16, "split encoding needs 3*in <= 16");
@@ -629,7 +705,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     // whatever order they become ready, so the two tiles drift into anti-phase: the tensor pipe works
     // on one tile while the other tile's epilogue (or prologue / output store) runs.
     const uint32_t sW_addr = smem_u32(sW);
-    int st[2] = {0, 0};
+    int st[2] = {NET::FIRST_STAGE, NET::FIRST_STAGE};
     uint32_t n_ready[2] = {0, 0};
     int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
     bool live[2] = {ITER || tile[0] < ntiles, NSLOT > 1 && (ITER || tile[1] < ntiles)};
@@ -639,7 +715,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
 #pragma unroll
       for (int slot = 0; slot < NSLOT; ++slot)
         if (live[slot] && elect_one())
-          stream_op(smem + (size_t)(slot * 2) * NET::MAXOP, blob + s_opoff[0], s_opbytes[0], &bar_wfull[slot][0]);
+          stream_op(smem + (size_t)(slot * 2) * NET::MAXOP, blob + s_opoff[NET::FIRST_STAGE], s_opbytes[NET::FIRST_STAGE],
+                    &bar_wfull[slot][0]);
       __syncwarp();
     }
     while (live[0] || live[1]) {
@@ -652,7 +729,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         n_ready[slot]++;
         tc_fence_after();
         if constexpr (ITER) {
-          if (st[slot] == 0 && s_slot_live[slot] == 0) {
+          if (st[slot] == NET::FIRST_STAGE && s_slot_live[slot] == 0) {
             // the slot's epilogue found no live trajectory and the queue is empty: retire the slot (after draining
             // the operand prefetch that was issued for the iteration that will not happen)
             live[slot] = false;
@@ -670,8 +747,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         }
         issue_stage_dyn<NET, FMT>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
         if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 2);
-        if (++st[slot] == NET::STAGES) {
-          st[slot] = 0;
+        if (++st[slot] == NET::END_STAGE) {
+          st[slot] = NET::FIRST_STAGE;
           it_dbg[slot]++;
           if constexpr (!ITER) {
             tile[slot] += (int64_t)gridDim.x * NSLOT;
@@ -789,17 +866,32 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
               save_cols<LAT / 2>(tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row), NET::XR + 2 * F, la);
             }
           }
-          tc_wait_st();
-          tc_fence_before();
-          mbar_arrive(&bar_ready[slot]);
+          if constexpr (!NET::ENC_CUDA) {
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&bar_ready[slot]);
+          }
         }
         // ---- stage 1: phases -> sin / cos -> rest of enc_raw / enc_act ----
         {
-          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
-          tc_fence_after();
           uint32_t ph[F];
-          tmem_load<F>(dD, ph);
-          tc_wait_ld();
+          if constexpr (NET::ENC_CUDA) {
+            // phases x.B in fp32 on the CUDA cores (in*F FMAs), no MMA round trip; the accumulator is free (the
+            // previous tile's output was read), so the init layer's bias goes in right away
+            const float* sB = sBias + Y.basis_f32_off;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+              float p = x[0] * sB[f];
+#pragma unroll
+              for (int j = 1; j < IN; ++j) p = fmaf(x[j], sB[j * NET::FP + f], p);
+              ph[f] = __float_as_uint(p);
+            }
+          } else {
+            mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+            tc_fence_after();
+            tmem_load<F>(dD, ph);
+            tc_wait_ld();
+          }
           preload_bias<H>(dD, sBias + s_bias[1]);
           uint32_t sr[F / 2], cr[F / 2], sa[F / 2], ca[F / 2];
 #pragma unroll
@@ -830,8 +922,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           mbar_arrive(&bar_ready[slot]);
         }
         // ---- stages 2 .. L+1: hidden activations ----
+        constexpr int NHID = NET::FUSE_OUT ? L : L + 1;   // epilogues that feed another MMA stage
 #pragma unroll 1
-        for (int st = 0; st <= L; ++st) {
+        for (int st = 0; st < NHID; ++st) {
           estamp(2 + st, 3);
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
@@ -852,7 +945,22 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           estamp(2 + st, 7);
         }
         // ---- output layer ----
-        {
+        if constexpr (NET::FUSE_OUT) {
+          // last hidden activations and the (tiny) output layer in one pass, fp32 on the CUDA cores
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          float o[NET::OUT];
+#pragma unroll
+          for (int j = 0; j < NET::OUT; ++j) o[j] = sBias[s_bias[NET::STAGES - 1] + j];
+          if constexpr (SV::kOn)
+            convert_row_out<NET::ACT, FMT, H, NET::OUT, true>(dD, sBias + Y.wout_f32_off, o,
+                tile_row_ptr(sv.acts, (int64_t)L * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row));
+          else
+            convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(dD, sBias + Y.wout_f32_off, o);
+          if constexpr (ITER) { if (valid) io.consume(state, o); }
+          else { if (valid) io.store(m, o); }
+          tc_fence_before();
+        } else {
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
           constexpr int OC = (NET::OUT + 7) / 8 * 8;
