@@ -10,6 +10,7 @@ precision = "f32"
 TC_NETS = {
     (3, 0, 16, 128, 5, 3, 65, 0),   # NeRFLE.first
     (70, 0, 16, 64, 8, 3, 3, 0),    # NeRFLE.second (point light)
+    (115, 0, 16, 64, 8, 3, 3, 0),   # NeRFLE.second (environment-light code)
     (3, 0, 64, 96, 6, 3, 3, 0),     # NeuralBSDF.mlp
     (5, 0, 16, 64, 8, 3, 1, 0),     # occlusion MLP
     (3, 0, 32, 128, 8, 3, 1, 1),    # SphereSDF.shift (softplus; weights streamed through shared memory)
@@ -24,6 +25,7 @@ train_precision = "f32"
 TRAIN_TC_NETS = {
     (3, 0, 16, 128, 5, 3, 65, 0),   # NeRFLE.first
     (70, 0, 16, 64, 8, 3, 3, 0),    # NeRFLE.second (point light)
+    (115, 0, 16, 64, 8, 3, 3, 0),   # NeRFLE.second (environment-light code)
 }
 
 

@@ -495,8 +495,8 @@ struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; };
 
 template <int FMT>
 __global__ void __launch_bounds__(160, 1)
-k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_bytes, float* __restrict__ g_params,
-               const float* __restrict__ scale) {
+k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_bytes, int s0_off, int s1_off,
+               float* __restrict__ g_params, const float* __restrict__ scale) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[2];
   __shared__ __align__(8) uint64_t bar_empty[2];
@@ -541,10 +541,11 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
           mbar_expect_tx(&bar_full[slot], a_bytes + s0_bytes + s1_bytes);
           bulk_g2s(sb, job.a_tiles + t * (int64_t)(job.a_rows * 128), a_bytes, &bar_full[slot]);
           for (uint32_t off = 0; off < s0_bytes; off += 32768u)
-            bulk_g2s(sb + 32768 + off, reinterpret_cast<const uint8_t*>(job.s0_tiles + t * (int64_t)(job.s0_rows * 128)) + off,
+            bulk_g2s(sb + s0_off + off, reinterpret_cast<const uint8_t*>(job.s0_tiles + t * (int64_t)(job.s0_rows * 128)) + off,
                      min(32768u, s0_bytes - off), &bar_full[slot]);
-          if (s1_bytes)
-            bulk_g2s(sb + 32768 + 40960, job.s1_tiles + t * (int64_t)(job.s1_rows * 128), s1_bytes, &bar_full[slot]);
+          for (uint32_t off = 0; off < s1_bytes; off += 32768u)
+            bulk_g2s(sb + s1_off + off, reinterpret_cast<const uint8_t*>(job.s1_tiles + t * (int64_t)(job.s1_rows * 128)) + off,
+                     min(32768u, s1_bytes - off), &bar_full[slot]);
         }
         __syncwarp();
       }
@@ -555,7 +556,7 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
         if (elect_one()) {
           const uint32_t sb = smem_u32(smem + (size_t)slot * stage_bytes);
           const uint32_t lbo_a = (uint32_t)job.a_rows * 16u, lbo0 = (uint32_t)job.s0_rows * 16u, lbo1 = (uint32_t)job.s1_rows * 16u;
-          const uint64_t ad = make_desc(sb, lbo_a, 128), b0 = make_desc(sb + 32768, lbo0, 128), b1 = make_desc(sb + 32768 + 40960, lbo1, 128);
+          const uint64_t ad = make_desc(sb, lbo_a, 128), b0 = make_desc(sb + (uint32_t)s0_off, lbo0, 128), b1 = make_desc(sb + (uint32_t)s1_off, lbo1, 128);
           for (int kc = 0; kc < 8; ++kc) {
             const uint32_t acc = (j > 0 || kc > 0) ? 1u : 0u;
             // D'[tmem] (+)= A''[smem] * B''[smem]^T
@@ -615,6 +616,7 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
 
 using NetNerfFirst = Net<3, 0, 16, 128, 5, 3, 65, NRT_ACT_LEAKY_RELU>;
 using NetNerfSecondPT = Net<70, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;
+using NetNerfSecondLE = Net<115, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;
 
 template <class NET>
 static bool matches(const MlpDev& d) {
@@ -686,16 +688,22 @@ static int train_backward(const nrt_mlp_t* m, const MlpDev& d, int out_act, int6
   const unsigned slot = __atomic_fetch_add(&d_jobs_next, 1u, __ATOMIC_RELAXED) % 64;
   if (d_jobs[slot] == nullptr) NRT_CUDA(cudaMalloc(&d_jobs[slot], sizeof(WgradJobs)));
   NRT_CUDA(cudaMemcpyAsync(d_jobs[slot], &jobs, sizeof(WgradJobs), cudaMemcpyHostToDevice, st));
-  // stage: [A'' 32 KB][source 0 <= 40 KB][source 1 <= 32 KB] ; + 32 KB tail so that the M = 128 operand may over-read
-  static_assert(FRA * 256 <= 40960 && FRE * 256 <= 32768 && H * 256 <= 32768, "wgrad stage layout");
-  const int stage_bytes = 32768 + 40960 + 32768;
-  const size_t bytes = 2 * (size_t)stage_bytes + 16384;
+  // stage: [A'' | source 0 | source 1].  The M = 128 operand reads 128 rows per sample group whatever a_rows is, so its
+  // region spans (15 * a_rows + 128) * 16 bytes; the garbage rows only reach accumulator lanes >= a_rows (ignored)
+  constexpr int A_ROWS = H > NOP ? H : NOP;
+  constexpr int S0_OFF = ((15 * A_ROWS + 128) * 16 + 1023) / 1024 * 1024;
+  constexpr int S0_BYTES = (FRA > FRE ? FRA : FRE) * 256;
+  constexpr int S1_OFF = S0_OFF + S0_BYTES;
+  const int stage_bytes = S1_OFF + FRE * 256;
+  const size_t bytes = 2 * (size_t)stage_bytes + 8192;
+  static_assert(2 * (S1_OFF + FRE * 256) + 8192 + 1024 <= 227 * 1024, "wgrad stages do not fit in shared memory");
+  static_assert(FRA + FRE <= 512 && FRA <= 256 && FRE <= 256, "wgrad accumulator / MMA N limits");
   auto kern = k_mlp_wgrad_tc<FMT>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jobs.n - 1) / jobs.n));
   {
     NrtProfScope _ps(TAG_TC_WGRAD, st);
-    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(d_jobs[slot], nt, stage_bytes, g_params, ws.scale);
+    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(d_jobs[slot], nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);
   }
   NRT_CUDA(cudaGetLastError());
   (void)m;
@@ -710,6 +718,7 @@ using namespace tc;
 static int train_net_id(const MlpDev& d) {
   if (matches<NetNerfFirst>(d)) return 1;
   if (matches<NetNerfSecondPT>(d)) return 2;
+  if (matches<NetNerfSecondLE>(d)) return 3;
   return 0;
 }
 
@@ -765,8 +774,11 @@ extern "C" int nrt_mlp_forward_train_tc(const nrt_mlp_t* m, int prec, int out_ac
     case 2:
       if (prec == NRT_PREC_F16) return train_forward<NetNerfSecondPT, 0>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
       return train_forward<NetNerfSecondPT, 1>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
+    case 3:
+      if (prec == NRT_PREC_F16) return train_forward<NetNerfSecondLE, 0>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
+      return train_forward<NetNerfSecondLE, 1>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
   }
-  nrt_set_error("tensor-core training path: this MLP shape is not instantiated (NeRFLE.first / NeRFLE.second are)");
+  nrt_set_error("tensor-core training path: this MLP shape is not instantiated (NeRFLE.first / NeRFLE.second PT and LE are)");
   return NRT_E_UNSUPPORTED;
 }
 
@@ -797,6 +809,13 @@ extern "C" int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, in
       }
       if (f16) return train_backward<NetNerfSecondPT, false, 0>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
       return train_backward<NetNerfSecondPT, false, 1>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
+    case 3:
+      if (g_x) {
+        if (f16) return train_backward<NetNerfSecondLE, true, 0>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, g_x, st);
+        return train_backward<NetNerfSecondLE, true, 1>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, g_x, st);
+      }
+      if (f16) return train_backward<NetNerfSecondLE, false, 0>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
+      return train_backward<NetNerfSecondLE, false, 1>(m, d, out_act, M, out, g_out, dgrad_blob, ws, g_params, nullptr, st);
   }
   nrt_set_error("tensor-core training path: this MLP shape is not instantiated");
   return NRT_E_UNSUPPORTED;

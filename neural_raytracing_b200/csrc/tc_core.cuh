@@ -548,7 +548,6 @@ struct Net {
   static_assert(COLS <= 512, "network does not fit in TMEM");
   static_assert(XR % 16 == 0 && F % 16 == 0 && LAT % 16 == 0 && KRAW == KE, "encoding segments must be multiples of 16");
   static_assert(!SPLIT || 3 * IN <= 16, "split encoding needs 3*in <= 16");
-  static_assert(SPLIT || IN % 2 == 0, "unsplit inputs must come in pairs");
   static_assert(H % 16 == 0 && H <= 256, "hidden must be a multiple of 16");
   // Weights that do not fit in shared memory are STREAMED: each tile slot owns two stage buffers and the MMA warp
   // prefetches the next stage's operand (cp.async.bulk from L2) while the current stage computes.
@@ -835,9 +834,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             for (int j = 0; j < IN; ++j) ex[j] = (uint32_t)a[2 * j] | ((uint32_t)a[2 * j + 1] << 16);
           } else {
 #pragma unroll
-            for (int j = 0; j < IN / 2; ++j) {
-              ax[j] = E::pack(x[2 * j], x[2 * j + 1]);
-              ex[j] = E::pack(act_fast<NET::ACT>(x[2 * j]), act_fast<NET::ACT>(x[2 * j + 1]));
+            for (int j = 0; j < (IN + 1) / 2; ++j) {
+              const float xa = x[2 * j], xb = (2 * j + 1 < IN) ? x[2 * j + 1 < IN ? 2 * j + 1 : 0] : 0.0f;   // odd in: zero pad
+              ax[j] = E::pack(xa, xb);
+              ex[j] = E::pack(act_fast<NET::ACT>(xa), (2 * j + 1 < IN) ? act_fast<NET::ACT>(xb) : 0.0f);
             }
           }
           tmem_store<NET::KX / 2>(aU, ax);

@@ -79,7 +79,7 @@ class NeRFLE(nn.Module):
             N = rays.shape[0]
             per_view = rays[0].numel() // 6
             view = torch.arange(N, device=device, dtype=torch.int32).repeat_interleave(per_view)
-            prec = config.precision if (config.precision != "f32" and not self.envmap) else "f32"
+            prec = config.precision
             return ops.nerfle_render(self.first.packed(), self.second.packed(), rays.detach().float(), ts,
                                      code.detach().float(), view, prec=prec)
         # differentiable path: fused MLP kernels where available + CUDA compositing

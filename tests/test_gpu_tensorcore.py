@@ -71,6 +71,24 @@ def test_tc_nerfle_render_reference_mode(R):
         assert helpers.psnr(r16, ro) > 60 and helpers.psnr(rbf, ro) > 50
 
 
+@pytest.mark.parametrize("R", [5, 300])
+def test_tc_nerfle_render_envmap_code(R):
+    """NeRFLE(envmap=True): the second MLP takes [latent | r_d | 48-float environment code] (nerf.py:184-195), 115 inputs."""
+    from neural_raytracing_b200 import ops
+    w1, w2 = helpers.nerfle_weights(True)
+    rays = synth.camera_rays(34, R)
+    ts = np.linspace(0, 2.06, 64).astype(np.float32)
+    code = (0.3 * np.random.RandomState(3).standard_normal((1, 48))).astype(np.float32)
+    ro = c_oracle.nerfle_render(helpers.oracle_mlp(w1), helpers.oracle_mlp(w2), rays, ts=ts, light_code=code)
+    m1, m2 = helpers.cuda_mlp(w1), helpers.cuda_mlp(w2)
+    r32 = ops.nerfle_render(m1, m2, _t(rays), _t(ts), _t(code), prec="f32").cpu().numpy()
+    assert np.array_equal(r32.view(np.uint32), ro.view(np.uint32))
+    r16 = ops.nerfle_render(m1, m2, _t(rays), _t(ts), _t(code), prec="f16").cpu().numpy()
+    assert np.abs(r16 - ro).max() < 1e-3
+    if R >= 300:
+        assert helpers.psnr(r16, ro) > 60
+
+
 def test_tc_nerfle_golden_views():
     """Against the unmodified reference's own output (two views, per-view light)."""
     from neural_raytracing_b200 import ops
