@@ -253,12 +253,45 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
         prof = ops.profile_collect(); ops.profile_enable(False)
         ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / steps)
         ar_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ar) / steps)
+        loss_val = float(loss.detach())
+        del loss          # drop the last eager autograd graph (its AccumulateGrad nodes would leak into a later capture)
         return {"ms_per_step": ms, "rays_per_sec": total_rays / ms * 1e3, "mlp_samples_per_sec": total_rays * 64 / ms * 1e3,
+
                 "model_tflops_fwd_bwd": total_rays * 64 * (FLOP_FIRST + FLOP_SECOND) * 3 / ms / 1e9,
                 "grad_allreduce_ms": ar_ms, "grad_bucket_bytes": 4 * sum(p.numel() for p in net.parameters()),
                 "kernel_ms_per_step": {k: round(v[0] / steps, 3) for k, v in prof.items() if v[1]},
                 "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
-                "loss": float(loss.detach()), "scaling": "strong", "train_precision": config.train_precision}
+                "loss": loss_val, "scaling": "strong", "train_precision": config.train_precision}
+
+    def graph_bench(total_rays, side):
+        """The same step captured in CUDA graphs (training.GraphedStep): zero_grad + forward + backward | all-reduce | AdamW."""
+        import gc
+        from neural_raytracing_b200.training import GraphedStep
+        gc.collect()
+        torch.manual_seed(1)
+        net = NeRFLE(device=dev)
+        with torch.no_grad():
+            net.first.out.bias[0] = 0.5
+        net.far_jitter = torch.full((1,), 0.5, device=dev)
+        opt_g = torch.optim.AdamW(net.parameters(), lr=8e-5, weight_decay=0, capturable=True)
+        rays_all = torch.from_numpy(camera_rays(side, 0)).to(dev)
+        lo, hi = D.shard_range(total_rays, rank, world)
+        rays = rays_all[lo:hi].reshape(1, hi - lo, 1, 1, 6).contiguous()
+        lights = PointLights(device=dev, location=torch.tensor([[0.4, 1.0, 0.3]], device=dev), scale=10)
+        target = torch.full((1, hi - lo, 1, 1, 3), 0.5, device=dev)
+        gstep = GraphedStep(lambda: (net(rays, lights) - target).square().sum() / (total_rays * 3), opt_g, modules=[net],
+                            allreduce=(lambda: D.allreduce_gradients(net.parameters(), average=False)) if world > 1 else None)
+        for _ in range(2):
+            gstep()
+        sync()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(steps):
+            gstep()
+        g1.record()
+        sync()
+        ms = max_over_ranks(g0.elapsed_time(g1) / steps)
+        return {"ms_per_step": ms, "rays_per_sec": total_rays / ms * 1e3, "loss": float(gstep.loss.detach())}
 
     prev = config.train_precision
     try:
@@ -304,6 +337,17 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             out["cfg1_sdf_march_512x512"] = res
         except Exception as e:   # noqa: BLE001
             out["cfg1_sdf_march_512x512"] = {"error": repr(e)[:300]}
+    # CUDA-graph captured steps last: a failed capture must not disturb the measurements above
+    try:
+        config.set_train_precision("f16")
+        for name, total, side in (("cfg5_train_65536rays", 65536, 256),) + ((("cfg3_train_4096rays", 4096, 64),) if world == 1 else ()):
+            try:
+                out[name]["cuda_graph"] = graph_bench(total, side)
+            except Exception as e:   # noqa: BLE001
+                out[name]["cuda_graph"] = {"error": repr(e)[:300]}
+                break
+    finally:
+        config.set_train_precision(prev)
     return out
 
 

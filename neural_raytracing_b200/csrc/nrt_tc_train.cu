@@ -495,7 +495,7 @@ struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; };
 
 template <int FMT>
 __global__ void __launch_bounds__(160, 1)
-k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_bytes, int s0_off, int s1_off,
+k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int stage_bytes, int s0_off, int s1_off,
                float* __restrict__ g_params, const float* __restrict__ scale) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[2];
@@ -505,7 +505,7 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
   __shared__ WgradJob job;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    job = jobs_g->j[blockIdx.y];
+    job = jobs_g.j[blockIdx.y];
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
     mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
     mbar_init(&bar_done, 1);
@@ -580,8 +580,8 @@ k_mlp_wgrad_tc(const WgradJobs* __restrict__ jobs_g, int64_t ntiles, int stage_b
     tc_fence_after();
     const int unit = tid;   // 0..127
     const uint32_t trow = tmem + (((uint32_t)(warp * 32)) << 16);
-    const Layout y = jobs_g->y;
-    const int in_size = jobs_g->in_size;
+    const Layout& y = jobs_g.y;
+    const int in_size = jobs_g.in_size;
     const int ncols = job.s0_rows + (job.s1_tiles ? job.s1_rows : 0);
     const float inv_s = scale[2];
     for (int c0 = 0; c0 < ncols; c0 += 16) {
@@ -683,11 +683,6 @@ static int train_backward(const nrt_mlp_t* m, const MlpDev& d, int out_act, int6
       if (is_skip(li - 1, NET::SKIP, L)) { j.s1_tiles = ws.enc_act; j.s1_rows = FRE; }
     }
   }
-  static WgradJobs* d_jobs[64] = {nullptr};
-  static unsigned d_jobs_next = 0;
-  const unsigned slot = __atomic_fetch_add(&d_jobs_next, 1u, __ATOMIC_RELAXED) % 64;
-  if (d_jobs[slot] == nullptr) NRT_CUDA(cudaMalloc(&d_jobs[slot], sizeof(WgradJobs)));
-  NRT_CUDA(cudaMemcpyAsync(d_jobs[slot], &jobs, sizeof(WgradJobs), cudaMemcpyHostToDevice, st));
   // stage: [A'' | source 0 | source 1].  The M = 128 operand reads 128 rows per sample group whatever a_rows is, so its
   // region spans (15 * a_rows + 128) * 16 bytes; the garbage rows only reach accumulator lanes >= a_rows (ignored)
   constexpr int A_ROWS = H > NOP ? H : NOP;
@@ -703,7 +698,7 @@ static int train_backward(const nrt_mlp_t* m, const MlpDev& d, int out_act, int6
   const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jobs.n - 1) / jobs.n));
   {
     NrtProfScope _ps(TAG_TC_WGRAD, st);
-    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(d_jobs[slot], nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);
+    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(jobs, nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);   // job table by value (2 KB of kernel parameters): no copy, graph-capturable
   }
   NRT_CUDA(cudaGetLastError());
   (void)m;

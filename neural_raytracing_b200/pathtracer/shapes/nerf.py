@@ -55,6 +55,14 @@ class NeRFLE(nn.Module):
         self.second = SkipConnMLP(in_size=self.latent_size + (6 if not envmap else 3 + bins * bins * 3), out=3,
                                   device=device).to(device)
         self.envmap = envmap
+        # optional device tensor in [0,1): when set, replaces random.random() of the far-plane jitter (nerf.py:178) so
+        # that a CUDA-graph-captured step (neural_raytracing_b200.training.GraphedStep) still jitters per replay
+        self.far_jitter = None
+
+    def _sample_ts(self, device):
+        if getattr(self, "far_jitter", None) is not None:
+            return torch.linspace(0, 1, 64, device=device) * (2 + self.far_jitter.reshape(()).to(device) * 0.1)
+        return torch.linspace(0, 2 + random.random() * 0.1, 64, device=device)
 
     def _light_code(self, lights, device):
         """[n_views, 3] light location, or the [n_views, 3*bins^2] environment code (nerf.py:184-197)."""
@@ -72,7 +80,7 @@ class NeRFLE(nn.Module):
     def forward(self, rays, lights):
         r_o, r_d = rays.split([3, 3], dim=-1)
         device = r_o.device
-        ts = torch.linspace(0, 2 + random.random() * 0.1, 64, device=device)
+        ts = self._sample_ts(device)
         code = self._light_code(lights, device)
         if rays.is_cuda and not self._needs_grad(rays):
             # fused render: rays in, rgb out
