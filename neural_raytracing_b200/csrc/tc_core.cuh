@@ -430,8 +430,11 @@ template <int FMT> __device__ __forceinline__ uint16_t one16() { return FMT == 0
 
 // One accumulator row (H fp32 columns at dD) -> activated 16-bit operand columns at aU, in 32-column chunks:
 // the tcgen05.ld of chunk c+1 is in flight while chunk c is converted (64 + 16 live registers instead of 192).
+// (H here is the number of columns THIS thread converts: the whole layer, or one half of it in the 8-warp variant;
+//  dD / aU already point at the thread's first column, col0 is that column's index for the saved tile)
 template <int ACT, int FMT, int H, bool SAVE = false>
-__device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* save_row = nullptr) {
+__device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* save_row = nullptr, int col0 = 0,
+                                            int one_col = -1) {
   static_assert(H % 32 == 0, "hidden width must be a multiple of 32");
   constexpr int NC = H / 32;
   uint32_t buf[2][32];
@@ -443,10 +446,10 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
     uint32_t pk[16];
     convert32<ACT, FMT>(buf[c & 1], pk);
     TmemIO<16>::st(aU + 16 * c, pk);
-    if constexpr (SAVE) save_cols<16>(save_row, 32 * c, pk);
+    if constexpr (SAVE) save_cols<16>(save_row, col0 + 32 * c, pk);
     if (c + 1 < NC) tc_wait_ld();
   }
-  if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
+  if constexpr (SAVE) { if (one_col >= 0) save_row[tile_elem(one_col)] = one16<FMT>(); }
 }
 
 // Last hidden layer of a network with a tiny output layer: act(accumulator row) . W_out (fp32, [H][4] in shared
@@ -541,6 +544,12 @@ struct Net {
   //    epilogue thread that owns the sample, together with sin / cos, BEFORE the first MMA (stage 0 disappears);
   //  * out <= 4: the output layer is H*out FMAs per sample -> accumulated in fp32 while the last hidden
   //    activations are produced (the last stage disappears, and that layer no longer rounds to 16 bits).
+  // warps per tile slot.  8 = two warps per TMEM lane quarter, each converting half of the columns of a hidden layer
+  // (k_mlp_tc implements both).  Measured on B200 the 8-warp variant is SLOWER (NeRFLE.first +6 %, .second +25 %,
+  // SDF march +15 %): the epilogue is bound by the throughput of the conversion pipes of the SM sub-partition
+  // (F2FP.PACK_AB ~4 cycles, HMUL2 / HMNMX2 2 cycles per warp instruction: ~512 cycles per 128x128 tile layer),
+  // not by the latency of one warp's dependent chain, and 17 warps cap the kernel at 96 registers per thread.
+  static constexpr int WPS = 4;
   static constexpr bool ENC_CUDA = Y.basis_f32_off >= 0;
   static constexpr bool FUSE_OUT = Y.wout_f32_off >= 0;
   static constexpr int FIRST_STAGE = ENC_CUDA ? 1 : 0;
@@ -625,9 +634,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <class NET, class IO, int FMT, class SV = NoSave>
-__global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
+template <class NET, class IO, int FMT, class SV = NoSave, int WPS = NET::WPS>
+__global__ void __launch_bounds__(WPS * 64 + 32, 1)
 k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg, SV sv = SV{}) {
+  constexpr int EPI = WPS * 32;                 // epilogue threads per tile slot
   // dbg (development only, tools/tc_timeline.py): clock64 stamps of CTA 0 for a few tile iterations
   constexpr int kDbgIt0 = 4, kDbgIts = 4;
   auto stamp = [&](int it, int st, int slot, int k) {
@@ -655,7 +665,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const bool is_mma_warp = warp == 8;
+  const bool is_mma_warp = warp == 2 * WPS;
   const int64_t ntiles = (M + 127) / 128;
   if (tid < NET::STAGES) {
     s_bias[tid] = (uint32_t)Y.bias_off[tid];
@@ -667,7 +677,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     s_slot_live[0] = 1; s_slot_live[1] = 1;
     mbar_init(&bar_w, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&bar_ready[s], kEpiThreads); mbar_init(&bar_done[s], 1);
+      mbar_init(&bar_ready[s], EPI); mbar_init(&bar_done[s], 1);
       mbar_init(&bar_wfull[s][0], 1); mbar_init(&bar_wfull[s][1], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -771,8 +781,13 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     }
   } else {
     // ===================== epilogue warpgroups (one per tile slot) =====================
-    const int slot = warp >> 2;
-    const int lane_row = tid & 127;               // TMEM lane == row of the tile == sample
+    const int slot = warp / WPS;
+    // 8-warp variant: warps q and q+4 of a slot share TMEM lane quarter q; `half` selects the columns a warp converts.
+    // Half 0 ("primary") also owns the sample: input load / encoding / output; half 1 only helps in the hidden layers.
+    const int half = (WPS == 8) ? ((warp >> 2) & 1) : 0;
+    const bool primary = half == 0;
+    const int lane_row = (warp & 3) * 32 + (tid & 31);   // TMEM lane == row of the tile == sample
+    constexpr int HW = (WPS == 8) ? H / 2 : H;            // hidden columns converted per thread
     if (slot < NSLOT) {
       const uint32_t lane_off = ((uint32_t)((warp & 3) * 32)) << 16;
       const uint32_t base = tmem + slot * NET::COLS + lane_off;
@@ -787,10 +802,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         bool valid;
         float x[IN + LAT];
         if constexpr (ITER) {
-          valid = io.next(state, x);
+          valid = primary ? io.next(state, x) : false;
           const unsigned bal = __ballot_sync(0xffffffffu, valid);
-          if ((tid & 31) == 0) s_warp_live[slot][warp & 3] = bal;
-          named_bar_sync(1 + slot, kEpiThreads);
+          if (primary && (tid & 31) == 0) s_warp_live[slot][warp & 3] = bal;
+          named_bar_sync(1 + slot, EPI);
           const bool any = (s_warp_live[slot][0] | s_warp_live[slot][1] | s_warp_live[slot][2] | s_warp_live[slot][3]) != 0;
           if (!any) {
             if (lane_row == 0) s_slot_live[slot] = 0;
@@ -802,8 +817,16 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           if (tile >= ntiles) break;
           m = tile * 128 + lane_row;
           valid = m < M;
-          if (valid) io.load(m, x);
+          if (valid && primary) io.load(m, x);
         }
+        if (!primary) {
+          // the helper half has no work before the first hidden layer: keep in phase with the barriers only
+          if constexpr (!NET::ENC_CUDA) {
+            mbar_arrive(&bar_ready[slot]);
+            mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          }
+          mbar_arrive(&bar_ready[slot]);
+        } else {
         // ---- stage 0: inputs -> encode-GEMM A operand (+ x / latent parts of enc_raw, enc_act) ----
         {
           if (!valid) {
@@ -921,6 +944,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           tc_fence_before();
           mbar_arrive(&bar_ready[slot]);
         }
+        }   // primary
         // ---- stages 2 .. L+1: hidden activations ----
         constexpr int NHID = NET::FUSE_OUT ? L : L + 1;   // epilogues that feed another MMA stage
 #pragma unroll 1
@@ -930,14 +954,21 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           tc_fence_after();
           estamp(2 + st, 4);
           estamp(2 + st, 5);
+          const int coff = half * HW;     // this thread's first hidden column
           if constexpr (SV::kOn)
-            convert_row<NET::ACT, FMT, H, true>(dD, aU, tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row));
+            convert_row<NET::ACT, FMT, HW, true>(dD + coff, aU + coff / 2,
+                tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row), coff, primary ? H : -1);
           else
-            convert_row<NET::ACT, FMT, H>(dD, aU);
+            convert_row<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2);
           // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
-          // the conversion so the accumulator registers are dead and all 32 LDS.128 can be in flight
-          if (st < L) preload_bias<H>(dD, sBias + s_bias[2 + st]);
-          else preload_bias<NET::NOP>(dD, sBias + s_bias[NET::STAGES - 1]);
+          // the conversion so the accumulator registers are dead and all LDS.128 can be in flight
+          if (st < L) preload_bias<HW>(dD + coff, sBias + s_bias[2 + st] + coff);
+          else {
+            // output-layer bias: every half writes only the accumulator columns it has just read
+            constexpr int N0 = NET::NOP < HW ? NET::NOP : HW, N1 = NET::NOP > HW ? NET::NOP - HW : 0;
+            if (primary) preload_bias<N0>(dD, sBias + s_bias[NET::STAGES - 1]);
+            else if constexpr (N1 > 0) preload_bias<N1>(dD + HW, sBias + s_bias[NET::STAGES - 1] + HW);
+          }
           estamp(2 + st, 6);
           tc_wait_st();
           tc_fence_before();
@@ -945,7 +976,11 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           estamp(2 + st, 7);
         }
         // ---- output layer ----
-        if constexpr (NET::FUSE_OUT) {
+        if (!primary) {
+          mbar_wait(&bar_done[slot], n_done & 1); n_done++;
+          tc_fence_after();
+          tc_fence_before();
+        } else if constexpr (NET::FUSE_OUT) {
           // last hidden activations and the (tiny) output layer in one pass, fp32 on the CUDA cores
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
@@ -976,7 +1011,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           tc_fence_before();
         }
       }
-      if constexpr (ITER) io.finish(state);
+      if constexpr (ITER) { if (primary) io.finish(state); }
     }
   }
   tc_fence_before();
