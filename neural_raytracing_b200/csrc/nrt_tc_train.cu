@@ -89,6 +89,7 @@ struct TrainWs {
   uint16_t* enc_act;   // [ntiles][(KE+16) x 128]
   uint16_t* dz;        // [L+1][ntiles][H x 128]
   uint16_t* gout;      // [ntiles][NOP x 128]
+  uint32_t* masks;     // [L+1][H/32][ntiles*128] sign bits of a_l
   float* scale;        // [0]: max |g_out * out_act'| as float bits (atomicMax), [1]: loss scale S, [2]: 1/S
   int64_t ntiles;
   size_t bytes;
@@ -104,13 +105,14 @@ static TrainWs carve_ws(const Layout& y, int h, int L, int64_t M, void* base) {
   const size_t o_ea = take(nt * (y.KE + kTileRowsExtra) * 128 * 2);
   const size_t o_dz = take((size_t)(L + 1) * nt * h * 128 * 2);
   const size_t o_go = take(nt * y.NOP * 128 * 2);
+  const size_t o_mk = take((size_t)(L + 1) * (h / 32) * nt * 128 * 4);
   const size_t o_sc = take(256);
   w.bytes = off;
   uint8_t* b = reinterpret_cast<uint8_t*>(base);
   if (b) {
     w.acts = (uint16_t*)(b + o_acts); w.enc_raw = (uint16_t*)(b + o_er); w.enc_act = (uint16_t*)(b + o_ea);
     w.dz = (uint16_t*)(b + o_dz); w.gout = (uint16_t*)(b + o_go);
-    w.scale = (float*)(b + o_sc);
+    w.scale = (float*)(b + o_sc); w.masks = (uint32_t*)(b + o_mk);
   }
   return w;
 }
@@ -331,6 +333,7 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
       const uint32_t base = tmem + slot * DN::COLS + lane_off;
       const uint32_t dM = base, dE = base + DN::MC, aA = base + DN::MC + DN::EC;
       uint32_t n_done = 0;
+      const int64_t mpad = ntiles * 128;
       for (int64_t t0 = (int64_t)blockIdx.x * NSLOT; t0 < ntiles; t0 += (int64_t)gridDim.x * NSLOT) {
         const int64_t tile = t0 + slot;
         if (tile >= ntiles) break;
@@ -358,27 +361,11 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
 #pragma unroll 1
         for (int i = 0; i <= L; ++i) {
           const int l = L - i;
-          // leaky_relu'(z_l): the sign bits of the saved a_l row of this sample (16-byte loads, packed into one word
-          // per 32 features while the layer's MMA is still in flight)
+          // leaky_relu'(z_l): the sign bits of a_l, written by the forward as one word per 32 features (coalesced over
+          // the samples); loaded before the wait so that the latency hides under the layer's MMA
           uint32_t mask[NC];
-          {
-            const uint16_t* arow = tile_row_ptr(ws.acts, (int64_t)l * ntiles + tile, H + kTileRowsExtra, lane_row);
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-              uint32_t w = 0;
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                const uint4 q = __ldg(reinterpret_cast<const uint4*>(arow + (4 * c + g) * 64));
-                const uint32_t r[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  w |= ((r[e] >> 15) & 1u) << (8 * g + 2 * e);
-                  w |= (r[e] >> 31) << (8 * g + 2 * e + 1);
-                }
-              }
-              mask[c] = w;
-            }
-          }
+          for (int c = 0; c < NC; ++c) mask[c] = __ldg(ws.masks + ((int64_t)(l * NC + c)) * mpad + m);
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
           uint16_t* zrow = tile_row_ptr(ws.dz, (int64_t)l * ntiles + tile, H, lane_row);
@@ -627,7 +614,7 @@ static bool matches(const MlpDev& d) {
 template <class NET, int FMT>
 static int train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_t M, float* out, const TrainWs& ws, cudaStream_t st) {
   IoTrainFwd<NET::IN, NET::OUT> io{x, out, out_act};
-  SaveTiles sv{ws.acts, ws.enc_raw, ws.enc_act, ws.ntiles};
+  SaveTiles sv{ws.acts, ws.enc_raw, ws.enc_act, ws.masks, ws.ntiles};
   const size_t bytes = (size_t)NET::SMEM_BYTES + 256;
   auto kern = k_mlp_tc<NET, decltype(io), FMT, SaveTiles>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));

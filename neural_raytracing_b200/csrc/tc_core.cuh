@@ -411,8 +411,20 @@ struct SaveTiles {
   uint16_t* acts;      // [L+1][ntiles] tiles of (H+16) x 128: a_l = act(z) feeding hidden layer l (l = L: output layer)
   uint16_t* enc_raw;   // [ntiles] tiles of (KE+16) x 128: the encoding as the init layer sees it
   uint16_t* enc_act;   // [ntiles] tiles of (KE+16) x 128: act(encoding) as the skip layers see it
+  uint32_t* masks;     // [L+1][H/32][ntiles*128]: sign bits of a_l (what leaky_relu' needs), one word per 32 features
   int64_t ntiles;
 };
+// sign bits of 16 packed 16-bit pairs (32 features) -> one word, bit j = sign of feature j
+__device__ __forceinline__ uint32_t sign_mask32(const uint32_t* pk) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    // high bytes of the four halves of two registers -> one register; keep the sign bits; gather them into a nibble
+    const uint32_t b = __byte_perm(pk[2 * q], pk[2 * q + 1], 0x7531) & 0x80808080u;
+    w |= ((b * 0x00204081u) >> 28) << (4 * q);
+  }
+  return w;
+}
 // thread-private view of one tile: pointer to (feature 0, this thread's sample)
 __device__ __forceinline__ uint16_t* tile_row_ptr(uint16_t* tiles, int64_t tile, int FR, int s) {
   return tiles + tile * (int64_t)(FR * 128) + (s >> 3) * (FR * 8) + (s & 7) * 8;
@@ -434,7 +446,7 @@ template <int FMT> __device__ __forceinline__ uint16_t one16() { return FMT == 0
 //  dD / aU already point at the thread's first column, col0 is that column's index for the saved tile)
 template <int ACT, int FMT, int H, bool SAVE = false>
 __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* save_row = nullptr, int col0 = 0,
-                                            int one_col = -1) {
+                                            int one_col = -1, uint32_t* mask_ptr = nullptr, int64_t mask_stride = 0) {
   static_assert(H % 32 == 0, "hidden width must be a multiple of 32");
   constexpr int NC = H / 32;
   uint32_t buf[2][32];
@@ -446,7 +458,10 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
     uint32_t pk[16];
     convert32<ACT, FMT>(buf[c & 1], pk);
     TmemIO<16>::st(aU + 16 * c, pk);
-    if constexpr (SAVE) save_cols<16>(save_row, col0 + 32 * c, pk);
+    if constexpr (SAVE) {
+      save_cols<16>(save_row, col0 + 32 * c, pk);
+      mask_ptr[(int64_t)(col0 / 32 + c) * mask_stride] = sign_mask32(pk);
+    }
     if (c + 1 < NC) tc_wait_ld();
   }
   if constexpr (SAVE) { if (one_col >= 0) save_row[tile_elem(one_col)] = one16<FMT>(); }
@@ -456,7 +471,8 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
 // memory, broadcast reads) accumulated on the fly; o[] must hold the output bias on entry.
 template <int ACT, int FMT, int H, int OUT, bool SAVE>
 __device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __restrict__ wout, float* __restrict__ o,
-                                                uint16_t* save_row = nullptr) {
+                                                uint16_t* save_row = nullptr, uint32_t* mask_ptr = nullptr,
+                                                int64_t mask_stride = 0) {
   static_assert(H % 32 == 0 && OUT <= 4, "fused output layer");
   constexpr int NC = H / 32;
   uint32_t buf[2][32];
@@ -496,7 +512,10 @@ __device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __rest
         for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(a[2 * i], a[2 * i + 1]);
       }
     }
-    if constexpr (SAVE) save_cols<16>(save_row, 32 * c, pk);
+    if constexpr (SAVE) {
+      save_cols<16>(save_row, 32 * c, pk);
+      mask_ptr[(int64_t)c * mask_stride] = sign_mask32(pk);
+    }
     if (c + 1 < NC) tc_wait_ld();
   }
   if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
@@ -957,7 +976,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           const int coff = half * HW;     // this thread's first hidden column
           if constexpr (SV::kOn)
             convert_row<NET::ACT, FMT, HW, true>(dD + coff, aU + coff / 2,
-                tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row), coff, primary ? H : -1);
+                tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row), coff, primary ? H : -1,
+                sv.masks + (int64_t)st * (H / 32) * (sv.ntiles * 128) + m, sv.ntiles * 128);
           else
             convert_row<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2);
           // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
@@ -989,7 +1009,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           for (int j = 0; j < NET::OUT; ++j) o[j] = sBias[s_bias[NET::STAGES - 1] + j];
           if constexpr (SV::kOn)
             convert_row_out<NET::ACT, FMT, H, NET::OUT, true>(dD, sBias + Y.wout_f32_off, o,
-                tile_row_ptr(sv.acts, (int64_t)L * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row));
+                tile_row_ptr(sv.acts, (int64_t)L * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row),
+                sv.masks + (int64_t)L * (H / 32) * (sv.ntiles * 128) + m, sv.ntiles * 128);
           else
             convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(dD, sBias + Y.wout_f32_off, o);
           if constexpr (ITER) { if (valid) io.consume(state, o); }
