@@ -122,3 +122,63 @@ def test_nerfle_through_pathtrace_sample():
     assert np.abs(rgb2.detach().cpu().numpy() - g["pt_rgb"]).max() < 1e-4
     rgb2.square().mean().backward()
     assert n.first.init.weight.grad.abs().sum() > 0 and n.second.out.weight.grad.abs().sum() > 0
+
+
+def test_colocate_style_pathtrace_tensor_core_precision():
+    """The same colocate-style render with config.set_precision("f16"): march, shadow march, min scan, NeuralBSDF and
+    occlusion MLPs on the tcgen05 kernels.  north_star gate for the 16-bit path: >= 50 dB PSNR on the rendered image
+    against the UNMODIFIED reference's output, radiance within 1e-3 on (nearly) all pixels."""
+    torch, P, g = _setup()
+    from neural_raytracing_b200 import config
+    from neural_raytracing_b200.pathtracer.cameras import NeRFCamera
+    size = 16
+    shape, sphere, bsdf, lights, integrator, w_isect = scenes.build_pipeline(P, "colocate", device="cuda")
+    c2w, focal = synth.nerf_cameras(1, size, device="cuda")
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cuda")
+    try:
+        config.set_precision("f16")
+        with torch.no_grad():
+            img, mi = P.pathtrace(shape, size=size, chunk_size=size, bundle_size=1, bsdf=bsdf, integrator=integrator,
+                                  lights=lights, cameras=cam, device="cuda", silent=True, background=0, w_isect=w_isect,
+                                  with_noise=False, addition=lambda it: it)
+    finally:
+        config.set_precision("f32")
+    img = img.cpu().numpy()
+    ref = g["colocate_img"]
+    err = np.abs(img - ref).max(axis=-1)
+    assert (err < 1e-3).mean() >= 0.95, (err.max(), (err < 1e-3).mean())
+    assert helpers.psnr(img, ref) > 50, helpers.psnr(img, ref)
+    assert abs(mi.raw_normals.shape[0] - g["colocate_raw_normals"].shape[0]) <= 2
+
+
+def test_nerfle_module_tensor_core_precision():
+    torch, P, g0 = _setup()
+    from neural_raytracing_b200 import config
+    from neural_raytracing_b200.pathtracer.shapes.nerf import NeRFLE
+    from neural_raytracing_b200.pathtracer.lights import PointLights
+    g = helpers.golden("nerfle")
+    random.random = lambda: float(g["fixed_random"])
+    n = NeRFLE(device="cuda")
+    w1, w2 = helpers.nerfle_weights(False)
+    for mod, w in ((n.first, w1), (n.second, w2)):
+        mod.basis_p = torch.from_numpy(w["basis"]).cuda()
+        for lin, W, b in zip([mod.init] + list(mod.layers) + [mod.out], w["W"], w["b"]):
+            with torch.no_grad():
+                lin.weight.copy_(torch.from_numpy(W)); lin.bias.copy_(torch.from_numpy(b))
+    rays = torch.from_numpy(g["pt_rays"]).cuda()
+    lights = PointLights(device="cuda", location=torch.from_numpy(g["pt_light_loc"]).cuda(), scale=10)
+    try:
+        config.set_precision("f16")
+        config.set_train_precision("f16")
+        with torch.no_grad():
+            rgb = n(rays, lights)
+        rgb2 = n(rays, lights)          # differentiable: tensor-core training forward + CUDA compositing
+        rgb2.square().mean().backward()
+    finally:
+        config.set_precision("f32")
+        config.set_train_precision("f32")
+    ref = g["pt_rgb"]
+    assert np.abs(rgb.cpu().numpy() - ref).max() < 1e-3 and helpers.psnr(rgb.cpu().numpy(), ref) > 60
+    assert np.abs(rgb2.detach().cpu().numpy() - ref).max() < 1e-3
+    assert torch.isfinite(n.first.init.weight.grad).all() and n.first.init.weight.grad.abs().sum() > 0
+    assert n.second.out.weight.grad.abs().sum() > 0
