@@ -621,7 +621,7 @@ static int train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_
   const int grid = (int)std::min<int64_t>((ws.ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
   {
     NrtProfScope _ps(TAG_TC_TRAIN_FWD, st);
-    kern<<<grid, NET::WPS * 64 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, nullptr, sv);
+    kern<<<grid, NET::NWG * NET::WPS * 32 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, nullptr, sv);
   }
   NRT_CUDA(cudaGetLastError());
   NRT_CUDA(cudaGetLastError());

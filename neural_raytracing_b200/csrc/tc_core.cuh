@@ -521,6 +521,20 @@ __device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __rest
   if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
 }
 
+// leaky_relu on a packed 16-bit pair
+template <int FMT>
+__device__ __forceinline__ uint32_t leaky_packed(uint32_t v) {
+  if constexpr (FMT == 0) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&v);
+    const __half2 r = __hmax2(h, __hmul2(h, __floats2half2_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  } else {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&v);
+    const __nv_bfloat162 r = __hmax2(h, __hmul2(h, __floats2bfloat162_rn(0.01f, 0.01f)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+}
+
 // D[lane][0..N) = bias[0..N): the next layer's MMA then only accumulates (no bias add in its epilogue)
 template <int N>
 __device__ __forceinline__ void preload_bias(uint32_t dD, const float* __restrict__ bias) {
@@ -553,10 +567,22 @@ struct Net {
   static constexpr bool SPLIT = Y.split != 0;
   static constexpr int XR = Y.XR, KE = Y.KE, KX = Y.KX, FP = Y.FP, NOP = Y.NOP, KRAW = Y.KRAW;
   static constexpr int DC = imax(H, imax(NOP, FP));       // fp32 accumulator columns
-  static constexpr int UC = imax(H, imax(KE, KX)) / 2;    // union region: encode A / enc_raw / hidden
-  static constexpr int EC = KE / 2;                       // act(enc) region
+  // TMEM plan per tile slot.  Standard: accumulator | union region (phase-GEMM operand -> raw encoding -> hidden
+  // activations) | act(encoding).  In-place plan: the raw encoding is written into the encoding region, read there by
+  // the init layer's MMA, and converted to act(encoding) IN PLACE by the first hidden epilogue (nothing reads the raw
+  // encoding after the init layer); the union region then only holds the phase operand / hidden activations.  It is
+  // used when it buys another tile slot (NeRFLE.second: 176 -> 160 columns = three tiles in flight).
+  static constexpr int EC = KE / 2;                       // (act) encoding region
+  static constexpr int UC_STD = imax(H, imax(KE, KX)) / 2;
+  static constexpr int UC_INP = imax(H, KX) / 2;
+  static constexpr int kMaxSlots = 3;
+  static constexpr int slots_of(int cols) { return 512 / cols < kMaxSlots ? 512 / cols : kMaxSlots; }
+  static constexpr bool INPLACE = (ACT == NRT_ACT_LEAKY_RELU) && LAT == 0 &&
+                                  slots_of(DC + UC_INP + EC) > slots_of(DC + UC_STD + EC);
+  static constexpr int UC = INPLACE ? UC_INP : UC_STD;
   static constexpr int COLS = DC + UC + EC;
-  static constexpr int NSLOT = (2 * COLS <= 512) ? 2 : 1;
+  static constexpr int NSLOT = slots_of(COLS);
+  static constexpr int NWG = NSLOT < 2 ? 2 : NSLOT;       // epilogue warpgroups launched
   static constexpr int STAGES = L + 3;                    // encode, init, L layers, out
   // Two of those stages need no tensor core and cost a full MMA -> commit -> wait round trip each:
   //  * split-precision inputs (in <= 5): the Fourier phases are in*F FMAs per sample -> computed in fp32 by the
@@ -605,7 +631,9 @@ __device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32
                              ((uint32_t)(128 >> 4) << 24);
   constexpr uint32_t lbo = N * 16, sbo = 128;
   constexpr int kch = Y.opK[ST] / 16;
-  constexpr int k_u = (ST >= 2 && ST < NET::STAGES - 1) ? NET::H / 16 : kch;   // K chunks taken from U
+  // K chunks taken from U: the hidden part of a hidden layer; everything for the other stages, except that the
+  // in-place plan keeps the (raw) encoding in the encoding region for the init layer
+  constexpr int k_u = (ST >= 2 && ST < NET::STAGES - 1) ? NET::H / 16 : ((NET::INPLACE && ST == 1) ? 0 : kch);
   if (elect_one()) {
     const uint64_t bd0 = make_desc(b_addr, lbo, sbo);
 #pragma unroll
@@ -654,13 +682,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <class NET, class IO, int FMT, class SV = NoSave, int WPS = NET::WPS>
-__global__ void __launch_bounds__(WPS * 64 + 32, 1)
+__global__ void __launch_bounds__(NET::NWG * WPS * 32 + 32, 1)
 k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg, SV sv = SV{}) {
   constexpr int EPI = WPS * 32;                 // epilogue threads per tile slot
   // dbg (development only, tools/tc_timeline.py): clock64 stamps of CTA 0 for a few tile iterations
   constexpr int kDbgIt0 = 4, kDbgIts = 4;
   auto stamp = [&](int it, int st, int slot, int k) {
-    if (dbg != nullptr && blockIdx.x == 0 && it >= kDbgIt0 && it < kDbgIt0 + kDbgIts)
+    if (dbg != nullptr && slot < 2 && blockIdx.x == 0 && it >= kDbgIt0 && it < kDbgIt0 + kDbgIts)
       dbg[(((it - kDbgIt0) * NET::STAGES + st) * 2 + slot) * 8 + k] = clock64();
   };
   using E = Elem<FMT>;
@@ -672,19 +700,19 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   uint16_t* sW = reinterpret_cast<uint16_t*>(smem);
   const float* sBias = reinterpret_cast<const float*>(smem + (STREAM ? (size_t)NSLOT * 2 * NET::MAXOP : (size_t)Y.w_elems * 2));
   __shared__ __align__(8) uint64_t bar_w;
-  __shared__ __align__(8) uint64_t bar_wfull[2][2];   // streaming: stage buffer b of slot s has landed
+  __shared__ __align__(8) uint64_t bar_wfull[3][2];   // streaming: stage buffer b of slot s has landed
   __shared__ uint32_t s_opoff[NET::STAGES], s_opbytes[NET::STAGES];
-  __shared__ __align__(8) uint64_t bar_ready[2];
-  __shared__ __align__(8) uint64_t bar_done[2];
+  __shared__ __align__(8) uint64_t bar_ready[3];
+  __shared__ __align__(8) uint64_t bar_done[3];
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_bias[NET::STAGES];
   constexpr bool ITER = IsIterative<IO>::value;
-  __shared__ volatile uint32_t s_slot_live[2];   // iterative policies: 0 once the slot's queue has run dry
-  __shared__ uint32_t s_warp_live[2][4];
+  __shared__ volatile uint32_t s_slot_live[3];   // iterative policies: 0 once the slot's queue has run dry
+  __shared__ uint32_t s_warp_live[3][4];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const bool is_mma_warp = warp == 2 * WPS;
+  const bool is_mma_warp = warp == NET::NWG * WPS;
   const int64_t ntiles = (M + 127) / 128;
   if (tid < NET::STAGES) {
     s_bias[tid] = (uint32_t)Y.bias_off[tid];
@@ -693,9 +721,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   }
 
   if (tid == 0) {
-    s_slot_live[0] = 1; s_slot_live[1] = 1;
+    s_slot_live[0] = 1; s_slot_live[1] = 1; s_slot_live[2] = 1;
     mbar_init(&bar_w, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 3; ++s) {
       mbar_init(&bar_ready[s], EPI); mbar_init(&bar_done[s], 1);
       mbar_init(&bar_wfull[s][0], 1); mbar_init(&bar_wfull[s][1], 1);
     }
@@ -733,12 +761,12 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     // whatever order they become ready, so the two tiles drift into anti-phase: the tensor pipe works
     // on one tile while the other tile's epilogue (or prologue / output store) runs.
     const uint32_t sW_addr = smem_u32(sW);
-    int st[2] = {NET::FIRST_STAGE, NET::FIRST_STAGE};
-    uint32_t n_ready[2] = {0, 0};
-    int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
-    bool live[2] = {ITER || tile[0] < ntiles, NSLOT > 1 && (ITER || tile[1] < ntiles)};
-    int it_dbg[2] = {0, 0};
-    uint32_t n_issued[2] = {0, 0};      // streaming: stages issued per slot (selects the stage buffer)
+    int st[3] = {NET::FIRST_STAGE, NET::FIRST_STAGE, NET::FIRST_STAGE};
+    uint32_t n_ready[3] = {0, 0, 0};
+    int64_t tile[3] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1, (int64_t)blockIdx.x * NSLOT + 2};
+    bool live[3] = {ITER || tile[0] < ntiles, NSLOT > 1 && (ITER || tile[1] < ntiles), NSLOT > 2 && (ITER || tile[2] < ntiles)};
+    int it_dbg[3] = {0, 0, 0};
+    uint32_t n_issued[3] = {0, 0, 0};   // streaming: stages issued per slot (selects the stage buffer)
     if (STREAM) {
 #pragma unroll
       for (int slot = 0; slot < NSLOT; ++slot)
@@ -747,7 +775,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
                     &bar_wfull[slot][0]);
       __syncwarp();
     }
-    while (live[0] || live[1]) {
+    while (live[0] || live[1] || live[2]) {
       bool progressed = false;
 #pragma unroll
       for (int slot = 0; slot < NSLOT; ++slot) {
@@ -883,13 +911,14 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             }
           }
           tmem_store<NET::KX / 2>(aU, ax);
-          tmem_store<NET::XR / 2>(aE, ex);
+          if constexpr (NET::INPLACE) tmem_store<NET::XR / 2>(aE, ax);   // raw x part; activated in place later
+          else tmem_store<NET::XR / 2>(aE, ex);
           if constexpr (SV::kOn) {
             static_assert(!ITER, "activation tiles are saved by the tile policies only");
             uint16_t* rr = tile_row_ptr(sv.enc_raw, m >> 7, NET::KE + kTileRowsExtra, lane_row);
             uint16_t* ra = tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row);
             save_cols<NET::KX / 2>(rr, 0, ax);
-            save_cols<NET::XR / 2>(ra, 0, ex);
+            if constexpr (!NET::INPLACE) save_cols<NET::XR / 2>(ra, 0, ex);
             rr[tile_elem(NET::KE)] = one16<FMT>();
             ra[tile_elem(NET::KE)] = one16<FMT>();
           }
@@ -945,17 +974,24 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             sa[j] = E::pack(act_fast<NET::ACT>(s0), act_fast<NET::ACT>(s1));
             ca[j] = E::pack(act_fast<NET::ACT>(c0), act_fast<NET::ACT>(c1));
           }
-          tmem_store<F / 2>(aU + NET::XR / 2, sr);
-          tmem_store<F / 2>(aU + NET::XR / 2 + F / 2, cr);
-          tmem_store<F / 2>(aE + NET::XR / 2, sa);
-          tmem_store<F / 2>(aE + NET::XR / 2 + F / 2, ca);
+          if constexpr (NET::INPLACE) {
+            tmem_store<F / 2>(aE + NET::XR / 2, sr);
+            tmem_store<F / 2>(aE + NET::XR / 2 + F / 2, cr);
+          } else {
+            tmem_store<F / 2>(aU + NET::XR / 2, sr);
+            tmem_store<F / 2>(aU + NET::XR / 2 + F / 2, cr);
+            tmem_store<F / 2>(aE + NET::XR / 2, sa);
+            tmem_store<F / 2>(aE + NET::XR / 2 + F / 2, ca);
+          }
           if constexpr (SV::kOn) {
             uint16_t* rr = tile_row_ptr(sv.enc_raw, m >> 7, NET::KE + kTileRowsExtra, lane_row);
             uint16_t* ra = tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row);
             save_cols<F / 2>(rr, NET::XR, sr);
             save_cols<F / 2>(rr, NET::XR + F, cr);
-            save_cols<F / 2>(ra, NET::XR, sa);
-            save_cols<F / 2>(ra, NET::XR + F, ca);
+            if constexpr (!NET::INPLACE) {
+              save_cols<F / 2>(ra, NET::XR, sa);
+              save_cols<F / 2>(ra, NET::XR + F, ca);
+            }
           }
           // (the raw-x segment keeps the phase-GEMM tile [x_hi | x_lo | x_hi | 0]; the init / skip weights
           //  of the third copy and of the padding are zero, see enc_ref_index)
@@ -982,6 +1018,23 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             convert_row<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2);
           // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
           // the conversion so the accumulator registers are dead and all LDS.128 can be in flight
+          if constexpr (NET::INPLACE) {
+            if (st == 0 && primary) {
+              // the init layer has consumed the raw encoding: turn it into act(encoding) for the skip layers
+              static_assert(NET::KE % 16 == 0, "encoding width");
+#pragma unroll
+              for (int c = 0; c < NET::EC / 8; ++c) {
+                uint32_t e[8];
+                TmemIO<8>::ld(aE + 8 * c, e);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) e[j] = leaky_packed<FMT>(e[j]);
+                TmemIO<8>::st(aE + 8 * c, e);
+                if constexpr (SV::kOn)
+                  save_cols<8>(tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row), 16 * c, e);
+              }
+            }
+          }
           if (st < L) preload_bias<HW>(dD + coff, sBias + s_bias[2 + st] + coff);
           else {
             // output-layer bias: every half writes only the accumulator columns it has just read
