@@ -18,6 +18,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I" + os.pat
           "-I" + CSRC]
 # per-translation-unit extra flags.  The fp32 "exact" path must not contract a*b+c on its own:
 # every fused multiply-add there is an explicit fmaf (see include/nrt_detmath.h).
+EXTRA_ENV = os.environ.get("NRT_EXTRA_NVCC_FLAGS", "").split()
 EXTRA = {
     "nrt_f32.cu": ["-fmad=false"],
     "nrt_f32_bwd.cu": ["-fmad=false"],
@@ -45,7 +46,7 @@ def _digest(path, flags):
 
 def _compile(src):
     name = os.path.basename(src)
-    flags = ARCH + COMMON + EXTRA.get(name, [])
+    flags = ARCH + COMMON + EXTRA.get(name, []) + EXTRA_ENV
     obj = os.path.join(OBJ, name + ".o")
     stamp = obj + ".sha"
     dg = _digest(src, flags)

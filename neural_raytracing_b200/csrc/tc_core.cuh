@@ -635,7 +635,9 @@ __device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32
   // in-place plan keeps the (raw) encoding in the encoding region for the init layer
   constexpr int k_u = (ST >= 2 && ST < NET::STAGES - 1) ? NET::H / 16 : ((NET::INPLACE && ST == 1) ? 0 : kch);
   if (elect_one()) {
-    const uint64_t bd0 = make_desc(b_addr, lbo, sbo);
+    // resident weights: b_addr is the base of the weight area and the operand offset is a compile-time constant;
+    // streamed weights: b_addr is the stage buffer
+    const uint64_t bd0 = make_desc(NET::STREAM ? b_addr : b_addr + (uint32_t)Y.op_off[ST] * 2u, lbo, sbo);
 #pragma unroll
     for (int kc = 0; kc < kch; ++kc) {
       const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
@@ -647,13 +649,20 @@ __device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32
   }
   __syncwarp();
 }
-template <class NET, int FMT, int ST = 0>
+// runtime stage -> compile-time stage through a jump table (a linear if-chain cost up to ~150 cycles of taken
+// branches per stage on the single issuing warp, which serves every tile slot)
+template <class NET, int FMT>
 __device__ __forceinline__ void issue_stage_dyn(int st, uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE,
                                                 uint64_t* done_bar) {
-  if constexpr (ST < NET::STAGES) {
-    if (st == ST) issue_stage<NET, FMT, ST>(b_addr, dD, aU, aE, done_bar);
-    else issue_stage_dyn<NET, FMT, ST + 1>(st, b_addr, dD, aU, aE, done_bar);
+#define NRT_STAGE_CASE(S) case S: if constexpr (S < NET::STAGES) issue_stage<NET, FMT, S>(b_addr, dD, aU, aE, done_bar); break;
+  switch (st) {
+    NRT_STAGE_CASE(0) NRT_STAGE_CASE(1) NRT_STAGE_CASE(2) NRT_STAGE_CASE(3) NRT_STAGE_CASE(4) NRT_STAGE_CASE(5)
+    NRT_STAGE_CASE(6) NRT_STAGE_CASE(7) NRT_STAGE_CASE(8) NRT_STAGE_CASE(9) NRT_STAGE_CASE(10) NRT_STAGE_CASE(11)
+    NRT_STAGE_CASE(12) NRT_STAGE_CASE(13) NRT_STAGE_CASE(14) NRT_STAGE_CASE(15) NRT_STAGE_CASE(16) NRT_STAGE_CASE(17)
+    NRT_STAGE_CASE(18) NRT_STAGE_CASE(19) NRT_STAGE_CASE(20) NRT_STAGE_CASE(21) NRT_STAGE_CASE(22)
+    default: break;
   }
+#undef NRT_STAGE_CASE
 }
 // bulk copy of one stage operand (<= 32 KB pieces) from the blob into a stage buffer; completes on `bar`
 __device__ __forceinline__ void stream_op(uint8_t* dst, const uint8_t* src, uint32_t bytes, uint64_t* bar) {
@@ -752,7 +761,11 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  // The whole TMEM (512 columns) is allocated, so the base address is lane 0 / column 0.  Treating it as the
+  // compile-time constant 0 lets every tcgen05.mma operand of a (slot, stage) pair be an immediate: otherwise the
+  // base comes out of shared memory into a vector register and costs ~7 R2UR moves in front of every stage.
+  if (tmem_base_s != 0u) __trap();
+  constexpr uint32_t tmem = 0u;
   mbar_wait(&bar_w, 0);
 
   if (is_mma_warp) {
@@ -795,7 +808,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         }
         if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 1);
         const uint32_t base = tmem + slot * NET::COLS;
-        uint32_t b_addr = sW_addr + s_opoff[st[slot]];
+        uint32_t b_addr = sW_addr;
         if (STREAM) {
           const uint32_t b = n_issued[slot] & 1;
           mbar_wait(&bar_wfull[slot][b], (n_issued[slot] >> 1) & 1);
@@ -824,7 +837,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         }
       }
       // this warp shares an SM sub-partition with two epilogue warps: do not burn their issue slots
-      if (!progressed) __nanosleep(32);
+#ifndef NRT_MMA_POLL_SLEEP_NS
+#define NRT_MMA_POLL_SLEEP_NS 32
+#endif
+      if (NRT_MMA_POLL_SLEEP_NS > 0 && !progressed) __nanosleep(NRT_MMA_POLL_SLEEP_NS);
     }
   } else {
     // ===================== epilogue warpgroups (one per tile slot) =====================
