@@ -47,46 +47,85 @@ __global__ void k_stratified_ts(int64_t R, int64_t r_off, int S, float t_near, f
 }
 
 // ---- importance resampling (standard NeRF sample_pdf, inverse CDF over the coarse bins) ----------
-// One thread per ray.  weights come from the coarse pass with the reference's compositing formula.
-__global__ void k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_shared,
-                             const float* __restrict__ ts_c_per_ray, int Sc, int Sf, int64_t R, int64_t r_off,
-                             uint64_t seed, float* __restrict__ ts_f) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
-  const float* sig = sigma_c + r * Sc;
-  const float* tc = ts_c_per_ray ? ts_c_per_ray + r * Sc : ts_c_shared;
-  // total weight (interior samples 1..Sc-2 define Sc-2 bins between mid points, as in NeRF)
-  float cp = 1.0f, total = 0.0f;
-  for (int s = 0; s < Sc; ++s) {
-    const float a = 1.0f - __expf(-fmaxf(sig[s], 0.0f) * tc[s]);
-    if (s >= 1 && s <= Sc - 2) total += a * cp + 1e-5f;
-    cp *= fmaxf(1.0f - a, 1e-10f);
-  }
-  // walk the CDF once while emitting the Sf sorted samples
-  float* out = ts_f + r * Sf;
-  int s = 1;
-  cp = 1.0f;
-  {
-    const float a0 = 1.0f - __expf(-fmaxf(sig[0], 0.0f) * tc[0]);
-    cp *= fmaxf(1.0f - a0, 1e-10f);
-  }
-  float a = 1.0f - __expf(-fmaxf(sig[1], 0.0f) * tc[1]);
-  float w = (a * cp + 1e-5f) / total;
-  float cdf_lo = 0.0f;
-  for (int j = 0; j < Sf; ++j) {
-    const float jit = seed ? hash_u01(seed ^ 0x5bd1e995u, (uint64_t)(r + r_off), (uint64_t)j) : 0.5f;
-    const float u = ((float)j + jit) / (float)Sf;
-    while (s < Sc - 2 && u > cdf_lo + w) {
-      cdf_lo += w;
-      cp *= fmaxf(1.0f - a, 1e-10f);
-      ++s;
-      a = 1.0f - __expf(-fmaxf(sig[s], 0.0f) * tc[s]);
-      w = (a * cp + 1e-5f) / total;
+// One WARP per ray (HBM-bound: 8 B per coarse sample read, 4 B per fine sample written, both coalesced): every lane
+// owns a contiguous run of coarse samples; transmittance = exclusive warp-scan product, cdf = inclusive warp-scan sum
+// (weights from the coarse pass with the reference's compositing formula, interior samples 1..Sc-2 as in NeRF), then
+// lane j, j+32, ... binary-search the cdf in shared memory and write the fine distances.
+constexpr int kPdfWarps = 4;
+__global__ void __launch_bounds__(kPdfWarps * 32)
+k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_shared,
+             const float* __restrict__ ts_c_per_ray, int Sc, int Sf, int64_t R, int64_t r_off,
+             uint64_t seed, float* __restrict__ ts_f) {
+  extern __shared__ float sm[];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* s_t = sm + (size_t)wid * 3 * Sc;
+  float* s_cdf = s_t + Sc;     // inclusive cdf over the interior samples (index = sample)
+  float* s_pdf = s_cdf + Sc;
+  const int per = (Sc + 31) / 32;
+  for (int64_t r = (int64_t)blockIdx.x * kPdfWarps + wid; r < R; r += (int64_t)gridDim.x * kPdfWarps) {
+    const float* sig = sigma_c + r * Sc;
+    const float* tc = ts_c_per_ray ? ts_c_per_ray + r * Sc : ts_c_shared;
+    const int e0 = lane * per, e1 = min(Sc, e0 + per);
+    // alpha and the local transmittance product of this lane's run
+    float prod = 1.0f;
+    for (int e = e0; e < e1; ++e) {
+      const float t = tc[e];
+      s_t[e] = t;
+      const float a = 1.0f - __expf(-fmaxf(sig[e], 0.0f) * t);
+      s_pdf[e] = a;                                  // alpha for now
+      prod *= fmaxf(1.0f - a, 1e-10f);
     }
-    const float lo = 0.5f * (tc[s - 1] + tc[s]);
-    const float hi = 0.5f * (tc[s] + tc[s + 1]);
-    const float f = fminf(fmaxf((u - cdf_lo) / w, 0.0f), 1.0f);
-    out[j] = lo + f * (hi - lo);
+    float incl = prod;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl *= v;
+    }
+    float cp = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) cp = 1.0f;
+    // un-normalised weights of the interior samples and their local sum
+    float wsum = 0.0f;
+    for (int e = e0; e < e1; ++e) {
+      const float a = s_pdf[e];
+      const float w = (e >= 1 && e <= Sc - 2) ? a * cp + 1e-5f : 0.0f;
+      s_pdf[e] = w;
+      wsum += w;
+      cp *= fmaxf(1.0f - a, 1e-10f);
+    }
+    float run = wsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float v = __shfl_up_sync(0xffffffffu, run, o);
+      if (lane >= o) run += v;
+    }
+    const float total = __shfl_sync(0xffffffffu, run, 31);
+    float c = run - wsum;                            // exclusive prefix of this lane's run
+    const float inv = 1.0f / total;
+    for (int e = e0; e < e1; ++e) {
+      const float p = s_pdf[e] * inv;
+      c += s_pdf[e];
+      s_pdf[e] = p;
+      s_cdf[e] = c * inv;
+    }
+    __syncwarp();
+    float* out = ts_f + r * Sf;
+    for (int j = lane; j < Sf; j += 32) {
+      const float jit = seed ? hash_u01(seed ^ 0x5bd1e995u, (uint64_t)(r + r_off), (uint64_t)j) : 0.5f;
+      const float u = ((float)j + jit) / (float)Sf;
+      // first interior sample s in [1, Sc-2] with u <= cdf[s]; the last one otherwise
+      int lo = 1, hi = Sc - 2;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (u > s_cdf[mid]) lo = mid + 1; else hi = mid;
+      }
+      const int sidx = lo;
+      const float p = s_pdf[sidx];
+      const float f = fminf(fmaxf((u - (s_cdf[sidx] - p)) / p, 0.0f), 1.0f);
+      const float tl = 0.5f * (s_t[sidx - 1] + s_t[sidx]);
+      const float th = 0.5f * (s_t[sidx] + s_t[sidx + 1]);
+      out[j] = tl + f * (th - tl);
+    }
+    __syncwarp();
   }
 }
 
@@ -249,7 +288,9 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
     if (rc != NRT_OK) return rc;
     if (Sf > 0) {
       { NrtProfScope _ps(TAG_SAMPLE_PDF, st);
-      k_sample_pdf<<<nrt_cdiv(n, 128), 128, 0, st>>>(sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f); }
+      const int grid = (int)std::min<int64_t>((n + kPdfWarps - 1) / kPdfWarps, (int64_t)nrt_sm_count() * 16);
+      k_sample_pdf<<<grid, kPdfWarps * 32, (size_t)kPdfWarps * 3 * Sc * sizeof(float), st>>>(
+          sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f); }
       NRT_CUDA(cudaGetLastError());
       rc = nerf_pass(first, second, prec, c_rays, n, nullptr, ts_f, Sf, light_code, light_dim, c_view, nullptr,
                      sig_f, rgb_f, tcws, tcws_bytes, st);
