@@ -181,6 +181,42 @@ def gen_nerfle():
     print("nerfle.npz rgb mean", float(out["pt_rgb"].mean()), float(out["le_rgb"].mean()))
 
 
+def gen_nerfle_train():
+    """nerfle.py:104-116-style step on the UNMODIFIED reference: NeRFLE forward -> mse -> backward.  Stores the loss and
+    the gradient of every Linear (flattened in module order) for the point-light and the environment-light model."""
+    out = {}
+    random.random = lambda: FIXED_RANDOM
+    for tag, envmap in (("pt", False), ("le", True)):
+        n = NeRFLE(envmap=envmap, device="cpu")
+        w1 = synth.mlp_weights(seed=31, in_size=3, out=65, num_layers=5, hidden=128, freqs=16, sigma=32.0)
+        in2 = 64 + (6 if not envmap else 3 + 16 * 3)
+        w2 = synth.mlp_weights(seed=32 + envmap, in_size=in2, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0)
+        w1["b"][-1][0] = 0.8
+        load_mlp(n.first, w1)
+        load_mlp(n.second, w2)
+        N, Wd, Hd = 2, 16, 12
+        rays = synth.camera_rays(35, N * Wd * Hd).reshape(N, Wd, Hd, 1, 6)
+        loc = np.array([[0.4, 1.0, 0.3], [-0.8, 0.5, 0.6]], np.float32)
+        lights = PointLights(device="cpu", location=T(loc), scale=10)
+        target = torch.full((N, Wd, Hd, 1, 3), 0.5)
+        rgb = n(T(rays), lights)
+        loss = F.mse_loss(rgb, target)           # nerfle.py:113
+        loss.backward()
+        out[tag + "_rays"] = rays
+        out[tag + "_light_loc"] = loc
+        out[tag + "_loss"] = np.array(loss.item(), np.float64)
+        out[tag + "_rgb"] = rgb.detach().numpy()
+        for name, mod in (("first", n.first), ("second", n.second)):
+            lins = [mod.init] + list(mod.layers) + [mod.out]
+            out["%s_g_%s_w" % (tag, name)] = np.concatenate([l.weight.grad.numpy().ravel() for l in lins])
+            out["%s_g_%s_b" % (tag, name)] = np.concatenate([l.bias.grad.numpy().ravel() for l in lins])
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("shapes/nerf.py:175-214 NeRFLE.forward + torch autograd of F.mse_loss (scripts/nerfle.py:113-116)")
+    np.savez_compressed(os.path.join(HERE, "nerfle_train.npz"), **out)
+    print("nerfle_train.npz: loss pt %.6f le %.6f, |g first| %.3e" % (out["pt_loss"], out["le_loss"],
+                                                                      np.linalg.norm(out["pt_g_first_w"])))
+
+
 def gen_composite():
     rs = np.random.RandomState(41)
     out = {}
@@ -284,7 +320,7 @@ def gen_pipeline():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "composite", "shading", "pipeline"]
+    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()

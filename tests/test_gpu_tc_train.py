@@ -224,3 +224,48 @@ def test_graphed_training_step_matches_eager():
     # packed-parameter caches are invalidated by GraphedStep): its loss equals what the next replay computes
     next_loss = float(step().detach())
     assert abs(eager_loss - next_loss) < 2e-3 * max(1.0, next_loss), (eager_loss, next_loss, losses_b)
+
+
+@pytest.mark.parametrize("envmap", [False, True])
+@pytest.mark.parametrize("tprec,loss_tol,min_cos", [("f32", 2e-5, 0.9999), ("f16", 1e-3, 0.985)])
+def test_nerfle_training_step_vs_unmodified_reference(envmap, tprec, loss_tol, min_cos):
+    """Loss and the gradient of every Linear of a nerfle.py-style step (NeRFLE forward -> mse -> backward) against the
+    fixture produced by the UNMODIFIED reference on CPU fp32 (tests/golden/make_golden.py::gen_nerfle_train).  Exact
+    fp32 kernels: cosine >= 0.9999; tensor-core training kernels (fp16 operands): >= 0.985 over all weights of an MLP
+    (the forward's rounding moves leaky_relu kinks, see the module docstring); 0.96 for the environment-light model,
+    whose 115 second-MLP inputs enter the sigma = 32 Fourier phases rounded to fp16 (phase error ~0.05 rad)."""
+    import random
+    import torch
+    from neural_raytracing_b200 import config
+    from neural_raytracing_b200.pathtracer.lights import PointLights
+    from neural_raytracing_b200.pathtracer.shapes.nerf import NeRFLE
+    g = helpers.golden("nerfle_train")
+    tag = "le" if envmap else "pt"
+    random.random = lambda: float(g["fixed_random"])
+    n = NeRFLE(envmap=envmap, device="cuda")
+    w1, w2 = helpers.nerfle_weights(envmap)
+    for mod, w in ((n.first, w1), (n.second, w2)):
+        mod.basis_p = torch.from_numpy(w["basis"]).cuda()
+        for lin, W, b in zip([mod.init] + list(mod.layers) + [mod.out], w["W"], w["b"]):
+            with torch.no_grad():
+                lin.weight.copy_(torch.from_numpy(W)); lin.bias.copy_(torch.from_numpy(b))
+    rays = torch.from_numpy(g[tag + "_rays"]).cuda()
+    lights = PointLights(device="cuda", location=torch.from_numpy(g[tag + "_light_loc"]).cuda(), scale=10)
+    target = torch.full(tuple(rays.shape[:-1]) + (3,), 0.5, device="cuda")
+    try:
+        config.set_train_precision(tprec)
+        loss = torch.nn.functional.mse_loss(n(rays, lights), target)
+        loss.backward()
+    finally:
+        config.set_train_precision("f32")
+    ref_loss = float(g[tag + "_loss"])
+    assert abs(float(loss.detach()) - ref_loss) <= loss_tol * max(1.0, ref_loss), (float(loss.detach()), ref_loss)
+    for name, mod in (("first", n.first), ("second", n.second)):
+        lins = [mod.init] + list(mod.layers) + [mod.out]
+        gw = torch.cat([l.weight.grad.reshape(-1) for l in lins]).cpu().numpy().astype(np.float64)
+        gb = torch.cat([l.bias.grad.reshape(-1) for l in lins]).cpu().numpy().astype(np.float64)
+        for got, key in ((gw, "%s_g_%s_w" % (tag, name)), (gb, "%s_g_%s_b" % (tag, name))):
+            ref = g[key].astype(np.float64)
+            cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
+            assert cos > (0.96 if (envmap and tprec == "f16") else min_cos), (key, tprec, cos)
+            assert abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) < (1e-3 if tprec == "f32" else 3e-2), key
