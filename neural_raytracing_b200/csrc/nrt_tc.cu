@@ -223,46 +223,51 @@ struct IoMarch {
 };
 
 // a5: SDF.throughput min-along-ray scan (sdfs.py:232-249): n_steps+1 evaluations per ray, strict-< running argmin.
-struct IoMinScan {
+// The scan positions do not depend on the SDF values, so the scan is a BATCHED evaluation (sample m = ray * (n+1) + k,
+// every MMA row busy whatever the ray count; the per-thread state machine of the march would serialise the n+1
+// evaluations of a ray: 129 x ~25 us for a small ray batch) followed by a warp-per-ray argmin.
+struct IoScanEval {
   SdfDev sd;
-  const float* rays; int64_t R; double step; int n_steps;
-  int32_t* best_idx; float* best_pos; float* min_val; unsigned long long* counter;
-  struct State { float o[3], d[3], p[3], cur_min; int j, idx; long long r; bool dry; };
-  __device__ __forceinline__ void init(State& s) const { s.r = -1; s.dry = false; s.j = 0; s.idx = 0; s.cur_min = 0.0f; }
-  __device__ __forceinline__ bool next(State& s, float* x) const {
-    if (s.r >= 0 && s.j > n_steps) {
-      best_idx[s.r] = s.idx;
-      if (min_val) min_val[s.r] = s.cur_min;
-      const float tb = __fmul_rn((float)s.idx, (float)step);   // best_pos = r_o + (idx.float() * fl32(step)) * d
+  const float* rays; double step; int n1; float* val;
+  __device__ __forceinline__ void point(int64_t m, float* p) const {
+    const int64_t ray = m / n1;
+    const int k = (int)(m - ray * n1);
+    const float* rp = rays + ray * 6;
+    const float t = (float)(step * (double)k);   // python float (double) product, rounded to fp32 when it scales d
 #pragma unroll
-      for (int j = 0; j < 3; ++j) best_pos[s.r * 3 + j] = __fadd_rn(s.o[j], __fmul_rn(tb, s.d[j]));
-      s.r = -1;
-    }
-    const bool need = s.r < 0 && !s.dry;
-    const long long r = grab_ray(counter, R, need);
-    if (need) {
-      if (r < 0) s.dry = true;
-      else {
-        const float* rp = rays + r * 6;
-        s.o[0] = __ldg(rp); s.o[1] = __ldg(rp + 1); s.o[2] = __ldg(rp + 2);
-        s.d[0] = __ldg(rp + 3); s.d[1] = __ldg(rp + 4); s.d[2] = __ldg(rp + 5);
-        s.j = 0; s.r = r;
-      }
-    }
-    if (s.r < 0) return false;
-    const float t = (float)(step * (double)s.j);
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { s.p[j] = (s.j == 0) ? s.o[j] : __fadd_rn(s.o[j], __fmul_rn(t, s.d[j])); x[j] = s.p[j]; }
-    return true;
+    for (int j = 0; j < 3; ++j) p[j] = (k == 0) ? __ldg(rp + j) : __fadd_rn(__ldg(rp + j), __fmul_rn(t, __ldg(rp + 3 + j)));
   }
-  __device__ __forceinline__ void consume(State& s, const float* o) const {
-    const float v = sphere_smin_fast(sd, s.p[0], s.p[1], s.p[2]) + o[0];
-    if (s.j == 0) { s.cur_min = v; s.idx = 0; }
-    else { if (v < s.cur_min) s.idx = s.j; s.cur_min = fminf(s.cur_min, v); }
-    s.j++;
+  __device__ __forceinline__ void load(int64_t m, float* x) const { point(m, x); }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+    float p[3];
+    point(m, p);
+    val[m] = sphere_smin_fast(sd, p[0], p[1], p[2]) + o[0];
   }
-  __device__ __forceinline__ void finish(State&) const {}
 };
+__global__ void k_scan_argmin(const float* __restrict__ val, const float* __restrict__ rays, int64_t R, int n1, double step,
+                              int32_t* __restrict__ best_idx, float* __restrict__ best_pos, float* __restrict__ min_val) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= R) return;
+  const float* v = val + r * n1;
+  float best = 3.0e38f;
+  int idx = 0x7fffffff;
+  for (int k = lane; k < n1; k += 32) {
+    const float x = v[k];
+    if (x < best) { best = x; idx = k; }        // strict <: the first minimum wins (k ascends within a lane)
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ob < best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  if (lane == 0) {
+    best_idx[r] = idx;
+    if (min_val) min_val[r] = best;
+    const float tb = __fmul_rn((float)idx, (float)step);   // best_pos = r_o + (idx.float() * fl32(step)) * d  (sdfs.py:247-248)
+    for (int j = 0; j < 3; ++j) best_pos[r * 3 + j] = __fadd_rn(rays[r * 6 + j], __fmul_rn(tb, rays[r * 6 + 3 + j]));
+  }
+}
 
 template <class NET, class IO, int FMT>
 static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP) {
@@ -394,9 +399,26 @@ int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "unknown precision %d", prec);
   NRT_REQUIRE(s->shift.params_tc != nullptr, "sdf.shift.params_tc is NULL: call nrt_mlp_pack_tc first");
   NRT_REQUIRE(matches<NetSdfShift>(d.mlp), "tensor-core SDF path: shift must be the 8x128 softplus MLP with 32 frequencies");
-  IoMinScan io{d, rays, R, step, n_steps, best_idx, best_pos, min_val, counter};
-  if (fmt_of(prec) == 0) return launch<NetSdfShift, IoMinScan, 0>(s->shift.params_tc, io, R, st, TAG_TC_MIN_SCAN);
-  return launch<NetSdfShift, IoMinScan, 1>(s->shift.params_tc, io, R, st, TAG_TC_MIN_SCAN);
+  (void)counter;
+  const int n1 = n_steps + 1;
+  const int64_t kChunk = 262144;                       // rays per pass: bounds the scratch to 135 MB at n = 128
+  const int64_t C = std::min<int64_t>(R, kChunk);
+  float* val = nullptr;
+  NRT_CUDA(cudaMallocAsync((void**)&val, (size_t)C * n1 * sizeof(float), st));
+  for (int64_t r0 = 0; r0 < R; r0 += kChunk) {
+    const int64_t n = std::min<int64_t>(kChunk, R - r0);
+    IoScanEval io{d, rays + r0 * 6, step, n1, val};
+    rc = fmt_of(prec) == 0 ? launch<NetSdfShift, IoScanEval, 0>(s->shift.params_tc, io, n * n1, st, TAG_TC_MIN_SCAN)
+                           : launch<NetSdfShift, IoScanEval, 1>(s->shift.params_tc, io, n * n1, st, TAG_TC_MIN_SCAN);
+    if (rc != NRT_OK) break;
+    NrtProfScope _ps(TAG_TC_MIN_SCAN, st);
+    k_scan_argmin<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(val, rays + r0 * 6, n, n1, step, best_idx + r0, best_pos + r0 * 3,
+                                                                     min_val ? min_val + r0 : nullptr);
+  }
+  cudaFreeAsync(val, st);
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
 }
 
 size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t*, int64_t R, int S) {
