@@ -337,6 +337,37 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             out["cfg1_sdf_march_512x512"] = res
         except Exception as e:   # noqa: BLE001
             out["cfg1_sdf_march_512x512"] = {"error": repr(e)[:300]}
+    # cfg5 (i): ray-sharded 4K render (3840x2160 = 8,294,400 rays, the reference's single uniform pass of 64 samples,
+    # nerf.py:175-214) on the tensor-core kernels: rank g renders its contiguous slice, no data-path collective
+    try:
+        w1, w2 = synthetic_weights(0)
+
+        def to_packed(w):
+            Ws = [torch.from_numpy(x).to(dev) for x in w["W"]]
+            bs = [torch.from_numpy(x).to(dev) for x in w["b"]]
+            return ops.PackedMLP(w["in_size"], 0, w["freqs"], w["hidden"], w["num_layers"], w["skip"], w["out"],
+                                 ops.ACT_LEAKY_RELU, torch.from_numpy(w["basis"]).to(dev), ops.PackedMLP.pack(Ws, bs))
+        m1, m2 = to_packed(w1), to_packed(w2)
+        total = 3840 * 2160
+        lo, hi = D.shard_range(total, rank, world)
+        base = torch.from_numpy(camera_rays(1080, 0)).to(dev)                 # 1,166,400 distinct rays, tiled to the slice
+        rays4k = base.repeat((hi - lo + base.shape[0] - 1) // base.shape[0], 1)[: hi - lo].contiguous()
+        ts = torch.linspace(0, 2.05, 64, device=dev)
+        code = torch.tensor([[0.4, 1.0, 0.3]], device=dev)
+        ops.nerfle_render(m1, m2, rays4k, ts, code, prec="f16")
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        img = ops.nerfle_render(m1, m2, rays4k, ts, code, prec="f16")
+        b.record()
+        sync()
+        ms = max_over_ranks(a.elapsed_time(b))
+        out["cfg5_render_4k_64samples"] = {"ms_per_frame": ms, "rays_per_sec": total / ms * 1e3, "mlp_samples_per_sec": total * 64 / ms * 1e3,
+                                           "model_tflops": total * 64 * (FLOP_FIRST + FLOP_SECOND) / ms / 1e9, "scaling": "strong",
+                                           "finite": bool(torch.isfinite(img).all())}
+        del rays4k, img, base
+    except Exception as e:   # noqa: BLE001
+        out["cfg5_render_4k_64samples"] = {"error": repr(e)[:300]}
     # CUDA-graph captured steps last: a failed capture must not disturb the measurements above
     try:
         config.set_train_precision("f16")
