@@ -335,6 +335,9 @@ static int forward_plain(const nrt_mlp_t* m, int prec, int out_act, const float*
   return launch<NET, decltype(io), 1>(m->params_tc, io, M, st);
 }
 
+int nrt_mlp_forward_tc_wide(const nrt_mlp_t* m, const MlpDev& d, int prec, int out_act, const float* x, int64_t M, float* out,
+                            cudaStream_t st, bool* handled);   // nrt_tc_wide.cu
+
 int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent, int64_t M,
                        float* out, cudaStream_t st) {
   MlpDev d;
@@ -348,6 +351,11 @@ int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x
   if (matches<NetNeuralBsdf>(d)) return forward_plain<NetNeuralBsdf>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetOcc>(d)) return forward_plain<NetOcc>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetSdfShift>(d)) return forward_plain<NetSdfShift>(m, prec, out_act, x, latent, M, out, st);
+  {
+    bool handled = false;   // the 256-wide networks (weights streamed in K-chunks, nrt_tc_wide.cu)
+    rc = nrt_mlp_forward_tc_wide(m, d, prec, out_act, x, M, out, st, &handled);
+    if (handled) return rc;
+  }
   nrt_set_error("tensor-core path: MLP shape (in %d, latent %d, freqs %d, hidden %d, layers %d, out %d, act %d) is not "
                 "instantiated; use NRT_PREC_F32", d.in_size, d.latent, d.freqs, d.hidden, d.L, d.out, d.act);
   return NRT_E_UNSUPPORTED;
@@ -403,6 +411,18 @@ int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   const int n1 = n_steps + 1;
   const int64_t kChunk = 262144;                       // rays per pass: bounds the scratch to 135 MB at n = 128
   const int64_t C = std::min<int64_t>(R, kChunk);
+  // stream-ordered scratch from the device's default memory pool; without a release threshold the pool hands the
+  // memory back to the OS at every synchronisation and each call pays a multi-millisecond re-allocation
+  static bool pool_configured = false;
+  if (!pool_configured) {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      uint64_t keep = 1ull << 30;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_configured = true;
+  }
   float* val = nullptr;
   NRT_CUDA(cudaMallocAsync((void**)&val, (size_t)C * n1 * sizeof(float), st));
   for (int64_t r0 = 0; r0 < R; r0 += kChunk) {

@@ -599,7 +599,7 @@ struct Net {
   static constexpr bool FUSE_OUT = Y.wout_f32_off >= 0;
   static constexpr int FIRST_STAGE = ENC_CUDA ? 1 : 0;
   static constexpr int END_STAGE = FUSE_OUT ? STAGES - 1 : STAGES;   // one past the last MMA stage
-  static_assert(COLS <= 512, "network does not fit in TMEM");
+  static constexpr bool FITS_TMEM = COLS <= 512;          // asserted by k_mlp_tc (the wide kernel has its own plan)
   static_assert(XR % 16 == 0 && F % 16 == 0 && LAT % 16 == 0 && KRAW == KE, "encoding segments must be multiples of 16");
   static_assert(!SPLIT || 3 * IN <= 16, "split encoding needs 3*in <= 16");
   static_assert(H % 16 == 0 && H <= 256, "hidden must be a multiple of 16");
@@ -615,7 +615,7 @@ struct Net {
   static constexpr int MAXOP = max_op_bytes();
   static constexpr int BIAS_BYTES = Y.bias_floats * 4;
   static constexpr int SMEM_BYTES = STREAM ? NSLOT * 2 * MAXOP + BIAS_BYTES : Y.bytes;
-  static_assert(SMEM_BYTES <= kSmemBudget, "stage buffers do not fit in shared memory");
+  static constexpr bool FITS_SMEM = SMEM_BYTES <= kSmemBudget;
 };
 
 constexpr int kEpiThreads = 128;
@@ -694,6 +694,8 @@ template <class NET, class IO, int FMT, class SV = NoSave, int WPS = NET::WPS>
 __global__ void __launch_bounds__(NET::NWG * WPS * 32 + 32, 1)
 k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg, SV sv = SV{}) {
   constexpr int EPI = WPS * 32;                 // epilogue threads per tile slot
+  static_assert(NET::FITS_TMEM, "network does not fit in TMEM");
+  static_assert(NET::FITS_SMEM, "stage buffers do not fit in shared memory");
   // dbg (development only, tools/tc_timeline.py): clock64 stamps of CTA 0 for a few tile iterations
   constexpr int kDbgIt0 = 4, kDbgIts = 4;
   auto stamp = [&](int it, int st, int slot, int k) {

@@ -44,6 +44,31 @@ def test_tc_mlp_forward_vs_oracle(name, M):
         assert np.abs(y - yo).max() < tol, (prec, np.abs(y - yo).max())
 
 
+WIDE_CASES = {
+    # ComposeSpatialVarying.sp_var_fn (bsdfs.py:487-496, 4 bases) and LightField.light_field_approx (lights.py:159-164):
+    # 256-wide, weights streamed in K-chunks, encoding operand in shared memory (csrc/nrt_tc_wide.cu)
+    "sp_var": dict(seed=51, in_size=3, out=4, num_layers=16, hidden=256, freqs=128, sigma=128.0),
+    "light_field": dict(seed=52, in_size=3, out=3, num_layers=10, hidden=256, freqs=16, sigma=32.0),
+}
+
+
+@pytest.mark.parametrize("name", list(WIDE_CASES))
+@pytest.mark.parametrize("M", [1, 128, 129, 4000])
+def test_tc_wide_mlp_forward_vs_oracle(name, M):
+    from neural_raytracing_b200 import ops
+    kw = WIDE_CASES[name]
+    w = synth.mlp_weights(**kw)
+    x = (0.5 * np.random.RandomState(M).standard_normal((M, 3))).astype(np.float32)
+    yo = c_oracle.mlp_forward(helpers.oracle_mlp(w), x)
+    m = helpers.cuda_mlp(w)
+    for prec, tol in (("f16", 1e-3), ("bf16", 5e-3)):
+        y = ops.mlp_forward(m, _t(x), prec=prec).cpu().numpy()
+        assert y.shape == yo.shape and np.isfinite(y).all()
+        assert np.abs(y - yo).max() < tol, (prec, np.abs(y - yo).max())
+    ys = ops.mlp_forward(m, _t(x), prec="f16", out_act=ops.OUT_SIGMOID).cpu().numpy()      # bsdfs.py:536
+    assert np.abs(ys - 1 / (1 + np.exp(-yo))).max() < 1e-3
+
+
 def test_tc_unsupported_shape_fails_loudly():
     from neural_raytracing_b200 import ops
     kw, act = helpers.MLP_CASES["latent_small"]
