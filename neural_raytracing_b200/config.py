@@ -15,6 +15,8 @@ TC_NETS = {
     (5, 0, 16, 64, 8, 3, 1, 0),     # occlusion MLP
     (3, 0, 32, 128, 8, 3, 1, 1),    # SphereSDF.shift (softplus; weights streamed through shared memory)
     (3, 0, 128, 256, 16, 3, 4, 0),  # ComposeSpatialVarying.sp_var_fn, 4 bases (K-chunk streamed, nrt_tc_wide.cu)
+    (3, 0, 128, 256, 16, 3, 8, 0),  # ... 8 bases (nerf_synthetic.py)
+    (3, 0, 128, 256, 16, 3, 16, 0), # ... 16 bases (dtu.py)
     (3, 0, 16, 256, 10, 3, 3, 0),   # LightField.light_field_approx (K-chunk streamed)
 }
 

@@ -24,9 +24,12 @@ template <class NET>
 struct Wide {
   static constexpr Layout Y = NET::Y;
   static constexpr int H = NET::H, L = NET::L, KE = NET::KE, F = NET::F, IN = NET::IN;
-  static_assert(H == 256 && NET::ENC_CUDA && NET::FUSE_OUT && NET::ACT == NRT_ACT_LEAKY_RELU && NET::LAT == 0,
-                "wide kernel: 256 hidden units, 3-D input, out <= 4, leaky_relu");
-  static constexpr int N_OPS = L + 1;                       // init + L hidden layers (blob ops 1 .. L+1)
+  static_assert(H == 256 && NET::ENC_CUDA && NET::ACT == NRT_ACT_LEAKY_RELU && NET::LAT == 0,
+                "wide kernel: 256 hidden units, 3-D input, leaky_relu");
+  // init + L hidden layers (blob ops 1 .. L+1); out <= 4: the output layer runs in the last epilogue (fp32), else it is
+  // one more streamed op with N = NOP
+  static constexpr int N_OPS = L + 1 + (NET::FUSE_OUT ? 0 : 1);
+  static constexpr int NOP = NET::NOP;
   static constexpr int CH_BYTES = H * kWideKC * 2;          // 32 KB
   static constexpr int ENC_BYTES = KE * 128 * 2;            // encoding as an A operand
   static constexpr int BIAS_BYTES = Y.bias_floats * 4;
@@ -45,10 +48,12 @@ struct ChunkCursor {
   __device__ __forceinline__ void advance() {
     if (++chunk == chunks_of(op)) { chunk = 0; if (++op == W::N_OPS) op = 0; }
   }
-  __device__ __forceinline__ static int k_of(int o) {          // runtime op -> K (init / plain / skip layer)
+  __device__ __forceinline__ static int k_of(int o) {          // runtime op -> K (init / plain / skip layer / out)
     if (o == 0) return W::KE;
+    if (o == W::L + 1) return W::H;
     return W::H + (is_skip(o - 1, 3, W::L) ? W::KE : 0);
   }
+  __device__ __forceinline__ static int n_of(int o) { return o == W::L + 1 ? W::NOP : W::H; }
   __device__ __forceinline__ static int chunks_of(int o) { return (k_of(o) + kWideKC - 1) / kWideKC; }
 };
 
@@ -98,7 +103,8 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
     int64_t p_i = 0, c_i = 0;
     uint32_t n_ready = 0;
     const uint32_t ring_addr = smem_u32(sRing), enc_addr = smem_u32(sEnc);
-    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_h = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t idesc_o = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | ((uint32_t)(W::NOP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     auto top_up = [&]() {
       while (p_i < total_chunks && p_i - c_i < kWideNB) {
         const int b = (int)(p_i % kWideNB);
@@ -106,8 +112,9 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
         if (elect_one()) {
           const int K = ChunkCursor<W>::k_of(pc.op);
           const int k0 = pc.chunk * kWideKC;
-          const uint32_t bytes = (uint32_t)(min(kWideKC, K - k0) * H * 2);
-          const uint8_t* src = blob + (size_t)Y.op_off[1 + pc.op] * 2 + (size_t)(k0 / 8) * H * 16;
+          const int N = ChunkCursor<W>::n_of(pc.op);
+          const uint32_t bytes = (uint32_t)(min(kWideKC, K - k0) * N * 2);
+          const uint8_t* src = blob + (size_t)Y.op_off[1 + pc.op] * 2 + (size_t)(k0 / 8) * N * 16;
           mbar_expect_tx(&bar_full[b], bytes);
           bulk_g2s(sRing + (size_t)b * W::CH_BYTES, src, bytes, &bar_full[b]);
         }
@@ -122,6 +129,8 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
         mbar_wait(&bar_ready, n_ready & 1); n_ready++;
         tc_fence_after();
         const int K = ChunkCursor<W>::k_of(op);
+        const int N = ChunkCursor<W>::n_of(op);
+        const uint32_t idesc = (op == L + 1) ? idesc_o : idesc_h;
         const int nch = (K + kWideKC - 1) / kWideKC;
         for (int c = 0; c < nch; ++c) {
           top_up();
@@ -130,10 +139,10 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
           tc_fence_after();
           if (elect_one()) {
             const int k0 = c * kWideKC, kc = min(kWideKC, K - k0);
-            const uint64_t bd0 = make_desc(ring_addr + (uint32_t)b * W::CH_BYTES, H * 16, 128);
+            const uint64_t bd0 = make_desc(ring_addr + (uint32_t)b * W::CH_BYTES, (uint32_t)N * 16u, 128);
             for (int j = 0; j < kc / 16; ++j) {
               const int k = k0 + 16 * j;                  // K index inside the op: [hidden 256 | encoding KE], init: encoding only
-              const uint64_t bd = bd0 + (uint64_t)((j * 2 * H * 16) >> 4);
+              const uint64_t bd = bd0 + (uint64_t)((j * 2 * N * 16) >> 4);
               const int ke = (op == 0) ? k : k - H;       // index into the encoding (>= 0: SS MMA, A from shared memory)
               // every layer's accumulator was pre-loaded with its bias by the epilogue: always accumulate
               if (ke >= 0) {
@@ -213,13 +222,18 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
         mbar_arrive(&bar_ready);
       }
       // ---- hidden layers ----
+      constexpr int NHID = NET::FUSE_OUT ? L : L + 1;      // epilogues that feed another MMA op
 #pragma unroll 1
-      for (int st = 0; st < L; ++st) {
+      for (int st = 0; st < NHID; ++st) {
         mbar_wait(&bar_done, n_done & 1); n_done++;
         tc_fence_after();
         convert_row<NET::ACT, FMT, H>(tD, tU);
+        if (st < L) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) preload_bias<64>(tD + 64 * c, sBias + Y.bias_off[2 + st] + 64 * c);
+          for (int c = 0; c < 4; ++c) preload_bias<64>(tD + 64 * c, sBias + Y.bias_off[2 + st] + 64 * c);
+        } else {
+          preload_bias<NET::NOP>(tD, sBias + Y.bias_off[NET::STAGES - 1]);
+        }
         if (st == 0) {
           // the init layer has consumed the raw encoding: activate it in place for the skip layers
 #pragma unroll 1
@@ -251,14 +265,24 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
         tc_fence_before();
         mbar_arrive(&bar_ready);
       }
-      // ---- last hidden activations + output layer (fp32, CUDA cores) ----
+      // ---- output ----
       {
         mbar_wait(&bar_done, n_done & 1); n_done++;
         tc_fence_after();
         float o[NET::OUT];
+        if constexpr (NET::FUSE_OUT) {
+          // last hidden activations + output layer (fp32, CUDA cores)
 #pragma unroll
-        for (int j = 0; j < NET::OUT; ++j) o[j] = sBias[Y.bias_off[NET::STAGES - 1] + j];
-        convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(tD, sBias + Y.wout_f32_off, o);
+          for (int j = 0; j < NET::OUT; ++j) o[j] = sBias[Y.bias_off[NET::STAGES - 1] + j];
+          convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(tD, sBias + Y.wout_f32_off, o);
+        } else {
+          constexpr int OC = (NET::OUT + 7) / 8 * 8;
+          uint32_t acc[OC];
+          tmem_load<OC>(tD, acc);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < NET::OUT; ++j) o[j] = __uint_as_float(acc[j]);   // bias pre-loaded into the accumulator
+        }
         if (valid) io.store(m, o);
         tc_fence_before();
       }
@@ -315,9 +339,11 @@ static int forward_wide(const nrt_mlp_t* m, int prec, int out_act, const float* 
   return NRT_OK;
 }
 
-// ComposeSpatialVarying.sp_var_fn for nb = 2, 4 (colocate.py: 4 bases) and the DTU configuration's 16 bases would need
-// out <= 4: instantiated for 4 bases; LightField.light_field_approx
+// ComposeSpatialVarying.sp_var_fn with 4 bases (colocate.py:70-78), 8 (nerf_synthetic.py:68-75) and 16 (dtu.py:101-106);
+// LightField.light_field_approx
 using NetSpVar4 = Net<3, 0, 128, 256, 16, 3, 4, NRT_ACT_LEAKY_RELU>;
+using NetSpVar8 = Net<3, 0, 128, 256, 16, 3, 8, NRT_ACT_LEAKY_RELU>;
+using NetSpVar16 = Net<3, 0, 128, 256, 16, 3, 16, NRT_ACT_LEAKY_RELU>;
 using NetLightField = Net<3, 0, 16, 256, 10, 3, 3, NRT_ACT_LEAKY_RELU>;
 
 }  // namespace tc
@@ -329,6 +355,8 @@ int nrt_mlp_forward_tc_wide(const nrt_mlp_t* m, const MlpDev& d, int prec, int o
                             cudaStream_t st, bool* handled) {
   *handled = true;
   if (matches_w<NetSpVar4>(d)) return forward_wide<NetSpVar4>(m, prec, out_act, x, M, out, st);
+  if (matches_w<NetSpVar8>(d)) return forward_wide<NetSpVar8>(m, prec, out_act, x, M, out, st);
+  if (matches_w<NetSpVar16>(d)) return forward_wide<NetSpVar16>(m, prec, out_act, x, M, out, st);
   if (matches_w<NetLightField>(d)) return forward_wide<NetLightField>(m, prec, out_act, x, M, out, st);
   *handled = false;
   return NRT_OK;

@@ -49,6 +49,8 @@ WIDE_CASES = {
     # 256-wide, weights streamed in K-chunks, encoding operand in shared memory (csrc/nrt_tc_wide.cu)
     "sp_var": dict(seed=51, in_size=3, out=4, num_layers=16, hidden=256, freqs=128, sigma=128.0),
     "light_field": dict(seed=52, in_size=3, out=3, num_layers=10, hidden=256, freqs=16, sigma=32.0),
+    "sp_var8": dict(seed=53, in_size=3, out=8, num_layers=16, hidden=256, freqs=128, sigma=128.0),     # nerf_synthetic.py
+    "sp_var16": dict(seed=54, in_size=3, out=16, num_layers=16, hidden=256, freqs=128, sigma=128.0),   # dtu.py
 }
 
 
