@@ -337,6 +337,43 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             out["cfg1_sdf_march_512x512"] = res
         except Exception as e:   # noqa: BLE001
             out["cfg1_sdf_march_512x512"] = {"error": repr(e)[:300]}
+    # cfg1: the whole colocate.py-style pipeline through the drop-in pathtrace() (sphere-trace + normals + 2 NeuralBSDF +
+    # diffuse + conductor mixed by the 16x256 sp_var MLP, point light, learned-occlusion MLP + shadow march, silhouette
+    # scan), 512x512 rays in one chunk, forward, tensor-core precision vs the exact fp32 kernels
+    if world == 1:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import scenes
+            import synth
+            import neural_raytracing_b200.pathtracer as P
+            from neural_raytracing_b200.pathtracer.cameras import NeRFCamera
+            shape_c, _sph, bsdf_c, lights_c, integ_c, w_isect = scenes.build_pipeline(P, "colocate", device=dev)
+            c2w, focal = synth.nerf_cameras(1, 512, device=dev)
+            cam = NeRFCamera(cam_to_world=c2w, focal=focal, device=dev)
+            res = {}
+            prev_p = config.precision
+            for prec in ("f16", "f32"):
+                config.set_precision(prec)
+
+                def frame():
+                    with torch.no_grad():
+                        return P.pathtrace(shape_c, size=512, chunk_size=512, bundle_size=1, bsdf=bsdf_c, integrator=integ_c,
+                                           lights=lights_c, cameras=cam, device=dev, silent=True, background=0, w_isect=w_isect,
+                                           with_noise=False)
+                frame(); frame()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                n_it = 3 if prec == "f16" else 1
+                a.record()
+                for _ in range(n_it):
+                    img = frame()
+                b.record(); torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / n_it
+                res[prec] = {"ms_per_frame": ms, "rays_per_sec": 512 * 512 / ms * 1e3}
+            config.set_precision(prev_p)
+            out["cfg1_colocate_pipeline_512x512"] = res
+        except Exception as e:   # noqa: BLE001
+            out["cfg1_colocate_pipeline_512x512"] = {"error": repr(e)[:300]}
     # cfg5 (i): ray-sharded 4K render (3840x2160 = 8,294,400 rays, the reference's single uniform pass of 64 samples,
     # nerf.py:175-214) on the tensor-core kernels: rank g renders its contiguous slice, no data-path collective
     try:
