@@ -58,6 +58,10 @@ SIGNATURES = {
     "nrt_mlp_pack_tc_dgrad": (c_int, [_PM, c_int, c_int, c_vp, c_vp]),
     "nrt_mlp_forward_train_tc": (c_int, [_PM, c_int, c_int, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]),
     "nrt_mlp_backward_tc": (c_int, [_PM, c_int, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp, c_vp]),
+    "nrt_nerfle_train_forward": (c_int, [_PM, _PM, c_int, c_vp, c_i64, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp, c_sz, c_vp, c_sz, c_vp]),
+    "nrt_nerfle_train_backward": (c_int, [_PM, _PM, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                          c_vp, c_vp, c_vp, c_vp]),
     "nrt_sdf_eval": (c_int, [_PS, c_int, c_vp, c_i64, c_vp, c_vp]),
     "nrt_sdf_value_grad": (c_int, [_PS, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nrt_sdf_sphere_trace": (c_int, [_PS, c_int, c_vp, c_vp, c_i64, c_f32, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),

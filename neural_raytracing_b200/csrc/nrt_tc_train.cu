@@ -611,12 +611,20 @@ static bool matches(const MlpDev& d) {
          d.skip == NET::SKIP && d.out == NET::OUT && d.act == NET::ACT;
 }
 
+template <class NET, int FMT, class IO>
+static int train_forward_io(const nrt_mlp_t* m, const IO& io, int64_t M, const TrainWs& ws, cudaStream_t st);
+
 template <class NET, int FMT>
 static int train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_t M, float* out, const TrainWs& ws, cudaStream_t st) {
   IoTrainFwd<NET::IN, NET::OUT> io{x, out, out_act};
+  return train_forward_io<NET, FMT>(m, io, M, ws, st);
+}
+
+template <class NET, int FMT, class IO>
+static int train_forward_io(const nrt_mlp_t* m, const IO& io, int64_t M, const TrainWs& ws, cudaStream_t st) {
   SaveTiles sv{ws.acts, ws.enc_raw, ws.enc_act, ws.masks, ws.ntiles};
   const size_t bytes = (size_t)NET::SMEM_BYTES + 256;
-  auto kern = k_mlp_tc<NET, decltype(io), FMT, SaveTiles>;
+  auto kern = k_mlp_tc<NET, IO, FMT, SaveTiles>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int grid = (int)std::min<int64_t>((ws.ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
   {
@@ -628,21 +636,34 @@ static int train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_
   return NRT_OK;
 }
 
+template <class NET, bool NEEDX, int FMT, class IO>
+static int train_backward_io(const nrt_mlp_t* m, const MlpDev& d, IO io, int64_t M, const void* dblob, const TrainWs& ws,
+                             float* g_params, cudaStream_t st);
+
 template <class NET, bool NEEDX, int FMT>
 static int train_backward(const nrt_mlp_t* m, const MlpDev& d, int out_act, int64_t M, const float* out, const float* g_out,
                           const void* dblob, const TrainWs& ws, float* g_params, float* g_x, cudaStream_t st) {
-  using DN = DNet<NET, NEEDX>;
   IoGrad<NET::IN, NET::OUT> io{out, g_out, g_x, out_act, ws.scale};
+  return train_backward_io<NET, NEEDX, FMT>(m, d, io, M, dblob, ws, g_params, st);
+}
+
+// IO: g_pre(m, j) (gradient w.r.t. the pre-activation output, un-scaled), load_g(m, g) (scaled by scale[1]),
+// store_gx1(m, j, v) (NEEDX; must un-scale by scale[2]); the member `scale` is set here.
+template <class NET, bool NEEDX, int FMT, class IO>
+static int train_backward_io(const nrt_mlp_t* m, const MlpDev& d, IO io, int64_t M, const void* dblob, const TrainWs& ws,
+                             float* g_params, cudaStream_t st) {
+  using DN = DNet<NET, NEEDX>;
+  io.scale = ws.scale;
   {
     NrtProfScope _ps(TAG_TC_DGRAD, st);
     NRT_CUDA(cudaMemsetAsync(ws.scale, 0, 16, st));
-    k_grad_absmax<decltype(io), NET::OUT><<<(int)std::min<int64_t>((M * NET::OUT + 255) / 256, 148 * 8), 256, 0, st>>>(io, M, ws.scale);
+    k_grad_absmax<IO, NET::OUT><<<(int)std::min<int64_t>((M * NET::OUT + 255) / 256, 148 * 8), 256, 0, st>>>(io, M, ws.scale);
     k_grad_scale<<<1, 1, 0, st>>>(ws.scale);
     NRT_CUDA(cudaGetLastError());
   }
   {
     const size_t bytes = (size_t)DN::DY.bytes + 256;
-    auto kern = k_mlp_dgrad_tc<NET, DN, decltype(io), FMT>;
+    auto kern = k_mlp_dgrad_tc<NET, DN, IO, FMT>;
     NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const int grid = (int)std::min<int64_t>((ws.ntiles + DN::NSLOT - 1) / DN::NSLOT, (int64_t)nrt_sm_count());
     NrtProfScope _ps(TAG_TC_DGRAD, st);
@@ -691,6 +712,93 @@ static int train_backward(const nrt_mlp_t* m, const MlpDev& d, int out_act, int6
   (void)m;
   return NRT_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// NeRFLE (nerf.py:175-214) training through both MLPs without materialising their inputs / outputs in fp32:
+// samples are indexed sample-major like the reference (m = s * R + ray), so sigma [S,R] and rgb [S,R,3] feed the
+// compositing kernels directly; the 64-d latent travels between the two MLPs as 16-bit (what the second MLP's operand
+// rounds to anyway), its gradient back as fp32.
+// ---------------------------------------------------------------------------------------------
+struct IoNerfTrainFirst {
+  const float* rays; const float* ts; int64_t R; float* sigma; uint16_t* latent; int fmt;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+    const int64_t s = m / R, ray = m - s * R;
+    const float t = __ldg(ts + s);
+    const float* r = rays + ray * 6;
+    v[0] = __ldg(r) + t * __ldg(r + 3); v[1] = __ldg(r + 1) + t * __ldg(r + 4); v[2] = __ldg(r + 2) + t * __ldg(r + 5);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+    sigma[m] = o[0];
+    uint4* dst = reinterpret_cast<uint4*>(latent + m * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint4 q;
+      if (fmt == 0) {
+        q.x = Elem<0>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<0>::pack(o[3 + 8 * j], o[4 + 8 * j]);
+        q.z = Elem<0>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<0>::pack(o[7 + 8 * j], o[8 + 8 * j]);
+      } else {
+        q.x = Elem<1>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<1>::pack(o[3 + 8 * j], o[4 + 8 * j]);
+        q.z = Elem<1>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<1>::pack(o[7 + 8 * j], o[8 + 8 * j]);
+      }
+      dst[j] = q;
+    }
+  }
+};
+template <int LD>
+struct IoNerfTrainSecond {
+  const float* rays; const uint16_t* latent; const float* light_code; const int32_t* view_of_ray; int64_t R; float* rgb; int fmt;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+    const int64_t s = m / R, ray = m - s * R;
+    const uint4* src = reinterpret_cast<const uint4*>(latent + m * 64);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint4 q = __ldg(src + j);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (fmt == 0) { v[8 * j + 2 * e] = Elem<0>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<0>::back((uint16_t)(w[e] >> 16)); }
+        else { v[8 * j + 2 * e] = Elem<1>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<1>::back((uint16_t)(w[e] >> 16)); }
+      }
+    }
+    const float* r = rays + ray * 6;
+    v[64] = __ldg(r + 3); v[65] = __ldg(r + 4); v[66] = __ldg(r + 5);
+    const int view = view_of_ray ? __ldg(view_of_ray + ray) : 0;
+#pragma unroll
+    for (int j = 0; j < LD; ++j) v[67 + j] = __ldg(light_code + (int64_t)view * LD + j);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) rgb[m * 3 + j] = 1.0f / (1.0f + __expf(-o[j]));     // nerf.py:203
+  }
+};
+struct IoNerfGradSecond {      // g w.r.t. sigmoid(rgb) in, g w.r.t. the latent out
+  const float* rgb; const float* g_rgb; float* g_latent; const float* scale;
+  __device__ __forceinline__ float g_pre(int64_t m, int j) const {
+    const float y = __ldg(rgb + m * 3 + j);
+    return __ldg(g_rgb + m * 3 + j) * y * (1.0f - y);
+  }
+  __device__ __forceinline__ void load_g(int64_t m, float* g) const {
+    const float S = scale[1];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g[j] = g_pre(m, j) * S;
+  }
+  __device__ __forceinline__ void store_gx1(int64_t m, int j, float v) const { if (j < 64) g_latent[m * 64 + j] = v * scale[2]; }
+};
+struct IoNerfGradFirst {       // [g_sigma | g_latent] in
+  const float* g_sigma; const float* g_latent; const float* scale;
+  __device__ __forceinline__ float g_pre(int64_t m, int j) const { return j == 0 ? __ldg(g_sigma + m) : __ldg(g_latent + m * 64 + j - 1); }
+  __device__ __forceinline__ void load_g(int64_t m, float* g) const {
+    const float S = scale[1];
+    g[0] = __ldg(g_sigma + m) * S;
+    const float4* src = reinterpret_cast<const float4*>(g_latent + m * 64);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 q = __ldg(src + j);
+      g[1 + 4 * j] = q.x * S; g[2 + 4 * j] = q.y * S; g[3 + 4 * j] = q.z * S; g[4 + 4 * j] = q.w * S;
+    }
+  }
+  __device__ __forceinline__ void store_gx1(int64_t, int, float) const {}
+};
 
 }  // namespace tc
 
@@ -801,4 +909,80 @@ extern "C" int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, in
   }
   nrt_set_error("tensor-core training path: this MLP shape is not instantiated");
   return NRT_E_UNSUPPORTED;
+}
+
+// ---- NeRFLE fused training entry points ----------------------------------------------------------------------
+static int nerfle_train_nets(const nrt_mlp_t* first, const nrt_mlp_t* second, int light_dim, MlpDev* d1, MlpDev* d2, int* id2) {
+  int rc = nrt_build_mlp_dev(first, d1);
+  if (rc != NRT_OK) return rc;
+  rc = nrt_build_mlp_dev(second, d2);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(train_net_id(*d1) == 1, "NeRFLE training path: first MLP must be NeRFLE.first (3->65, 5x128)");
+  *id2 = train_net_id(*d2);
+  NRT_REQUIRE((*id2 == 2 && light_dim == 3) || (*id2 == 3 && light_dim == 48),
+              "NeRFLE training path: second MLP must be NeRFLE.second with a point light (70 inputs) or the 48-float environment code (115)");
+  return NRT_OK;
+}
+
+extern "C" int nrt_nerfle_train_forward(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
+                                        const float* ts, int S, const float* light_code, int light_dim,
+                                        const int32_t* view_of_ray, float* sigma, float* rgb, void* latent16,
+                                        void* ws_first, size_t ws_first_bytes, void* ws_second, size_t ws_second_bytes,
+                                        void* stream) {
+  MlpDev d1, d2;
+  int id2 = 0;
+  int rc = nerfle_train_nets(first, second, light_dim, &d1, &d2, &id2);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "tensor-core training path: prec must be F16 or BF16");
+  NRT_REQUIRE(R >= 0 && S >= 1, "nrt_nerfle_train_forward: bad arguments");
+  if (R == 0) return NRT_OK;
+  NRT_REQUIRE(rays && ts && light_code && sigma && rgb && latent16 && ws_first && ws_second, "nrt_nerfle_train_forward: null pointer");
+  NRT_REQUIRE(first->params_tc && second->params_tc, "params_tc is NULL: call nrt_mlp_pack_tc (same prec) first");
+  NRT_REQUIRE(((uintptr_t)latent16 & 15) == 0, "latent16 must be 16-byte aligned");
+  const int64_t M = R * S;
+  const Layout y1 = make_layout(d1.in_size, d1.latent, d1.freqs, d1.hidden, d1.L, d1.skip, d1.out);
+  const Layout y2 = make_layout(d2.in_size, d2.latent, d2.freqs, d2.hidden, d2.L, d2.skip, d2.out);
+  const TrainWs w1 = carve_ws(y1, d1.hidden, d1.L, M, ws_first), w2 = carve_ws(y2, d2.hidden, d2.L, M, ws_second);
+  NRT_REQUIRE(ws_first_bytes >= w1.bytes && ws_second_bytes >= w2.bytes, "training workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int fmt = prec == NRT_PREC_BF16 ? 1 : 0;
+  IoNerfTrainFirst io1{rays, ts, R, sigma, (uint16_t*)latent16, fmt};
+  rc = fmt == 0 ? train_forward_io<NetNerfFirst, 0>(first, io1, M, w1, st) : train_forward_io<NetNerfFirst, 1>(first, io1, M, w1, st);
+  if (rc != NRT_OK) return rc;
+  if (id2 == 2) {
+    IoNerfTrainSecond<3> io2{rays, (const uint16_t*)latent16, light_code, view_of_ray, R, rgb, fmt};
+    return fmt == 0 ? train_forward_io<NetNerfSecondPT, 0>(second, io2, M, w2, st) : train_forward_io<NetNerfSecondPT, 1>(second, io2, M, w2, st);
+  }
+  IoNerfTrainSecond<48> io2{rays, (const uint16_t*)latent16, light_code, view_of_ray, R, rgb, fmt};
+  return fmt == 0 ? train_forward_io<NetNerfSecondLE, 0>(second, io2, M, w2, st) : train_forward_io<NetNerfSecondLE, 1>(second, io2, M, w2, st);
+}
+
+extern "C" int nrt_nerfle_train_backward(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, int64_t R, int S,
+                                         int light_dim, const float* rgb, const float* g_sigma, const float* g_rgb,
+                                         const void* dgrad_blob_first, const void* dgrad_blob_second, void* ws_first,
+                                         void* ws_second, float* g_latent_scratch, float* g_params_first,
+                                         float* g_params_second, void* stream) {
+  MlpDev d1, d2;
+  int id2 = 0;
+  int rc = nerfle_train_nets(first, second, light_dim, &d1, &d2, &id2);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "tensor-core training path: prec must be F16 or BF16");
+  if (R == 0) return NRT_OK;
+  NRT_REQUIRE(rgb && g_sigma && g_rgb && dgrad_blob_first && dgrad_blob_second && ws_first && ws_second && g_latent_scratch &&
+              g_params_first && g_params_second, "nrt_nerfle_train_backward: null pointer");
+  const int64_t M = R * S;
+  const Layout y1 = make_layout(d1.in_size, d1.latent, d1.freqs, d1.hidden, d1.L, d1.skip, d1.out);
+  const Layout y2 = make_layout(d2.in_size, d2.latent, d2.freqs, d2.hidden, d2.L, d2.skip, d2.out);
+  const TrainWs w1 = carve_ws(y1, d1.hidden, d1.L, M, ws_first), w2 = carve_ws(y2, d2.hidden, d2.L, M, ws_second);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool f16 = prec == NRT_PREC_F16;
+  IoNerfGradSecond g2{rgb, g_rgb, g_latent_scratch, nullptr};
+  if (id2 == 2) rc = f16 ? train_backward_io<NetNerfSecondPT, true, 0>(second, d2, g2, M, dgrad_blob_second, w2, g_params_second, st)
+                         : train_backward_io<NetNerfSecondPT, true, 1>(second, d2, g2, M, dgrad_blob_second, w2, g_params_second, st);
+  else rc = f16 ? train_backward_io<NetNerfSecondLE, true, 0>(second, d2, g2, M, dgrad_blob_second, w2, g_params_second, st)
+                : train_backward_io<NetNerfSecondLE, true, 1>(second, d2, g2, M, dgrad_blob_second, w2, g_params_second, st);
+  if (rc != NRT_OK) return rc;
+  IoNerfGradFirst g1{g_sigma, g_latent_scratch, nullptr};
+  return f16 ? train_backward_io<NetNerfFirst, false, 0>(first, d1, g1, M, dgrad_blob_first, w1, g_params_first, st)
+             : train_backward_io<NetNerfFirst, false, 1>(first, d1, g1, M, dgrad_blob_first, w1, g_params_first, st);
 }

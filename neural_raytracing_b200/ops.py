@@ -225,6 +225,54 @@ def mlp_backward_tc(m: PackedMLP, M: int, out: torch.Tensor, g_out: torch.Tensor
     return g_params, g_x
 
 
+def nerfle_train_forward(first: PackedMLP, second: PackedMLP, rays: torch.Tensor, ts: torch.Tensor, light_code: torch.Tensor,
+                         view_of_ray: Optional[torch.Tensor] = None, prec=PREC_F16):
+    """Both NeRFLE MLPs under autograd on the tensor cores (nrt_nerfle_train_forward): rays [R,6], ts [S] ->
+    sigma [S,R], rgb [S,R,3] (sample-major) and the opaque state for nerfle_train_backward."""
+    prec = prec_id(prec)
+    r2 = _chk(rays, "rays").reshape(-1, 6)
+    R, S = r2.shape[0], ts.numel()
+    t = _chk(ts, "ts").reshape(S)
+    code = _chk(light_code, "light_code").reshape(-1, light_code.shape[-1])
+    view = _chk(view_of_ray, "view_of_ray", torch.int32) if view_of_ray is not None else None
+    dev = rays.device
+    sigma = torch.empty((S, R), dtype=torch.float32, device=dev)
+    rgb = torch.empty((S, R, 3), dtype=torch.float32, device=dev)
+    lat = torch.empty(S * R * 64 * 2, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        c1, c2 = first.c_struct(prec), second.c_struct(prec)
+        n1 = N.lib().nrt_mlp_train_tc_workspace_bytes(ctypes.byref(c1), S * R)
+        n2 = N.lib().nrt_mlp_train_tc_workspace_bytes(ctypes.byref(c2), S * R)
+        if n1 < 0 or n2 < 0:
+            N.check(int(min(n1, n2)))
+        ws1 = torch.empty(int(n1), dtype=torch.uint8, device=dev)
+        ws2 = torch.empty(int(n2), dtype=torch.uint8, device=dev)
+        N.check(N.lib().nrt_nerfle_train_forward(ctypes.byref(c1), ctypes.byref(c2), prec, _ptr(r2), R, _ptr(t), S, _ptr(code),
+                                                 code.shape[-1], _ptr(view), _ptr(sigma), _ptr(rgb), _ptr(lat), _ptr(ws1),
+                                                 ws1.numel(), _ptr(ws2), ws2.numel(), _stream()))
+    return sigma, rgb, (ws1, ws2, R, S, code.shape[-1])
+
+
+def nerfle_train_backward(first: PackedMLP, second: PackedMLP, rgb: torch.Tensor, g_sigma: torch.Tensor, g_rgb: torch.Tensor,
+                          state, prec=PREC_F16):
+    """(g_params_first, g_params_second), packed-f32 layout."""
+    prec = prec_id(prec)
+    ws1, ws2, R, S, light_dim = state
+    dev = rgb.device
+    gs = _chk(g_sigma, "g_sigma").reshape(S, R)
+    gc = _chk(g_rgb, "g_rgb").reshape(S, R, 3)
+    y = _chk(rgb, "rgb").reshape(S, R, 3)
+    g1, g2 = torch.zeros_like(first.params), torch.zeros_like(second.params)
+    scratch = torch.empty(S * R * 64, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        c1, c2 = first.c_struct(prec), second.c_struct(prec)
+        b1, b2 = first.dgrad_blob(False, prec), second.dgrad_blob(True, prec)
+        N.check(N.lib().nrt_nerfle_train_backward(ctypes.byref(c1), ctypes.byref(c2), prec, R, S, light_dim, _ptr(y), _ptr(gs),
+                                                  _ptr(gc), _ptr(b1), _ptr(b2), _ptr(ws1), _ptr(ws2), _ptr(scratch), _ptr(g1),
+                                                  _ptr(g2), _stream()))
+    return g1, g2
+
+
 def sdf_eval(s: PackedSDF, p: torch.Tensor, prec=PREC_F32) -> torch.Tensor:
     prec = prec_id(prec)
     batch = p.shape[:-1]

@@ -43,6 +43,35 @@ def composite(sigma_raw, rgb, ts):
     return composite_reference_ops(sigma_raw, rgb, ts)
 
 
+class _NerfleFused(torch.autograd.Function):
+    """first MLP -> [latent | r_d | light] -> second MLP -> sigmoid on the tensor-core training kernels, nothing but
+    sigma [S,...] and rgb [S,...,3] materialised in fp32 (ops.nerfle_train_forward / _backward).  Gradients reach the
+    weights of both MLPs; rays, ts and the light code are treated as constants (as in nerfle.py, where only
+    `model.parameters()` are optimised)."""
+
+    @staticmethod
+    def forward(ctx, module, rays, ts, code, view, prec, *params):
+        p1, p2 = module.first.packed(), module.second.packed()
+        sigma, rgb, state = ops.nerfle_train_forward(p1, p2, rays.detach().float(), ts.detach().float(), code.detach().float(), view, prec)
+        ctx.p1, ctx.p2, ctx.state, ctx.prec = p1, p2, state, prec
+        ctx.n1 = len(module.first._flat_params())
+        ctx.save_for_backward(rgb)
+        lead = tuple(rays.shape[:-1])
+        return sigma.reshape((ts.numel(),) + lead), rgb.reshape((ts.numel(),) + lead + (3,))
+
+    @staticmethod
+    def backward(ctx, g_sigma, g_rgb):
+        rgb, = ctx.saved_tensors
+        g1, g2 = ops.nerfle_train_backward(ctx.p1, ctx.p2, rgb, g_sigma.contiguous().float(), g_rgb.contiguous().float(),
+                                           ctx.state, ctx.prec)
+        flat = []
+        for pk, g in ((ctx.p1, g1), (ctx.p2, g2)):
+            gW, gb = pk.unpack(g)
+            for w, b in zip(gW, gb):
+                flat += [w, b]
+        return (None, None, None, None, None, None) + tuple(flat)
+
+
 class NeRFLE(nn.Module):
     """NeRF with a point light / environment-light code (nerf.py:153-214)."""
 
@@ -91,6 +120,14 @@ class NeRFLE(nn.Module):
             return ops.nerfle_render(self.first.packed(), self.second.packed(), rays.detach().float(), ts,
                                      code.detach().float(), view, prec=prec)
         # differentiable path: fused MLP kernels where available + CUDA compositing
+        tprec = self.first.train_precision()
+        if rays.is_cuda and tprec != "f32" and self.second.train_precision() == tprec and not rays.requires_grad \
+                and not code.requires_grad:
+            N = rays.shape[0]
+            view = torch.arange(N, device=device, dtype=torch.int32).repeat_interleave(rays[0].numel() // 6)
+            alpha, rgb = _NerfleFused.apply(self, rays, ts, code, view, tprec, *self.first._flat_params(),
+                                            *self.second._flat_params())
+            return composite(alpha, rgb, ts)
         pts = r_o.unsqueeze(0) + torch.tensordot(ts, r_d, dims=0)
         first_out = self.first(pts)
         latent, alpha = first_out[..., 1:], first_out[..., 0]
