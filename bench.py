@@ -242,7 +242,7 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             if i is not None:
                 ar[i][1].record()
             opt.step()
-            return loss
+            return loss.detach()     # do not keep the autograd graph (and its 28 GB of saved tiles) alive across steps
         for _ in range(warmup):
             one()
         sync()
@@ -253,8 +253,8 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
         prof = ops.profile_collect(); ops.profile_enable(False)
         ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev) / steps)
         ar_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ar) / steps)
-        loss_val = float(loss.detach())
-        del loss          # drop the last eager autograd graph (its AccumulateGrad nodes would leak into a later capture)
+        loss_val = float(loss)
+        del loss
         return {"ms_per_step": ms, "rays_per_sec": total_rays / ms * 1e3, "mlp_samples_per_sec": total_rays * 64 / ms * 1e3,
 
                 "model_tflops_fwd_bwd": total_rays * 64 * (FLOP_FIRST + FLOP_SECOND) * 3 / ms / 1e9,
