@@ -374,6 +374,49 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             out["cfg1_colocate_pipeline_512x512"] = res
         except Exception as e:   # noqa: BLE001
             out["cfg1_colocate_pipeline_512x512"] = {"error": repr(e)[:300]}
+    # cfg2b: the pipeline nerf_synthetic.py itself builds (nerf_synthetic.py:61-75): SDF(SphereSDF(n=128), max_steps=64) +
+    # Direct + LightField + ComposeSpatialVarying of 8 NeuralBSDF(Softplus), NeRFCamera, 800x800 rays, forward
+    if world == 1:
+        try:
+            import torch.nn as nn
+            import synth
+            import neural_raytracing_b200.pathtracer as P
+            from neural_raytracing_b200.pathtracer.cameras import NeRFCamera
+            torch.manual_seed(3)
+            sph = SphereSDF(n=128, device=dev)
+            with torch.no_grad():
+                for q in sph.shift.parameters():
+                    q.normal_(0, 0.02)
+                sph.shift.out.weight.mul_(0.1); sph.shift.out.bias.zero_()
+                sph.radii.abs_().add_(0.05)
+            shp = SDF(device=dev, sdf=sph, max_steps=64)
+            kids = [P.bsdf.NeuralBSDF(activation=nn.Softplus(), device=dev) for _ in range(8)]
+            bsdf8 = P.bsdf.ComposeSpatialVarying(kids, device=dev)
+            lf = P.lights.LightField(device=dev)
+            with torch.no_grad():
+                lf.light_field_approx.out.bias.add_(0.5)
+            c2w, focal = synth.nerf_cameras(1, 800, device=dev)
+            cam8 = NeRFCamera(cam_to_world=c2w, focal=focal, device=dev)
+            res = {}
+            prev_p = config.precision
+            for prec in ("f16", "f32"):
+                config.set_precision(prec)
+
+                def frame8():
+                    with torch.no_grad():
+                        return P.pathtrace(shp, size=800, chunk_size=800, bundle_size=1, bsdf=bsdf8, integrator=P.integrators.Direct(),
+                                           lights=lf, cameras=cam8, device=dev, silent=True, background=0, with_noise=False)
+                frame8()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); img8, _ = frame8(); b.record(); torch.cuda.synchronize()
+                ms = a.elapsed_time(b)
+                res[prec] = {"ms_per_frame": ms, "rays_per_sec": 800 * 800 / ms * 1e3, "finite": bool(torch.isfinite(img8).all()),
+                             "lit_fraction": float((img8.abs().sum(-1) > 0).float().mean())}
+            config.set_precision(prev_p)
+            out["cfg2b_nerf_synthetic_pipeline_800x800"] = res
+        except Exception as e:   # noqa: BLE001
+            out["cfg2b_nerf_synthetic_pipeline_800x800"] = {"error": repr(e)[:300]}
     # cfg5 (i): ray-sharded 4K render (3840x2160 = 8,294,400 rays, the reference's single uniform pass of 64 samples,
     # nerf.py:175-214) on the tensor-core kernels: rank g renders its contiguous slice, no data-path collective
     try:
