@@ -1,17 +1,21 @@
-// tcgen05 / TMEM fused SkipConnMLP kernels (sm_100a).
+// tcgen05 / TMEM fused SkipConnMLP kernels (sm_100a): IO policies and host entry points of the gradient-free paths.
 //
-// One persistent CTA per SM keeps ALL weights of the network resident in shared memory
-// (pre-packed fp16/bf16 UMMA tiles, loaded once with cp.async.bulk) and pushes 128-sample tiles
-// through every layer with tcgen05.mma (kind::f16, M=128, fp32 accumulators in TMEM).  The
-// activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, apply
-// bias + activation, and write the next layer's A operand straight back into TMEM with
-// tcgen05.st (the MMA reads A from TMEM, B from shared memory).  Two tiles are in flight per CTA
-// (two epilogue warpgroups, one MMA-issuer warp) so the tensor pipe works on one tile while the
-// other tile's epilogue runs.
+// k_mlp_tc (tc_core.cuh): one persistent CTA per SM keeps the weights of the network resident in shared memory
+// (pre-packed fp16/bf16 UMMA tiles, one cp.async.bulk; the 333 KB SDF network streams its stage operands instead) and
+// pushes 128-sample tiles through every layer with tcgen05.mma (kind::f16, M = 128, fp32 accumulators in TMEM).  The
+// activations never leave the SM: the epilogue warps read the accumulator with tcgen05.ld, apply activation (the bias
+// was pre-loaded into the accumulator), and write the next layer's A operand straight back into TMEM with tcgen05.st
+// (the MMA reads A from TMEM, B from shared memory).  Two or three tiles are in flight per CTA (one epilogue warpgroup
+// each, one MMA-issuer warp), so the tensor pipe works on one tile while the other tiles' epilogues run.
 //
-// Reference semantics: pytorch3d/pathtracer/neural_blocks.py:75-86, utils.py:37-40.  The
-// Fourier phases x.B are themselves a tiny MMA with x (and B) split into hi+lo halves so that
-// the arguments of sin/cos keep ~fp32 accuracy (SURVEY.md hard part 2).
+// What a kernel instance does with the tiles is an IO policy (this file): plain [M,in] -> [M,out] evaluation, the two
+// NeRFLE render passes (points generated from rays, 16-bit latent hand-off), SDF evaluation, the batched min-along-ray
+// scan, and the sphere-trace / shadow marches, where every epilogue thread runs one ray's state machine and pulls new
+// rays from a global queue (compaction).
+//
+// Reference semantics: pytorch3d/pathtracer/neural_blocks.py:75-86, utils.py:37-40, shapes/sdfs.py:111-181, 232-249,
+// shapes/nerf.py:175-214.  Fourier phases keep ~fp32 accuracy: fp32 FMAs on the CUDA cores for 3..5-D inputs, a small
+// MMA with hi+lo split operands otherwise.
 #include "tc_core.cuh"
 
 namespace tc {
