@@ -269,3 +269,26 @@ def test_nerfle_training_step_vs_unmodified_reference(envmap, tprec, loss_tol, m
             cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
             assert cos > (0.96 if (envmap and tprec == "f16") else min_cos), (key, tprec, cos)
             assert abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) < (1e-3 if tprec == "f32" else 3e-2), key
+
+
+def test_tc_train_large_weights_do_not_overflow():
+    """A network whose layers amplify activations and gradients (weights 3x the default init: ~700x over the chain): the
+    fp16 forward and data-gradient chain must stay finite (loss-scale head-room + saturating conversion) and agree with
+    float64 autograd of the identically rounded network."""
+    import torch
+    from neural_raytracing_b200 import ops
+    kw, _ = helpers.MLP_CASES["nerf_first"]
+    w = synth.mlp_weights(**kw)
+    w["W"] = [3.0 * a for a in w["W"]]
+    m = helpers.cuda_mlp(w)
+    M = 1500
+    g = torch.Generator(device="cuda").manual_seed(8)
+    x = 0.6 * torch.randn(M, 3, device="cuda", generator=g)
+    gy = torch.randn(M, 65, device="cuda", generator=g)
+    out, ws = ops.mlp_forward_train_tc(m, x)
+    gp, _ = ops.mlp_backward_tc(m, M, out, gy, ws)
+    assert torch.isfinite(out).all() and torch.isfinite(gp).all()
+    y, xr, Ws, bs = _ref(w, x, False, True, True)
+    (y * gy.double()).sum().backward()
+    gW, gb = m.unpack(gp)
+    assert min(_cos(a, r.grad) for a, r in zip(gW, Ws)) > 0.995
