@@ -344,6 +344,9 @@ __device__ __forceinline__ uint32_t act_pack(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&r);
   }
 }
+#ifndef NRT_SOFTPLUS_POLY
+#define NRT_SOFTPLUS_POLY 0
+#endif
 // 32 accumulator columns -> act -> 16 packed operand columns.  Written structure-of-arrays over groups of 8
 // elements so that every step is 8 independent instructions: a single epilogue warp has its SM sub-partition
 // (almost) to itself, so the conversion runs at the speed of its dependent chains unless the ILP is explicit
@@ -358,12 +361,28 @@ __device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint
       for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[8 * g + i]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] = ex2_approx(-1.4426950408889634f * fabsf(x[i]));
-      // (a one-MUFU variant, ex2 + degree-5 polynomial for log1p on the FMA pipe, measured the same row time here
-      //  and is slightly less accurate: tools/softplus_bw.cu, profiles/r01_kernel_optimisation_log.md)
+#if NRT_SOFTPLUS_POLY
+      // log1p(u) on (0,1]: degree-5 minimax polynomial (max error 1.0e-5) on the FMA pipe instead of a second MUFU:
+      // ncu shows the XU pipe (MUFU + F2FP) 77 % busy with the two-MUFU form
+      float q[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(3.044916823e-02f, u[i], -1.315825124e-01f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 2.852736055e-01f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], -4.902312316e-01f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 9.992355931e-01f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 9.968642295e-06f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) u[i] = fmaxf(x[i], 0.0f) + q[i];
+#else
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] = fmaf(0.6931471805599453f, u[i], fmaxf(x[i], 0.0f));
+#endif
 #pragma unroll
       for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(u[2 * i], u[2 * i + 1]);
     }
