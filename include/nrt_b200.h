@@ -179,6 +179,19 @@ int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M,
 /* a6: value and analytic d(sdf)/dp (replaces SDF.autograd_diff, sdfs.py:184-197). */
 int nrt_sdf_value_grad(const nrt_sphere_sdf_t* s, const float* p, int64_t M, float* value,
                        float* grad, void* stream);
+/* a6 + a22 (training): the same forward-mode evaluation for a bare SkipConnMLP with in_size 3 (SphereSDF.shift),
+ * keeping what the reverse pass needs, and that reverse pass.  Together they replace the create_graph autograd of
+ * SDF.autograd_diff (sdfs.py:184-197) and the double backward that loss.backward() runs through it for
+ * eikonal_loss (utils.py:294) and the shading normals (sdfs.py:156-159).
+ *   forward : p [M,3] -> value [M,out], jac [M,out,3] = d value / d p;  acts (optional) receives the post-activation
+ *             states of the four-column network, [(num_layers+1)*hidden][4*M] floats.
+ *   backward: g_value [M,out], g_jac [M,out,3] -> g_params (packed-f32 layout, ACCUMULATED into: zero it first).
+ *             params_nk as for nrt_mlp_backward.  p carries no gradient (the march is no_grad in the reference). */
+int nrt_mlp_value_jac_forward(const nrt_mlp_t* m, const float* p, int64_t M, float* value, float* jac,
+                              float* acts, void* stream);
+int nrt_mlp_value_jac_backward(const nrt_mlp_t* m, const float* p, int64_t M, const float* acts,
+                               const float* g_value, const float* g_jac, const float* params_nk,
+                               float* g_params, void* stream);
 
 /* ---- a4: SDF.intersect march loop (sdfs.py:111-131) ---------------------------------- */
 /* depth [R] (final `depths`), hit [R] uint8 (`out_active`).  `active` (optional, [R]

@@ -123,7 +123,7 @@ __device__ void dgrad_hidden(const float* __restrict__ Wnk, int Kfull, const flo
 
 // wgrad: gW[k][n] += sum_m in[k][m] g[n][m] for k < K (rows from in0 then in1), n < N; gb[n] += sum_m g[n][m].
 // Register tile 4 (k) x 8 (n, interleaved); partial sums go to global memory with red.add.
-template <int TM>
+template <int TM, bool JAC = false>
 __device__ void wgrad_tile(const float* __restrict__ in0, int K0, const float* __restrict__ in1, int K1,
                            const float* __restrict__ g, int N, float* __restrict__ gW, float* __restrict__ gb) {
   constexpr int S = Pad<TM>::S;
@@ -175,7 +175,7 @@ __device__ void wgrad_tile(const float* __restrict__ in0, int K0, const float* _
   }
   for (int n = threadIdx.x; n < N; n += kThreads) {
     float s = 0.0f;
-    for (int mm = 0; mm < TM; ++mm) s += g[n * S + mm];
+    for (int mm = 0; mm < TM; mm += (JAC ? 4 : 1)) s += g[n * S + mm];   // JAC: tangent columns see no bias
     atomicAdd(gb + n, s);
   }
 }
@@ -309,6 +309,129 @@ k_mlp_bwd(MlpDev m, BwdArgs a) {
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reverse pass of the forward-mode (value, Jacobian) evaluation of k_mlp_value_jac (nrt_sdf_grad.cu): what
+// loss.backward() does through SDF.autograd_diff's create_graph normals in the reference (sdfs.py:184-197 feeding
+// eikonal_loss utils.py:294 and the shading frame), i.e. a double backward, as ONE first-order pass over the
+// four-column network.  Every point owns four tile columns [value, d/dp0, d/dp1, d/dp2]:
+//   z_c = W a_c (+ b for the value column),   a_v = act(z_v),   a_t = act'(z_v) * z_t
+// so the Linear layers are ordinary dgrad / wgrad over 4M columns (bias gradient from the value columns only) and
+// the activation couples the columns of a point:
+//   g_z_t = act'(z_v) g_a_t,    g_z_v = act'(z_v) g_a_v + act''(z_v) sum_t g_a_t z_t.
+// With s = act'(z_v) taken from the saved OUTPUT a_v (softplus: 1 - exp(-a_v); leaky: sign) and z_t = a_t / s the
+// second term is (1 - s) sum_t g_a_t a_t for softplus (act'' = s (1 - s)) and 0 for leaky_relu.
+// The Fourier basis is not trained and p carries no gradient in the reference (the march is no_grad), so nothing
+// flows into the encoding.
+struct JacBwdArgs {
+  const float* p; const float* acts; const float* g_value; const float* g_jac;
+  const float* w_nk; float* g_params; int64_t M;
+  int wnk_off[NRT_NLIN];
+};
+
+template <int TM>
+__device__ __forceinline__ void jac_act_backward(int act, const float* __restrict__ gin, const float* __restrict__ hin,
+                                                 float* __restrict__ gz, int H) {
+  constexpr int S = Pad<TM>::S;
+  for (int idx = threadIdx.x; idx < H * (TM / 4); idx += kThreads) {
+    const int k = idx / (TM / 4), q = idx - k * (TM / 4);
+    const float4 a = *reinterpret_cast<const float4*>(hin + k * S + 4 * q);
+    const float4 g = *reinterpret_cast<const float4*>(gin + k * S + 4 * q);
+    const float s = act_grad_from_out(act, a.x);
+    float gv = s * g.x;
+    if (act == NRT_ACT_SOFTPLUS) gv += (1.0f - s) * (g.y * a.y + g.z * a.z + g.w * a.w);
+    *reinterpret_cast<float4*>(gz + k * S + 4 * q) = make_float4(gv, s * g.y, s * g.z, s * g.w);
+  }
+}
+
+template <int H, int TM>
+__global__ void __launch_bounds__(kThreads, 1)
+k_mlp_jac_bwd(MlpDev m, JacBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int S = Pad<TM>::S;
+  constexpr int PTS = TM / 4;
+  const int DP = m.dim_p, OUT = m.out;
+  TileSmem ts;
+  float* p = smem;
+  const int r1 = max(2 * DP * TM, 3 * H * S);
+  ts.enc_raw = p;
+  ts.enc_act = p + DP * TM;
+  float* hin = p;
+  float* gz = p + H * S;
+  float* gin = p + 2 * H * S;
+  p += r1;
+  ts.h0 = ts.h1 = nullptr; ts.outb = nullptr;
+  ts.wbuf = p; p += 2 * kKC * H;
+  float* encr = p; p += DP * S;
+  float* enca = p; p += DP * S;
+  float* go = p; p += OUT * S;
+  const int tid = threadIdx.x;
+  const int64_t Mc = a.M * 4;                       // columns of the saved activations
+  const int64_t ntiles = (a.M + PTS - 1) / PTS;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t pb = tile * PTS;
+    const int valid = (int)min((int64_t)PTS, a.M - pb) * 4;     // valid columns
+    // ---- recompute the four-column encoding (value + tangents) ----
+    for (int idx = tid; idx < PTS * 3; idx += kThreads) {
+      const int q = idx / 3, j = idx - q * 3;
+      ts.enc_raw[j * TM + 4 * q] = (pb + q < a.M) ? a.p[(pb + q) * 3 + j] : 0.0f;
+    }
+    __syncthreads();
+    encode_tile<TM, true>(m, ts);
+    for (int idx = tid; idx < DP * TM; idx += kThreads) {
+      const int k = idx / TM, mm = idx - k * TM;
+      encr[k * S + mm] = ts.enc_raw[idx];
+      enca[k * S + mm] = ts.enc_act[idx];
+    }
+    __syncthreads();     // the unpadded encoding buffers alias hin / gz / gin
+    for (int idx = tid; idx < OUT * TM; idx += kThreads) {
+      const int n = idx / TM, mm = idx - n * TM;
+      const int64_t pt = pb + (mm >> 2);
+      const int c = mm & 3;
+      float g = 0.0f;
+      if (mm < valid) g = (c == 0) ? a.g_value[pt * OUT + n] : a.g_jac[(pt * OUT + n) * 3 + c - 1];
+      go[n * S + mm] = g;
+    }
+    auto load_acts = [&](int l) {
+      for (int idx = tid; idx < H * TM; idx += kThreads) {
+        const int k = idx / TM, mm = idx - k * TM;
+        hin[k * S + mm] = (mm < valid) ? a.acts[((size_t)l * H + k) * Mc + pb * 4 + mm] : 0.0f;
+      }
+    };
+    load_acts(m.L);
+    __syncthreads();
+    {
+      const int li = m.n_lin - 1;
+      wgrad_tile<TM, true>(hin, H, nullptr, 0, go, OUT, a.g_params + m.w_off[li], a.g_params + m.b_off[li]);
+      const float* Wkn = m.params + m.w_off[li];
+      for (int idx = tid; idx < H * TM; idx += kThreads) {
+        const int k = idx / TM, mm = idx - k * TM;
+        float acc = 0.0f;
+        for (int n = 0; n < OUT; ++n) acc = nrt_fma(__ldg(Wkn + k * OUT + n), go[n * S + mm], acc);
+        gin[k * S + mm] = acc;
+      }
+    }
+    __syncthreads();
+    jac_act_backward<TM>(m.act, gin, hin, gz, H);
+    __syncthreads();
+    for (int i = m.L - 1; i >= 0; --i) {
+      const int li = 1 + i;
+      const bool sk = (m.skip_mask >> i) & 1u;
+      const int Kfull = H + (sk ? DP : 0);
+      load_acts(i);
+      __syncthreads();
+      wgrad_tile<TM, true>(hin, H, enca, sk ? DP : 0, gz, H, a.g_params + m.w_off[li], a.g_params + m.b_off[li]);
+      __syncthreads();
+      dgrad_hidden<H, TM>(a.w_nk + a.wnk_off[li], Kfull, gz, gin, ts.wbuf);
+      jac_act_backward<TM>(m.act, gin, hin, gz, H);
+      __syncthreads();
+    }
+    wgrad_tile<TM, true>(encr, DP, nullptr, 0, gz, H, a.g_params + m.w_off[0], a.g_params + m.b_off[0]);
+    __syncthreads();
+  }
+}
+
 }  // namespace nrt
 using namespace nrt;
 
@@ -350,5 +473,44 @@ extern "C" int nrt_mlp_backward(const nrt_mlp_t* mm, int out_act, const float* x
   NRT_BWD_CASE(256, 16)
 #undef NRT_BWD_CASE
   nrt_set_error("nrt_mlp_backward: unsupported hidden size %d", d.hidden);
+  return NRT_E_UNSUPPORTED;
+}
+
+extern "C" int nrt_mlp_value_jac_backward(const nrt_mlp_t* mm, const float* p, int64_t M, const float* acts,
+                                          const float* g_value, const float* g_jac, const float* params_nk,
+                                          float* g_params, void* stream) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(mm, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(M >= 0, "nrt_mlp_value_jac_backward: negative M");
+  NRT_REQUIRE(d.in_size == 3 && d.latent == 0, "nrt_mlp_value_jac_backward: needs in_size 3 and no latent");
+  if (M == 0) return NRT_OK;
+  NRT_REQUIRE(p && acts && g_value && g_jac && params_nk && g_params, "nrt_mlp_value_jac_backward: null pointer");
+  NRT_REQUIRE(((uintptr_t)params_nk & 15) == 0, "params_nk must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  JacBwdArgs a{p, acts, g_value, g_jac, params_nk, g_params, M, {0}};
+  {
+    int off = 0;
+    for (int li = 0; li < d.n_lin; ++li) { a.wnk_off[li] = off; off += d.K[li] * d.N[li]; }
+  }
+#define NRT_JBWD_CASE(HV, TMV)                                                                                     \
+  if (d.hidden == HV) {                                                                                            \
+    const size_t fl = std::max<size_t>((size_t)2 * d.dim_p * TMV, (size_t)3 * HV * (TMV + 4)) + 2 * kKC * HV +     \
+                      (size_t)(2 * d.dim_p + d.out) * (TMV + 4);                                                    \
+    const size_t bytes = fl * sizeof(float);                                                                       \
+    NRT_REQUIRE(bytes <= 227 * 1024, "nrt_mlp_value_jac_backward: %zu bytes of shared memory needed", bytes);      \
+    NRT_CUDA(cudaFuncSetAttribute(k_mlp_jac_bwd<HV, TMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
+    const int64_t ntiles = (M + TMV / 4 - 1) / (TMV / 4);                                                          \
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count() * 4);                                  \
+    NrtProfScope _ps(TAG_MLP_BWD_F32, st);                                                                         \
+    k_mlp_jac_bwd<HV, TMV><<<grid, kThreads, bytes, st>>>(d, a);                                                   \
+    NRT_CUDA(cudaGetLastError());                                                                                  \
+    return NRT_OK;                                                                                                 \
+  }
+  NRT_JBWD_CASE(32, 64)
+  NRT_JBWD_CASE(64, 64)
+  NRT_JBWD_CASE(128, 64)
+#undef NRT_JBWD_CASE
+  nrt_set_error("nrt_mlp_value_jac_backward: unsupported hidden size %d", d.hidden);
   return NRT_E_UNSUPPORTED;
 }

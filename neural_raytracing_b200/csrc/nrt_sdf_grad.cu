@@ -73,6 +73,42 @@ k_sdf_value_grad(SdfDev sd, const float* __restrict__ p, int64_t M, float* __res
   }
 }
 
+
+// MLP-only variant that also saves the post-activation states of the four-column network for
+// nrt_mlp_value_jac_backward (training: SDF.autograd_diff with a graph, sdfs.py:184-197).
+template <int H, int TM>
+__global__ void __launch_bounds__(kThreads, 1)
+k_mlp_value_jac(MlpDev m, const float* __restrict__ p, int64_t M, float* __restrict__ value, float* __restrict__ jac,
+                float* __restrict__ acts) {
+  extern __shared__ __align__(16) float smem[];
+  TileSmem s;
+  carve_tile(s, smem, m.dim_p, H, m.out, TM);
+  constexpr int PTS = TM / 4;
+  const int64_t ntiles = (M + PTS - 1) / PTS;
+  const int OUT = m.out;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t pb = tile * PTS;
+    const int tid = threadIdx.x;
+    const int valid_pts = (int)min((int64_t)PTS, M - pb);
+    if (tid < PTS) {
+      float pt[3] = {0.0f, 0.0f, 0.0f};
+      if (tid < valid_pts) { pt[0] = p[(pb + tid) * 3]; pt[1] = p[(pb + tid) * 3 + 1]; pt[2] = p[(pb + tid) * 3 + 2]; }
+      s.enc_raw[0 * TM + 4 * tid] = pt[0]; s.enc_raw[1 * TM + 4 * tid] = pt[1]; s.enc_raw[2 * TM + 4 * tid] = pt[2];
+    }
+    __syncthreads();
+    mlp_tile_forward<H, TM, true>(m, s, acts, M * 4, pb * 4, valid_pts * 4);
+    for (int idx = tid; idx < OUT * TM; idx += kThreads) {
+      const int n = idx / TM, mm = idx - n * TM;
+      const int q = mm >> 2, c = mm & 3;
+      if (q < valid_pts) {
+        if (c == 0) value[(pb + q) * OUT + n] = s.outb[idx];
+        else jac[((pb + q) * OUT + n) * 3 + c - 1] = s.outb[idx];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace nrt
 using namespace nrt;
 
@@ -102,5 +138,35 @@ extern "C" int nrt_sdf_value_grad(const nrt_sphere_sdf_t* s, const float* p, int
   NRT_VG_CASE(32, 64)
 #undef NRT_VG_CASE
   nrt_set_error("nrt_sdf_value_grad: unsupported hidden size %d", d.mlp.hidden);
+  return NRT_E_UNSUPPORTED;
+}
+
+extern "C" int nrt_mlp_value_jac_forward(const nrt_mlp_t* mm, const float* p, int64_t M, float* value, float* jac,
+                                         float* acts, void* stream) {
+  MlpDev d;
+  int rc = nrt_build_mlp_dev(mm, &d);
+  if (rc != NRT_OK) return rc;
+  NRT_REQUIRE(M >= 0, "nrt_mlp_value_jac_forward: negative M");
+  NRT_REQUIRE(d.in_size == 3 && d.latent == 0, "nrt_mlp_value_jac_forward: needs in_size 3 and no latent");
+  if (M == 0) return NRT_OK;
+  NRT_REQUIRE(p && value && jac, "nrt_mlp_value_jac_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+#define NRT_VJ_CASE(HV, TMV)                                                                             \
+  if (d.hidden == HV) {                                                                                  \
+    const size_t bytes = tile_smem_floats(d.dim_p, HV, d.out, TMV) * sizeof(float);                      \
+    NRT_REQUIRE(bytes <= 227 * 1024, "shared memory");                                                   \
+    NRT_CUDA(cudaFuncSetAttribute(k_mlp_value_jac<HV, TMV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes)); \
+    const int64_t ntiles = (M + TMV / 4 - 1) / (TMV / 4);                                                \
+    const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count() * 4);                        \
+    NrtProfScope _ps(TAG_SDF_GRAD_F32, st);                                                              \
+    k_mlp_value_jac<HV, TMV><<<grid, kThreads, bytes, st>>>(d, p, M, value, jac, acts);                  \
+    NRT_CUDA(cudaGetLastError());                                                                        \
+    return NRT_OK;                                                                                       \
+  }
+  NRT_VJ_CASE(128, 64)
+  NRT_VJ_CASE(64, 64)
+  NRT_VJ_CASE(32, 64)
+#undef NRT_VJ_CASE
+  nrt_set_error("nrt_mlp_value_jac_forward: unsupported hidden size %d", d.hidden);
   return NRT_E_UNSUPPORTED;
 }

@@ -295,6 +295,35 @@ def sdf_value_grad(s: PackedSDF, p: torch.Tensor):
     return val.reshape(batch), grad.reshape(batch + (3,))
 
 
+def mlp_value_jac_forward(m: PackedMLP, p: torch.Tensor, save_acts=False):
+    """Forward-mode (value, d value / d p) of a SkipConnMLP with in_size 3: p [M,3] -> value [M,out], jac [M,out,3]
+    (+ the saved four-column activations for mlp_value_jac_backward)."""
+    p2 = _chk(p, "p").reshape(-1, 3)
+    M = p2.shape[0]
+    val = torch.empty((M, m.out_size), dtype=torch.float32, device=p.device)
+    jac = torch.empty((M, m.out_size, 3), dtype=torch.float32, device=p.device)
+    acts = torch.empty(((m.num_layers + 1) * m.hidden, 4 * M), dtype=torch.float32, device=p.device) if save_acts else None
+    with torch.cuda.device(p.device):
+        c = m.c_struct()
+        N.check(N.lib().nrt_mlp_value_jac_forward(ctypes.byref(c), _ptr(p2), M, _ptr(val), _ptr(jac), _ptr(acts), _stream()))
+    return val, jac, acts
+
+
+def mlp_value_jac_backward(m: PackedMLP, p: torch.Tensor, acts: torch.Tensor, g_value: torch.Tensor, g_jac: torch.Tensor):
+    """Reverse pass of mlp_value_jac_forward into the packed-f32 parameter gradient (the reference's double backward
+    through SDF.autograd_diff, sdfs.py:184-197)."""
+    p2 = _chk(p, "p").reshape(-1, 3)
+    M = p2.shape[0]
+    gv = _chk(g_value, "g_value").reshape(M, m.out_size)
+    gj = _chk(g_jac, "g_jac").reshape(M, m.out_size, 3)
+    g_params = torch.zeros_like(m.params)
+    with torch.cuda.device(p.device):
+        c = m.c_struct()
+        N.check(N.lib().nrt_mlp_value_jac_backward(ctypes.byref(c), _ptr(p2), M, _ptr(acts), _ptr(gv), _ptr(gj),
+                                                   _ptr(m.params_nk()), _ptr(g_params), _stream()))
+    return g_params
+
+
 def sphere_trace(s: PackedSDF, rays: torch.Tensor, epsilon=1e-3, max_steps=64, max_t=10.0,
                  active: Optional[torch.Tensor] = None, prec=PREC_F32, steps_counter: Optional[torch.Tensor] = None):
     """SDF.intersect march loop (sdfs.py:111-131).  rays [...,6] -> depth [...], hit [...] (bool)."""

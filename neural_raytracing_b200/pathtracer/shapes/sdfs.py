@@ -2,8 +2,11 @@
 
 The three gradient-free scan loops that are >95 % of a reference step (march :119-131, min scan
 :232-249, shadow march :169-180) run in the fused CUDA kernels of libnrt_b200 (persistent,
-slot-compacted).  Everything autograd has to see (sdf(best_pos), normals) follows the reference's
-own differentiable definition."""
+slot-compacted).  What autograd has to see: sdf(best_pos) goes through the fused MLP forward /
+backward kernels; the normals (sdfs.py:184-197, a create_graph autograd in the reference, whose
+double backward carries the eikonal and shading losses into the SDF weights) are the forward-mode
+analytic Jacobian kernel with its own hand-written reverse pass (nrt_mlp_value_jac_forward /
+_backward).  Only the 3 kFLOP/sample smooth-min of the sphere set stays a torch expression."""
 import random
 
 import torch
@@ -18,6 +21,32 @@ from ..neural_blocks import SkipConnMLP
 
 def SPHERE_SDF(p):
     return torch.norm(p, dim=-1) - 1
+
+
+class _MlpValueJac(torch.autograd.Function):
+    """(value, d value / d p) of SphereSDF.shift at p, forward mode, with the hand-written reverse pass into the
+    weights.  p itself carries no gradient: in the reference the hit points come out of a no_grad march and
+    autograd_diff makes them leaves (sdfs.py:119-131, 186-187)."""
+
+    @staticmethod
+    def forward(ctx, module, p, *params):
+        pk = module.packed()
+        x = p.detach().float().reshape(-1, 3).contiguous()
+        val, jac, acts = ops.mlp_value_jac_forward(pk, x, save_acts=True)
+        ctx.pk = pk
+        ctx.save_for_backward(x, acts)
+        return val, jac
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_val, g_jac):
+        x, acts = ctx.saved_tensors
+        g_params = ops.mlp_value_jac_backward(ctx.pk, x, acts, g_val.contiguous().float(), g_jac.contiguous().float())
+        gW, gb = ctx.pk.unpack(g_params)
+        flat = []
+        for w, b in zip(gW, gb):
+            flat += [w, b]
+        return (None, None) + tuple(flat)
 
 
 class SphereSDF(nn.Module):
@@ -44,11 +73,31 @@ class SphereSDF(nn.Module):
     def _needs_grad(self, p):
         return torch.is_grad_enabled() and (p.requires_grad or any(q.requires_grad for q in self.parameters()))
 
-    def forward_reference_ops(self, p):
+    def sphere_set(self, p):
+        """Smooth-min of the warped spheres (sdfs.py:37-45, utils.py:385-387) as a torch expression: 3 kFLOP per
+        sample against 331 kFLOP for `shift`, differentiable to any order."""
         q = self.transform(p.reshape(-1, 3).unsqueeze(0)) - self.centers.unsqueeze(1)
         sd = q.norm(p=2, dim=-1) - self.radii.unsqueeze(-1)
-        out = U.smooth_min(sd, k=32.).reshape(p.shape[:-1])
+        return U.smooth_min(sd, k=32.).reshape(p.shape[:-1])
+
+    def forward_reference_ops(self, p):
+        out = self.sphere_set(p)
         return out + self.shift.forward_reference_ops(p).reshape_as(out)
+
+    def _fusable_grad(self, p):
+        return p.is_cuda and not p.requires_grad and ops.HAS_SDF_VALUE_GRAD and self.shift.in_size == 3 and \
+            self.shift.latent_size == 0 and self.shift.init.out_features in (32, 64, 128)
+
+    def value_and_normal(self, p):
+        """sdf(p) and d sdf / d p for leaf points p [K,3], both carrying the graph to the parameters: the residual MLP
+        through the analytic-Jacobian kernels, the sphere set through torch's create_graph autograd."""
+        pl = p.detach().reshape(-1, 3).requires_grad_()
+        with torch.enable_grad():
+            s = self.sphere_set(pl)
+            n_s, = torch.autograd.grad(inputs=pl, outputs=s, grad_outputs=torch.ones_like(s), create_graph=True,
+                                       retain_graph=True, only_inputs=True)
+            v_m, j_m = _MlpValueJac.apply(self.shift, pl.detach(), *self.shift._flat_params())
+        return s + v_m[:, 0], n_s + j_m[:, 0, :]
 
     def precision(self):
         """Arithmetic of the gradient-free SDF evaluations: config.precision when the residual MLP has the shape
@@ -58,6 +107,10 @@ class SphereSDF(nn.Module):
     def forward(self, p):
         if p.is_cuda and not self._needs_grad(p):
             return ops.sdf_eval(self.packed(), p.detach().float(), prec=self.precision())
+        if p.is_cuda:
+            # first-order graph: the residual MLP through the fused forward / backward kernels (_FusedMLP)
+            out = self.sphere_set(p)
+            return out + self.shift(p).reshape_as(out)
         return self.forward_reference_ops(p)
 
 
@@ -144,14 +197,17 @@ class SDF:
         return (depths >= max_t).squeeze(-1) | remaining
 
     def autograd_diff(self, p):
-        """d sdf / d p at p (sdfs.py:184-197).  With gradients enabled this is the reference's
-        create_graph autograd (so eikonal / shading losses reach the SDF weights); without, the
-        fused analytic-Jacobian kernel."""
+        """d sdf / d p at p (sdfs.py:184-197).  Without a graph: the fused analytic-Jacobian kernel.  With gradients
+        enabled: the same forward-mode kernel for the residual MLP with its hand-written reverse pass (so eikonal /
+        shading losses reach the SDF weights), the sphere set through create_graph autograd.  Callables other than
+        SphereSDF (and points that themselves require grad) take the reference's create_graph autograd."""
         s = self.sdf
         wants_graph = torch.is_grad_enabled() and (not isinstance(s, SphereSDF) or
                                                    any(q.requires_grad for q in s.parameters()))
         if isinstance(s, SphereSDF) and p.is_cuda and not wants_graph and ops.HAS_SDF_VALUE_GRAD:
             return ops.sdf_value_grad(s.packed(), p.detach())[1]
+        if isinstance(s, SphereSDF) and s._fusable_grad(p):
+            return s.value_and_normal(p)[1].reshape(p.shape)
         with torch.enable_grad():
             if not p.requires_grad:
                 p = p.requires_grad_()

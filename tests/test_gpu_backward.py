@@ -122,3 +122,93 @@ def test_nerfle_training_step_gradients():
     assert abs(loss.item() - loss64.item()) < 1e-5
     for (pname, p32), p64 in zip(n.named_parameters(), n64.parameters()):
         _close(p32.grad, p64.grad, pname, **(LOOSE_X if pname.startswith("first.") else LOOSE))
+
+
+@pytest.mark.parametrize("case", ["sdf_softplus_128", "leaky_64", "softplus_32_out2"])
+@pytest.mark.parametrize("M", [1, 16, 203])
+def test_value_jacobian_reverse_pass_matches_double_backward(case, M):
+    """nrt_mlp_value_jac_forward / _backward (forward-mode Jacobian + hand-written reverse pass) vs FLOAT64 torch
+    autograd: jac = autograd.grad(y, p, create_graph=True) and a loss on (y, jac) back-propagated into the weights --
+    the double backward the reference runs through SDF.autograd_diff (sdfs.py:184-197) for eikonal_loss
+    (utils.py:294).  Ragged M (1, 16 = one full tile, 203) covers partial tiles."""
+    import torch
+    import torch.nn.functional as F
+    from neural_raytracing_b200 import ops
+    from neural_raytracing_b200.pathtracer import neural_blocks as nb
+    kw = {"sdf_softplus_128": dict(in_size=3, out=1, num_layers=8, hidden_size=128, freqs=32, activation=F.softplus),
+          "leaky_64": dict(in_size=3, out=1, num_layers=5, hidden_size=64, freqs=16),
+          "softplus_32_out2": dict(in_size=3, out=2, num_layers=4, hidden_size=32, freqs=16, sigma=4,
+                                   activation=F.softplus)}[case]
+    torch.manual_seed(0)
+    mlp = nb.SkipConnMLP(device="cuda", **kw).to("cuda")
+    synth.fill_module(mlp, 11)
+    if kw.get("sigma", 32) == 32:
+        mlp.basis_p = mlp.basis_p * 0.25        # keeps the Jacobian O(1..10) so that absolute tolerances mean something
+    g = torch.Generator("cuda").manual_seed(M + 1)
+    p = 0.5 * torch.randn(M, 3, device="cuda", generator=g)
+    gv = torch.randn(M, kw["out"], device="cuda", generator=g)
+    gj = torch.randn(M, kw["out"], 3, device="cuda", generator=g)
+
+    pk = mlp.packed()
+    val, jac, acts = ops.mlp_value_jac_forward(pk, p, save_acts=True)
+    g_params = ops.mlp_value_jac_backward(pk, p, acts, gv, gj)
+    gW, gb = pk.unpack(g_params)
+
+    m64 = copy.deepcopy(mlp).cpu().double()
+    m64.basis_p = mlp.basis_p.detach().cpu().double()
+    p64 = p.detach().cpu().double().requires_grad_()
+    y64 = m64.forward_reference_ops(p64)
+    rows = []
+    for n in range(kw["out"]):
+        jn, = torch.autograd.grad(y64[:, n].sum(), p64, create_graph=True)
+        rows.append(jn)
+    j64 = torch.stack(rows, dim=1)                                        # [M, out, 3]
+    scale_v, scale_j = y64.abs().max().item() + 1e-6, j64.abs().max().item() + 1e-6
+    assert (val.cpu().double() - y64.detach()).abs().max().item() < 2e-5 * max(1.0, scale_v)
+    assert (jac.cpu().double() - j64.detach()).abs().max().item() < 1e-4 * max(1.0, scale_j)
+    ((y64 * gv.cpu().double()).sum() + (j64 * gj.cpu().double()).sum()).backward()
+    lin64 = [m64.init] + list(m64.layers) + [m64.out]
+    for i, (w, b, l64) in enumerate(zip(gW, gb, lin64)):
+        _close(w, l64.weight.grad, "W%d" % i, rtol=5e-4, min_cos=0.9999)
+        _close(b, l64.bias.grad, "b%d" % i, rtol=5e-4, min_cos=0.9999)
+
+
+def test_sdf_normals_with_graph_use_the_jacobian_kernels():
+    """SDF.autograd_diff with gradients enabled (training): normals equal the no-grad analytic kernel's, and an
+    eikonal + normal-dependent loss reaches SphereSDF.shift, centers, radii and tfs like the reference-op autograd."""
+    import torch
+    from neural_raytracing_b200.pathtracer.shapes import sdfs
+    from neural_raytracing_b200.pathtracer.utils import eikonal_loss
+    torch.manual_seed(0)
+    s = sdfs.SphereSDF(n=64, device="cuda")
+    synth.fill_module(s.shift, 5)
+    with torch.no_grad():
+        for lin in [s.shift.init] + list(s.shift.layers) + [s.shift.out]:
+            lin.weight.mul_(0.5)
+        s.tfs.add_(0.05 * torch.randn_like(s.tfs))
+    shape = sdfs.SDF(sdf=s, device="cuda")
+    p = (0.35 * torch.randn(300, 3, device="cuda"))
+    with torch.no_grad():
+        n0 = shape.autograd_diff(p.clone())
+    n1 = shape.autograd_diff(p.clone())
+    assert n1.grad_fn is not None
+    assert (n0 - n1).abs().max().item() < 1e-4 * max(1.0, n0.abs().max().item())
+    w = torch.randn(300, 3, device="cuda")
+
+    def loss_of(n):
+        return eikonal_loss(n) + 0.1 * (torch.nn.functional.normalize(n, dim=-1) * w).sum(-1).mean()
+
+    loss_of(n1).backward()
+    got = {k: v.grad.detach().clone() for k, v in s.named_parameters()}
+    s.zero_grad()
+    # reference-op autograd (create_graph through the whole SphereSDF), fp32 on the GPU
+    pr = p.clone().requires_grad_()
+    out = s.forward_reference_ops(pr)
+    nr, = torch.autograd.grad(out, pr, torch.ones_like(out), create_graph=True)
+    loss_of(nr).backward()
+    for k, v in s.named_parameters():
+        if k == "shift.out.bias":       # a constant offset of the SDF: the normals do not depend on it
+            assert got[k].abs().max().item() == 0 and (v.grad is None or v.grad.abs().max().item() == 0)
+            continue
+        assert got[k].abs().max().item() > 0, k
+        _close(got[k], v.grad, k, rtol=5e-3, min_cos=0.999)
