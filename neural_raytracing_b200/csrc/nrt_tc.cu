@@ -281,7 +281,7 @@ static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, in
   const int64_t ntiles = (M + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
   NrtProfScope _ps(tag, st);
-  kern<<<grid, NET::NWG * NET::WPS * 32 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M, g_dbg_timeline, NoSave{});
+  kern<<<grid, NET::threads(NET::WPS), bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M, g_dbg_timeline, NoSave{});
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
 }

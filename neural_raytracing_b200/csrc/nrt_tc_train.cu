@@ -632,7 +632,7 @@ static int train_forward_io(const nrt_mlp_t* m, const IO& io, int64_t M, const T
   const int grid = (int)std::min<int64_t>((ws.ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
   {
     NrtProfScope _ps(TAG_TC_TRAIN_FWD, st);
-    kern<<<grid, NET::NWG * NET::WPS * 32 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, nullptr, sv);
+    kern<<<grid, NET::threads(NET::WPS), bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, nullptr, sv);
   }
   NRT_CUDA(cudaGetLastError());
   NRT_CUDA(cudaGetLastError());

@@ -486,6 +486,35 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
   if constexpr (SAVE) { if (one_col >= 0) save_row[tile_elem(one_col)] = one16<FMT>(); }
 }
 
+// K-split variant (see Net::KSPLIT): whole row into registers, `pre()` (bias of the next layer into the now free
+// accumulator, in-place encoding activation), first half -> arrive on bar_a, second half -> arrive on bar_b.
+template <int ACT, int FMT, int H, class PRE>
+__device__ __forceinline__ void convert_row_split(uint32_t dD, uint32_t aU, uint64_t* bar_a, uint64_t* bar_b, PRE pre,
+                                                  long long* t_loaded = nullptr, long long* t_a = nullptr) {
+  static_assert(H % 64 == 0, "two halves of whole 32-column chunks");
+  constexpr int NC = H / 32;
+  uint32_t acc[H];
+  tmem_load<H>(dD, acc);
+  tc_wait_ld();
+  if (t_loaded) *t_loaded = clock64();
+  pre();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t pk[16];
+    convert32<ACT, FMT>(acc + 32 * c, pk);
+    TmemIO<16>::st(aU + 16 * c, pk);
+    if (c == NC / 2 - 1) {
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bar_a);
+      if (t_a) *t_a = clock64();
+    }
+  }
+  tc_wait_st();
+  tc_fence_before();
+  mbar_arrive(bar_b);
+}
+
 // Last hidden layer of a network with a tiny output layer: act(accumulator row) . W_out (fp32, [H][4] in shared
 // memory, broadcast reads) accumulated on the fly; o[] must hold the output bias on entry.
 template <int ACT, int FMT, int H, int OUT, bool SAVE>
@@ -602,6 +631,12 @@ struct Net {
   static constexpr int COLS = DC + UC + EC;
   static constexpr int NSLOT = slots_of(COLS);
   static constexpr int NWG = NSLOT < 2 ? 2 : NSLOT;       // epilogue warpgroups launched
+  // one MMA-issuing warp per tile slot (NRT_MMA_WARP_PER_SLOT=0: a single warp that serves the slots in ready order)
+#ifndef NRT_MMA_WARP_PER_SLOT
+#define NRT_MMA_WARP_PER_SLOT 1
+#endif
+  static constexpr int NMMA = NRT_MMA_WARP_PER_SLOT ? NSLOT : 1;
+  static constexpr int threads(int wps) { return NWG * wps * 32 + 32 * NMMA; }
   static constexpr int STAGES = L + 3;                    // encode, init, L layers, out
   // Two of those stages need no tensor core and cost a full MMA -> commit -> wait round trip each:
   //  * split-precision inputs (in <= 5): the Fourier phases are in*F FMAs per sample -> computed in fp32 by the
@@ -614,6 +649,15 @@ struct Net {
   // (F2FP.PACK_AB ~4 cycles, HMUL2 / HMNMX2 2 cycles per warp instruction: ~512 cycles per 128x128 tile layer),
   // not by the latency of one warp's dependent chain, and 17 warps cap the kernel at 96 registers per thread.
   static constexpr int WPS = 4;
+  // K-split early start (k_mlp_tc): a hidden epilogue pulls the WHOLE accumulator row into registers first (the
+  // accumulator is then free: bias in), converts the first half of the columns, arrives on `ready_a`, converts the
+  // second half, arrives on `ready`.  The MMA warp issues the K-chunks of the first half (and the encoding chunks of
+  // a skip layer) on `ready_a`, i.e. UNDER the conversion of the second half, and only the remaining chunks after
+  // `ready`: the per-layer dependency chain  MMA -> epilogue -> MMA  loses about half a layer of tensor time.
+#ifndef NRT_KSPLIT
+#define NRT_KSPLIT 0
+#endif
+  static constexpr bool KSPLIT = NRT_KSPLIT != 0 && H % 64 == 0 && H <= 128;
   static constexpr bool ENC_CUDA = Y.basis_f32_off >= 0;
   static constexpr bool FUSE_OUT = Y.wout_f32_off >= 0;
   static constexpr int FIRST_STAGE = ENC_CUDA ? 1 : 0;
@@ -642,7 +686,9 @@ constexpr int kEpiThreads = 128;
 // Issues the MMAs of stage ST of one tile slot.  Called by the WHOLE MMA warp (convergent); one elected lane
 // issues.  (Issuing from a divergent single lane makes the compiler wrap every UTCHMMA in an
 // ELECT / R2UR / BRA.U.ANY serialisation loop: ~135 cycles per MMA instead of ~72, see profiles/.)
-template <class NET, int FMT, int ST>
+// PART 0: the whole stage; 1: first half of the hidden K-chunks + the encoding chunks, no commit (K-split, on
+// `ready_a`); 2: second half of the hidden K-chunks + commit (on `ready`).
+template <class NET, int FMT, int ST, int PART = 0>
 __device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE, uint64_t* done_bar) {
   constexpr Layout Y = NET::Y;
   constexpr uint32_t N = (uint32_t)Y.opN[ST];
@@ -659,21 +705,23 @@ __device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32
     const uint64_t bd0 = make_desc(NET::STREAM ? b_addr : b_addr + (uint32_t)Y.op_off[ST] * 2u, lbo, sbo);
 #pragma unroll
     for (int kc = 0; kc < kch; ++kc) {
+      if (PART == 1 && kc >= k_u / 2 && kc < k_u) continue;
+      if (PART == 2 && (kc < k_u / 2 || kc >= k_u)) continue;
       const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
       // every layer's accumulator was pre-loaded with its bias by the previous epilogue; only the
       // phase GEMM (stage 0) starts from zero
       mma_ts(dD, a, bd0 + (uint64_t)((kc * 2 * lbo) >> 4), idesc, (ST > 0 || kc > 0) ? 1u : 0u);
     }
-    tc_commit(done_bar);
+    if (PART != 1) tc_commit(done_bar);
   }
   __syncwarp();
 }
 // runtime stage -> compile-time stage through a jump table (a linear if-chain cost up to ~150 cycles of taken
 // branches per stage on the single issuing warp, which serves every tile slot)
-template <class NET, int FMT>
+template <class NET, int FMT, int PART = 0>
 __device__ __forceinline__ void issue_stage_dyn(int st, uint32_t b_addr, uint32_t dD, uint32_t aU, uint32_t aE,
                                                 uint64_t* done_bar) {
-#define NRT_STAGE_CASE(S) case S: if constexpr (S < NET::STAGES) issue_stage<NET, FMT, S>(b_addr, dD, aU, aE, done_bar); break;
+#define NRT_STAGE_CASE(S) case S: if constexpr (S < NET::STAGES && (PART == 0 || S >= 2)) issue_stage<NET, FMT, S, PART>(b_addr, dD, aU, aE, done_bar); break;
   switch (st) {
     NRT_STAGE_CASE(0) NRT_STAGE_CASE(1) NRT_STAGE_CASE(2) NRT_STAGE_CASE(3) NRT_STAGE_CASE(4) NRT_STAGE_CASE(5)
     NRT_STAGE_CASE(6) NRT_STAGE_CASE(7) NRT_STAGE_CASE(8) NRT_STAGE_CASE(9) NRT_STAGE_CASE(10) NRT_STAGE_CASE(11)
@@ -710,7 +758,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 template <class NET, class IO, int FMT, class SV = NoSave, int WPS = NET::WPS>
-__global__ void __launch_bounds__(NET::NWG * WPS * 32 + 32, 1)
+__global__ void __launch_bounds__(NET::threads(WPS), 1)
 k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg, SV sv = SV{}) {
   constexpr int EPI = WPS * 32;                 // epilogue threads per tile slot
   static_assert(NET::FITS_TMEM, "network does not fit in TMEM");
@@ -733,7 +781,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   __shared__ __align__(8) uint64_t bar_wfull[3][2];   // streaming: stage buffer b of slot s has landed
   __shared__ uint32_t s_opoff[NET::STAGES], s_opbytes[NET::STAGES];
   __shared__ __align__(8) uint64_t bar_ready[3];
+  __shared__ __align__(8) uint64_t bar_ready_a[3];    // K-split: first half of the activations is in place
   __shared__ __align__(8) uint64_t bar_done[3];
+  // K-split early start: not with the 8-warp epilogue, not while saving activation tiles (training forward)
+  constexpr bool KSPLIT = NET::KSPLIT && WPS == 4 && !SV::kOn;
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_bias[NET::STAGES];
   constexpr bool ITER = IsIterative<IO>::value;
@@ -742,7 +793,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const bool is_mma_warp = warp == NET::NWG * WPS;
+  const int mma_id = warp - NET::NWG * WPS;          // >= 0: MMA-issuing warp
+  const bool is_mma_warp = mma_id == 0;              // the one that also owns TMEM allocation and the weight load
   const int64_t ntiles = (M + 127) / 128;
   if (tid < NET::STAGES) {
     s_bias[tid] = (uint32_t)Y.bias_off[tid];
@@ -754,7 +806,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     s_slot_live[0] = 1; s_slot_live[1] = 1; s_slot_live[2] = 1;
     mbar_init(&bar_w, 1);
     for (int s = 0; s < 3; ++s) {
-      mbar_init(&bar_ready[s], EPI); mbar_init(&bar_done[s], 1);
+      mbar_init(&bar_ready[s], EPI); mbar_init(&bar_done[s], 1); mbar_init(&bar_ready_a[s], EPI);
       mbar_init(&bar_wfull[s][0], 1); mbar_init(&bar_wfull[s][1], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -789,16 +841,29 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   constexpr uint32_t tmem = 0u;
   mbar_wait(&bar_w, 0);
 
-  if (is_mma_warp) {
-    // ===================== MMA issuer =====================
-    // The whole warp runs this loop convergently (one elected lane issues).  Slots are served in
-    // whatever order they become ready, so the two tiles drift into anti-phase: the tensor pipe works
-    // on one tile while the other tile's epilogue (or prologue / output store) runs.
+  if (mma_id >= 0) {
+    // ===================== MMA issuer(s) =====================
+    // The whole warp runs this loop convergently (one elected lane issues).  With one MMA warp per tile slot
+    // (NET::NMMA == NSLOT) every warp blocks on its own slot's `ready` barrier: a slot is served as soon as its
+    // epilogue arrives, instead of after the other slots' stages (a single warp needs 50-60 cycles per tcgen05.mma
+    // it issues, 300-700 per stage, and served the slots round robin).  With a single MMA warp the slots are polled
+    // and served in whatever order they become ready.  Either way the tiles drift into anti-phase: the tensor pipe
+    // works on one tile while the other tile's epilogue (or prologue / output store) runs.
+    constexpr int NMMA = NET::NMMA;
+    constexpr bool OWN = NMMA == NSLOT;      // this warp serves exactly one slot: blocking waits
+    auto mine = [&](int slot) { return slot % NMMA == mma_id; };
+    auto is_ready = [&](uint64_t* bar, uint32_t parity) {
+      if constexpr (OWN) { mbar_wait(bar, parity); return true; }
+      else return mbar_test(bar, parity);
+    };
     const uint32_t sW_addr = smem_u32(sW);
     int st[3] = {NET::FIRST_STAGE, NET::FIRST_STAGE, NET::FIRST_STAGE};
     uint32_t n_ready[3] = {0, 0, 0};
+    uint32_t n_ready_a[3] = {0, 0, 0};
+    bool half_issued[3] = {false, false, false};
     int64_t tile[3] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1, (int64_t)blockIdx.x * NSLOT + 2};
-    bool live[3] = {ITER || tile[0] < ntiles, NSLOT > 1 && (ITER || tile[1] < ntiles), NSLOT > 2 && (ITER || tile[2] < ntiles)};
+    bool live[3] = {mine(0) && (ITER || tile[0] < ntiles), NSLOT > 1 && mine(1) && (ITER || tile[1] < ntiles),
+                    NSLOT > 2 && mine(2) && (ITER || tile[2] < ntiles)};
     int it_dbg[3] = {0, 0, 0};
     uint32_t n_issued[3] = {0, 0, 0};   // streaming: stages issued per slot (selects the stage buffer)
     if (STREAM) {
@@ -814,7 +879,27 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
 #pragma unroll
       for (int slot = 0; slot < NSLOT; ++slot) {
         if (!live[slot]) continue;
-        if (!mbar_test(&bar_ready[slot], n_ready[slot] & 1)) continue;
+        if constexpr (KSPLIT) {
+          if (st[slot] >= 2 && !half_issued[slot]) {
+            // first half of a hidden stage's operand is in place: issue its K-chunks under the rest of the epilogue
+            if (!is_ready(&bar_ready_a[slot], n_ready_a[slot] & 1)) continue;
+            progressed = true;
+            n_ready_a[slot]++;
+            half_issued[slot] = true;
+            tc_fence_after();
+            const uint32_t base = tmem + slot * NET::COLS;
+            uint32_t b_addr = sW_addr;
+            if (STREAM) {
+              const uint32_t b = n_issued[slot] & 1;
+              mbar_wait(&bar_wfull[slot][b], (n_issued[slot] >> 1) & 1);
+              b_addr = sW_addr + (uint32_t)((slot * 2 + b) * NET::MAXOP);
+            }
+            if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 0);
+            issue_stage_dyn<NET, FMT, 1>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+            continue;
+          }
+        }
+        if (!is_ready(&bar_ready[slot], n_ready[slot] & 1)) continue;
         progressed = true;
         n_ready[slot]++;
         tc_fence_after();
@@ -835,7 +920,12 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           mbar_wait(&bar_wfull[slot][b], (n_issued[slot] >> 1) & 1);
           b_addr = sW_addr + (uint32_t)((slot * 2 + b) * NET::MAXOP);
         }
-        issue_stage_dyn<NET, FMT>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+        if (KSPLIT && half_issued[slot]) {
+          half_issued[slot] = false;
+          issue_stage_dyn<NET, FMT, 2>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+        } else {
+          issue_stage_dyn<NET, FMT>(st[slot], b_addr, base, base + NET::DC, base + NET::DC + NET::UC, &bar_done[slot]);
+        }
         if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 2);
         if (++st[slot] == NET::END_STAGE) {
           st[slot] = NET::FIRST_STAGE;
@@ -1045,45 +1135,60 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           tc_fence_after();
           estamp(2 + st, 4);
-          estamp(2 + st, 5);
+          if constexpr (!KSPLIT) estamp(2 + st, 5);
           const int coff = half * HW;     // this thread's first hidden column
+          // everything that must be in place before the next stage's MMAs: the bias of the layer that consumes
+          // these activations (into the accumulator, free once its row has been read) and, for the in-place plan,
+          // the activated encoding
+          auto pre = [&]() {
+            if constexpr (NET::INPLACE) {
+              if (st == 0 && primary) {
+                // the init layer has consumed the raw encoding: turn it into act(encoding) for the skip layers
+                static_assert(NET::KE % 16 == 0, "encoding width");
+#pragma unroll
+                for (int c = 0; c < NET::EC / 8; ++c) {
+                  uint32_t e[8];
+                  TmemIO<8>::ld(aE + 8 * c, e);
+                  tc_wait_ld();
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) e[j] = leaky_packed<FMT>(e[j]);
+                  TmemIO<8>::st(aE + 8 * c, e);
+                  if constexpr (SV::kOn)
+                    save_cols<8>(tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row), 16 * c, e);
+                }
+              }
+            }
+            if (st < L) preload_bias<HW>(dD + coff, sBias + s_bias[2 + st] + coff);
+            else {
+              // output-layer bias: every half writes only the accumulator columns it has just read
+              constexpr int N0 = NET::NOP < HW ? NET::NOP : HW, N1 = NET::NOP > HW ? NET::NOP - HW : 0;
+              if (primary) preload_bias<N0>(dD, sBias + s_bias[NET::STAGES - 1]);
+              else if constexpr (N1 > 0) preload_bias<N1>(dD + HW, sBias + s_bias[NET::STAGES - 1] + HW);
+            }
+          };
+          if constexpr (KSPLIT) {
+            // (one convergent call: the tcgen05 instructions inside are .sync.aligned; only lane_row 0 gets stamp slots)
+            long long* d = nullptr;
+            if (dbg != nullptr && lane_row == 0 && slot < 2 && blockIdx.x == 0 && it_dbg >= kDbgIt0 && it_dbg < kDbgIt0 + kDbgIts)
+              d = dbg + (((it_dbg - kDbgIt0) * NET::STAGES + 2 + st) * 2 + slot) * 8;
+            convert_row_split<NET::ACT, FMT, HW>(dD, aU, &bar_ready_a[slot], &bar_ready[slot], pre, d ? d + 5 : nullptr,
+                                                 d ? d + 6 : nullptr);
+            estamp(2 + st, 7);
+          } else {
           if constexpr (SV::kOn)
             convert_row<NET::ACT, FMT, HW, true>(dD + coff, aU + coff / 2,
                 tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row), coff, primary ? H : -1,
                 sv.masks + (int64_t)st * (H / 32) * (sv.ntiles * 128) + m, sv.ntiles * 128);
           else
             convert_row<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2);
-          // bias of the layer that consumes these activations goes into the (now free) accumulator; done after
-          // the conversion so the accumulator registers are dead and all LDS.128 can be in flight
-          if constexpr (NET::INPLACE) {
-            if (st == 0 && primary) {
-              // the init layer has consumed the raw encoding: turn it into act(encoding) for the skip layers
-              static_assert(NET::KE % 16 == 0, "encoding width");
-#pragma unroll
-              for (int c = 0; c < NET::EC / 8; ++c) {
-                uint32_t e[8];
-                TmemIO<8>::ld(aE + 8 * c, e);
-                tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 8; ++j) e[j] = leaky_packed<FMT>(e[j]);
-                TmemIO<8>::st(aE + 8 * c, e);
-                if constexpr (SV::kOn)
-                  save_cols<8>(tile_row_ptr(sv.enc_act, m >> 7, NET::KE + kTileRowsExtra, lane_row), 16 * c, e);
-              }
-            }
-          }
-          if (st < L) preload_bias<HW>(dD + coff, sBias + s_bias[2 + st] + coff);
-          else {
-            // output-layer bias: every half writes only the accumulator columns it has just read
-            constexpr int N0 = NET::NOP < HW ? NET::NOP : HW, N1 = NET::NOP > HW ? NET::NOP - HW : 0;
-            if (primary) preload_bias<N0>(dD, sBias + s_bias[NET::STAGES - 1]);
-            else if constexpr (N1 > 0) preload_bias<N1>(dD + HW, sBias + s_bias[NET::STAGES - 1] + HW);
-          }
+          // done after the conversion so the accumulator registers are dead and all LDS.128 can be in flight
+          pre();
           estamp(2 + st, 6);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&bar_ready[slot]);
           estamp(2 + st, 7);
+          }
         }
         // ---- output layer ----
         if (!primary) {
