@@ -508,6 +508,10 @@ __device__ __forceinline__ void convert_row_split(uint32_t dD, uint32_t aU, uint
       tc_fence_before();
       mbar_arrive(bar_a);
       if (t_a) *t_a = clock64();
+      // keep the compiler from hoisting the second half's conversion above the arrive (volatile asm statements
+      // stay in order; the conversion is register-only code and would otherwise be scheduled first)
+#pragma unroll
+      for (int i = H / 2; i < H; ++i) asm volatile("" : "+r"(acc[i]));
     }
   }
   tc_wait_st();
@@ -631,12 +635,6 @@ struct Net {
   static constexpr int COLS = DC + UC + EC;
   static constexpr int NSLOT = slots_of(COLS);
   static constexpr int NWG = NSLOT < 2 ? 2 : NSLOT;       // epilogue warpgroups launched
-  // one MMA-issuing warp per tile slot (NRT_MMA_WARP_PER_SLOT=0: a single warp that serves the slots in ready order)
-#ifndef NRT_MMA_WARP_PER_SLOT
-#define NRT_MMA_WARP_PER_SLOT 1
-#endif
-  static constexpr int NMMA = NRT_MMA_WARP_PER_SLOT ? NSLOT : 1;
-  static constexpr int threads(int wps) { return NWG * wps * 32 + 32 * NMMA; }
   static constexpr int STAGES = L + 3;                    // encode, init, L layers, out
   // Two of those stages need no tensor core and cost a full MMA -> commit -> wait round trip each:
   //  * split-precision inputs (in <= 5): the Fourier phases are in*F FMAs per sample -> computed in fp32 by the
@@ -670,6 +668,15 @@ struct Net {
   // prefetches the next stage's operand (cp.async.bulk from L2) while the current stage computes.
   static constexpr int kSmemBudget = 227 * 1024 - 2048;
   static constexpr bool STREAM = Y.bytes > kSmemBudget;
+  // One MMA-issuing warp per tile slot for the networks with resident weights (NRT_MMA_WARP_PER_SLOT=0: always a
+  // single warp that serves the slots in ready order).  Measured on B200: NeRFLE.first 32.3 -> 30.7 ms, .second
+  // 32.2 -> 24.3 ms per 800x800x192 frame; the weight-streaming softplus SDF net is SFU-bound in its epilogue and
+  // is 7 % FASTER with the single warp (march 10.6 vs 11.3 ms), so it keeps one.
+#ifndef NRT_MMA_WARP_PER_SLOT
+#define NRT_MMA_WARP_PER_SLOT 1
+#endif
+  static constexpr int NMMA = (NRT_MMA_WARP_PER_SLOT && !STREAM) ? NSLOT : 1;
+  static constexpr int threads(int wps) { return NWG * wps * 32 + 32 * NMMA; }
   static constexpr int max_op_bytes() {
     int m = 0;
     for (int o = 0; o < Y.n_ops; ++o) m = imax(m, Y.opN[o] * Y.opK[o] * 2);
@@ -971,6 +978,15 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
       auto estamp = [&](int st, int k) { if (lane_row == 0) stamp(it_dbg, st, slot, k); };
       typename StateOf<IO>::type state;
       if constexpr (ITER) io.init(state);
+#ifndef NRT_SLOT_STAGGER
+#define NRT_SLOT_STAGGER 900
+#endif
+      if (NRT_SLOT_STAGGER > 0 && slot > 0) {
+        // start the slots out of phase (cycles per slot index): slots that reach their MMA stages together interleave
+        // in the in-order tensor pipe and then run their epilogues together as well (measured: 57.3 -> 56.4 ms/frame)
+        const long long t_start = clock64();
+        while (clock64() - t_start < (long long)slot * NRT_SLOT_STAGGER) {}
+      }
       for (int64_t t0 = (int64_t)blockIdx.x * NSLOT;; t0 += (int64_t)gridDim.x * NSLOT, ++it_dbg) {
         int64_t m = 0;
         bool valid;
