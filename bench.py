@@ -32,6 +32,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: with NCCL_DEBUG=VERSION/INFO in the environment NCCL prints its version banner
+# to stdout at the first collective, so the library is held to warnings (set NRT_KEEP_NCCL_DEBUG=1 to keep the setting)
+if not os.environ.get("NRT_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np  # noqa: E402
 
 IMG = 800
