@@ -1,0 +1,3 @@
+"""Mirror of the pieces of `pytorch3d.renderer` that the path tracer's scripts import (cameras only)."""
+from .cameras import (FoVPerspectiveCameras, OpenGLPerspectiveCameras, camera_position_from_spherical_angles,  # noqa: F401
+                      look_at_rotation, look_at_view_transform)

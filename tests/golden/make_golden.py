@@ -319,8 +319,38 @@ def gen_pipeline():
     print("pipeline.npz: colocate img mean %.4f hits %d; dtu loss %.5f" % (out["colocate_img"].mean(), len(out["colocate_raw_normals"]), loss.item()))
 
 
+def gen_cameras():
+    """look_at_view_transform + OpenGLPerspectiveCameras.sample_positions as colocate.py:54-56 / nerfle.py:96 /
+    training_utils.py:198 use them (renderer/cameras.py:539-575, 1313-1422)."""
+    from pytorch3d.renderer import OpenGLPerspectiveCameras, look_at_view_transform
+    from pytorch3d.pathtracer.samplers import Sampler
+    out = {}
+    elev = torch.linspace(0, 45, 5)
+    azim = torch.linspace(-90, 90, 5)
+    R, Tt = look_at_view_transform(dist=1.0, elev=elev, azim=azim)
+    out["elev"], out["azim"], out["R"], out["T"] = elev.numpy(), azim.numpy(), R.numpy(), Tt.numpy()
+    R2, T2 = look_at_view_transform(dist=2.7, elev=30.0, azim=200.0, at=((0.1, -0.2, 0.05),))
+    out["R2"], out["T2"] = R2.numpy(), T2.numpy()
+    R3, T3 = look_at_view_transform(eye=((0.0, 1.5, 0.0), (0.4, 0.3, -1.0)), at=((0.0, 0.0, 0.0),))   # first one: up || view
+    out["R3"], out["T3"] = R3.numpy(), T3.numpy()
+    cams = OpenGLPerspectiveCameras(device="cpu", R=R, T=Tt)
+    out["centers"] = cams.get_camera_center().numpy()
+    size = 16
+    gx, gy = torch.meshgrid(torch.arange(4, 12, dtype=torch.float), torch.arange(2, 10, dtype=torch.float))
+    pos = torch.stack([gy, gx], dim=-1)
+    out["positions"] = pos.numpy()
+    rays = cams.sample_positions(pos, Sampler(device="cpu"), bundle_size=2, size=size, N=len(cams), with_noise=False)
+    out["rays"] = rays.numpy()
+    cam1 = OpenGLPerspectiveCameras(device="cpu", R=R2, T=T2, fov=45.0, znear=0.5, zfar=20.0)
+    out["rays_fov45"] = cam1.sample_positions(pos, Sampler(device="cpu"), bundle_size=1, size=size, N=1, with_noise=False).numpy()
+    out["center_fov45"] = cam1.get_camera_center().numpy()
+    out["src"] = np.array("pytorch3d/renderer/cameras.py:125-150, 539-575, 1284-1422")
+    np.savez_compressed(os.path.join(HERE, "cameras.npz"), **out)
+    print("cameras.npz: rays", out["rays"].shape, "dir norm", np.linalg.norm(out["rays"][..., 3:], axis=-1).mean())
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline"]
+    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
