@@ -96,6 +96,25 @@ def rand_uv(w: int, h: int, size: int):
     return random.randint(0, w - size), random.randint(0, h - size)
 
 
+def rand_uv_mask(mask, size: int):
+    """utils.py:378-383: top-left corner of a crop, drawn among the mask's non-zero pixels that keep the crop
+    (and half a crop of margin) inside the image; python RNG like the reference."""
+    half = int(math.ceil(size / 2))
+    valid = mask[half:-half - size, half:-half - size, ...]
+    p, q = valid.nonzero(as_tuple=True)[:2]
+    idx = random.randint(0, len(p) - 1)
+    return p[idx], q[idx]
+
+
+def load_image(src, resize=None):
+    """utils.py:365-369: image file -> float tensor in [0, 1]."""
+    from PIL import Image
+    img = Image.open(src)
+    if resize is not None:
+        img = img.resize(resize)
+    return torch.from_numpy(np.array(img, dtype=float) / 255).float()
+
+
 class LossSampler:
     """utils.py:134-147: samples view indices proportionally to the square of their last loss."""
 
@@ -117,10 +136,16 @@ class LossSampler:
 
 
 def masked_loss(got, exp, throughput, exp_mask, eps: float = 1e-10, trim: int = 0, mask_weight: float = 1,
-                with_logits: bool = True, tone_mapping: bool = False, ssim_fn=None):
-    """utils.py:307-359.  The SSIM term of the reference comes from the unpinned third-party
-    `pytorch_msssim`; pass `ssim_fn(a, b) -> scalar` to include it, otherwise it is omitted
-    (SURVEY.md section 8c)."""
+                with_logits: bool = True, tone_mapping: bool = False, ssim_fn="default"):
+    """utils.py:307-359: 10 * (l2 + rmse + l1 - log ssim) on the hit pixels + mask_weight * BCE on the misses.
+    The SSIM term of the reference comes from the unpinned third-party `pytorch_msssim`; the default here is the
+    in-repo restatement (pathtracer/ssim.py, parity unpinned).  `ssim_fn=None` drops the term
+    (what the benchmarks do), any callable `(a, b) -> scalar` replaces it."""
+    if ssim_fn == "default":
+        from .ssim import ssim as _ssim
+
+        def ssim_fn(a, b):
+            return _ssim(a, b, data_range=1, size_average=True)
     active = ((throughput > 0) & (exp_mask == 1)).squeeze(-1)
     misses = ~active
     color_loss = 0

@@ -349,8 +349,55 @@ def gen_cameras():
     print("cameras.npz: rays", out["rays"].shape, "dir norm", np.linalg.norm(out["rays"][..., 3:], axis=-1).mean())
 
 
+def train_loop_case(P, train_nerf, device):
+    """The tiny nerf_synthetic.py-style problem both the reference and the mirror train on (shared by the test)."""
+    import scenes
+    shape, sphere, bsdf, lights, _integ, _w = scenes.build_pipeline(P, "dtu", device=device)
+    size, crop = 16, 4
+    c2w, focal = synth.nerf_cameras(3, size, device=device)
+    gx, gy = np.meshgrid(np.linspace(0, 1, size), np.linspace(0, 1, size), indexing="ij")
+    imgs, masks = [], []
+    for i in range(3):
+        img = np.stack([0.3 + 0.4 * gx, 0.5 + 0.0 * gy, 0.6 - 0.3 * gy], axis=-1) * (0.8 + 0.1 * i)
+        m = ((gx - 0.5) ** 2 + (gy - 0.5) ** 2 < 0.2).astype(np.float32)
+        imgs.append(torch.tensor(img, dtype=torch.float, device=device))
+        masks.append(torch.tensor(m, dtype=torch.float, device=device))
+    params = list(sphere.parameters()) + list(bsdf.parameters()) + list(lights.parameters())
+    opt = torch.optim.AdamW(params, lr=8e-5, weight_decay=0)
+    random.seed(5); np.random.seed(5); torch.manual_seed(5)
+    losses = train_nerf(shape, bsdf, P.integrators.Direct(), lights, [c for c in c2w], focal, imgs, masks, opt, size, crop,
+                        N=2, iters=3, num_ckpts=1, save_freq=10**6, valid_freq=10**6, silent=True)
+    return losses, sphere, bsdf
+
+
+def gen_train_loop():
+    """Three iterations of the UNMODIFIED reference's train_nerf (training_utils.py:211-300) on a 16x16, 3-view
+    problem.  Patched for the run: save_image (matplotlib is stubbed) and the `ssim` that utils.masked_loss imports
+    from the absent pytorch_msssim, which is replaced by the in-repo restatement (so the SSIM term itself stays
+    unpinned; on 4x4 crops it is the per-pixel formula without any window)."""
+    import pytorch3d.pathtracer as P
+    import pytorch3d.pathtracer.training_utils as TU
+    import pytorch3d.pathtracer.utils as RU
+    import pytorch3d.pathtracer.shapes.sdfs, pytorch3d.pathtracer.bsdf, pytorch3d.pathtracer.lights  # noqa: F401
+    import pytorch3d.pathtracer.integrators, pytorch3d.pathtracer.neural_blocks, pytorch3d.pathtracer.cameras  # noqa: F401
+    from neural_raytracing_b200.pathtracer.ssim import ssim as our_ssim
+    RU.ssim = our_ssim
+    TU.ssim = our_ssim
+    TU.save_image = lambda *a, **k: None
+    random.random = lambda: FIXED_RANDOM
+    losses, sphere, bsdf = train_loop_case(P, TU.train_nerf, "cpu")
+    out = {"losses": np.array(losses, np.float64),
+           "sdf_out_w_after": sphere.shift.out.weight.detach().numpy().copy(),
+           "spvar_out_b_after": bsdf.sp_var_fn.out.bias.detach().numpy().copy(),
+           "fixed_random": np.array(FIXED_RANDOM, np.float64),
+           "src": np.array("pytorch3d/pathtracer/training_utils.py:211-300; utils.py:134-147, 307-359, 378-383")}
+    np.savez_compressed(os.path.join(HERE, "train_loop.npz"), **out)
+    print("train_loop.npz: losses", losses)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras"]
+    which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
+                             "train_loop"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
