@@ -1,0 +1,107 @@
+"""GPU tests (-m gpu) at BASELINE.json's full sizes through size-independent properties, plus the empty-input edge
+of every entry point.  (Parity against the oracle is established at sizes the oracle finishes in seconds:
+test_gpu_parity.py, test_gpu_tensorcore.py.)"""
+import numpy as np
+import pytest
+
+import helpers
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_cfg2_full_frame_properties():
+    """800 x 800 rays, 64 coarse + 128 fine samples (the bench workload), tensor-core path, deterministic sampling:
+    finite and in [0, 1]; any subset of the rays rendered on its own gives bit-identical radiance (rays are
+    independent units: this is what makes the ray sharding of section 8e exact); a permutation of the rays permutes
+    the image."""
+    import torch
+    from neural_raytracing_b200 import ops
+    w1, w2 = helpers.nerfle_weights(False)
+    m1, m2 = helpers.cuda_mlp(w1), helpers.cuda_mlp(w2)
+    R = 800 * 800
+    rays = _t(synth.camera_rays(71, R))
+    code = _t(np.array([[0.4, 1.0, 0.3]], np.float32))
+    kw = dict(prec="f16", n_coarse=64, n_fine=128, t_near=0.0, t_far=2.05, jitter_seed=0)
+    full = ops.nerfle_render(m1, m2, rays, None, code, **kw)
+    assert tuple(full.shape) == (R, 3) and torch.isfinite(full).all()
+    assert full.min().item() >= 0.0 and full.max().item() <= 1.0 + 1e-6
+    idx = torch.arange(7, R, 311, device="cuda")                       # 2,058 rays spread over all 10 chunks
+    sub = ops.nerfle_render(m1, m2, rays[idx].contiguous(), None, code, **kw)
+    assert torch.equal(sub, full[idx])
+    g = torch.Generator(device="cuda").manual_seed(3)
+    perm = torch.randperm(R, device="cuda", generator=g)
+    shuffled = ops.nerfle_render(m1, m2, rays[perm].contiguous(), None, code, **kw)
+    assert torch.equal(shuffled, full[perm])
+
+
+def test_compositing_is_linear_in_radiance_at_scale():
+    """nerf.py:205-213: for fixed densities the composite is a linear map of the per-sample colours (the weights
+    depend on sigma and t only), checked at 100,000 rays x 192 samples; and its backward is that map's adjoint."""
+    import torch
+    from neural_raytracing_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    S, R = 192, 100_000
+    sigma = torch.randn(S, R, device="cuda", generator=g) * 2
+    ts = torch.linspace(0.01, 2.0, S, device="cuda")
+    c1 = torch.rand(S, R, 3, device="cuda", generator=g)
+    c2 = torch.rand(S, R, 3, device="cuda", generator=g)
+    o1, o2 = ops.composite_forward(sigma, c1, ts), ops.composite_forward(sigma, c2, ts)
+    o12 = ops.composite_forward(sigma, 0.25 * c1 + 3.0 * c2, ts)
+    scale = o12.abs().max().item()
+    assert (o12 - (0.25 * o1 + 3.0 * o2)).abs().max().item() < 2e-5 * max(1.0, scale)
+    go = torch.randn(R, 3, device="cuda", generator=g)
+    g_sigma, g_rgb = ops.composite_backward(sigma, c1, ts, go)
+    # adjoint identity <go, A c2> = <A^T go, c2>
+    lhs = (go * o2).sum().item()
+    rhs = (g_rgb * c2).sum().item()
+    assert abs(lhs - rhs) < 1e-3 * max(1.0, abs(lhs))
+    assert torch.isfinite(g_sigma).all()
+
+
+def test_sphere_trace_full_crop_is_subset_invariant():
+    """65,536-ray training crop (colocate.py:122,127) on the exact fp32 march: a subset of the rays marched alone
+    gives bit-identical depths and hit flags (slot compaction / the ray queue must not couple rays)."""
+    import torch
+    from neural_raytracing_b200 import ops
+    w = helpers.golden_sdf_weights()
+    s = helpers.cuda_sdf(w)
+    rays = _t(synth.camera_rays(72, 65536))
+    d, h = ops.sphere_trace(s, rays, 1e-3, 64, 10.0)
+    idx = torch.arange(3, 65536, 97, device="cuda")
+    d2, h2 = ops.sphere_trace(s, rays[idx].contiguous(), 1e-3, 64, 10.0)
+    assert torch.equal(h2, h[idx]) and torch.equal(d2.view(torch.int32), d[idx].view(torch.int32))
+    assert 0 < int(h.sum()) < 65536
+
+
+def test_empty_inputs_everywhere():
+    """Zero rays / samples: every op returns an empty result of the right shape and launches nothing."""
+    import torch
+    from neural_raytracing_b200 import ops
+    w1, w2 = helpers.nerfle_weights(False)
+    m1, m2 = helpers.cuda_mlp(w1), helpers.cuda_mlp(w2)
+    e3, e6 = torch.zeros(0, 3, device="cuda"), torch.zeros(0, 6, device="cuda")
+    ts = torch.linspace(0, 2.0, 64, device="cuda")
+    code = torch.tensor([[0.4, 1.0, 0.3]], device="cuda")
+    for prec in ("f32", "f16"):
+        assert tuple(ops.mlp_forward(m1, e3, prec=prec).shape) == (0, 65)
+        assert tuple(ops.nerfle_render(m1, m2, e6, ts, code, prec=prec).shape) == (0, 3)
+    s = helpers.cuda_sdf(helpers.golden_sdf_weights())
+    for prec in ("f32", "f16"):
+        d, h = ops.sphere_trace(s, e6, 1e-3, 64, 10.0, prec=prec)
+        assert d.numel() == 0 and h.numel() == 0
+        assert ops.sdf_eval(s, e3, prec=prec).numel() == 0
+        assert ops.shadow_test(s, e6, torch.zeros(0, device="cuda"), 1e-3, 64, prec=prec).numel() == 0
+    v, gr = ops.sdf_value_grad(s, e3)
+    assert v.numel() == 0 and tuple(gr.shape) == (0, 3)
+    val, jac, acts = ops.mlp_value_jac_forward(s.shift, e3, save_acts=True)
+    assert tuple(val.shape) == (0, 1) and tuple(jac.shape) == (0, 1, 3)
+    gp = ops.mlp_value_jac_backward(s.shift, e3, acts, val, jac)
+    assert gp.abs().sum().item() == 0
+    assert ops.composite_forward(torch.zeros(64, 0, device="cuda"), torch.zeros(64, 0, 3, device="cuda"), ts).numel() == 0
+    assert ops.param_rusin2(e3, e3).numel() == 0
