@@ -197,4 +197,6 @@ class _FusedMLP(torch.autograd.Function):
         for w, b in zip(gW, gb):
             flat += [w, b]
         gx = None if g_x is None else g_x.reshape(x.shape)
+        if g_lat is not None:
+            g_lat = g_lat.reshape(lat.shape)          # the kernels see [M, latent]; autograd wants the caller's shape
         return (None, gx, g_lat, None) + tuple(flat)

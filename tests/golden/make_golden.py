@@ -395,9 +395,44 @@ def gen_train_loop():
     print("train_loop.npz: losses", losses)
 
 
+def gen_plain_nerf():
+    """PlainNeRF.forward (shapes/nerf.py:46-74) with its density noise (:66) switched off (torch.randn_like -> 0 for
+    the call) and the far-plane jitter fixed; plus the parameter names / shapes of every learned component of the path
+    (what a checkpoint of the reference holds: dtu.py:93-108 pickles / jit-saves these modules)."""
+    from pytorch3d.pathtracer.shapes.nerf import PlainNeRF
+    out = {}
+    random.random = lambda: FIXED_RANDOM
+    n = PlainNeRF(device="cpu")
+    synth.fill_module(n, 81)
+    with torch.no_grad():
+        n.first.out.bias[0] = 0.8        # positive density, otherwise every weight is 0 and the image is 0.5
+    rays = T(synth.camera_rays(9, 2 * 6 * 5).reshape(2, 6, 5, 1, 6))
+    latent = T(np.random.RandomState(4).standard_normal((2, 32)).astype(np.float32) * 0.5)
+    n.assign_latent(latent)
+    real = torch.randn_like
+    torch.randn_like = lambda t, **k: torch.zeros_like(t)
+    try:
+        with torch.no_grad():
+            rgb = n(rays, None)
+    finally:
+        torch.randn_like = real
+    out["rays"], out["latent"], out["rgb"] = rays.numpy(), latent.numpy(), rgb.numpy()
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    # parameter inventory of the learned components
+    mods = {"SphereSDF": SphereSDF(n=64, device="cpu"), "NeRFLE": NeRFLE(device="cpu"), "NeRFLE_envmap": NeRFLE(envmap=True, device="cpu"),
+            "PlainNeRF": n, "NeuralBSDF": NeuralBSDF(device="cpu"), "LightField": LightField(device="cpu"),
+            "ComposeSpatialVarying": ComposeSpatialVarying([NeuralBSDF(device="cpu"), Diffuse(device="cpu")], device="cpu")}
+    for name, m in mods.items():
+        sd = m.state_dict()
+        out["sd_" + name] = np.array([k + ":" + "x".join(str(d) for d in v.shape) for k, v in sd.items()])
+    out["src"] = np.array("pytorch3d/pathtracer/shapes/nerf.py:9-74; state_dict() of sdfs.py:16-31, nerf.py:153-172, bsdfs.py:482-496, 613-621, lights.py:155-164")
+    np.savez_compressed(os.path.join(HERE, "plain_nerf.npz"), **out)
+    print("plain_nerf.npz: rgb", out["rgb"].shape, "mean", out["rgb"].mean(), "std", out["rgb"].std(), "; state dicts", {k: len(out["sd_" + k]) for k in mods})
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop"]
+                             "train_loop", "plain_nerf"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
