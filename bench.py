@@ -32,10 +32,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# stdout carries exactly ONE JSON line: with NCCL_DEBUG=VERSION/INFO in the environment NCCL prints its version banner
-# to stdout at the first collective, so the library is held to warnings (set NRT_KEEP_NCCL_DEBUG=1 to keep the setting)
-if not os.environ.get("NRT_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there at the first collective, whatever NCCL_DEBUG says on this image), so descriptor 1 is pointed at
+# stderr for the whole run and the result line goes to a private duplicate of the original stdout.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit_result(line: dict):
+    os.write(_RESULT_FD, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -183,7 +190,7 @@ def run_reference(args, rank):
         "e2e": {"value": rate, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 def workload_config(precision):
@@ -626,7 +633,7 @@ def main():
             "cpu_baseline": cpu,
             "also": also,
         }
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if world > 1:
         dist.destroy_process_group()
 
