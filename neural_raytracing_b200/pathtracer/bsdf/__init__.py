@@ -1,1 +1,1 @@
-from .bsdfs import BSDF, ComposeSpatialVarying, Conductor, Diffuse, NeuralBSDF, fresnel_conductor
+from .bsdfs import BSDF, BSDFSample, ComposeSpatialVarying, Conductor, Diffuse, NeuralBSDF, fresnel_conductor

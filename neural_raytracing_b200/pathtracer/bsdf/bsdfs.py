@@ -1,6 +1,8 @@
 """BSDFs used by the hot path (pytorch3d/pathtracer/bsdf/bsdfs.py): Diffuse, Conductor,
-NeuralBSDF and the spatially varying composition."""
+NeuralBSDF and the spatially varying composition; `eval_and_pdf` for the Direct integrator, `sample` for the
+multi-bounce Path integrator."""
 import math
+from dataclasses import dataclass
 from itertools import chain
 
 import torch
@@ -10,6 +12,7 @@ import torch.nn.functional as F
 from ... import ops
 from ..neural_blocks import SkipConnMLP
 from ..utils import param_rusin2
+from ..warps import square_to_cos_hemisphere
 
 
 def identity(x):
@@ -23,6 +26,39 @@ def identity_div_pi(x):
 def square_to_cos_hemisphere_pdf(v):
     """warps.py: cosine-hemisphere pdf = cos(theta) / pi."""
     return v[..., 2] / math.pi
+
+
+def local_reflect(v):
+    """bsdfs.py:126-129: mirror about the local normal (0, 0, 1)."""
+    return torch.cat([-v[..., 0:1], -v[..., 1:2], v[..., 2:3]], dim=-1)
+
+
+@dataclass
+class BSDFSample:
+    """One sampled bounce (bsdfs.py:22-63): local outgoing direction and its pdf."""
+    pdf: torch.Tensor = 0
+    wo: torch.Tensor = 0
+    eta: torch.Tensor = 1
+
+    @classmethod
+    def zeros_like(cls, like):
+        return cls(pdf=torch.zeros(like.shape[:-1], device=like.device), wo=torch.zeros_like(like), eta=1)
+
+    @staticmethod
+    def compose(samples, k, selections):
+        """Per point, the sample of the selected child; its pdf times the selection weight (bsdfs.py:44-63)."""
+        nb = k.shape[-1]
+        rows = torch.arange(selections.shape[0], device=selections.device)
+        pdfs = torch.stack([s.pdf for s in samples], dim=-1).reshape(-1, nb)
+        pdf = (pdfs[rows, selections] * k.reshape(-1, nb)[rows, selections]).reshape_as(samples[0].pdf)
+        wos = torch.stack([s.wo for s in samples], dim=-1).reshape(-1, 3, nb)
+        wo = wos[rows, :, selections].reshape_as(samples[0].wo)
+        return BSDFSample(pdf=pdf, wo=F.normalize(wo, dim=-1), eta=samples[0].eta)
+
+
+def _cos_hemisphere_sample(it, sampler):
+    wo = F.normalize(square_to_cos_hemisphere(sampler.sample(it.shape()[:-1] + (2,), device=it.device())), dim=-1)
+    return BSDFSample(pdf=square_to_cos_hemisphere_pdf(wo), wo=wo, eta=1.0)
 
 
 class BSDF(nn.Module):
@@ -60,6 +96,15 @@ class Diffuse(BSDF):
     def random(self):
         self.reflectance = torch.rand_like(self.reflectance, requires_grad=True)
         return self
+
+    def sample(self, it, sampler, active=True):
+        """bsdfs.py:88-106: cosine-hemisphere direction; the spectrum is preproc(reflectance) on every point (the
+        reference leaves the masking of inactive points commented out)."""
+        active = (it.wi[..., 2] > 0) & active
+        if not active.any():
+            return BSDFSample.zeros_like(it.p), torch.zeros_like(it.p)
+        bs = _cos_hemisphere_sample(it, sampler)
+        return bs, self.preproc(self.reflectance).expand(*it.shape()).clone()
 
     def eval_and_pdf(self, it, wo, active=True):
         spectrum = self.preproc(wo[..., 2].unsqueeze(-1) * self.reflectance)
@@ -100,6 +145,17 @@ class Conductor(BSDF):
     def parameters(self):
         return [self.eta, self.k, self.specular]
 
+    def sample(self, it, sampler, active=True):
+        """bsdfs.py:390-400: the mirror direction with pdf 1, specular * Fresnel on the front-facing active points.
+        (The reference calls the two-argument `reflect(n, v)` with one argument there and raises; this is the
+        local-frame mirror `local_reflect` that the call evidently means.)"""
+        cos_i = it.wi[..., 2]
+        active = (cos_i > 0) & active
+        bs = BSDFSample(pdf=torch.ones_like(active), wo=local_reflect(it.wi), eta=1)
+        f = fresnel_conductor(cos_i, self.eta.to(it.wi.device), self.k.to(it.wi.device)).unsqueeze(-1)
+        spectrum = torch.where(active.unsqueeze(-1), self.specular * f, torch.zeros_like(it.p))
+        return bs, spectrum
+
     def eval_and_pdf(self, it, wo, active=True):
         wi = it.wi
         refl = torch.cat([-wi[..., 0:1], -wi[..., 1:2], wi[..., 2:3]], dim=-1)
@@ -125,6 +181,11 @@ class NeuralBSDF(BSDF):
 
     def random(self):
         return self
+
+    def sample(self, it, sampler, active=True):
+        """bsdfs.py:625-633: cosine-hemisphere direction, spectrum = act(MLP(rusinkiewicz(wi, wo))) on every point."""
+        bs = _cos_hemisphere_sample(it, sampler)
+        return bs, self.act(self.mlp(param_rusin2(it.wi, bs.wo)))
 
     def eval_and_pdf(self, it, wo, active=True, rusin=None):
         coords = param_rusin2(it.wi, wo) if rusin is None else rusin
@@ -155,6 +216,18 @@ class ComposeSpatialVarying(BSDF):
         w = self.sp_var_fn(self.preprocess(p)).reshape(p.shape[:-1] + (len(self.bsdfs),))
         setattr(it, "nonnormalized_weights", w)
         return w.sigmoid()
+
+    def sample(self, it, sampler, active=True):
+        """bsdfs.py:500-513: every child proposes a bounce, one child per point is drawn from the (un-normalised,
+        sigmoid) spatial weights with torch.multinomial, and that child's direction / spectrum is kept."""
+        samples, spectrums = zip(*[b.sample(it, sampler, active) for b in self.bsdfs])
+        nb = len(self.bsdfs)
+        k = self.normalized_weights(it.p, it)
+        selections = torch.multinomial(k.reshape(-1, nb), num_samples=1).squeeze(-1)
+        stacked = torch.stack(spectrums, dim=-1).reshape(-1, 3, nb)
+        rows = torch.arange(stacked.shape[0], device=stacked.device)
+        spectrum = stacked[rows, :, selections].reshape_as(it.p)
+        return BSDFSample.compose(samples, k, selections), spectrum
 
     def eval_and_pdf(self, it, wo, active=True):
         k = self.normalized_weights(it.p, it)

@@ -1,1 +1,1 @@
-from .integrators import Debug, Direct, Integrator, Mask, NeRFIntegrator, NeRFReproduce, Silhouette
+from .integrators import Debug, Direct, Integrator, Mask, NeRFIntegrator, NeRFReproduce, Path, Silhouette

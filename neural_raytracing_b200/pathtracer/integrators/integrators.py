@@ -125,3 +125,57 @@ class NeRFReproduce(Integrator):
         class Dummy:
             ...
         return result, torch.tensor(True, device=result.device), Dummy()
+
+
+class Path(Integrator):
+    """Multi-bounce light path integrator (integrators.py:274-354; scripts/path_nerv.py): direct lighting at every
+    vertex, then a BSDF-sampled bounce whose secondary rays go through the same march kernels
+    (`intersect(primary=False)`: no silhouette scan).  Kept from the reference: MIS weights are 1, the throughput is
+    detached between bounces, Russian roulette is not implemented (the reference asserts when depth exceeds
+    `rr_depth`; so does this), emitters are sampled at the bounce vertices only through the light sampler."""
+
+    def __init__(self, training=False, **kwargs):
+        super().__init__(**kwargs)
+        self.training = training
+
+    def dims(self):
+        return 3
+
+    def _emitter_fn(self, kwargs):
+        w_isect = kwargs.get("w_isect", False)
+        if isinstance(w_isect, SkipConnMLP):
+            return lambda it, shapes, lights, sampler, active: \
+                sample_emitter_dir_w_learned_occ(it, shapes, lights, sampler, w_isect, active)
+        if w_isect is True:
+            return sample_emitter_dir_w_isect
+        return kwargs.get("sample_emitter_fn", sample_emitter_dir_wo_isect)
+
+    def sample(self, shapes, rays, bsdf, **kwargs):
+        sampler = kwargs.get("sampler", self.sampler)
+        lights = kwargs.get("lights", self.lights)
+        sample_emitter = self._emitter_fn(kwargs)
+        throughput = torch.ones(*rays.shape[:-1], 3, device=rays.device)
+        result = torch.zeros_like(throughput)
+        first_it, active = shapes.intersect(rays, primary=self.training)
+        if not active.any():
+            return result, active, first_it
+        first_active = active.clone()
+        it = first_it
+        for depth in range(self.max_depth):
+            assert depth <= self.rr_depth, "Russian roulette is not implemented (neither in the reference)"
+            if active.any():
+                ds, emitter_val = sample_emitter(it, shapes, lights=lights, sampler=sampler, active=active)
+                lit = active & (ds.pdf > 0)
+                bsdf_val, _pdf = bsdf.eval_and_pdf(it, it.to_local(ds.d), active=lit)
+                result = result + torch.where(lit.unsqueeze(-1), throughput * bsdf_val * emitter_val,
+                                              torch.zeros_like(result))
+            bs, bounce_val = bsdf.sample(it, sampler=sampler, active=active)
+            throughput = (bounce_val.clamp(min=1e-10) * throughput).detach()
+            active = active & (throughput > 0).any(-1)
+            if not active.any():
+                break
+            it, hits = shapes.intersect(it.spawn_rays(it.from_local(bs.wo)), active=active, primary=False)
+            active = active & hits
+            if not active.any():
+                break
+        return result, first_active, first_it

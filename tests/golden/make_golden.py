@@ -430,9 +430,66 @@ def gen_plain_nerf():
     print("plain_nerf.npz: rgb", out["rgb"].shape, "mean", out["rgb"].mean(), "std", out["rgb"].std(), "; state dicts", {k: len(out["sd_" + k]) for k in mods})
 
 
+class GoldenRatioSampler:
+    """Deterministic stand-in for Sampler (samplers.py:14-20): call c returns frac((i + 1 + 977 c) * phi), i the flat
+    index.  Shared by the reference run and the GPU test so that both trace the same bounces."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def sample(self, shape, device="cpu"):
+        n = int(np.prod(shape))
+        i = torch.arange(n, dtype=torch.float64) + 1 + 977 * self.calls
+        self.calls += 1
+        return ((i * 0.6180339887498949) % 1.0).float().reshape(tuple(shape)).to(device)
+
+
+def gen_path():
+    """Path integrator (integrators.py:274-354) with two bounces on the DTU-style scene: ComposeSpatialVarying of two
+    NeuralBSDFs and a Diffuse (a Conductor child makes the reference raise: bsdfs.py:395 calls reflect() with one
+    argument), learned light field, deterministic sampler, torch.multinomial replaced by argmax for the run.
+    Also the warp fixtures (warps.py:10-52)."""
+    import pytorch3d.pathtracer as P
+    import pytorch3d.pathtracer.shapes.sdfs, pytorch3d.pathtracer.bsdf, pytorch3d.pathtracer.lights  # noqa: F401
+    import pytorch3d.pathtracer.integrators, pytorch3d.pathtracer.neural_blocks, pytorch3d.pathtracer.cameras  # noqa: F401
+    from pytorch3d.pathtracer.cameras import NeRFCamera
+    from pytorch3d.pathtracer.integrators import Path
+    from pytorch3d.pathtracer.warps import square_to_cos_hemisphere, square_to_uniform_disk_concentric
+    import scenes
+    out = {}
+    u = GoldenRatioSampler().sample((257, 2))
+    u[0] = 0.5                                       # the centre of the square (v == 0 branch)
+    out["warp_u"] = u.numpy()
+    out["warp_disk"] = square_to_uniform_disk_concentric(u).numpy()
+    out["warp_hemi"] = square_to_cos_hemisphere(u).numpy()
+    random.random = lambda: FIXED_RANDOM
+    shape, sphere, bsdf, lights, _integ, _w = scenes.build_pipeline(P, "dtu", device="cpu")
+    size = 16
+    c2w, focal = synth.nerf_cameras(1, size)
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cpu")
+    real = torch.multinomial
+    torch.multinomial = lambda k, num_samples=1, **kw: k.argmax(dim=-1, keepdim=True)
+    try:
+        with torch.no_grad():
+            img, _ = P.pathtrace(shape, size=size, chunk_size=size, bundle_size=1, bsdf=bsdf, integrator=Path(max_depth=2),
+                                 lights=lights, cameras=cam, device="cpu", silent=True, background=0, with_noise=False,
+                                 sampler=GoldenRatioSampler())
+            img1, _ = P.pathtrace(shape, size=size, chunk_size=size, bundle_size=1, bsdf=bsdf, integrator=Path(max_depth=1),
+                                  lights=lights, cameras=cam, device="cpu", silent=True, background=0, with_noise=False,
+                                  sampler=GoldenRatioSampler())
+    finally:
+        torch.multinomial = real
+    out["img_depth2"], out["img_depth1"] = img.numpy(), img1.numpy()
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("pytorch3d/pathtracer/integrators/integrators.py:274-354; bsdf/bsdfs.py:22-63, 88-106, 500-513, 625-633; warps.py:10-52")
+    np.savez_compressed(os.path.join(HERE, "path.npz"), **out)
+    print("path.npz: depth2 mean %.5f depth1 mean %.5f, second bounce adds %.5f on %d pixels" %
+          (img.mean(), img1.mean(), (img - img1).abs().max(), int(((img - img1).abs().max(-1)[0] > 1e-6).sum())))
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf"]
+                             "train_loop", "plain_nerf", "path"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()

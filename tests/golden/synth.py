@@ -106,3 +106,19 @@ def nerf_cameras(n_views, size, device="cpu"):
         m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, c
         mats.append(m)
     return torch.tensor(np.stack(mats), dtype=torch.float, device=device), 0.5 * size / np.tan(np.radians(25))
+
+
+class GoldenRatioSampler:
+    """Deterministic stand-in for the path tracer's Sampler (samplers.py:14-20): call c returns
+    frac((i + 1 + 977 c) * phi), i the flat index.  The same class body is used by tests/golden/make_golden.py for the
+    reference run, so both sides trace the same bounces."""
+
+    def __init__(self):
+        self.calls = 0
+
+    def sample(self, shape, device="cpu"):
+        import torch
+        n = int(np.prod(shape))
+        i = torch.arange(n, dtype=torch.float64) + 1 + 977 * self.calls
+        self.calls += 1
+        return ((i * 0.6180339887498949) % 1.0).float().reshape(tuple(shape)).to(device)
