@@ -210,6 +210,20 @@ k_mlp_bwd(MlpDev m, BwdArgs a) {
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t mb = tile * TM;
     const int valid = (int)min((int64_t)TM, a.M - mb);
+    // ---- tiles whose incoming gradient is exactly zero contribute nothing: skip them ----
+    // (the shading masks its MLP outputs with where(active, ., 0), bsdfs.py:521-525: for a DTU-style crop 60-80 % of
+    //  the rays are misses, spatially coherent, and their g_out is exactly 0)
+    {
+      int nz = 0;
+      for (int idx = tid; idx < OUT * valid; idx += kThreads) nz |= (a.g_out[mb * OUT + idx] != 0.0f) ? 1 : 0;
+      if (!__syncthreads_or(nz)) {
+        if (a.g_x != nullptr)
+          for (int idx = tid; idx < valid * m.in_size; idx += kThreads) a.g_x[mb * m.in_size + idx] = 0.0f;
+        if (a.g_latent != nullptr)
+          for (int idx = tid; idx < valid * m.latent; idx += kThreads) a.g_latent[mb * m.latent + idx] = 0.0f;
+        continue;
+      }
+    }
     // ---- recompute the encoding ----
     for (int idx = tid; idx < TM * m.in_size; idx += kThreads) {
       const int mm = idx / m.in_size, j = idx - mm * m.in_size;
