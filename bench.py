@@ -611,6 +611,25 @@ def main():
                     "peak_source": peak_src, "launches": first_n, "avg_launch_ms": first_ms / first_n,
                     "algorithmic_flop_per_sample": FLOP_FIRST,
                     "share_of_step": first_ms / total_ms if total_ms else None}
+        # the other kernels of the step, each against the roof that bounds it (live CUDA-event times of this run)
+        others = {}
+
+        def _other(tag, kernel, bound, work_per_step, peak, unit, note):
+            t_ms, n = prof.get(tag, (0.0, 0))
+            if n and t_ms > 0:
+                ach = work_per_step * args.steps / (t_ms * 1e-3)
+                others[tag] = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
+                               "frac": ach / peak, "launches": n, "share_of_step": t_ms / total_ms if total_ms else None,
+                               "algorithmic_work_per_step": note}
+        _other("mlp_tc_nerf_second", "k_mlp_tc<NeRFLE.second>", "tensor", R * (N_COARSE + N_FINE) * FLOP_SECOND / 1e12, peak_tf,
+               "TFLOP/s", "%d samples x %d FLOP" % (R * (N_COARSE + N_FINE), FLOP_SECOND))
+        _other("merge_composite", "k_merge_composite", "hbm", R * ((N_COARSE + N_FINE) * 20 + 12) / 1e9, peak_gbs, "GB/s",
+               "%d rays x (192 samples x 20 B (t, sigma, rgb) + 12 B out)" % R)
+        _other("sample_pdf", "k_sample_pdf", "hbm", R * (N_COARSE * 8 + N_FINE * 4) / 1e9, peak_gbs, "GB/s",
+               "%d rays x (64 x 8 B (t, sigma) read + 128 x 4 B written)" % R)
+        _other("stratified_ts", "k_stratified_ts", "hbm", R * N_COARSE * 4 / 1e9, peak_gbs, "GB/s", "%d rays x 64 x 4 B written" % R)
+        if roof is not None:
+            roof["other_kernels"] = others
         elif args.precision == "f32":
             fm, fn = prof.get("nerfle_fused_f32", (0.0, 0))
             if fn and fm > 0:
