@@ -33,6 +33,17 @@ TRAIN_TC_NETS = {
 }
 
 
+# networks whose TRAINING forward runs on the tensor cores while their backward stays the fused fp32 kernel (the forward
+# kernel writes the post-activation layer inputs in the fp32 layout nrt_mlp_backward reads): the 256-wide nets
+# (nrt_tc_wide.cu), NeuralBSDF.mlp and the occlusion MLP (k_mlp_tc with the SaveF32 policy)
+TRAIN_TC_FWD_NETS = {
+    (3, 0, 128, 256, 16, 3, 4, 0), (3, 0, 128, 256, 16, 3, 8, 0), (3, 0, 128, 256, 16, 3, 16, 0),   # sp_var_fn
+    (3, 0, 16, 256, 10, 3, 3, 0),                                                                      # LightField
+    (3, 0, 64, 96, 6, 3, 3, 0),                                                                        # NeuralBSDF.mlp
+    (5, 0, 16, 64, 8, 3, 1, 0),                                                                        # occlusion MLP
+}
+
+
 def set_train_precision(p):
     global train_precision
     assert p in ("f32", "f16", "bf16"), p

@@ -594,7 +594,7 @@ static int next_counter(cudaStream_t st, unsigned long long** out) {
 }
 
 int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent,
-                       int64_t M, float* out, cudaStream_t st);  // nrt_tc.cu
+                       int64_t M, float* out, float* acts, cudaStream_t st);  // nrt_tc.cu
 int nrt_sdf_eval_tc(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M, float* out,
                     cudaStream_t st);
 int nrt_sdf_march_tc(int shadow, const nrt_sphere_sdf_t* s, int prec, const float* rays, const float* max_t_per_ray,
@@ -616,8 +616,7 @@ extern "C" int nrt_mlp_forward(const nrt_mlp_t* m, int prec, int out_act, const 
   NRT_REQUIRE(d.latent == 0 || latent != nullptr, "nrt_mlp_forward: latent_size=%d but latent is NULL", d.latent);
   cudaStream_t st = (cudaStream_t)stream;
   if (prec != NRT_PREC_F32) {
-    NRT_REQUIRE(acts == nullptr, "nrt_mlp_forward: saved activations are only produced by NRT_PREC_F32");
-    return nrt_mlp_forward_tc(m, prec, out_act, x, latent, M, out, st);
+    return nrt_mlp_forward_tc(m, prec, out_act, x, latent, M, out, acts, st);
   }
   NRT_DISPATCH_H(d.hidden, {
     const size_t bytes = tile_smem_floats(d.dim_p, H, d.out, TM) * sizeof(float);

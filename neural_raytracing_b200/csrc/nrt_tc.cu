@@ -273,15 +273,15 @@ __global__ void k_scan_argmin(const float* __restrict__ val, const float* __rest
   }
 }
 
-template <class NET, class IO, int FMT>
-static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP) {
+template <class NET, class IO, int FMT, class SV = NoSave>
+static int launch(const void* blob, const IO& io, int64_t M, cudaStream_t st, int tag = TAG_TC_MLP, SV sv = SV{}) {
   const size_t bytes = (size_t)NET::SMEM_BYTES + 256;
-  auto kern = k_mlp_tc<NET, IO, FMT>;
+  auto kern = k_mlp_tc<NET, IO, FMT, SV>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   const int64_t ntiles = (M + 127) / 128;
   const int grid = (int)std::min<int64_t>((ntiles + NET::NSLOT - 1) / NET::NSLOT, (int64_t)nrt_sm_count());
   NrtProfScope _ps(tag, st);
-  kern<<<grid, NET::threads(NET::WPS), bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M, g_dbg_timeline, NoSave{});
+  kern<<<grid, NET::threads(NET::WPS), bytes, st>>>(reinterpret_cast<const uint8_t*>(blob), io, M, g_dbg_timeline, sv);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
 }
@@ -338,17 +338,37 @@ static int forward_plain(const nrt_mlp_t* m, int prec, int out_act, const float*
   if (fmt_of(prec) == 0) return launch<NET, decltype(io), 0>(m->params_tc, io, M, st);
   return launch<NET, decltype(io), 1>(m->params_tc, io, M, st);
 }
+// the same forward, also writing the post-activation layer inputs for the fused fp32 backward (training)
+template <class NET>
+static int forward_plain_save(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent, int64_t M,
+                              float* out, float* acts, cudaStream_t st) {
+  IoPlain<NET::IN, NET::LAT, NET::OUT> io{x, latent, out, out_act};
+  SaveF32 sv{acts, M};
+  if (fmt_of(prec) == 0) return launch<NET, decltype(io), 0, SaveF32>(m->params_tc, io, M, st, TAG_TC_MLP, sv);
+  return launch<NET, decltype(io), 1, SaveF32>(m->params_tc, io, M, st, TAG_TC_MLP, sv);
+}
 
 int nrt_mlp_forward_tc_wide(const nrt_mlp_t* m, const MlpDev& d, int prec, int out_act, const float* x, int64_t M, float* out,
-                            cudaStream_t st, bool* handled);   // nrt_tc_wide.cu
+                            float* acts, cudaStream_t st, bool* handled);   // nrt_tc_wide.cu
 
 int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent, int64_t M,
-                       float* out, cudaStream_t st) {
+                       float* out, float* acts, cudaStream_t st) {
   MlpDev d;
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
   NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "unknown precision %d", prec);
   NRT_REQUIRE(m->params_tc != nullptr, "mlp.params_tc is NULL: call nrt_mlp_pack_tc first");
+  if (acts != nullptr) {
+    // saved activations for nrt_mlp_backward on a tensor-core forward: the 256-wide networks, NeuralBSDF, occlusion MLP
+    bool handled = false;
+    rc = nrt_mlp_forward_tc_wide(m, d, prec, out_act, x, M, out, acts, st, &handled);
+    if (handled) return rc;
+    if (matches<NetNeuralBsdf>(d)) return forward_plain_save<NetNeuralBsdf>(m, prec, out_act, x, latent, M, out, acts, st);
+    if (matches<NetOcc>(d)) return forward_plain_save<NetOcc>(m, prec, out_act, x, latent, M, out, acts, st);
+    nrt_set_error("nrt_mlp_forward: saved activations with a 16-bit precision are produced for the 256-wide networks, "
+                  "NeuralBSDF.mlp and the occlusion MLP only");
+    return NRT_E_UNSUPPORTED;
+  }
   if (matches<NetNerfFirst>(d)) return forward_plain<NetNerfFirst>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetNerfSecondPT>(d)) return forward_plain<NetNerfSecondPT>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetNerfSecondLE>(d)) return forward_plain<NetNerfSecondLE>(m, prec, out_act, x, latent, M, out, st);
@@ -357,7 +377,7 @@ int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x
   if (matches<NetSdfShift>(d)) return forward_plain<NetSdfShift>(m, prec, out_act, x, latent, M, out, st);
   {
     bool handled = false;   // the 256-wide networks (weights streamed in K-chunks, nrt_tc_wide.cu)
-    rc = nrt_mlp_forward_tc_wide(m, d, prec, out_act, x, M, out, st, &handled);
+    rc = nrt_mlp_forward_tc_wide(m, d, prec, out_act, x, M, out, nullptr, st, &handled);
     if (handled) return rc;
   }
   nrt_set_error("tensor-core path: MLP shape (in %d, latent %d, freqs %d, hidden %d, layers %d, out %d, act %d) is not "

@@ -57,9 +57,10 @@ struct ChunkCursor {
   __device__ __forceinline__ static int chunks_of(int o) { return (k_of(o) + kWideKC - 1) / kWideKC; }
 };
 
-template <class NET, class IO, int FMT>
+// (convert_row_savef32 / convert_row_out_savef32: tc_core.cuh)
+template <class NET, class IO, int FMT, bool SAVEF32 = false>
 __global__ void __launch_bounds__(160, 1)
-k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
+k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, float* __restrict__ acts_g = nullptr) {
   using W = Wide<NET>;
   using E = Elem<FMT>;
   constexpr Layout Y = NET::Y;
@@ -227,7 +228,10 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
       for (int st = 0; st < NHID; ++st) {
         mbar_wait(&bar_done, n_done & 1); n_done++;
         tc_fence_after();
-        convert_row<NET::ACT, FMT, H>(tD, tU);
+        if constexpr (SAVEF32)
+          convert_row_savef32<NET::ACT, FMT, H>(tD, tU, valid ? acts_g + ((int64_t)st * H) * M + m : nullptr, M);
+        else
+          convert_row<NET::ACT, FMT, H>(tD, tU);
         if (st < L) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) preload_bias<64>(tD + 64 * c, sBias + Y.bias_off[2 + st] + 64 * c);
@@ -274,7 +278,11 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M) {
           // last hidden activations + output layer (fp32, CUDA cores)
 #pragma unroll
           for (int j = 0; j < NET::OUT; ++j) o[j] = sBias[Y.bias_off[NET::STAGES - 1] + j];
-          convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(tD, sBias + Y.wout_f32_off, o);
+          if constexpr (SAVEF32)
+            convert_row_out_savef32<NET::ACT, FMT, H, NET::OUT>(tD, sBias + Y.wout_f32_off, o,
+                                                                  valid ? acts_g + ((int64_t)L * H) * M + m : nullptr, M);
+          else
+            convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(tD, sBias + Y.wout_f32_off, o);
         } else {
           constexpr int OC = (NET::OUT + 7) / 8 * 8;
           uint32_t acc[OC];
@@ -318,25 +326,27 @@ static bool matches_w(const MlpDev& d) {
          d.skip == NET::SKIP && d.out == NET::OUT && d.act == NET::ACT;
 }
 
-template <class NET>
-static int forward_wide(const nrt_mlp_t* m, int prec, int out_act, const float* x, int64_t M, float* out, cudaStream_t st) {
+template <class NET, int FMT, bool SAVE>
+static int launch_wide(const nrt_mlp_t* m, int out_act, const float* x, int64_t M, float* out, float* acts, cudaStream_t st) {
   using W = Wide<NET>;
   IoPlainWide<NET::IN, NET::OUT> io{x, out, out_act};
   const size_t bytes = (size_t)W::SMEM_BYTES + 1024;
   const int64_t ntiles = (M + 127) / 128;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count());
+  auto kern = k_mlp_wide_tc<NET, decltype(io), FMT, SAVE>;
+  NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   NrtProfScope _ps(TAG_TC_MLP_WIDE, st);
-  if (prec == NRT_PREC_BF16) {
-    auto kern = k_mlp_wide_tc<NET, decltype(io), 1>;
-    NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    kern<<<grid, 160, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M);
-  } else {
-    auto kern = k_mlp_wide_tc<NET, decltype(io), 0>;
-    NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    kern<<<grid, 160, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M);
-  }
+  kern<<<grid, 160, bytes, st>>>(reinterpret_cast<const uint8_t*>(m->params_tc), io, M, acts);
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
+}
+
+template <class NET>
+static int forward_wide(const nrt_mlp_t* m, int prec, int out_act, const float* x, int64_t M, float* out, float* acts,
+                        cudaStream_t st) {
+  if (prec == NRT_PREC_BF16)
+    return acts ? launch_wide<NET, 1, true>(m, out_act, x, M, out, acts, st) : launch_wide<NET, 1, false>(m, out_act, x, M, out, nullptr, st);
+  return acts ? launch_wide<NET, 0, true>(m, out_act, x, M, out, acts, st) : launch_wide<NET, 0, false>(m, out_act, x, M, out, nullptr, st);
 }
 
 // ComposeSpatialVarying.sp_var_fn with 4 bases (colocate.py:70-78), 8 (nerf_synthetic.py:68-75) and 16 (dtu.py:101-106);
@@ -351,13 +361,14 @@ using NetLightField = Net<3, 0, 16, 256, 10, 3, 3, NRT_ACT_LEAKY_RELU>;
 using namespace tc;
 
 // returns NRT_E_UNSUPPORTED (without setting an error) when the shape is not one of the wide networks
+// (acts, optional: the post-activation layer inputs for nrt_mlp_backward, [(num_layers + 1) * 256][M] floats)
 int nrt_mlp_forward_tc_wide(const nrt_mlp_t* m, const MlpDev& d, int prec, int out_act, const float* x, int64_t M, float* out,
-                            cudaStream_t st, bool* handled) {
+                            float* acts, cudaStream_t st, bool* handled) {
   *handled = true;
-  if (matches_w<NetSpVar4>(d)) return forward_wide<NetSpVar4>(m, prec, out_act, x, M, out, st);
-  if (matches_w<NetSpVar8>(d)) return forward_wide<NetSpVar8>(m, prec, out_act, x, M, out, st);
-  if (matches_w<NetSpVar16>(d)) return forward_wide<NetSpVar16>(m, prec, out_act, x, M, out, st);
-  if (matches_w<NetLightField>(d)) return forward_wide<NetLightField>(m, prec, out_act, x, M, out, st);
+  if (matches_w<NetSpVar4>(d)) return forward_wide<NetSpVar4>(m, prec, out_act, x, M, out, acts, st);
+  if (matches_w<NetSpVar8>(d)) return forward_wide<NetSpVar8>(m, prec, out_act, x, M, out, acts, st);
+  if (matches_w<NetSpVar16>(d)) return forward_wide<NetSpVar16>(m, prec, out_act, x, M, out, acts, st);
+  if (matches_w<NetLightField>(d)) return forward_wide<NetLightField>(m, prec, out_act, x, M, out, acts, st);
   *handled = false;
   return NRT_OK;
 }

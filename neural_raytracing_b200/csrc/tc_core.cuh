@@ -424,9 +424,12 @@ __device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint
 // feeds it to tcgen05.mma as is (K' = samples, a_major = b_major = MN).  Activation tiles carry 16 extra rows;
 // row F is the constant 1 (its product with dZ is the bias gradient), rows F+1..F+15 are never written nor used.
 constexpr int kTileRowsExtra = 16;
-struct NoSave { static constexpr bool kOn = false; };
+struct NoSave { static constexpr bool kOn = false; static constexpr bool kF32 = false; };
+// fp32 activations for the fused fp32 backward (nrt_mlp_backward): acts[(l * H + k) * M + m]
+struct SaveF32 { static constexpr bool kOn = false; static constexpr bool kF32 = true; float* acts; int64_t M; };
 struct SaveTiles {
   static constexpr bool kOn = true;
+  static constexpr bool kF32 = false;
   uint16_t* acts;      // [L+1][ntiles] tiles of (H+16) x 128: a_l = act(z) feeding hidden layer l (l = L: output layer)
   uint16_t* enc_raw;   // [ntiles] tiles of (KE+16) x 128: the encoding as the init layer sees it
   uint16_t* enc_act;   // [ntiles] tiles of (KE+16) x 128: act(encoding) as the skip layers see it
@@ -571,6 +574,59 @@ __device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __rest
     if (c + 1 < NC) tc_wait_ld();
   }
   if constexpr (SAVE) save_row[tile_elem(H)] = one16<FMT>();
+}
+
+// Training forward with a tensor-core forward and the fused fp32 backward (256-wide nets, NeuralBSDF, occlusion MLP):
+// the forward kernel also writes the post-activation layer inputs in the layout of
+// the fused fp32 backward (nrt_mlp_backward: acts[(l * H + k) * M + m], fp32) -- the values the next layer's operand
+// actually holds (rounded to the operand format), so the backward differentiates the forward that ran.  For fixed k
+// the 32 lanes of a warp write 32 consecutive samples: coalesced 128-byte stores.
+template <int ACT, int FMT, int H>
+__device__ __forceinline__ void convert_row_savef32(uint32_t dD, uint32_t aU, float* __restrict__ acts, int64_t stride) {
+  constexpr int NC = H / 32;
+  uint32_t buf[2][32];
+  TmemIO<32>::ld(dD, buf[0]);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) TmemIO<32>::ld(dD + 32 * (c + 1), buf[(c + 1) & 1]);
+    uint32_t pk[16];
+    convert32<ACT, FMT>(buf[c & 1], pk);
+    TmemIO<16>::st(aU + 16 * c, pk);
+    if (acts != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        acts[(int64_t)(32 * c + 2 * i) * stride] = Elem<FMT>::back((uint16_t)(pk[i] & 0xffffu));
+        acts[(int64_t)(32 * c + 2 * i + 1) * stride] = Elem<FMT>::back((uint16_t)(pk[i] >> 16));
+      }
+    }
+    if (c + 1 < NC) tc_wait_ld();
+  }
+}
+// last hidden layer with the fused (out <= 4) output layer: activations stay fp32 here, and are saved as such
+template <int ACT, int FMT, int H, int OUT>
+__device__ __forceinline__ void convert_row_out_savef32(uint32_t dD, const float* __restrict__ wout, float* __restrict__ o,
+                                                        float* __restrict__ acts, int64_t stride) {
+  constexpr int NC = H / 32;
+  uint32_t buf[2][32];
+  TmemIO<32>::ld(dD, buf[0]);
+  tc_wait_ld();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) TmemIO<32>::ld(dD + 32 * (c + 1), buf[(c + 1) & 1]);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float z = __uint_as_float(buf[c & 1][i]);
+      const float a = act_fast<ACT>(z);
+      const float4 w = *reinterpret_cast<const float4*>(wout + (32 * c + i) * 4);
+      o[0] = fmaf(a, w.x, o[0]);
+      if constexpr (OUT > 1) o[1] = fmaf(a, w.y, o[1]);
+      if constexpr (OUT > 2) o[2] = fmaf(a, w.z, o[2]);
+      if constexpr (OUT > 3) o[3] = fmaf(a, w.w, o[3]);
+      if (acts != nullptr) acts[(int64_t)(32 * c + i) * stride] = a;
+    }
+    if (c + 1 < NC) tc_wait_ld();
+  }
 }
 
 // leaky_relu on a packed 16-bit pair
@@ -791,7 +847,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   __shared__ __align__(8) uint64_t bar_ready_a[3];    // K-split: first half of the activations is in place
   __shared__ __align__(8) uint64_t bar_done[3];
   // K-split early start: not with the 8-warp epilogue, not while saving activation tiles (training forward)
-  constexpr bool KSPLIT = NET::KSPLIT && WPS == 4 && !SV::kOn;
+  constexpr bool KSPLIT = NET::KSPLIT && WPS == 4 && !SV::kOn && !SV::kF32;
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_bias[NET::STAGES];
   constexpr bool ITER = IsIterative<IO>::value;
@@ -1195,6 +1251,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             convert_row<NET::ACT, FMT, HW, true>(dD + coff, aU + coff / 2,
                 tile_row_ptr(sv.acts, (int64_t)st * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row), coff, primary ? H : -1,
                 sv.masks + (int64_t)st * (H / 32) * (sv.ntiles * 128) + m, sv.ntiles * 128);
+          else if constexpr (SV::kF32)
+            convert_row_savef32<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2,
+                                                   valid ? sv.acts + ((int64_t)st * H) * sv.M + m : nullptr, sv.M);
           else
             convert_row<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2);
           // done after the conversion so the accumulator registers are dead and all LDS.128 can be in flight
@@ -1222,6 +1281,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             convert_row_out<NET::ACT, FMT, H, NET::OUT, true>(dD, sBias + Y.wout_f32_off, o,
                 tile_row_ptr(sv.acts, (int64_t)L * sv.ntiles + (m >> 7), H + kTileRowsExtra, lane_row),
                 sv.masks + (int64_t)L * (H / 32) * (sv.ntiles * 128) + m, sv.ntiles * 128);
+          else if constexpr (SV::kF32)
+            convert_row_out_savef32<NET::ACT, FMT, H, NET::OUT>(dD, sBias + Y.wout_f32_off, o,
+                                                                  valid ? sv.acts + ((int64_t)L * H) * sv.M + m : nullptr, sv.M);
           else
             convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(dD, sBias + Y.wout_f32_off, o);
           if constexpr (ITER) { if (valid) io.consume(state, o); }

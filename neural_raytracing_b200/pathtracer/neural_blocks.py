@@ -110,6 +110,15 @@ class SkipConnMLP(nn.Module):
                m.out.out_features, _activation_id(m.activation))
         return config.train_precision if key in config.TRAIN_TC_NETS else "f32"
 
+    def train_forward_precision(self):
+        """Arithmetic of the training FORWARD of a network whose backward is the fused fp32 kernel."""
+        if config.train_precision == "f32" or self.latent_size:
+            return "f32"
+        m = self
+        key = (m.in_size, m.latent_size, m.basis_p.shape[-1], m.init.out_features, len(m.layers), m.skip,
+               m.out.out_features, _activation_id(m.activation))
+        return config.train_precision if key in config.TRAIN_TC_FWD_NETS else "f32"
+
     def _needs_grad(self, *tensors):
         if not torch.is_grad_enabled():
             return False
@@ -171,7 +180,10 @@ class _FusedMLP(torch.autograd.Function):
             ctx.save_for_backward(out, ws)
             return out.reshape(p.shape[:-1] + (pk.out_size,))
         ctx.tc_prec = "f32"
-        out, acts = ops.mlp_forward(pk, x, lat, out_act=out_act, prec="f32", save_acts=True)
+        # 256-wide nets under a 16-bit train precision: tensor-core forward that saves its (operand-rounded)
+        # activations for the fused fp32 backward; everything else: the exact fp32 forward
+        fwd_prec = module.train_forward_precision() if lat is None else "f32"
+        out, acts = ops.mlp_forward(pk, x, lat, out_act=out_act, prec=fwd_prec, save_acts=True)
         ctx.save_for_backward(x, lat if lat is not None else x.new_empty(0), out, acts)
         return out
 

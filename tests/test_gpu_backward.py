@@ -242,3 +242,51 @@ def test_fused_backward_skips_zero_gradient_tiles_exactly():
     assert torch.equal(gx[~live], torch.zeros_like(gx[~live])) and torch.equal(gl[~live], torch.zeros_like(gl[~live]))
     _close(gx[live], gx2, "x", rtol=1e-5)
     _close(gl[live], gl2, "latent", rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["sp_var4", "sp_var16", "light_field", "neural_bsdf", "occ"])
+@pytest.mark.parametrize("M", [1, 300])
+def test_wide_nets_tensor_core_training_forward(name, M):
+    """config.set_train_precision("f16"): the 256-wide nets, NeuralBSDF.mlp and the occlusion MLP run their training
+    forward on the tcgen05 kernels, which save the operand-rounded activations in the layout of the fused fp32 backward.  Values within the 16-bit forward's
+    tolerance of the exact forward, weight / input gradients cos >= 0.999 against the all-fp32 path."""
+    import torch
+    from neural_raytracing_b200 import config, ops
+    from neural_raytracing_b200.pathtracer import neural_blocks as nb
+    kw = {"sp_var4": dict(num_layers=16, hidden_size=256, freqs=128, sigma=2 << 6, in_size=3, out=4, xavier_init=True),
+          "sp_var16": dict(num_layers=16, hidden_size=256, freqs=128, sigma=2 << 6, in_size=3, out=16, xavier_init=True),
+          "light_field": dict(num_layers=10, hidden_size=256, freqs=16, in_size=3, out=3),
+          "neural_bsdf": dict(in_size=3, out=3, num_layers=6, hidden_size=96, freqs=64),
+          "occ": dict(in_size=5, out=1)}[name]
+    torch.manual_seed(0)
+    mlp = nb.SkipConnMLP(device="cuda", **kw).to("cuda")
+    synth.fill_module(mlp, 17)
+    g = torch.Generator("cuda").manual_seed(M)
+    x0 = 0.4 * torch.randn(M, kw["in_size"], device="cuda", generator=g)
+    go = torch.randn(M, kw["out"], device="cuda", generator=g)
+
+    def run(tprec):
+        config.set_train_precision(tprec)
+        try:
+            mlp.zero_grad()
+            x = x0.clone().requires_grad_()
+            y = mlp(x, out_act=ops.OUT_SIGMOID)
+            assert type(y.grad_fn).__name__.startswith("_FusedMLP")
+            (y * go).sum().backward()
+            return y.detach().clone(), x.grad.clone(), {k: p.grad.clone() for k, p in mlp.named_parameters()}
+        finally:
+            config.set_train_precision("f32")
+
+    y32, gx32, gp32 = run("f32")
+    ops.profile_collect(); ops.profile_enable(True)
+    y16, gx16, gp16 = run("f16")
+    prof = ops.profile_collect(); ops.profile_enable(False)
+    tc_tag = "mlp_tc_wide" if kw.get("hidden_size", 64) == 256 else "mlp_tc_generic"
+    assert prof.get(tc_tag, (0, 0))[1] >= 1 and prof.get("mlp_bwd_f32", (0, 0))[1] >= 1, prof      # the path under test ran
+    assert (y16 - y32).abs().max().item() < 2e-3
+    flat32 = torch.cat([v.reshape(-1) for v in gp32.values()]).double()
+    flat16 = torch.cat([v.reshape(-1) for v in gp16.values()]).double()
+    cos = float(flat32 @ flat16 / (flat32.norm() * flat16.norm() + 1e-30))
+    assert cos > 0.999, cos
+    cx = float(gx32.double().reshape(-1) @ gx16.double().reshape(-1) / (gx32.double().norm() * gx16.double().norm() + 1e-30))
+    assert cx > 0.995, cx

@@ -88,6 +88,15 @@ for tprec in ("f32", "f16"):
 config.set_train_precision("f32")
 # ---- cfg4: DTU-style training step on a crop (SDF + 3-basis BSDF + LightField, eikonal + BCE) ----
 shape, sphere, bsdf, lights, integrator, w_isect = scenes.build_pipeline(P, "dtu", device="cuda")
+# the BSDF of dtu.py:101-106: 10 NeuralBSDF (Sigmoid) + 6 Diffuse(sigmoid) bases under a 16-way spatially varying blend
+import torch.nn as nn
+kids = [P.bsdf.NeuralBSDF(activation=nn.Sigmoid(), device="cuda") for _ in range(10)] + \
+       [P.bsdf.Diffuse(preprocess=torch.sigmoid, device="cuda").random() for _ in range(6)]
+for i, k in enumerate(kids[:10]):
+    synth.fill_module(k, 70 + i)
+bsdf = P.bsdf.ComposeSpatialVarying(kids, device="cuda")
+bsdf.sp_var_fn._synth_sigma = 128.0
+synth.fill_module(bsdf.sp_var_fn, 64)
 params = list(sphere.parameters()) + list(bsdf.parameters()) + list(lights.parameters())
 opt2 = torch.optim.AdamW(params, lr=8e-5, weight_decay=0)
 c2w, focal = synth.nerf_cameras(1, 512, device="cuda")
@@ -104,6 +113,7 @@ for size, crop, uv in ((512, 128, (190, 200)), (512, 512, (0, 0))):
         if prec == "f32" and crop > 128:
             continue
         config.set_precision(prec)
+        config.set_train_precision(prec)      # f16: the 256-wide nets' training forward on the tensor cores
         torch.cuda.reset_peak_memory_stats()
         ops.profile_collect(); ops.profile_enable(True)
         ms = timed(dtu_step, n=3, warm=2)
@@ -111,6 +121,7 @@ for size, crop, uv in ((512, 128, (190, 200)), (512, 512, (0, 0))):
         out["cfg4_dtu_style_step_%dx%dcrop_%s" % (crop, crop, prec)] = {
             "ms_per_step": ms, "rays_per_sec": crop * crop / ms * 1e3, "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2),
             "kernel_ms_per_step": {k: round(v[0] / 5, 3) for k, v in prof.items() if v[1]},
-            "note": "%d-ray crop, fwd + bwd + AdamW; gradient-free march + min-scan in `prec`; MLP backward fused fp32 kernels; normals through the analytic-Jacobian kernels (forward mode + hand-written reverse pass)" % (crop * crop)}
+            "note": "%d-ray crop, dtu.py BSDF (10 NeuralBSDF + 6 Diffuse, 16-way sp_var), LightField, fwd + bwd + AdamW; gradient-free march + min-scan in `prec`; MLP backward fused fp32 kernels (f16: the 256-wide nets' training forward on tcgen05); normals through the analytic-Jacobian kernels (forward mode + hand-written reverse pass)" % (crop * crop)}
 config.set_precision("f32")
+config.set_train_precision("f32")
 print(json.dumps(out, indent=1))
