@@ -180,7 +180,10 @@ __device__ void wgrad_tile(const float* __restrict__ in0, int K0, const float* _
   }
 }
 
-template <int H, int TM>
+// GX = false: no input / latent gradient is wanted, so the encoding-gradient buffer and every data-gradient product
+// into the encoding disappear; the shared memory that frees lets the 256-wide nets run 32-sample tiles instead of 16
+// (half the weight-gradient red.adds and half the weight re-streaming per sample; measured 3 % on a DTU-style step).
+template <int H, int TM, bool GX = true>
 __global__ void __launch_bounds__(kThreads, 1)
 k_mlp_bwd(MlpDev m, BwdArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -201,7 +204,7 @@ k_mlp_bwd(MlpDev m, BwdArgs a) {
   ts.wbuf = p; p += 2 * kKC * H;
   float* encr = p; p += DP * S;     // raw encoding (padded copy)
   float* enca = p; p += DP * S;     // activated encoding
-  float* genc = p; p += DP * S;     // gradient w.r.t. the raw encoding
+  float* genc = p; if (GX) p += DP * S;     // gradient w.r.t. the raw encoding (GX only)
   float* go = p; p += OUT * S;      // gradient w.r.t. the pre-output-activation result
   const int tid = threadIdx.x;
   const int lat0 = m.in_size + 2 * m.freqs;
@@ -239,7 +242,7 @@ k_mlp_bwd(MlpDev m, BwdArgs a) {
       const int k = idx / TM, mm = idx - k * TM;
       encr[k * S + mm] = ts.enc_raw[idx];
       enca[k * S + mm] = ts.enc_act[idx];
-      genc[k * S + mm] = 0.0f;
+      if (GX) genc[k * S + mm] = 0.0f;
     }
     __syncthreads();     // the unpadded encoding buffers alias hin / gz / gin
     // ---- gradient at the output (through the output activation) ----
@@ -285,7 +288,7 @@ k_mlp_bwd(MlpDev m, BwdArgs a) {
       __syncthreads();
       const float* Wl = a.w_nk + a.wnk_off[li];      // nn.Linear layout [H][Kfull] of this layer
       dgrad_hidden<H, TM>(Wl, Kfull, gz, gin, ts.wbuf);
-      if (sk) dgrad_generic<TM>(Wl, Kfull, H, DP, H, gz, genc, true, enca, m.act);
+      if (GX && sk) dgrad_generic<TM>(Wl, Kfull, H, DP, H, gz, genc, true, enca, m.act);
       __syncthreads();
       // gz <- gin * act'(hin)   (hin = act(z_i))
       for (int idx = tid; idx < H * TM; idx += kThreads) {
@@ -296,7 +299,7 @@ k_mlp_bwd(MlpDev m, BwdArgs a) {
     }
     // ---- init layer: input = raw encoding ----
     wgrad_tile<TM>(encr, DP, nullptr, 0, gz, H, a.g_params + m.w_off[0], a.g_params + m.b_off[0]);
-    if (a.g_x != nullptr || a.g_latent != nullptr) {
+    if (GX && (a.g_x != nullptr || a.g_latent != nullptr)) {
       dgrad_generic<TM>(a.w_nk, DP, 0, DP, H, gz, genc, false, nullptr, m.act);
       __syncthreads();
       // d enc / d x: [x, sin(xB), cos(xB)]
@@ -479,6 +482,22 @@ extern "C" int nrt_mlp_backward(const nrt_mlp_t* mm, int out_act, const float* x
     k_mlp_bwd<HV, TMV><<<grid, kThreads, bytes, st>>>(d, a);                                                       \
     NRT_CUDA(cudaGetLastError());                                                                                  \
     return NRT_OK;                                                                                                 \
+  }
+  if (d.hidden == 256 && g_x == nullptr && g_latent == nullptr) {
+    // no input gradient (sp_var on it.p, LightField on the hit points): 32-sample tiles
+    constexpr int HV = 256, TMV = 32;
+    const size_t fl = std::max<size_t>((size_t)2 * d.dim_p * TMV, (size_t)3 * HV * (TMV + 4)) + 2 * kKC * HV +
+                      (size_t)(2 * d.dim_p + d.out) * (TMV + 4);
+    const size_t bytes = fl * sizeof(float);
+    if (bytes <= 227 * 1024) {
+      NRT_CUDA(cudaFuncSetAttribute(k_mlp_bwd<HV, TMV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      const int64_t ntiles = (M + TMV - 1) / TMV;
+      const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count() * 4);
+      NrtProfScope _ps(TAG_MLP_BWD_F32, st);
+      k_mlp_bwd<HV, TMV, false><<<grid, kThreads, bytes, st>>>(d, a);
+      NRT_CUDA(cudaGetLastError());
+      return NRT_OK;
+    }
   }
   NRT_BWD_CASE(32, 64)
   NRT_BWD_CASE(64, 64)

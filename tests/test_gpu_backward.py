@@ -290,3 +290,26 @@ def test_wide_nets_tensor_core_training_forward(name, M):
     assert cos > 0.999, cos
     cx = float(gx32.double().reshape(-1) @ gx16.double().reshape(-1) / (gx32.double().norm() * gx16.double().norm() + 1e-30))
     assert cx > 0.995, cx
+
+
+@pytest.mark.parametrize("M", [1, 45, 200])
+def test_wide_backward_without_input_gradient_uses_32_sample_tiles(M):
+    """256-wide nets whose input carries no gradient (sp_var on it.p, LightField on the hit points) take the
+    k_mlp_bwd<256, 32, GX = false> instantiation: same weight gradients as float64 autograd."""
+    import torch
+    from neural_raytracing_b200.pathtracer import neural_blocks as nb
+    torch.manual_seed(0)
+    mlp = nb.SkipConnMLP(device="cuda", in_size=3, out=3, num_layers=10, hidden_size=256, freqs=16).to("cuda")
+    synth.fill_module(mlp, 7)
+    g = torch.Generator("cuda").manual_seed(M)
+    x = 0.5 * torch.randn(M, 3, device="cuda", generator=g)            # no requires_grad
+    go = torch.randn(M, 3, device="cuda", generator=g)
+    y = mlp(x, out_act=0)
+    assert type(y.grad_fn).__name__.startswith("_FusedMLP")
+    (y * go).sum().backward()
+    m64 = copy.deepcopy(mlp).cpu().double()
+    m64.basis_p = mlp.basis_p.detach().cpu().double()
+    y64 = m64.forward_reference_ops(x.cpu().double())
+    (y64 * go.cpu().double()).sum().backward()
+    for (pname, p32), p64 in zip(mlp.named_parameters(), m64.parameters()):
+        _close(p32.grad, p64.grad, pname)
