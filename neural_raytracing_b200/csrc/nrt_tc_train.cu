@@ -264,7 +264,7 @@ __device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uin
 }
 
 template <class NET, class DN, class IO, int FMT>
-__global__ void __launch_bounds__(kEpiThreads * 2 + 32, 1)
+__global__ void __launch_bounds__(kEpiThreads * 2 + 32 * DN::NSLOT, 1)
 k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
   using E = Elem<FMT>;
   constexpr DLayout D = DN::DY;
@@ -280,7 +280,8 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const bool is_mma_warp = warp == 8;
+  const int mma_id = warp - 8;                 // >= 0: MMA-issuing warp, one per tile slot (as in k_mlp_tc)
+  const bool is_mma_warp = mma_id == 0;        // the one that owns the TMEM allocation and the weight load
   const int64_t ntiles = (M + 127) / 128;
   if (tid == 0) {
     mbar_init(&bar_w, 1);
@@ -303,30 +304,21 @@ k_mlp_dgrad_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, TrainWs ws) {
   const uint32_t tmem = tmem_base_s;
   mbar_wait(&bar_w, 0);
 
-  if (is_mma_warp) {
+  if (mma_id >= 0) {
+    // each MMA warp blocks on the `ready` barrier of its own slot and issues that slot's stages
     const uint32_t sW_addr = smem_u32(smem);
-    int st[2] = {0, 0};
-    uint32_t n_ready[2] = {0, 0};
-    int64_t tile[2] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1};
-    bool live[2] = {tile[0] < ntiles, NSLOT > 1 && tile[1] < ntiles};
-    while (live[0] || live[1]) {
-      bool progressed = false;
-#pragma unroll
-      for (int slot = 0; slot < NSLOT; ++slot) {
-        if (!live[slot]) continue;
-        if (!mbar_test(&bar_ready[slot], n_ready[slot] & 1)) continue;
-        progressed = true;
-        n_ready[slot]++;
-        tc_fence_after();
-        const uint32_t base = tmem + slot * DN::COLS;
-        issue_dstage_dyn<NET, DN, FMT>(st[slot], sW_addr, base, base + DN::MC, base + DN::MC + DN::EC, &bar_done[slot]);
-        if (++st[slot] == DN::STAGES) {
-          st[slot] = 0;
-          tile[slot] += (int64_t)gridDim.x * NSLOT;
-          live[slot] = tile[slot] < ntiles;
+    const int slot = mma_id;
+    if (slot < NSLOT) {
+      const uint32_t base = tmem + slot * DN::COLS;
+      uint32_t n_ready = 0;
+      for (int64_t tile = (int64_t)blockIdx.x * NSLOT + slot; tile < ntiles; tile += (int64_t)gridDim.x * NSLOT) {
+        for (int st = 0; st < DN::STAGES; ++st) {
+          mbar_wait(&bar_ready[slot], n_ready & 1);
+          n_ready++;
+          tc_fence_after();
+          issue_dstage_dyn<NET, DN, FMT>(st, sW_addr, base, base + DN::MC, base + DN::MC + DN::EC, &bar_done[slot]);
         }
       }
-      if (!progressed) __nanosleep(32);
     }
   } else {
     const int slot = warp >> 2;
@@ -670,7 +662,7 @@ static int train_backward_io(const nrt_mlp_t* m, const MlpDev& d, IO io, int64_t
     NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     const int grid = (int)std::min<int64_t>((ws.ntiles + DN::NSLOT - 1) / DN::NSLOT, (int64_t)nrt_sm_count());
     NrtProfScope _ps(TAG_TC_DGRAD, st);
-    kern<<<grid, kEpiThreads * 2 + 32, bytes, st>>>(reinterpret_cast<const uint8_t*>(dblob), io, M, ws);
+    kern<<<grid, kEpiThreads * 2 + 32 * DN::NSLOT, bytes, st>>>(reinterpret_cast<const uint8_t*>(dblob), io, M, ws);
     NRT_CUDA(cudaGetLastError());
   }
   // ---- weight gradients: one job per linear layer ----
