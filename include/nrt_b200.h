@@ -157,14 +157,15 @@ int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, int64_t M, co
 /* ---- a18 (training): both NeRFLE MLPs of nerf.py:175-214 under autograd, fused --------------------------------- */
 /* Forward: rays [R,6], ts [S] (the shared sample distances), light_code [n_views, light_dim] (3: point-light location,
  * 48: environment code), view_of_ray [R] or NULL -> sigma [S,R] (pre-relu density) and rgb [S,R,3] (sigmoid), both
- * SAMPLE-major like the reference, ready for nrt_composite_forward/backward.  Nothing else is materialised in fp32:
- * the 64-d latent goes from the first to the second MLP as 16-bit (latent16: S*R*64*2 bytes, 16-byte aligned).
+ * SAMPLE-major like the reference, ready for nrt_composite_forward/backward.  The 64-d latent goes from the first to
+ * the second MLP through `latent` (ceil(S*R/128)*128*64 floats, 16-byte aligned; fp32 so that the second MLP's Fourier phases,
+ * sigma = 32 times its inputs, keep fp32 accuracy through a hi+lo split of the phase GEMM).
  * ws_first / ws_second: nrt_mlp_train_tc_workspace_bytes(first|second, S*R) bytes each, kept until the backward.
  * Backward: g_sigma [S,R], g_rgb [S,R,3] (from nrt_composite_backward) -> g_params_first / g_params_second (packed-f32
- * layout, ACCUMULATED into: zero them first); g_latent_scratch: S*R*64 floats of scratch. */
+ * layout, ACCUMULATED into: zero them first); g_latent_scratch: ceil(S*R/128)*128*64 floats of scratch. */
 int nrt_nerfle_train_forward(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays,
                              int64_t R, const float* ts, int S, const float* light_code, int light_dim,
-                             const int32_t* view_of_ray, float* sigma, float* rgb, void* latent16,
+                             const int32_t* view_of_ray, float* sigma, float* rgb, float* latent,
                              void* ws_first, size_t ws_first_bytes, void* ws_second, size_t ws_second_bytes,
                              void* stream);
 int nrt_nerfle_train_backward(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, int64_t R, int S,

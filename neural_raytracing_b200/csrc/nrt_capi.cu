@@ -24,14 +24,69 @@ int nrt_check_cuda(cudaError_t e, const char* what) {
 extern "C" const char* nrt_last_error(void) { return g_err; }
 extern "C" int nrt_abi_version(void) { return NRT_ABI_VERSION; }
 
+// ---- per-device state -------------------------------------------------------------------------------------------
+// Everything the library keeps between calls besides thread-local error text lives here, one record per CUDA device
+// (indexed by cudaGetDevice() at the time of the call), each guarded by its own mutex: the SM count, the ring of
+// ray-queue counters of the persistent march kernels and the grow-only scratch of the host-buffer entry point.
+#include <mutex>
+static NrtDeviceState g_dev_state[NRT_MAX_DEVICES];
+
+NrtDeviceState* nrt_device_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= NRT_MAX_DEVICES) return nullptr;
+  return &g_dev_state[dev];
+}
+
 int nrt_sm_count() {
-  static int cached = 0;
-  if (cached > 0) return cached;
+  NrtDeviceState* s = nrt_device_state();
+  if (s == nullptr) return 148;
+  std::lock_guard<std::mutex> lk(s->mu);
+  if (s->sm_count > 0) return s->sm_count;
   int dev = 0, n = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 148;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-  cached = n;
+  s->sm_count = n;
   return n;
+}
+
+// One zeroed 8-byte ray-queue counter for a persistent march launch on `st`, on the CURRENT device.  Eager launches
+// cycle a ring of kCounterRing slots (a slot is re-used 1,024 launches later, long after its kernel has drained on
+// any stream); launches recorded into a CUDA graph take a slot from a second region that is never recycled, so that
+// the address baked into the graph is private to it.
+int nrt_next_counter(cudaStream_t st, unsigned long long** out) {
+  NrtDeviceState* s = nrt_device_state();
+  NRT_REQUIRE(s != nullptr, "no current CUDA device (or device index >= %d)", NRT_MAX_DEVICES);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  NRT_CUDA(cudaStreamIsCapturing(st, &cap));
+  {
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (s->counters == nullptr) {
+      NRT_REQUIRE(cap == cudaStreamCaptureStatusNone,
+                  "the first march launch on a device cannot happen inside a CUDA-graph capture (run one eager step first)");
+      NRT_CUDA(cudaMalloc(&s->counters, 2 * NrtDeviceState::kCounterRing * sizeof(unsigned long long)));
+    }
+    if (cap == cudaStreamCaptureStatusNone) {
+      *out = s->counters + (s->counter_next++ % NrtDeviceState::kCounterRing);
+    } else {
+      NRT_REQUIRE(s->capture_next < NrtDeviceState::kCounterRing, "more than %u march launches captured into CUDA graphs",
+                  NrtDeviceState::kCounterRing);
+      *out = s->counters + NrtDeviceState::kCounterRing + s->capture_next++;
+    }
+  }
+  NRT_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
+  return NRT_OK;
+}
+
+// grow-only device scratch `slot` of the current device; the caller holds s->host_mu for the duration of its use
+int nrt_host_scratch(NrtDeviceState* s, int slot, size_t bytes, void** out) {
+  if (s->host_ws_bytes[slot] < bytes) {
+    if (s->host_ws[slot]) NRT_CUDA(cudaFree(s->host_ws[slot]));
+    s->host_ws[slot] = nullptr; s->host_ws_bytes[slot] = 0;
+    NRT_CUDA(cudaMalloc(&s->host_ws[slot], bytes));
+    s->host_ws_bytes[slot] = bytes;
+  }
+  *out = s->host_ws[slot];
+  return NRT_OK;
 }
 
 extern "C" int nrt_device_info(int* sm_count, int* cc_major, int* cc_minor) {
@@ -110,7 +165,6 @@ int nrt_build_sdf_dev(const nrt_sphere_sdf_t* s, SdfDev* out) {
 }
 
 // ---- launch accounting and optional CUDA-event timing of every kernel launch ----------------
-#include <mutex>
 #include <vector>
 static const char* kTagNames[TAG_COUNT] = {
     "mlp_fwd_f32", "sdf_eval_f32", "sdf_march_f32", "sdf_shadow_f32", "sdf_min_scan_f32", "nerfle_fused_f32",

@@ -50,7 +50,27 @@ int nrt_check_cuda(cudaError_t e, const char* what);
 
 int nrt_build_mlp_dev(const nrt_mlp_t* m, MlpDev* out);  // validates + resolves offsets
 int nrt_build_sdf_dev(const nrt_sphere_sdf_t* s, SdfDev* out);
-int nrt_sm_count();
+int nrt_sm_count();   // of the current device
+
+// Per-device state of the library (nrt_capi.cu): no process-global device pointers.
+#ifdef __cplusplus
+#include <mutex>
+#define NRT_MAX_DEVICES 64
+struct NrtDeviceState {
+  static const unsigned kCounterRing = 1024;
+  std::mutex mu;                       // guards the fields below
+  int sm_count = 0;
+  unsigned long long* counters = nullptr;   // [2 * kCounterRing]: eager ring, then graph-private slots
+  unsigned counter_next = 0, capture_next = 0;
+  bool pool_configured = false;
+  std::mutex host_mu;                  // held by nrt_nerfle_render_host for the whole call
+  void* host_ws[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t host_ws_bytes[4] = {0, 0, 0, 0};
+};
+NrtDeviceState* nrt_device_state();     // record of the current device (nullptr: no device)
+int nrt_next_counter(cudaStream_t st, unsigned long long** out);
+int nrt_host_scratch(NrtDeviceState* s, int slot, size_t bytes, void** out);
+#endif
 
 // launch accounting / optional per-kernel event timing (nrt_profile_* in the C ABI)
 enum NrtTag {

@@ -581,17 +581,8 @@ static int set_smem(K kernel, size_t bytes) {
   return NRT_OK;
 }
 
-// small ring of device counters for the persistent march kernels (zeroed per launch)
-static unsigned long long* g_counters = nullptr;
-static unsigned g_counter_next = 0;
-static const unsigned kCounterRing = 1024;
-static int next_counter(cudaStream_t st, unsigned long long** out) {
-  if (g_counters == nullptr) NRT_CUDA(cudaMalloc(&g_counters, kCounterRing * sizeof(unsigned long long)));
-  unsigned slot = __atomic_fetch_add(&g_counter_next, 1u, __ATOMIC_RELAXED) % kCounterRing;
-  *out = g_counters + slot;
-  NRT_CUDA(cudaMemsetAsync(*out, 0, sizeof(unsigned long long), st));
-  return NRT_OK;
-}
+// ray-queue counter of a persistent march launch: per device, see nrt_next_counter (nrt_capi.cu)
+static int next_counter(cudaStream_t st, unsigned long long** out) { return nrt_next_counter(st, out); }
 
 int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x, const float* latent,
                        int64_t M, float* out, float* acts, cudaStream_t st);  // nrt_tc.cu

@@ -52,6 +52,10 @@ __global__ void k_stratified_ts(int64_t R, int64_t r_off, int S, float t_near, f
 // (weights from the coarse pass with the reference's compositing formula, interior samples 1..Sc-2 as in NeRF), then
 // lane j, j+32, ... binary-search the cdf in shared memory and write the fine distances.
 constexpr int kPdfWarps = 4;
+// exp of the compositing weights: the exact fp32 path uses the deterministic nrt_expf of nrt_detmath.h like every other
+// fp32 kernel (and like the C oracle's restatement); the 16-bit path uses the SFU approximation
+template <bool EXACT> __device__ __forceinline__ float exp_w(float x) { return EXACT ? nrt_expf(x) : __expf(x); }
+template <bool EXACT>
 __global__ void __launch_bounds__(kPdfWarps * 32)
 k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_shared,
              const float* __restrict__ ts_c_per_ray, int Sc, int Sf, int64_t R, int64_t r_off,
@@ -71,7 +75,7 @@ k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_s
     for (int e = e0; e < e1; ++e) {
       const float t = tc[e];
       s_t[e] = t;
-      const float a = 1.0f - __expf(-fmaxf(sig[e], 0.0f) * t);
+      const float a = 1.0f - exp_w<EXACT>(-fmaxf(sig[e], 0.0f) * t);
       s_pdf[e] = a;                                  // alpha for now
       prod *= fmaxf(1.0f - a, 1e-10f);
     }
@@ -132,6 +136,7 @@ k_sample_pdf(const float* __restrict__ sigma_c, const float* __restrict__ ts_c_s
 // ---- merged compositing over coarse + fine samples (both sorted by t), ray-major ----------
 // Reads 16 B/sample (sigma + rgb) + 4 B/sample (t), writes 12 B/ray.  One warp per ray: lanes
 // merge by rank, then the transmittance product is a warp scan.
+template <bool EXACT>
 __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* __restrict__ rgb_c,
                                   const float* __restrict__ ts_c_shared, const float* __restrict__ ts_c_per_ray,
                                   int Sc, const float* __restrict__ sig_f, const float* __restrict__ rgb_f,
@@ -173,7 +178,7 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
   const int s0 = lane * per, s1 = min(S, s0 + per);
   float prod = 1.0f;
   for (int s = s0; s < s1; ++s) {
-    const float a = 1.0f - __expf(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
+    const float a = 1.0f - exp_w<EXACT>(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
     prod *= fmaxf(1.0f - a, 1e-10f);
   }
   float incl = prod;
@@ -186,7 +191,7 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
   const float total = __shfl_sync(0xffffffffu, incl, 31);
   float cp = excl, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
   for (int s = s0; s < s1; ++s) {
-    const float a = 1.0f - __expf(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
+    const float a = 1.0f - exp_w<EXACT>(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
     float w;
     if (s == 0) w = a * (S == 1 ? 1.0f : total);   // roll quirk: sample 0 gets the total product
     else if (s == S - 1) w = a;                      // last transmittance forced to 1
@@ -289,36 +294,33 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
     if (Sf > 0) {
       { NrtProfScope _ps(TAG_SAMPLE_PDF, st);
       const int grid = (int)std::min<int64_t>((n + kPdfWarps - 1) / kPdfWarps, (int64_t)nrt_sm_count() * 16);
-      k_sample_pdf<<<grid, kPdfWarps * 32, (size_t)kPdfWarps * 3 * Sc * sizeof(float), st>>>(
-          sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f); }
+      if (prec == NRT_PREC_F32)
+        k_sample_pdf<true><<<grid, kPdfWarps * 32, (size_t)kPdfWarps * 3 * Sc * sizeof(float), st>>>(
+            sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f);
+      else
+        k_sample_pdf<false><<<grid, kPdfWarps * 32, (size_t)kPdfWarps * 3 * Sc * sizeof(float), st>>>(
+            sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f); }
       NRT_CUDA(cudaGetLastError());
       rc = nerf_pass(first, second, prec, c_rays, n, nullptr, ts_f, Sf, light_code, light_dim, c_view, nullptr,
                      sig_f, rgb_f, tcws, tcws_bytes, st);
       if (rc != NRT_OK) return rc;
     }
     { NrtProfScope _ps(TAG_MERGE_COMPOSITE, st);
-    k_merge_composite<<<nrt_cdiv(n, warps), warps * 32, merge_smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f,
-                                                                          rgb_f, ts_f, Sf, n, c_out); }
+    if (prec == NRT_PREC_F32)
+      k_merge_composite<true><<<nrt_cdiv(n, warps), warps * 32, merge_smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f,
+                                                                                  rgb_f, ts_f, Sf, n, c_out);
+    else
+      k_merge_composite<false><<<nrt_cdiv(n, warps), warps * 32, merge_smem, st>>>(sig_c, rgb_c, ts_shared, ts_pr, Sc, sig_f,
+                                                                                   rgb_f, ts_f, Sf, n, c_out); }
     NRT_CUDA(cudaGetLastError());
   }
   return NRT_OK;
 }
 
-// grow-only device scratch of the host-buffer entry point (a stream-ordered pool would hand the memory
-// back at every synchronisation and re-allocate >1 GB per call)
-static void* g_host_ws[4] = {nullptr, nullptr, nullptr, nullptr};
-static size_t g_host_ws_bytes[4] = {0, 0, 0, 0};
-static int host_scratch(int slot, size_t bytes, void** out) {
-  if (g_host_ws_bytes[slot] < bytes) {
-    if (g_host_ws[slot]) NRT_CUDA(cudaFree(g_host_ws[slot]));
-    g_host_ws[slot] = nullptr; g_host_ws_bytes[slot] = 0;
-    NRT_CUDA(cudaMalloc(&g_host_ws[slot], bytes));
-    g_host_ws_bytes[slot] = bytes;
-  }
-  *out = g_host_ws[slot];
-  return NRT_OK;
-}
-
+// The host-buffer entry point keeps grow-only device scratch PER DEVICE (a stream-ordered pool would hand the memory
+// back at every synchronisation and re-allocate >1 GB per call); calls on the same device are serialised by the
+// record's host_mu, calls on different devices are independent.
+#include <mutex>
 extern "C" int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
                                       const float* rays_host, int64_t R, const float* ts_host, int S,
                                       const nrt_nerf_sampling_t* sampling, const float* light_code,
@@ -328,12 +330,15 @@ extern "C" int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* s
   NRT_REQUIRE(R >= 0, "nrt_nerfle_render_host: negative R");
   if (R == 0) return NRT_OK;
   void *d_rays = nullptr, *d_ts = nullptr, *d_out = nullptr, *ws = nullptr;
+  NrtDeviceState* ds = nrt_device_state();
+  NRT_REQUIRE(ds != nullptr, "nrt_nerfle_render_host: no current CUDA device");
+  std::lock_guard<std::mutex> host_lock(ds->host_mu);
   const size_t wsb = nrt_nerfle_render_workspace(first, second, prec, R, sampling);
-  int rc = host_scratch(0, (size_t)R * 24, &d_rays); if (rc != NRT_OK) return rc;
-  rc = host_scratch(1, (size_t)R * 12, &d_out); if (rc != NRT_OK) return rc;
-  rc = host_scratch(2, wsb, &ws); if (rc != NRT_OK) return rc;
+  int rc = nrt_host_scratch(ds, 0, (size_t)R * 24, &d_rays); if (rc != NRT_OK) return rc;
+  rc = nrt_host_scratch(ds, 1, (size_t)R * 12, &d_out); if (rc != NRT_OK) return rc;
+  rc = nrt_host_scratch(ds, 2, wsb, &ws); if (rc != NRT_OK) return rc;
   if (ts_host) {
-    rc = host_scratch(3, (size_t)S * 4, &d_ts); if (rc != NRT_OK) return rc;
+    rc = nrt_host_scratch(ds, 3, (size_t)S * 4, &d_ts); if (rc != NRT_OK) return rc;
     NRT_CUDA(cudaMemcpyAsync(d_ts, ts_host, (size_t)S * 4, cudaMemcpyHostToDevice, st));
   }
   NRT_CUDA(cudaMemcpyAsync(d_rays, rays_host, (size_t)R * 24, cudaMemcpyHostToDevice, st));

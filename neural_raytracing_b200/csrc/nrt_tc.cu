@@ -16,6 +16,8 @@
 // Reference semantics: pytorch3d/pathtracer/neural_blocks.py:75-86, utils.py:37-40, shapes/sdfs.py:111-181, 232-249,
 // shapes/nerf.py:175-214.  Fourier phases keep ~fp32 accuracy: fp32 FMAs on the CUDA cores for 3..5-D inputs, a small
 // MMA with hi+lo split operands otherwise.
+#include <stdlib.h>
+
 #include "tc_core.cuh"
 
 namespace tc {
@@ -44,11 +46,17 @@ struct IoPlain {   // materialised x [M,IN] (+ latent [M,LAT]) -> out [M,OUT] wi
   }
 };
 
-// NeRFLE.first: samples along rays in, (sigma_raw fp32, latent 16-bit) out.  nerf.py:178-183
+// NeRFLE.first: samples along rays in, (sigma_raw, latent) out.  nerf.py:178-183
+// The 64-d latent is handed to the second kernel as 16-bit (default: half the traffic, what the second MLP's
+// hidden-layer operands round to anyway) or as fp32 (lat32: the second MLP's Fourier phases are sigma = 32 times the
+// latent, so the 16-bit hand-off costs ~0.07*|latent| radians of phase error; see nerf_latent32()).  Sample m is produced and
+// consumed by the thread of the same tile / lane (m / 128, m % 128), so the scratch is TILE-INTERLEAVED:
+// 16-byte group g of sample m lives at ((m / 128) * G + g) * 128 + m % 128 (in 16-byte units, G groups per sample):
+// one warp-wide 16-byte store or load covers 512 contiguous bytes (4 lines instead of 32).
 template <int NLAT>
 struct IoNerfFirst {
   const float* rays; const float* ts; const float* ts_per_ray; int S;
-  float* sigma; uint16_t* latent; int fmt;
+  float* sigma; void* latent; int fmt; int lat32;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
     const int64_t ray = m / S;
     const int s = (int)(m - ray * S);
@@ -60,7 +68,13 @@ struct IoNerfFirst {
   }
   __device__ __forceinline__ void store(int64_t m, const float* o) const {
     sigma[m] = o[0];
-    uint4* dst = reinterpret_cast<uint4*>(latent + m * NLAT);
+    if (lat32) {
+      float4* dst = reinterpret_cast<float4*>(latent) + (m >> 7) * (int64_t)(NLAT / 4 * 128) + (m & 127);
+#pragma unroll
+      for (int j = 0; j < NLAT / 4; ++j) dst[j * 128] = make_float4(o[1 + 4 * j], o[2 + 4 * j], o[3 + 4 * j], o[4 + 4 * j]);
+      return;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(latent) + (m >> 7) * (int64_t)(NLAT / 8 * 128) + (m & 127);
 #pragma unroll
     for (int j = 0; j < NLAT / 8; ++j) {
       uint4 q;
@@ -71,7 +85,7 @@ struct IoNerfFirst {
         q.x = Elem<1>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<1>::pack(o[3 + 8 * j], o[4 + 8 * j]);
         q.z = Elem<1>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<1>::pack(o[7 + 8 * j], o[8 + 8 * j]);
       }
-      dst[j] = q;
+      dst[j * 128] = q;
     }
   }
 };
@@ -79,21 +93,30 @@ struct IoNerfFirst {
 // NeRFLE.second: [latent | r_d | light code] in, sigmoid(rgb) out.  nerf.py:199-203
 template <int NLAT, int LD>
 struct IoNerfSecond {
-  const float* rays; const uint16_t* latent; const float* light_code; const int32_t* view_of_ray; int S;
-  float* rgb; int fmt; int out_act;
+  const float* rays; const void* latent; const float* light_code; const int32_t* view_of_ray; int S;
+  float* rgb; int fmt; int out_act; int lat32;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
     const int64_t ray = m / S;
-    const uint4* src = reinterpret_cast<const uint4*>(latent + m * NLAT);
+    if (lat32) {
+      const float4* src = reinterpret_cast<const float4*>(latent) + (m >> 7) * (int64_t)(NLAT / 4 * 128) + (m & 127);
 #pragma unroll
-    for (int j = 0; j < NLAT / 8; ++j) {
-      const uint4 q = __ldg(src + j);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      for (int j = 0; j < NLAT / 4; ++j) {
+        const float4 q = __ldg(src + j * 128);
+        v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+      }
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(latent) + (m >> 7) * (int64_t)(NLAT / 8 * 128) + (m & 127);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (fmt == 0) {
-          v[8 * j + 2 * e] = Elem<0>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<0>::back((uint16_t)(w[e] >> 16));
-        } else {
-          v[8 * j + 2 * e] = Elem<1>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<1>::back((uint16_t)(w[e] >> 16));
+      for (int j = 0; j < NLAT / 8; ++j) {
+        const uint4 q = __ldg(src + j * 128);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          if (fmt == 0) {
+            v[8 * j + 2 * e] = Elem<0>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<0>::back((uint16_t)(w[e] >> 16));
+          } else {
+            v[8 * j + 2 * e] = Elem<1>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<1>::back((uint16_t)(w[e] >> 16));
+          }
         }
       }
     }
@@ -437,15 +460,17 @@ int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   const int64_t C = std::min<int64_t>(R, kChunk);
   // stream-ordered scratch from the device's default memory pool; without a release threshold the pool hands the
   // memory back to the OS at every synchronisation and each call pays a multi-millisecond re-allocation
-  static bool pool_configured = false;
-  if (!pool_configured) {
-    int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-      uint64_t keep = 1ull << 30;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  if (NrtDeviceState* ds = nrt_device_state()) {
+    std::lock_guard<std::mutex> lk(ds->mu);
+    if (!ds->pool_configured) {
+      int dev = 0;
+      cudaMemPool_t pool;
+      if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = 1ull << 30;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      ds->pool_configured = true;
     }
-    pool_configured = true;
   }
   float* val = nullptr;
   NRT_CUDA(cudaMallocAsync((void**)&val, (size_t)C * n1 * sizeof(float), st));
@@ -465,9 +490,20 @@ int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   return NRT_OK;
 }
 
+// Latent hand-off format of the RENDER path: 16-bit by default, fp32 with NRT_NERF_LATENT=f32 in the environment (read
+// once).  Measured on B200 (800x800x192, profiles/r02_kernel_log.md): the second kernel reads either at the same speed,
+// the first kernel is 12 % slower when it writes fp32 (32.0 vs 28.6 ms per frame).  With random-init or weight-decayed
+// networks |latent| is ~0.1 and the 16-bit rounding (2e-5) is below the error the latent already carries from its own
+// 16-bit GEMM (max 8e-5, tests/test_gpu_tensorcore.py); the training path always hands over fp32.
+static bool nerf_latent32() {
+  static const bool v = [] { const char* e = getenv("NRT_NERF_LATENT"); return e && (e[0] == 'f' || e[0] == 'F') && e[1] == '3'; }();
+  return v;
+}
+
 size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t*, int64_t R, int S) {
   const int nlat = first->out_size - 1;
-  return (size_t)R * S * nlat * 2 + 256;   // 16-bit latent scratch between the two kernels
+  const size_t mpad = ((size_t)R * S + 127) / 128 * 128;          // whole 128-sample tiles (tile-interleaved layout)
+  return mpad * nlat * (nerf_latent32() ? 4 : 2) + 256;           // latent scratch between the two kernels
 }
 
 int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
@@ -489,19 +525,20 @@ int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
               "tensor-core NeRF pass stores per-sample sigma/rgb (compositing is a separate kernel)");
   NRT_REQUIRE((ts != nullptr) != (ts_per_ray != nullptr), "exactly one of ts / ts_per_ray must be given");
   const int64_t M = R * S;
-  NRT_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)M * 64 * 2, "workspace too small");
-  uint16_t* lat = reinterpret_cast<uint16_t*>(workspace);
+  const int lat32 = nerf_latent32() ? 1 : 0;
+  NRT_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)((M + 127) / 128 * 128) * 64 * (lat32 ? 4 : 2), "workspace too small");
+  void* lat = workspace;
   const int fmt = fmt_of(prec);
-  IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt};
+  IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt, lat32};
   rc = fmt == 0 ? launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST)
                 : launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);
   if (rc != NRT_OK) return rc;
   if (pt) {
-    IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act};
+    IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
     return fmt == 0 ? launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
                     : launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
   }
-  IoNerfSecond<64, 48> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act};
+  IoNerfSecond<64, 48> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
   return fmt == 0 ? launch<NetNerfSecondLE, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
                   : launch<NetNerfSecondLE, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
 }

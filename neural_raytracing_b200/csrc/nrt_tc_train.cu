@@ -226,11 +226,16 @@ struct IoGrad {
 
 // loss scale: S = 2^(5 - ceil(log2(max|g|))) so that the largest scaled gradient entering the chain is in [16, 32):
 // 2000x head-room below fp16's 65504 for layers that amplify the gradient, 5e5x above its smallest normal number
+// (IO policies whose gradient source is column-interleaved declare kColMajor: consecutive threads then take consecutive
+//  samples of one output column, which is the coalesced order for them)
+template <class IO, class = void> struct GradColMajor : std::false_type {};
+template <class IO> struct GradColMajor<IO, std::void_t<decltype(IO::kColMajor)>> : std::true_type {};
 template <class IO, int OUT>
 __global__ void k_grad_absmax(IO io, int64_t M, float* __restrict__ scale) {
   float mx = 0.0f;
+  constexpr bool COL = GradColMajor<IO>::value;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M * OUT; idx += (int64_t)gridDim.x * blockDim.x) {
-    const float v = fabsf(io.g_pre(idx / OUT, (int)(idx % OUT)));
+    const float v = fabsf(COL ? io.g_pre(idx % M, (int)(idx / M)) : io.g_pre(idx / OUT, (int)(idx % OUT)));
     if (v < 3.0e38f) mx = fmaxf(mx, v);   // ignores inf / nan
   }
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -711,11 +716,11 @@ static int train_backward_io(const nrt_mlp_t* m, const MlpDev& d, IO io, int64_t
 // ---------------------------------------------------------------------------------------------
 // NeRFLE (nerf.py:175-214) training through both MLPs without materialising their inputs / outputs in fp32:
 // samples are indexed sample-major like the reference (m = s * R + ray), so sigma [S,R] and rgb [S,R,3] feed the
-// compositing kernels directly; the 64-d latent travels between the two MLPs as 16-bit (what the second MLP's operand
-// rounds to anyway), its gradient back as fp32.
+// compositing kernels directly; the 64-d latent travels between the two MLPs as fp32 (the second MLP splits it into
+// hi + lo operands for its Fourier-phase GEMM), and so does its gradient on the way back.
 // ---------------------------------------------------------------------------------------------
 struct IoNerfTrainFirst {
-  const float* rays; const float* ts; int64_t R; float* sigma; uint16_t* latent; int fmt;
+  const float* rays; const float* ts; int64_t R; float* sigma; float* latent;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
     const int64_t s = m / R, ray = m - s * R;
     const float t = __ldg(ts + s);
@@ -724,36 +729,22 @@ struct IoNerfTrainFirst {
   }
   __device__ __forceinline__ void store(int64_t m, const float* o) const {
     sigma[m] = o[0];
-    uint4* dst = reinterpret_cast<uint4*>(latent + m * 64);
+    // tile-interleaved scratch (see IoNerfFirst, nrt_tc.cu): warp-wide 16-byte stores cover 512 contiguous bytes
+    float4* dst = reinterpret_cast<float4*>(latent) + (m >> 7) * (int64_t)(16 * 128) + (m & 127);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      uint4 q;
-      if (fmt == 0) {
-        q.x = Elem<0>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<0>::pack(o[3 + 8 * j], o[4 + 8 * j]);
-        q.z = Elem<0>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<0>::pack(o[7 + 8 * j], o[8 + 8 * j]);
-      } else {
-        q.x = Elem<1>::pack(o[1 + 8 * j], o[2 + 8 * j]); q.y = Elem<1>::pack(o[3 + 8 * j], o[4 + 8 * j]);
-        q.z = Elem<1>::pack(o[5 + 8 * j], o[6 + 8 * j]); q.w = Elem<1>::pack(o[7 + 8 * j], o[8 + 8 * j]);
-      }
-      dst[j] = q;
-    }
+    for (int j = 0; j < 16; ++j) dst[j * 128] = make_float4(o[1 + 4 * j], o[2 + 4 * j], o[3 + 4 * j], o[4 + 4 * j]);
   }
 };
 template <int LD>
 struct IoNerfTrainSecond {
-  const float* rays; const uint16_t* latent; const float* light_code; const int32_t* view_of_ray; int64_t R; float* rgb; int fmt;
+  const float* rays; const float* latent; const float* light_code; const int32_t* view_of_ray; int64_t R; float* rgb;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
     const int64_t s = m / R, ray = m - s * R;
-    const uint4* src = reinterpret_cast<const uint4*>(latent + m * 64);
+    const float4* src = reinterpret_cast<const float4*>(latent) + (m >> 7) * (int64_t)(16 * 128) + (m & 127);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const uint4 q = __ldg(src + j);
-      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (fmt == 0) { v[8 * j + 2 * e] = Elem<0>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<0>::back((uint16_t)(w[e] >> 16)); }
-        else { v[8 * j + 2 * e] = Elem<1>::back((uint16_t)(w[e] & 0xffff)); v[8 * j + 2 * e + 1] = Elem<1>::back((uint16_t)(w[e] >> 16)); }
-      }
+    for (int j = 0; j < 16; ++j) {
+      const float4 q = __ldg(src + j * 128);
+      v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
     }
     const float* r = rays + ray * 6;
     v[64] = __ldg(r + 3); v[65] = __ldg(r + 4); v[66] = __ldg(r + 5);
@@ -777,20 +768,24 @@ struct IoNerfGradSecond {      // g w.r.t. sigmoid(rgb) in, g w.r.t. the latent 
 #pragma unroll
     for (int j = 0; j < 3; ++j) g[j] = g_pre(m, j) * S;
   }
-  __device__ __forceinline__ void store_gx1(int64_t m, int j, float v) const { if (j < 64) g_latent[m * 64 + j] = v * scale[2]; }
+  // g_latent scratch is tile-interleaved too: element j of sample m at ((m / 128) * 64 + j) * 128 + m % 128 (coalesced
+  // scalar stores here, coalesced scalar loads in IoNerfGradFirst)
+  __device__ __forceinline__ void store_gx1(int64_t m, int j, float v) const {
+    if (j < 64) g_latent[((m >> 7) * 64 + j) * 128 + (m & 127)] = v * scale[2];
+  }
 };
 struct IoNerfGradFirst {       // [g_sigma | g_latent] in
+  static constexpr bool kColMajor = true;
   const float* g_sigma; const float* g_latent; const float* scale;
-  __device__ __forceinline__ float g_pre(int64_t m, int j) const { return j == 0 ? __ldg(g_sigma + m) : __ldg(g_latent + m * 64 + j - 1); }
+  __device__ __forceinline__ float g_pre(int64_t m, int j) const {
+    return j == 0 ? __ldg(g_sigma + m) : __ldg(g_latent + ((m >> 7) * 64 + (j - 1)) * 128 + (m & 127));
+  }
   __device__ __forceinline__ void load_g(int64_t m, float* g) const {
     const float S = scale[1];
     g[0] = __ldg(g_sigma + m) * S;
-    const float4* src = reinterpret_cast<const float4*>(g_latent + m * 64);
+    const float* src = g_latent + (m >> 7) * (int64_t)(64 * 128) + (m & 127);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 q = __ldg(src + j);
-      g[1 + 4 * j] = q.x * S; g[2 + 4 * j] = q.y * S; g[3 + 4 * j] = q.z * S; g[4 + 4 * j] = q.w * S;
-    }
+    for (int j = 0; j < 64; ++j) g[1 + j] = __ldg(src + j * 128) * S;
   }
   __device__ __forceinline__ void store_gx1(int64_t, int, float) const {}
 };
@@ -921,7 +916,7 @@ static int nerfle_train_nets(const nrt_mlp_t* first, const nrt_mlp_t* second, in
 
 extern "C" int nrt_nerfle_train_forward(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
                                         const float* ts, int S, const float* light_code, int light_dim,
-                                        const int32_t* view_of_ray, float* sigma, float* rgb, void* latent16,
+                                        const int32_t* view_of_ray, float* sigma, float* rgb, float* latent,
                                         void* ws_first, size_t ws_first_bytes, void* ws_second, size_t ws_second_bytes,
                                         void* stream) {
   MlpDev d1, d2;
@@ -931,9 +926,9 @@ extern "C" int nrt_nerfle_train_forward(const nrt_mlp_t* first, const nrt_mlp_t*
   NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "tensor-core training path: prec must be F16 or BF16");
   NRT_REQUIRE(R >= 0 && S >= 1, "nrt_nerfle_train_forward: bad arguments");
   if (R == 0) return NRT_OK;
-  NRT_REQUIRE(rays && ts && light_code && sigma && rgb && latent16 && ws_first && ws_second, "nrt_nerfle_train_forward: null pointer");
+  NRT_REQUIRE(rays && ts && light_code && sigma && rgb && latent && ws_first && ws_second, "nrt_nerfle_train_forward: null pointer");
   NRT_REQUIRE(first->params_tc && second->params_tc, "params_tc is NULL: call nrt_mlp_pack_tc (same prec) first");
-  NRT_REQUIRE(((uintptr_t)latent16 & 15) == 0, "latent16 must be 16-byte aligned");
+  NRT_REQUIRE(((uintptr_t)latent & 15) == 0, "latent must be 16-byte aligned");
   const int64_t M = R * S;
   const Layout y1 = make_layout(d1.in_size, d1.latent, d1.freqs, d1.hidden, d1.L, d1.skip, d1.out);
   const Layout y2 = make_layout(d2.in_size, d2.latent, d2.freqs, d2.hidden, d2.L, d2.skip, d2.out);
@@ -941,14 +936,14 @@ extern "C" int nrt_nerfle_train_forward(const nrt_mlp_t* first, const nrt_mlp_t*
   NRT_REQUIRE(ws_first_bytes >= w1.bytes && ws_second_bytes >= w2.bytes, "training workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int fmt = prec == NRT_PREC_BF16 ? 1 : 0;
-  IoNerfTrainFirst io1{rays, ts, R, sigma, (uint16_t*)latent16, fmt};
+  IoNerfTrainFirst io1{rays, ts, R, sigma, latent};
   rc = fmt == 0 ? train_forward_io<NetNerfFirst, 0>(first, io1, M, w1, st) : train_forward_io<NetNerfFirst, 1>(first, io1, M, w1, st);
   if (rc != NRT_OK) return rc;
   if (id2 == 2) {
-    IoNerfTrainSecond<3> io2{rays, (const uint16_t*)latent16, light_code, view_of_ray, R, rgb, fmt};
+    IoNerfTrainSecond<3> io2{rays, latent, light_code, view_of_ray, R, rgb};
     return fmt == 0 ? train_forward_io<NetNerfSecondPT, 0>(second, io2, M, w2, st) : train_forward_io<NetNerfSecondPT, 1>(second, io2, M, w2, st);
   }
-  IoNerfTrainSecond<48> io2{rays, (const uint16_t*)latent16, light_code, view_of_ray, R, rgb, fmt};
+  IoNerfTrainSecond<48> io2{rays, latent, light_code, view_of_ray, R, rgb};
   return fmt == 0 ? train_forward_io<NetNerfSecondLE, 0>(second, io2, M, w2, st) : train_forward_io<NetNerfSecondLE, 1>(second, io2, M, w2, st);
 }
 

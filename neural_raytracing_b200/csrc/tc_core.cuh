@@ -18,7 +18,7 @@ namespace tc {
 constexpr int kMaxOps = NRT_MAX_LAYERS + 3;
 
 struct Layout {
-  int split, XR, KRAW, KE, KX, FP, NOP;
+  int split, XR, KRAW, KE, KX, KPH, FP, NOP;
   int n_ops;            // encB, init, layers[0..L-1], out
   int opN[kMaxOps], opK[kMaxOps];
   int op_off[kMaxOps];  // in 16-bit elements
@@ -44,13 +44,17 @@ __host__ __device__ constexpr Layout make_layout(int in, int lat, int f, int h, 
   y.KRAW = y.XR + 2 * f + lat;
   y.KE = c16(y.KRAW);
   y.KX = y.XR;
+  // K of the phase GEMM (op 0).  Inputs that are not split column-wise (in > 5) get their Fourier phases from a
+  // hi+lo split MMA: x.B ~= x_hi.B_hi + x_lo.B_hi + x_hi.B_lo, K = 3*XR (A chunks: x_hi, x_lo, x_hi again; B chunks:
+  // B_hi, B_hi, B_lo), so that sin / cos arguments of tens to hundreds of radians keep ~fp32 accuracy.
+  y.KPH = y.split ? y.KX : 3 * y.XR;
   y.FP = c16(f);
   y.NOP = c16(out);
   y.n_ops = L + 3;
   int off = 0, boff = 0;
   for (int o = 0; o < y.n_ops; ++o) {
     int N = 0, K = 0;
-    if (o == 0) { N = y.FP; K = y.KX; }
+    if (o == 0) { N = y.FP; K = y.KPH; }
     else if (o == 1) { N = h; K = y.KE; }
     else if (o == y.n_ops - 1) { N = y.NOP; K = h; }
     else { N = h; K = h + (is_skip(o - 2, skip, L) ? y.KE : 0); }
@@ -141,8 +145,14 @@ __global__ void k_pack_tc(MlpDev m, Layout y, uint8_t* __restrict__ blob) {
             const float hi = Elem<FMT>::back(Elem<FMT>::cvt(bv));
             v = (seg < 2) ? hi : (bv - hi);
           }
-        } else if (k < m.in_size) {
-          v = m.basis[k * m.freqs + n];
+        } else {
+          // hi+lo phase GEMM: K segments [B_hi | B_hi | B_lo], each XR wide
+          const int seg = k / y.XR, j = k - seg * y.XR;
+          if (j < m.in_size) {
+            const float bv = m.basis[j * m.freqs + n];
+            const float hi = Elem<FMT>::back(Elem<FMT>::cvt(bv));
+            v = (seg < 2) ? hi : (bv - hi);
+          }
         }
       }
     } else if (o == y.n_ops - 1) {
@@ -673,7 +683,7 @@ struct Net {
   static constexpr int IN = IN_, LAT = LAT_, F = F_, H = H_, L = L_, SKIP = SKIP_, OUT = OUT_, ACT = ACT_;
   static constexpr Layout Y = make_layout(IN, LAT, F, H, L, SKIP, OUT);
   static constexpr bool SPLIT = Y.split != 0;
-  static constexpr int XR = Y.XR, KE = Y.KE, KX = Y.KX, FP = Y.FP, NOP = Y.NOP, KRAW = Y.KRAW;
+  static constexpr int XR = Y.XR, KE = Y.KE, KX = Y.KX, KPH = Y.KPH, FP = Y.FP, NOP = Y.NOP, KRAW = Y.KRAW;
   static constexpr int DC = imax(H, imax(NOP, FP));       // fp32 accumulator columns
   // TMEM plan per tile slot.  Standard: accumulator | union region (phase-GEMM operand -> raw encoding -> hidden
   // activations) | act(encoding).  In-place plan: the raw encoding is written into the encoding region, read there by
@@ -770,7 +780,17 @@ __device__ __forceinline__ void issue_stage(uint32_t b_addr, uint32_t dD, uint32
     for (int kc = 0; kc < kch; ++kc) {
       if (PART == 1 && kc >= k_u / 2 && kc < k_u) continue;
       if (PART == 2 && (kc < k_u / 2 || kc >= k_u)) continue;
-      const uint32_t a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
+      uint32_t a;
+      if constexpr (ST == 0) {
+        // hi+lo phase GEMM (K = 3*XR): chunks [x_hi | x_lo | x_hi] against [B_hi | B_hi | B_lo].  x_hi sits where the
+        // raw encoding keeps it (in-place plan: the encoding region, else the union region), x_lo in the other one
+        // (free until the epilogue of this stage has run).
+        constexpr int xch = NET::XR / 16;
+        const uint32_t hi = NET::INPLACE ? aE : aU, lo = NET::INPLACE ? aU : aE;
+        a = (kc >= xch && kc < 2 * xch) ? (lo + (kc - xch) * 8) : (hi + (kc % xch) * 8);
+      } else {
+        a = (kc < k_u) ? (aU + kc * 8) : (aE + (kc - k_u) * 8);
+      }
       // every layer's accumulator was pre-loaded with its bias by the previous epilogue; only the
       // phase GEMM (stage 0) starts from zero
       mma_ts(dD, a, bd0 + (uint64_t)((kc * 2 * lbo) >> 4), idesc, (ST > 0 || kc > 0) ? 1u : 0u);
@@ -1074,13 +1094,13 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           mbar_arrive(&bar_ready[slot]);
         } else {
         // ---- stage 0: inputs -> encode-GEMM A operand (+ x / latent parts of enc_raw, enc_act) ----
+        uint32_t ex[NET::XR / 2];     // act(x): stored in stage 1 when the hi+lo phase GEMM borrows its place for x_lo
         {
           if (!valid) {
 #pragma unroll
             for (int j = 0; j < IN + LAT; ++j) x[j] = 0.0f;
           }
           uint32_t ax[NET::KX / 2];
-          uint32_t ex[NET::XR / 2];
 #pragma unroll
           for (int j = 0; j < NET::KX / 2; ++j) { ax[j] = 0; ex[j] = 0; }
           if constexpr (NET::SPLIT) {
@@ -1101,17 +1121,28 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             for (int j = 0; j < 8; ++j) ax[j] = (uint32_t)v[2 * j] | ((uint32_t)v[2 * j + 1] << 16);
 #pragma unroll
             for (int j = 0; j < IN; ++j) ex[j] = (uint32_t)a[2 * j] | ((uint32_t)a[2 * j + 1] << 16);
+            tmem_store<NET::KX / 2>(aU, ax);
+            if constexpr (NET::INPLACE) tmem_store<NET::XR / 2>(aE, ax);   // raw x part; activated in place later
+            else tmem_store<NET::XR / 2>(aE, ex);
           } else {
+            // x_hi (what the init / skip layers see) and x_lo = x - x_hi (second operand of the hi+lo phase GEMM)
+            uint32_t lx[NET::XR / 2];
+#pragma unroll
+            for (int j = 0; j < NET::XR / 2; ++j) lx[j] = 0;
 #pragma unroll
             for (int j = 0; j < (IN + 1) / 2; ++j) {
               const float xa = x[2 * j], xb = (2 * j + 1 < IN) ? x[2 * j + 1 < IN ? 2 * j + 1 : 0] : 0.0f;   // odd in: zero pad
               ax[j] = E::pack(xa, xb);
+              const float ha = E::back((uint16_t)(ax[j] & 0xffffu)), hb = E::back((uint16_t)(ax[j] >> 16));
+              lx[j] = E::pack(xa - ha, xb - hb);
               ex[j] = E::pack(act_fast<NET::ACT>(xa), (2 * j + 1 < IN) ? act_fast<NET::ACT>(xb) : 0.0f);
             }
+            // in-place plan: x_hi into the encoding region (its final place), x_lo into the union region;
+            // otherwise x_hi into the union region (its final place) and x_lo TEMPORARILY into the encoding region:
+            // act(x) is stored there in stage 1, once the phase GEMM has read x_lo
+            if constexpr (NET::INPLACE) { tmem_store<NET::XR / 2>(aE, ax); tmem_store<NET::XR / 2>(aU, lx); }
+            else { tmem_store<NET::XR / 2>(aU, ax); tmem_store<NET::XR / 2>(aE, lx); }
           }
-          tmem_store<NET::KX / 2>(aU, ax);
-          if constexpr (NET::INPLACE) tmem_store<NET::XR / 2>(aE, ax);   // raw x part; activated in place later
-          else tmem_store<NET::XR / 2>(aE, ex);
           if constexpr (SV::kOn) {
             static_assert(!ITER, "activation tiles are saved by the tile policies only");
             uint16_t* rr = tile_row_ptr(sv.enc_raw, m >> 7, NET::KE + kTileRowsExtra, lane_row);
@@ -1161,6 +1192,8 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             tc_fence_after();
             tmem_load<F>(dD, ph);
             tc_wait_ld();
+            // the phase GEMM has read x_lo: act(x) takes its place in the encoding region
+            if constexpr (!NET::INPLACE) tmem_store<NET::XR / 2>(aE, ex);
           }
           preload_bias<H>(dD, sBias + s_bias[1]);
           uint32_t sr[F / 2], cr[F / 2], sa[F / 2], ca[F / 2];

@@ -238,7 +238,7 @@ def nerfle_train_forward(first: PackedMLP, second: PackedMLP, rays: torch.Tensor
     dev = rays.device
     sigma = torch.empty((S, R), dtype=torch.float32, device=dev)
     rgb = torch.empty((S, R, 3), dtype=torch.float32, device=dev)
-    lat = torch.empty(S * R * 64 * 2, dtype=torch.uint8, device=dev)
+    lat = torch.empty((S * R + 127) // 128 * 128 * 64, dtype=torch.float32, device=dev)   # whole tiles (tile-interleaved)
     with torch.cuda.device(dev):
         c1, c2 = first.c_struct(prec), second.c_struct(prec)
         n1 = N.lib().nrt_mlp_train_tc_workspace_bytes(ctypes.byref(c1), S * R)
@@ -263,7 +263,7 @@ def nerfle_train_backward(first: PackedMLP, second: PackedMLP, rgb: torch.Tensor
     gc = _chk(g_rgb, "g_rgb").reshape(S, R, 3)
     y = _chk(rgb, "rgb").reshape(S, R, 3)
     g1, g2 = torch.zeros_like(first.params), torch.zeros_like(second.params)
-    scratch = torch.empty(S * R * 64, dtype=torch.float32, device=dev)
+    scratch = torch.empty((S * R + 127) // 128 * 128 * 64, dtype=torch.float32, device=dev)   # whole tiles
     with torch.cuda.device(dev):
         c1, c2 = first.c_struct(prec), second.c_struct(prec)
         b1, b2 = first.dgrad_blob(False, prec), second.dgrad_blob(True, prec)

@@ -90,9 +90,21 @@ class Direct(Integrator):
             wo = it.to_local(ds.d)
             bsdf_val, _pdf = bsdf.eval_and_pdf(it, wo, active=lit)
             result[lit] = result[lit] + bsdf_val[lit] * emitter_val[lit] / self.emitter_samples
-        if self.bsdf_samples:
-            raise NotImplementedError("BSDF sampling is not implemented in the reference either (integrators.py:198)")
+        self._bsdf_sample_loop(shapes, it, active, bsdf, lights, sampler)
         return result, active, it
+
+    def _bsdf_sample_loop(self, shapes, it, active, bsdf, lights, sampler):
+        """integrators.py:189-204: the unfinished BSDF-sampling loop.  It samples the BSDF, intersects the bounce with
+        the emitters and raises only if a bounce actually hits one; PointLights / LightField.intersect return
+        (None, False), so with those a script configured with bsdf_samples > 0 runs to completion (without any
+        contribution), exactly as in the reference."""
+        for _ in range(self.bsdf_samples):
+            bs, _bsdf_val = bsdf.sample(it, sampler=sampler, active=active)
+            _it2, snd_active = lights.intersect(it.spawn_rays(it.from_local(bs.wo)))
+            bsdf_active = active & snd_active
+            if bsdf_active.any():
+                raise NotImplementedError("BSDF-sampled emitter hits are not implemented in the reference either "
+                                          "(integrators.py:198)")
 
 
 class NeRFIntegrator(Integrator):

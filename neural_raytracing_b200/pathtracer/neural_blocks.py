@@ -49,12 +49,15 @@ class SkipConnMLP(nn.Module):
         self.init = nn.Linear(self.dim_p, hidden_size)
         self.layers = nn.ModuleList([nn.Linear(w, hidden_size) for w in widths])
         self.out = nn.Linear(hidden_size, out)
-        if zero_init or xavier_init:
+        # neural_blocks.py:66-71: the two inits are applied one after the other (zero first, then xavier overrides the
+        # weights when both flags are set); either one zeroes the biases
+        if zero_init:
             for lin in self._linears():
-                if zero_init:
-                    nn.init.zeros_(lin.weight)
-                else:
-                    nn.init.xavier_uniform_(lin.weight)
+                nn.init.zeros_(lin.weight)
+                nn.init.zeros_(lin.bias)
+        if xavier_init:
+            for lin in self._linears():
+                nn.init.xavier_uniform_(lin.weight)
                 nn.init.zeros_(lin.bias)
         self.activation = activation
         self._pack_key = None
@@ -90,6 +93,14 @@ class SkipConnMLP(nn.Module):
                                          basis.detach().contiguous().float(), flat)
             self._pack_key = key
         return self._packed
+
+    def invalidate_packed(self):
+        """Drops the cached device copies of the parameters (packed-f32 blob, tensor-core blobs, transposed weights).
+        The cache key is (data_ptr, _version) of every parameter: call this after a weight update that does not bump
+        tensor versions -- writes through `.data`, `p.set_()`, replays of a CUDA graph that contains the optimizer
+        step (training.GraphedStep does it itself)."""
+        self._pack_key = None
+        self._packed = None
 
     def precision(self):
         """Arithmetic used for gradient-free evaluation."""

@@ -116,7 +116,9 @@ class NeRFLE(nn.Module):
             N = rays.shape[0]
             per_view = rays[0].numel() // 6
             view = torch.arange(N, device=device, dtype=torch.int32).repeat_interleave(per_view)
-            prec = config.precision
+            # the fused tensor-core render instantiates the point-light and the bins = 4 environment net only: any
+            # other shape keeps the exact fp32 kernel (SkipConnMLP.precision() knows which shapes are instantiated)
+            prec = config.precision if self.first.precision() != "f32" and self.second.precision() != "f32" else "f32"
             return ops.nerfle_render(self.first.packed(), self.second.packed(), rays.detach().float(), ts,
                                      code.detach().float(), view, prec=prec)
         # differentiable path: fused MLP kernels where available + CUDA compositing

@@ -70,6 +70,10 @@ class SphereSDF(nn.Module):
     def packed(self) -> "ops.PackedSDF":
         return ops.PackedSDF(self.centers, self.radii, self.tfs, self.shift.packed())
 
+    def invalidate_packed(self):
+        """See SkipConnMLP.invalidate_packed (the sphere parameters are borrowed, never cached)."""
+        self.shift.invalidate_packed()
+
     def _needs_grad(self, p):
         return torch.is_grad_enabled() and (p.requires_grad or any(q.requires_grad for q in self.parameters()))
 

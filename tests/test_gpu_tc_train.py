@@ -6,9 +6,10 @@ Yardsticks (float64 torch autograd on the GPU):
     rounds them (straight-through rounding).  leaky_relu has a kink at 0, so WHICH units sit on the 0.01 slope is
     decided by the forward's rounding; against a reference that rounds identically the kernels must agree tightly:
     cosine >= 0.9995 per parameter tensor.  This is the implementation-correctness gate.
-  * exact reference (no rounding): reported precision of the 16-bit path.  NeRFLE.first >= 0.999 (SURVEY 8d gate);
-    the 8x64 NeRFLE.second with the small synthetic weights has many pre-activations within the fp16 rounding
-    distance of 0, its input-side layers reach ~0.985; gate 0.97.  bf16 operands are 8x coarser (0.99 / 0.90).
+  * exact reference (no rounding): the precision claim of the 16-bit path, SURVEY 8d's gate: cosine >= 0.999 per
+    parameter tensor for both NeRFLE networks with fp16 operands (measured on B200: first >= 0.9994, second >= 0.9995,
+    environment-light second >= 0.9994; the second MLP's Fourier phases come from a hi+lo split GEMM and the latent
+    reaches it as fp32).  bf16 operands are 8x coarser (>= 0.995) and do not meet the gate: fp16 is the training mode.
 """
 import numpy as np
 import pytest
@@ -35,12 +36,10 @@ def _ref(w, x, out_act_sigmoid, quantised, split_inputs):
     B = torch.tensor(w["basis"], dtype=torch.float64, device="cuda")
     x = x.double().requires_grad_()
     act = torch.nn.functional.leaky_relu
-    if quantised and not split_inputs:
-        xq = _q(x)
-        ph = xq @ B.half().double()
-    else:
-        xq = x        # split inputs enter as hi + lo: ~fp32
-        ph = x @ B
+    # Fourier phases keep ~fp32 accuracy for every network (fp32 FMAs for 3..5-D inputs, hi+lo split phase GEMM
+    # otherwise); the raw inputs enter the init / skip layers as hi + lo columns (<= 5-D) or rounded once (wider)
+    xq = _q(x) if (quantised and not split_inputs) else x
+    ph = x @ B
     s, c = ph.sin(), ph.cos()
     if quantised:
         s, c = _q(s), _q(c)
@@ -74,8 +73,8 @@ def _cos(a, b):
 LE_KW = dict(seed=33, in_size=115, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0)   # NeRFLE.second, envmap code
 
 
-@pytest.mark.parametrize("name,sig,need_x,gate_exact", [("nerf_first", False, False, 0.999), ("nerf_second", True, False, 0.97),
-                                                        ("nerf_second", True, True, 0.97), ("nerf_second_le", True, True, 0.97)])
+@pytest.mark.parametrize("name,sig,need_x,gate_exact", [("nerf_first", False, False, 0.999), ("nerf_second", True, False, 0.999),
+                                                        ("nerf_second", True, True, 0.999), ("nerf_second_le", True, True, 0.999)])
 @pytest.mark.parametrize("M", [1, 129, 5000])
 def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     import torch
@@ -104,8 +103,8 @@ def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
                 scale = float(ra.grad.abs().max())
                 assert float((a.double() - ra.grad).abs().max()) <= 0.05 * scale + 1e-12
         if need_x:
-            # d/dx of NeRFLE.second multiplies by the sigma = 32 basis and cancels (see test_gpu_backward.py): loose
-            assert _cos(gx, xr.grad) > (0.995 if quantised else 0.97), (_cos(gx, xr.grad), quantised)
+            # d/dx of NeRFLE.second multiplies by the sigma = 32 basis (measured 0.9999)
+            assert _cos(gx, xr.grad) > 0.999, (_cos(gx, xr.grad), quantised)
 
 
 def test_tc_train_bf16_runs_and_is_coarser():
@@ -175,7 +174,7 @@ def test_nerfle_training_step_tc_vs_fp32():
         config.set_train_precision("f32")
     assert abs(res["f32"][0] - res["f16"][0]) < 1e-3 * max(1.0, abs(res["f32"][0]))
     cs = [_cos(a, b) for a, b in zip(res["f32"][1], res["f16"][1]) if float(b.norm()) > 0]
-    assert min(cs) > 0.97 and float(np.median(cs)) > 0.995, (min(cs), float(np.median(cs)))
+    assert min(cs) > 0.997 and float(np.median(cs)) > 0.9995, (min(cs), float(np.median(cs)))
 
 
 def test_graphed_training_step_matches_eager():
@@ -227,13 +226,14 @@ def test_graphed_training_step_matches_eager():
 
 
 @pytest.mark.parametrize("envmap", [False, True])
-@pytest.mark.parametrize("tprec,loss_tol,min_cos", [("f32", 2e-5, 0.9999), ("f16", 1e-3, 0.985)])
-def test_nerfle_training_step_vs_unmodified_reference(envmap, tprec, loss_tol, min_cos):
+@pytest.mark.parametrize("tprec,loss_tol,min_cos,min_cos_tensor", [("f32", 2e-5, 0.9999, 0.9999), ("f16", 1e-4, 0.9998, 0.997)])
+def test_nerfle_training_step_vs_unmodified_reference(envmap, tprec, loss_tol, min_cos, min_cos_tensor):
     """Loss and the gradient of every Linear of a nerfle.py-style step (NeRFLE forward -> mse -> backward) against the
     fixture produced by the UNMODIFIED reference on CPU fp32 (tests/golden/make_golden.py::gen_nerfle_train).  Exact
-    fp32 kernels: cosine >= 0.9999; tensor-core training kernels (fp16 operands): >= 0.985 over all weights of an MLP
-    (the forward's rounding moves leaky_relu kinks, see the module docstring); 0.96 for the environment-light model,
-    whose 115 second-MLP inputs enter the sigma = 32 Fourier phases rounded to fp16 (phase error ~0.05 rad)."""
+    fp32 kernels: cosine >= 0.9999; tensor-core training kernels (fp16 operands): >= 0.9998 over all weights / all
+    biases of an MLP (0.999), point-light and environment-light model alike, and per parameter tensor
+    >= 0.999 everywhere except NeRFLE.first's init layer (35 inputs, 1 % of that MLP's gradient norm: 0.9977 / 0.9989;
+    the forward's 16-bit rounding decides which leaky_relu kinks its few large contributions pass through)."""
     import random
     import torch
     from neural_raytracing_b200 import config
@@ -264,11 +264,19 @@ def test_nerfle_training_step_vs_unmodified_reference(envmap, tprec, loss_tol, m
         lins = [mod.init] + list(mod.layers) + [mod.out]
         gw = torch.cat([l.weight.grad.reshape(-1) for l in lins]).cpu().numpy().astype(np.float64)
         gb = torch.cat([l.bias.grad.reshape(-1) for l in lins]).cpu().numpy().astype(np.float64)
-        for got, key in ((gw, "%s_g_%s_w" % (tag, name)), (gb, "%s_g_%s_b" % (tag, name))):
+        for got, key, sizes in ((gw, "%s_g_%s_w" % (tag, name), [l.weight.numel() for l in lins]),
+                                (gb, "%s_g_%s_b" % (tag, name), [l.bias.numel() for l in lins])):
             ref = g[key].astype(np.float64)
             cos = float(got @ ref / (np.linalg.norm(got) * np.linalg.norm(ref) + 1e-300))
-            assert cos > (0.96 if (envmap and tprec == "f16") else min_cos), (key, tprec, cos)
-            assert abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) < (1e-3 if tprec == "f32" else 3e-2), key
+            assert cos > min_cos, (key, tprec, cos)
+            assert abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) < (1e-3 if tprec == "f32" else 5e-3), key
+            off = 0
+            for i, k in enumerate(sizes):       # per parameter tensor
+                a, b = got[off:off + k], ref[off:off + k]
+                off += k
+                c = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300))
+                gate = min_cos_tensor if (name == "first" and i == 0) else max(min_cos_tensor, 0.999)
+                assert c > gate, (key, i, tprec, c)
 
 
 def test_tc_train_large_weights_do_not_overflow():

@@ -2,10 +2,10 @@
 
 Tolerances (north_star: "max-abs 1e-3 for the bf16/tf32 MLP path, >= 50 dB PSNR on rendered
 images"): fp16 operands / fp32 accumulation are held to max-abs 1e-3 and >= 60 dB on rendered
-radiance; bf16 operands (3 fewer mantissa bits) to 5e-3 and >= 50 dB.  The raw NeRFLE.second MLP on
-arbitrary O(1) inputs is looser: its Fourier phases reach hundreds of radians (sigma=32 over 70
-inputs), so 16-bit input rounding alone moves the phase by ~0.05 rad; inside the renderer the inputs
-are small latents and the error is ~1e-4."""
+radiance; bf16 operands (3 fewer mantissa bits) to 5e-3 and >= 50 dB.  That includes the raw
+NeRFLE.second MLP on arbitrary O(1) inputs, whose Fourier phases reach hundreds of radians (sigma = 32
+over 70 inputs): the phase GEMM runs on hi+lo split operands (x_hi.B_hi + x_lo.B_hi + x_hi.B_lo), so
+the phases keep ~fp32 accuracy (measured on B200: fp16 5.8e-5, bf16 4.4e-4 at |x| ~ 0.6)."""
 import numpy as np
 import pytest
 
@@ -19,7 +19,8 @@ TC_CASES = {
     "nerf_first": (helpers.MLP_CASES["nerf_first"][0], 1e-3, 5e-3),
     "neural_bsdf": (helpers.MLP_CASES["neural_bsdf"][0], 1e-3, 5e-3),
     "occ": (dict(seed=18, in_size=5, out=1, num_layers=8, hidden=64, freqs=16, sigma=32.0), 1e-3, 5e-3),
-    "nerf_second": (helpers.MLP_CASES["nerf_second"][0], 2e-2, 1e-1),
+    "nerf_second": (helpers.MLP_CASES["nerf_second"][0], 1e-3, 5e-3),
+    "nerf_second_le": (dict(seed=33, in_size=115, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0), 1e-3, 5e-3),
 }
 
 
