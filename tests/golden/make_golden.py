@@ -430,6 +430,88 @@ def gen_plain_nerf():
     print("plain_nerf.npz: rgb", out["rgb"].shape, "mean", out["rgb"].mean(), "std", out["rgb"].std(), "; state dicts", {k: len(out["sd_" + k]) for k in mods})
 
 
+def gen_colocate64():
+    """BASELINE configs[0] at its named size: colocate.py-style forward render, 64x64 camera rays, one chunk, bundle 1
+    (SURVEY 8d cfg1): SDF(SphereSDF(n=64), max_steps=64), ComposeSpatialVarying([NeuralBSDF x2, Diffuse(Softplus),
+    Conductor(Softplus)]), Direct, PointLights(scale=5), learned-occlusion MLP as w_isect."""
+    import pytorch3d.pathtracer as P
+    import pytorch3d.pathtracer.shapes.sdfs, pytorch3d.pathtracer.bsdf, pytorch3d.pathtracer.lights  # noqa: F401
+    import pytorch3d.pathtracer.integrators, pytorch3d.pathtracer.neural_blocks, pytorch3d.pathtracer.cameras  # noqa: F401
+    from pytorch3d.pathtracer.cameras import NeRFCamera
+    out = {}
+    random.random = lambda: FIXED_RANDOM
+    size = 64
+    c2w, focal = synth.nerf_cameras(1, size)
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cpu")
+    shape, sphere, bsdf, lights, integrator, w_isect = build_pipeline(P, "colocate")
+    with torch.no_grad():
+        img, mi = P.pathtrace(shape, size=size, chunk_size=size, bundle_size=1, bsdf=bsdf, integrator=integrator,
+                              lights=lights, cameras=cam, device="cpu", silent=True, background=0, w_isect=w_isect,
+                              with_noise=False, addition=lambda it: it)
+    out["img"] = img.numpy()
+    out["throughput"] = mi.throughput.reshape(-1).numpy()
+    out["weights"] = mi.normalized_weights.reshape(-1, 4).numpy().astype(np.float16)
+    out["raw_normals"] = mi.raw_normals.detach().numpy()
+    out["depth"] = mi.t.reshape(-1).numpy()
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("main.py:13-93; integrators/integrators.py:156-206; scene.py:301-318; shapes/sdfs.py:102-249; bsdf/bsdfs.py")
+    np.savez_compressed(os.path.join(HERE, "colocate64.npz"), **out)
+    print("colocate64.npz: img mean %.4f, %d hits of %d" % (out["img"].mean(), len(out["raw_normals"]), size * size))
+
+
+def gen_dtu16():
+    """BASELINE configs[3] with its named model (dtu.py:93-108: 10 NeuralBSDF + 6 Diffuse under a 16-way sp_var MLP,
+    LightField, NeRFIntegrator(Direct()), DTUCamera) on 2 views x 64x64 rays (the whole 1600x1200 field of view): one train_dtu iteration
+    (training_utils.py:385-405) -- pathtrace_sample, masked_loss(mask_weight=10) + eikonal_loss(raw_normals) --
+    forward and backward.  The SSIM term of masked_loss comes from the absent, unpinned pytorch_msssim: it is patched
+    to the constant 1 (-log 1 = 0) for the run, i.e. "masked_loss without SSIM" (SURVEY 8d cfg4).  Gradients are kept
+    as scenes.grad_block() of every parameter tensor."""
+    import pytorch3d.pathtracer as P
+    import pytorch3d.pathtracer.utils as RU
+    import pytorch3d.pathtracer.shapes.sdfs, pytorch3d.pathtracer.bsdf, pytorch3d.pathtracer.lights  # noqa: F401
+    import pytorch3d.pathtracer.integrators, pytorch3d.pathtracer.neural_blocks, pytorch3d.pathtracer.cameras  # noqa: F401
+    from pytorch3d.pathtracer.cameras import DTUCamera
+    import scenes
+    RU.ssim = lambda *a, **k: torch.ones(())
+    random.random = lambda: FIXED_RANDOM
+    out = {}
+    n_views, size, crop, uv = 2, 64, 64, (0, 0)
+    shape, sphere, bsdf, lights, integrator = scenes.build_dtu16(P)
+    pose, K = scenes.dtu_cameras(n_views)
+    cam = DTUCamera(pose=pose, intrinsic=K, device="cpu")
+    exp, mask = scenes.dtu_targets(n_views, crop)
+    got, mi = P.pathtrace_sample(shape, size=size, chunk_size=size, bundle_size=1, crop_size=crop, bsdf=bsdf,
+                                 integrator=integrator, cameras=cam, lights=lights, device="cpu", uv=uv, background=0,
+                                 addition=lambda mi: mi, squeeze_first=False, silent=True)
+    loss_img = RU.masked_loss(got[..., :3], exp, mi.throughput.squeeze(-1), mask, mask_weight=10, with_logits=mi.with_logits)
+    loss_eik = RU.eikonal_loss(mi.raw_normals)
+    loss = loss_img + loss_eik
+    loss.backward()
+    out["img"] = got.detach().numpy()
+    out["throughput"] = mi.throughput.detach().reshape(-1).numpy()
+    out["n_hits"] = np.array(len(mi.raw_normals))
+    out["loss"] = np.array([loss.item(), loss_img.item(), loss_eik.item()], np.float64)
+    groups = {"sdf": sphere, "spvar": bsdf.sp_var_fn, "light": lights}
+    for i, b in enumerate(bsdf.bsdfs[:10]):
+        groups["bsdf%d" % i] = b.mlp
+    names = []
+    for gname, mod in groups.items():
+        for pname, p in mod.named_parameters():
+            assert p.grad is not None, (gname, pname)
+            key = "g_%s.%s" % (gname, pname)
+            out[key] = scenes.grad_block(p.grad).numpy().copy()
+            out["n_" + key[2:]] = np.array(float(p.grad.norm()), np.float64)
+            names.append(key)
+    out["g_reflectance"] = np.stack([b.reflectance.grad.numpy() for b in bsdf.bsdfs[10:]])
+    out["grad_keys"] = np.array(names)
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["config"] = np.array([n_views, size, crop, uv[0], uv[1]])
+    out["src"] = np.array("scripts/dtu.py:93-146; training_utils.py:347-405; main.py:97-179; utils.py:294-359; cameras/cameras.py:132-192")
+    np.savez_compressed(os.path.join(HERE, "dtu16.npz"), **out)
+    print("dtu16.npz: loss %.5f (image %.5f, eikonal %.5f), %d hits of %d rays, %d gradient tensors" %
+          (loss.item(), loss_img.item(), loss_eik.item(), len(mi.raw_normals), n_views * crop * crop, len(names)))
+
+
 class GoldenRatioSampler:
     """Deterministic stand-in for Sampler (samplers.py:14-20): call c returns frac((i + 1 + 977 c) * phi), i the flat
     index.  Shared by the reference run and the GPU test so that both trace the same bounces."""
@@ -489,7 +571,7 @@ def gen_path():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf", "path"]
+                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
