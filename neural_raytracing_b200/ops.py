@@ -174,13 +174,23 @@ def mlp_forward(m: PackedMLP, x: torch.Tensor, latent: Optional[torch.Tensor] = 
     return (out, acts) if save_acts else out
 
 
-def mlp_backward(m: PackedMLP, x, latent, out, acts, g_out, out_act=OUT_NONE, need_input_grad=False):
+def _grad_out(m: PackedMLP, g_params):
+    """The packed-f32 gradient the kernels ACCUMULATE into: a fresh zero blob, or the caller's buffer (e.g. the slice
+    of training.FlatParameters' flat gradient that belongs to this MLP)."""
+    if g_params is None:
+        return torch.zeros_like(m.params)
+    if g_params.numel() != m.params.numel() or not g_params.is_contiguous() or g_params.dtype != torch.float32:
+        raise NrtError("g_params must be a contiguous fp32 buffer of %d floats" % m.params.numel())
+    return g_params
+
+
+def mlp_backward(m: PackedMLP, x, latent, out, acts, g_out, out_act=OUT_NONE, need_input_grad=False, g_params=None):
     x2 = _chk(x, "x").reshape(-1, m.in_size)
     M = x2.shape[0]
     lat = _chk(latent, "latent").reshape(M, m.latent_size) if m.latent_size else None
     out2 = _chk(out, "out").reshape(M, m.out_size)
     g2 = _chk(g_out, "g_out").reshape(M, m.out_size)
-    g_params = torch.zeros_like(m.params)
+    g_params = _grad_out(m, g_params)
     g_x = torch.empty_like(x2) if need_input_grad else None
     g_lat = torch.empty_like(lat) if (need_input_grad and lat is not None) else None
     with torch.cuda.device(x.device):
@@ -210,12 +220,12 @@ def mlp_forward_train_tc(m: PackedMLP, x: torch.Tensor, out_act=OUT_NONE, prec=P
 
 
 def mlp_backward_tc(m: PackedMLP, M: int, out: torch.Tensor, g_out: torch.Tensor, ws: torch.Tensor, out_act=OUT_NONE,
-                    need_input_grad=False, prec=PREC_F16):
+                    need_input_grad=False, prec=PREC_F16, g_params=None):
     """Tensor-core backward of mlp_forward_train_tc: (g_params packed-f32, g_x or None)."""
     prec = prec_id(prec)
     out2 = _chk(out, "out").reshape(M, m.out_size)
     g2 = _chk(g_out, "g_out").reshape(M, m.out_size)
-    g_params = torch.zeros_like(m.params)
+    g_params = _grad_out(m, g_params)
     g_x = torch.empty((M, m.in_size), dtype=torch.float32, device=out.device) if need_input_grad else None
     with torch.cuda.device(out.device):
         c = m.c_struct(prec)
@@ -254,15 +264,15 @@ def nerfle_train_forward(first: PackedMLP, second: PackedMLP, rays: torch.Tensor
 
 
 def nerfle_train_backward(first: PackedMLP, second: PackedMLP, rgb: torch.Tensor, g_sigma: torch.Tensor, g_rgb: torch.Tensor,
-                          state, prec=PREC_F16):
-    """(g_params_first, g_params_second), packed-f32 layout."""
+                          state, prec=PREC_F16, g_params_first=None, g_params_second=None):
+    """(g_params_first, g_params_second), packed-f32 layout (accumulated into the given buffers if any)."""
     prec = prec_id(prec)
     ws1, ws2, R, S, light_dim = state
     dev = rgb.device
     gs = _chk(g_sigma, "g_sigma").reshape(S, R)
     gc = _chk(g_rgb, "g_rgb").reshape(S, R, 3)
     y = _chk(rgb, "rgb").reshape(S, R, 3)
-    g1, g2 = torch.zeros_like(first.params), torch.zeros_like(second.params)
+    g1, g2 = _grad_out(first, g_params_first), _grad_out(second, g_params_second)
     scratch = torch.empty((S * R + 127) // 128 * 128 * 64, dtype=torch.float32, device=dev)   # whole tiles
     with torch.cuda.device(dev):
         c1, c2 = first.c_struct(prec), second.c_struct(prec)

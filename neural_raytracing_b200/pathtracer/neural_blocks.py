@@ -75,7 +75,27 @@ class SkipConnMLP(nn.Module):
 
     def packed(self) -> "ops.PackedMLP":
         """Device parameters in the C-ABI layout; rebuilt when a weight changed (optimizer step,
-        load_state_dict, .to(device), manual assignment)."""
+        load_state_dict, .to(device), manual assignment).  After training.FlatParameters re-homed the Linears into one
+        flat buffer in that very layout, the packed blob IS the parameter storage: nothing is copied, only the derived
+        16-bit blobs are dropped when the buffer changed (or while a CUDA graph is being captured, so that the pack
+        kernels are part of the graph)."""
+        flat = getattr(self, "_flat_view", None)
+        if flat is not None:
+            key = (flat.data_ptr(), flat._version, self.basis_p.data_ptr(), self.basis_p._version, id(self.activation))
+            capturing = flat.is_cuda and torch.cuda.is_current_stream_capturing()
+            if self._packed is None or self._pack_key is None or capturing or key[2:] != self._pack_key[2:]:
+                act = _activation_id(self.activation)
+                if act is None:
+                    raise ops.NrtError("SkipConnMLP: unsupported activation %r for the fused kernels" % (self.activation,))
+                basis = self.basis_p if self.basis_p.device == flat.device else self.basis_p.to(flat.device)
+                self.basis_p = basis
+                self._packed = ops.PackedMLP(self.in_size, self.latent_size, basis.shape[-1], self.init.out_features,
+                                             len(self.layers), self.skip, self.out.out_features, act,
+                                             basis.detach().contiguous().float(), flat.detach())
+            elif key != self._pack_key:
+                self._packed.tc_blobs.clear(); self._packed.dgrad_blobs.clear(); self._packed._params_nk = None
+            self._pack_key = key
+            return self._packed
         ps = self._flat_params()
         basis = self.basis_p
         if basis.device != ps[0].device:   # basis_p is a plain attribute: .to() does not move it
@@ -184,6 +204,7 @@ class _FusedMLP(torch.autograd.Function):
         ctx.has_latent = latent is not None
         ctx.need_in = p.requires_grad or (latent is not None and latent.requires_grad)
         ctx.tc_prec = module.train_precision()
+        ctx.flat_grad = getattr(module, "_flat_grad", None)
         if ctx.tc_prec != "f32" and (not ctx.need_in or pk.in_size > 5):
             # tensor-core training path: the workspace holds the saved activation tiles
             out, ws = ops.mlp_forward_train_tc(pk, x, out_act=out_act, prec=ctx.tc_prec)
@@ -204,7 +225,11 @@ class _FusedMLP(torch.autograd.Function):
             out, ws = ctx.saved_tensors
             M = out.shape[0]
             g_params, g_x = ops.mlp_backward_tc(ctx.pk, M, out, g.contiguous().float().reshape(M, -1), ws,
-                                                out_act=ctx.out_act, need_input_grad=ctx.need_in, prec=ctx.tc_prec)
+                                                out_act=ctx.out_act, need_input_grad=ctx.need_in, prec=ctx.tc_prec,
+                                                g_params=ctx.flat_grad)
+            if ctx.flat_grad is not None:    # accumulated straight into the flat gradient buffer (training.FlatParameters)
+                gx = None if g_x is None else g_x.reshape(ctx.lead + (ctx.pk.in_size,))
+                return (None, gx, None, None) + (None,) * (2 * len(ctx.pk.dims))
             gW, gb = ctx.pk.unpack(g_params)
             flat = []
             for w, b in zip(gW, gb):
@@ -214,7 +239,11 @@ class _FusedMLP(torch.autograd.Function):
         x, lat, out, acts = ctx.saved_tensors
         lat = lat if ctx.has_latent else None
         g_params, g_x, g_lat = ops.mlp_backward(ctx.pk, x, lat, out, acts, g.contiguous().float(), out_act=ctx.out_act,
-                                                need_input_grad=ctx.need_in)
+                                                need_input_grad=ctx.need_in, g_params=ctx.flat_grad)
+        if ctx.flat_grad is not None:
+            gx = None if g_x is None else g_x.reshape(x.shape)
+            g_lat = None if g_lat is None else g_lat.reshape(lat.shape)
+            return (None, gx, g_lat, None) + (None,) * (2 * len(ctx.pk.dims))
         gW, gb = ctx.pk.unpack(g_params)
         flat = []
         for w, b in zip(gW, gb):

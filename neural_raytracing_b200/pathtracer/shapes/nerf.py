@@ -54,6 +54,9 @@ class _NerfleFused(torch.autograd.Function):
         p1, p2 = module.first.packed(), module.second.packed()
         sigma, rgb, state = ops.nerfle_train_forward(p1, p2, rays.detach().float(), ts.detach().float(), code.detach().float(), view, prec)
         ctx.p1, ctx.p2, ctx.state, ctx.prec = p1, p2, state, prec
+        ctx.fg1, ctx.fg2 = getattr(module.first, "_flat_grad", None), getattr(module.second, "_flat_grad", None)
+        if (ctx.fg1 is None) != (ctx.fg2 is None):
+            ctx.fg1 = ctx.fg2 = None
         ctx.n1 = len(module.first._flat_params())
         ctx.save_for_backward(rgb)
         lead = tuple(rays.shape[:-1])
@@ -63,7 +66,9 @@ class _NerfleFused(torch.autograd.Function):
     def backward(ctx, g_sigma, g_rgb):
         rgb, = ctx.saved_tensors
         g1, g2 = ops.nerfle_train_backward(ctx.p1, ctx.p2, rgb, g_sigma.contiguous().float(), g_rgb.contiguous().float(),
-                                           ctx.state, ctx.prec)
+                                           ctx.state, ctx.prec, ctx.fg1, ctx.fg2)
+        if ctx.fg1 is not None:      # accumulated straight into training.FlatParameters' gradient buffer
+            return (None,) * (6 + 2 * (len(ctx.p1.dims) + len(ctx.p2.dims)))
         flat = []
         for pk, g in ((ctx.p1, g1), (ctx.p2, g2)):
             gW, gb = pk.unpack(g)
@@ -103,6 +108,15 @@ class NeRFLE(nn.Module):
             return code.reshape(code.shape[0], -1)
         return lights.location
 
+    def _view_index(self, rays):
+        """[R] int32: which view (light code row) each ray belongs to; cached per batch shape."""
+        key = (rays.shape[0], rays[0].numel() // 6, rays.device)
+        cache = self.__dict__.setdefault("_view_cache", {})
+        if key not in cache:
+            cache.clear()
+            cache[key] = torch.arange(key[0], device=rays.device, dtype=torch.int32).repeat_interleave(key[1])
+        return cache[key]
+
     def _needs_grad(self, rays):
         return torch.is_grad_enabled() and (rays.requires_grad or any(p.requires_grad for p in self.parameters()))
 
@@ -113,9 +127,7 @@ class NeRFLE(nn.Module):
         code = self._light_code(lights, device)
         if rays.is_cuda and not self._needs_grad(rays):
             # fused render: rays in, rgb out
-            N = rays.shape[0]
-            per_view = rays[0].numel() // 6
-            view = torch.arange(N, device=device, dtype=torch.int32).repeat_interleave(per_view)
+            view = self._view_index(rays)
             # the fused tensor-core render instantiates the point-light and the bins = 4 environment net only: any
             # other shape keeps the exact fp32 kernel (SkipConnMLP.precision() knows which shapes are instantiated)
             prec = config.precision if self.first.precision() != "f32" and self.second.precision() != "f32" else "f32"
@@ -125,8 +137,7 @@ class NeRFLE(nn.Module):
         tprec = self.first.train_precision()
         if rays.is_cuda and tprec != "f32" and self.second.train_precision() == tprec and not rays.requires_grad \
                 and not code.requires_grad:
-            N = rays.shape[0]
-            view = torch.arange(N, device=device, dtype=torch.int32).repeat_interleave(rays[0].numel() // 6)
+            view = self._view_index(rays)
             alpha, rgb = _NerfleFused.apply(self, rays, ts, code, view, tprec, *self.first._flat_params(),
                                             *self.second._flat_params())
             return composite(alpha, rgb, ts)

@@ -163,3 +163,44 @@ def torch_nerfle_render(w1, w2, rays, light_code, n_coarse, n_fine, t_near, t_fa
     sig = np.concatenate([sig_c, sig_f.numpy()], axis=1)[rows, order]
     rgb = np.concatenate([rgb_c, rgb_f.numpy()], axis=1)[rows, order]
     return composite_ray_major(sig, rgb, t_all[rows, order])
+
+
+class TorchNerfleTrainer:
+    """nerfle.py:104-120 on the CPU with torch autograd: NeRFLE.forward (nerf.py:175-214) -> F.mse_loss-style loss ->
+    backward -> AdamW(lr 8e-5, wd 0) (nerfle.py:55-57).  Same op sequence as the reference's eager step; used as the
+    CPU baseline of the training configs (bench.py) and nowhere in the product."""
+
+    def __init__(self, w1, w2, lr=8e-5):
+        import torch
+        self.torch = torch
+        self.w = []
+        for w in (w1, w2):
+            self.w.append(dict(w, W=[torch.tensor(v, requires_grad=True) for v in w["W"]],
+                               b=[torch.tensor(v, requires_grad=True) for v in w["b"]]))
+        self.params = [p for w in self.w for p in w["W"] + w["b"]]
+        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=0)
+
+    def forward(self, rays, ts, light_loc):
+        """rays [N,R,6], ts [S], light_loc [N,3] -> rgb [N,R,3] (sample-major inside, like the reference)."""
+        torch = self.torch
+        r_o, r_d = rays[..., :3], rays[..., 3:]
+        pts = r_o[None] + ts[:, None, None, None] * r_d[None]                       # [S,N,R,3]
+        f = torch_mlp(self.w[0], pts.reshape(-1, 3)).reshape(pts.shape[:-1] + (-1,))
+        latent, alpha = f[..., 1:], f[..., 0]
+        light = light_loc[None, :, None, :].expand(latent.shape[:-1] + (3,))
+        x2 = torch.cat([latent, r_d[None].expand(latent.shape[:-1] + (3,)), light], dim=-1)
+        rgb = torch_mlp(self.w[1], x2.reshape(-1, x2.shape[-1])).sigmoid().reshape(latent.shape[:-1] + (3,))
+        sigma_a = torch.relu(alpha)
+        a = 1 - torch.exp(-sigma_a * ts[:, None, None])
+        cp = torch.cumprod((1 - a).clamp(min=1e-10), dim=0)
+        cp = torch.roll(cp, 1, 0)
+        cp = torch.cat([cp[:-1], torch.ones_like(cp[:1])], dim=0)                   # cp[-1] = 1
+        return ((a * cp)[..., None] * rgb).sum(dim=0)
+
+    def step(self, rays, ts, light_loc, target, denom):
+        torch = self.torch
+        self.opt.zero_grad()
+        loss = (self.forward(rays, ts, light_loc) - target).square().sum() / denom
+        loss.backward()
+        self.opt.step()
+        return float(loss.detach())
