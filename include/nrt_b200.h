@@ -264,6 +264,61 @@ int nrt_to_local(const float* frame, const float* v, int64_t R, float* out, void
  * it.wi), b = second. out [R,3]. */
 int nrt_param_rusin2(const float* a, const float* b, int64_t R, float* out, void* stream);
 
+/* ---- a8-a16 fused: the shading glue of Direct.sample (integrators/integrators.py:156-206) on the K COMPACTED hit rays,
+ *      forward and backward, as three elementwise stages around the MLP evaluations (SURVEY 8b(8) `shade_direct`).
+ *      All arrays are fp32 device pointers of K rows; gradients of per-hit inputs are OVERWRITTEN, gradients of shared
+ *      parameters (g_amp, g_coef, g_sig_color, g_refl, g_cond_*) are ACCUMULATED into (zero them first). ------------ */
+#define NRT_MAX_BSDFS 16
+#define NRT_LIGHT_POINT 0   /* PointLights.sample_direction  lights/lights.py:89-110 */
+#define NRT_LIGHT_FIELD 1   /* LightField.sample_direction   lights/lights.py:175-195 */
+typedef struct nrt_light {
+  int32_t mode;               /* NRT_LIGHT_POINT | NRT_LIGHT_FIELD */
+  int32_t n_views;            /* point lights: rows of location / amp */
+  const float* location;      /* [n_views,3] */
+  const float* amp;           /* [n_views,3] = scale * normalize(intensity)              (lights.py:104) */
+  const float* coef;          /* [3] const, linear, square, each already clamp(min=1e-6)  (lights.py:105-107) */
+  const int32_t* view_of_hit; /* [K] row of location / amp per hit, or NULL (one view) */
+  const float* v;             /* light field: MLP output at the hit points [K,3]          (lights.py:181) */
+  const float* sig_color;     /* light field: sigmoid(color) [3]                          (lights.py:193) */
+} nrt_light_t;
+#define NRT_BSDF_NEURAL 0     /* NeuralBSDF.eval_and_pdf   bsdf/bsdfs.py:634-637 */
+#define NRT_BSDF_DIFFUSE 1    /* Diffuse.eval_and_pdf      bsdf/bsdfs.py:108-118 */
+#define NRT_BSDF_CONDUCTOR 2  /* Conductor.eval_and_pdf    bsdf/bsdfs.py:364-388 */
+typedef struct nrt_blend {
+  int32_t nb;                    /* children of ComposeSpatialVarying (bsdfs.py:482-540), <= NRT_MAX_BSDFS */
+  int32_t kind[NRT_MAX_BSDFS];   /* NRT_BSDF_* per child, in the order of the sp_var logits */
+  int32_t neural_act;            /* NeuralBSDF.act: 0 sigmoid, 1 softplus, 2 identity */
+  int32_t diffuse_pre;           /* Diffuse.preproc: 0 identity, 1 x / pi, 2 softplus, 3 sigmoid */
+} nrt_blend_t;
+/* sdfs.py:152-159, interaction.py:9-41: raw_n [K,3] (d sdf / d p at the hits), p_hit [K,3], rays_hit [K,6] ->
+ * n = normalize(raw_n, 1e-6), p_off = p_hit + eps5 * n, wi = to_local(frame(n), -r_d), frame [K,3,3] (or NULL). */
+int nrt_shade_geom_forward(const float* raw_n, const float* p_hit, const float* rays_hit, int64_t K, float eps5,
+                           float* n, float* p_off, float* wi, float* frame, void* stream);
+/* g_n / g_p_off / g_wi (any may be NULL) -> g_raw_n [K,3]. */
+int nrt_shade_geom_backward(const float* raw_n, const float* rays_hit, int64_t K, float eps5, const float* g_n,
+                            const float* g_p_off, const float* g_wi, float* g_raw_n, void* stream);
+/* lights.py:89-110 | 175-195, interaction.py:38-41, utils.py:233-258, 490-494: the light sample at every hit ->
+ * d [K,3] world direction to the light, dist [K] (distance | light-field magnitude), wo = to_local(frame(n), d),
+ * rusin = param_rusin2(wi, wo), e [K,3] emitter spectrum (before occlusion), elaz [K,2] = dir_to_elev_azim(d) or NULL. */
+int nrt_shade_light_forward(const nrt_light_t* light, const float* n, const float* wi, const float* p_off, int64_t K,
+                            float* d, float* dist, float* wo, float* rusin, float* e, float* elaz, void* stream);
+/* g_wo / g_rusin / g_e / g_elaz (any may be NULL) -> g_n, g_wi, g_pv [K,3] (w.r.t. p_off for point lights, w.r.t. v for
+ * the light field), and the reduced g_amp [n_views,3], g_coef [3] (point lights) or g_sig_color [3] (light field). */
+int nrt_shade_light_backward(const nrt_light_t* light, const float* n, const float* wi, const float* p_off, int64_t K,
+                             const float* g_wo, const float* g_rusin, const float* g_e, const float* g_elaz, float* g_n,
+                             float* g_wi, float* g_pv, float* g_amp, float* g_coef, float* g_sig_color, void* stream);
+/* bsdfs.py:515-536 + integrators.py:183-187: out [K,3] = (sum_b sigmoid(logits_b) * spectrum_b) * e * inv_samples with
+ * logits [K,nb] (sp_var MLP output), neural_raw [n_neural,K,3] (NeuralBSDF MLP outputs before `act`), refl
+ * [n_diffuse,3], cond_spec [3] = act(specular), cond_eta [1] = softplus(eta), e = emitter spectrum incl. occlusion. */
+int nrt_shade_blend_forward(const nrt_blend_t* cfg, const float* logits, const float* neural_raw, const float* wi,
+                            const float* wo, const float* e, const float* refl, const float* cond_spec,
+                            const float* cond_eta, float inv_samples, int64_t K, float* out, void* stream);
+int nrt_shade_blend_backward(const nrt_blend_t* cfg, const float* logits, const float* neural_raw, const float* wi,
+                             const float* wo, const float* e, const float* refl, const float* cond_spec,
+                             const float* cond_eta, float inv_samples, int64_t K, const float* g_out, float* g_logits,
+                             float* g_neural, float* g_wi, float* g_wo, float* g_e, float* g_refl, float* g_cond_spec,
+                             float* g_cond_eta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,11 +33,25 @@ class NrtNerfSampling(ctypes.Structure):
                 ("jitter_seed", ctypes.c_uint64)]
 
 
+MAX_BSDFS = 16
+
+
+class NrtLight(ctypes.Structure):
+    _fields_ = [("mode", ctypes.c_int32), ("n_views", ctypes.c_int32), ("location", c_vp), ("amp", c_vp), ("coef", c_vp),
+                ("view_of_hit", c_vp), ("v", c_vp), ("sig_color", c_vp)]
+
+
+class NrtBlend(ctypes.Structure):
+    _fields_ = [("nb", ctypes.c_int32), ("kind", ctypes.c_int32 * MAX_BSDFS), ("neural_act", ctypes.c_int32),
+                ("diffuse_pre", ctypes.c_int32)]
+
+
 class NrtError(RuntimeError):
     pass
 
 
 _PM, _PS, _PN = ctypes.POINTER(NrtMlp), ctypes.POINTER(NrtSphereSdf), ctypes.POINTER(NrtNerfSampling)
+_PL, _PB = ctypes.POINTER(NrtLight), ctypes.POINTER(NrtBlend)
 
 # every symbol declared in include/nrt_b200.h: name -> (restype, argtypes)
 SIGNATURES = {
@@ -77,6 +91,12 @@ SIGNATURES = {
     "nrt_shading_frame": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nrt_to_local": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "nrt_param_rusin2": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "nrt_shade_geom_forward": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nrt_shade_geom_backward": (c_int, [c_vp, c_vp, c_i64, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nrt_shade_light_forward": (c_int, [_PL, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nrt_shade_light_backward": (c_int, [_PL, c_vp, c_vp, c_vp, c_i64] + [c_vp] * 11),
+    "nrt_shade_blend_forward": (c_int, [_PB] + [c_vp] * 8 + [c_f32, c_i64, c_vp, c_vp]),
+    "nrt_shade_blend_backward": (c_int, [_PB] + [c_vp] * 8 + [c_f32, c_i64] + [c_vp] * 10),
 }
 
 _lib = None

@@ -24,6 +24,7 @@ EXTRA = {
     "nrt_f32_bwd.cu": ["-fmad=false"],
     "nrt_sdf_grad.cu": ["-fmad=false"],
     "nrt_shade.cu": ["-fmad=false"],
+    "nrt_shade_direct.cu": ["-fmad=false"],
 }
 
 

@@ -451,6 +451,110 @@ def param_rusin2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out.reshape(batch + (3,))
 
 
+# ---- fused shading glue of the Direct integrator on compacted hits (nrt_shade_*; include/nrt_b200.h) ----------------
+LIGHT_POINT, LIGHT_FIELD = 0, 1
+BSDF_NEURAL, BSDF_DIFFUSE, BSDF_CONDUCTOR = 0, 1, 2
+
+
+def _f32(t, name, shape=None):
+    t = _chk(t, name)
+    return t if shape is None else t.reshape(shape)
+
+
+def shade_geom_forward(raw_n, p_hit, rays_hit, eps5, want_frame=True):
+    K = raw_n.shape[0]
+    rn, ph, rh = _f32(raw_n, "raw_n", (K, 3)), _f32(p_hit, "p_hit", (K, 3)), _f32(rays_hit, "rays_hit", (K, 6))
+    n, p_off, wi = torch.empty_like(rn), torch.empty_like(rn), torch.empty_like(rn)
+    frame = torch.empty((K, 3, 3), dtype=torch.float32, device=rn.device) if want_frame else None
+    with torch.cuda.device(rn.device):
+        N.check(N.lib().nrt_shade_geom_forward(_ptr(rn), _ptr(ph), _ptr(rh), K, float(eps5), _ptr(n), _ptr(p_off), _ptr(wi),
+                                               _ptr(frame), _stream()))
+    return n, p_off, wi, frame
+
+
+def shade_geom_backward(raw_n, rays_hit, eps5, g_n, g_p_off, g_wi):
+    K = raw_n.shape[0]
+    rn, rh = _f32(raw_n, "raw_n", (K, 3)), _f32(rays_hit, "rays_hit", (K, 6))
+    opt = lambda g, nm: None if g is None else _f32(g, nm, (K, 3))
+    g = torch.empty_like(rn)
+    with torch.cuda.device(rn.device):
+        N.check(N.lib().nrt_shade_geom_backward(_ptr(rn), _ptr(rh), K, float(eps5), _ptr(opt(g_n, "g_n")),
+                                                _ptr(opt(g_p_off, "g_p_off")), _ptr(opt(g_wi, "g_wi")), _ptr(g), _stream()))
+    return g
+
+
+def _light_struct(mode, location, amp, coef, view_of_hit, v, sig_color):
+    n_views = 0 if location is None else location.shape[0]
+    return N.NrtLight(mode, n_views, *[None if t is None else t.data_ptr() for t in (location, amp, coef, view_of_hit, v, sig_color)])
+
+
+def shade_light_forward(mode, n, wi, p_off, location=None, amp=None, coef=None, view_of_hit=None, v=None, sig_color=None,
+                        want_elaz=False):
+    """-> d [K,3], dist [K], wo [K,3], rusin [K,3], e [K,3], elaz [K,2] or None."""
+    K = n.shape[0]
+    dev = n.device
+    d, wo, ru, e = (torch.empty((K, 3), dtype=torch.float32, device=dev) for _ in range(4))
+    dist = torch.empty(K, dtype=torch.float32, device=dev)
+    elaz = torch.empty((K, 2), dtype=torch.float32, device=dev) if want_elaz else None
+    L = _light_struct(mode, location, amp, coef, view_of_hit, v, sig_color)
+    with torch.cuda.device(dev):
+        N.check(N.lib().nrt_shade_light_forward(ctypes.byref(L), _ptr(n), _ptr(wi), _ptr(p_off), K, _ptr(d), _ptr(dist), _ptr(wo),
+                                                _ptr(ru), _ptr(e), _ptr(elaz), _stream()))
+    return d, dist, wo, ru, e, elaz
+
+
+def shade_light_backward(mode, n, wi, p_off, g_wo, g_rusin, g_e, g_elaz, location=None, amp=None, coef=None, view_of_hit=None,
+                         v=None, sig_color=None):
+    """-> g_n, g_wi, g_pv [K,3], g_amp [n_views,3] | None, g_coef [3] | None, g_sig_color [3] | None."""
+    K = n.shape[0]
+    dev = n.device
+    g_n, g_wi, g_pv = (torch.empty((K, 3), dtype=torch.float32, device=dev) for _ in range(3))
+    g_amp = torch.zeros_like(amp) if mode == LIGHT_POINT else None
+    g_coef = torch.zeros(3, dtype=torch.float32, device=dev) if mode == LIGHT_POINT else None
+    g_sig = torch.zeros(3, dtype=torch.float32, device=dev) if mode == LIGHT_FIELD else None
+    L = _light_struct(mode, location, amp, coef, view_of_hit, v, sig_color)
+    with torch.cuda.device(dev):
+        N.check(N.lib().nrt_shade_light_backward(ctypes.byref(L), _ptr(n), _ptr(wi), _ptr(p_off), K, _ptr(g_wo), _ptr(g_rusin),
+                                                 _ptr(g_e), _ptr(g_elaz), _ptr(g_n), _ptr(g_wi), _ptr(g_pv), _ptr(g_amp),
+                                                 _ptr(g_coef), _ptr(g_sig), _stream()))
+    return g_n, g_wi, g_pv, g_amp, g_coef, g_sig
+
+
+def _blend_struct(kinds, neural_act, diffuse_pre):
+    arr = (ctypes.c_int32 * N.MAX_BSDFS)(*([int(k) for k in kinds] + [0] * (N.MAX_BSDFS - len(kinds))))
+    return N.NrtBlend(len(kinds), arr, int(neural_act), int(diffuse_pre))
+
+
+def shade_blend_forward(kinds, neural_act, diffuse_pre, logits, neural_raw, wi, wo, e, refl, cond_spec, cond_eta, inv_samples):
+    K = logits.shape[0]
+    out = torch.empty((K, 3), dtype=torch.float32, device=logits.device)
+    B = _blend_struct(kinds, neural_act, diffuse_pre)
+    with torch.cuda.device(logits.device):
+        N.check(N.lib().nrt_shade_blend_forward(ctypes.byref(B), _ptr(logits), _ptr(neural_raw), _ptr(wi), _ptr(wo), _ptr(e),
+                                                _ptr(refl), _ptr(cond_spec), _ptr(cond_eta), float(inv_samples), K, _ptr(out),
+                                                _stream()))
+    return out
+
+
+def shade_blend_backward(kinds, neural_act, diffuse_pre, logits, neural_raw, wi, wo, e, refl, cond_spec, cond_eta, inv_samples,
+                         g_out):
+    K = logits.shape[0]
+    dev = logits.device
+    g_logits = torch.empty_like(logits)
+    g_neural = torch.empty_like(neural_raw) if neural_raw is not None else None
+    g_wi, g_wo, g_e = (torch.empty((K, 3), dtype=torch.float32, device=dev) for _ in range(3))
+    g_refl = torch.zeros_like(refl) if refl is not None else None
+    g_cs = torch.zeros_like(cond_spec) if cond_spec is not None else None
+    g_ce = torch.zeros_like(cond_eta) if cond_eta is not None else None
+    B = _blend_struct(kinds, neural_act, diffuse_pre)
+    with torch.cuda.device(dev):
+        N.check(N.lib().nrt_shade_blend_backward(ctypes.byref(B), _ptr(logits), _ptr(neural_raw), _ptr(wi), _ptr(wo), _ptr(e),
+                                                 _ptr(refl), _ptr(cond_spec), _ptr(cond_eta), float(inv_samples), K, _ptr(g_out),
+                                                 _ptr(g_logits), _ptr(g_neural), _ptr(g_wi), _ptr(g_wo), _ptr(g_e), _ptr(g_refl),
+                                                 _ptr(g_cs), _ptr(g_ce), _stream()))
+    return g_logits, g_neural, g_wi, g_wo, g_e, g_refl, g_cs, g_ce
+
+
 _ws_cache = {}
 
 

@@ -3,7 +3,9 @@ NeRFIntegrator, NeRFReproduce, plus the trivial debug views built on the same pr
 import torch
 import torch.nn as nn
 
+from .. import fused_shading
 from ..neural_blocks import SkipConnMLP
+from ..shapes.sdfs import SDF
 from ..scene import sample_emitter_dir_w_isect, sample_emitter_dir_w_learned_occ, sample_emitter_dir_wo_isect
 
 
@@ -68,6 +70,7 @@ class Direct(Integrator):
         self.emitter_samples = emitter_samples
         self.bsdf_samples = bsdf_samples
         self.training = training
+        self.fused = True       # fused shading on the compacted hits where it applies (not in the reference)
         super().__init__(**kwargs)
 
     def sample(self, shapes, rays, bsdf, **kwargs):
@@ -80,6 +83,14 @@ class Direct(Integrator):
         if isinstance(w_isect, SkipConnMLP):
             def emit(it, s, lights, sampler, active):
                 return sample_emitter_dir_w_learned_occ(it, s, lights, sampler, w_isect, active)
+        if self.fused and rays.is_cuda and isinstance(shapes, SDF) and fused_shading.supported(bsdf, lights, w_isect):
+            # compacted hits + three fused elementwise stages around the MLPs (fused_shading.py): same image, the K hits
+            # instead of all R rays through every shading MLP, ~25 launches instead of ~150
+            it, active = shapes.intersect(rays, primary=self.training, fused_hits=True)
+            result = fused_shading.shade_direct(shapes, rays, it, active, bsdf, lights, w_isect, self.emitter_samples)
+            if it._hits is not None:
+                self._bsdf_sample_loop(shapes, it, active, bsdf, lights, sampler)
+            return result, active, it
         result = torch.zeros(*rays.shape[:-1], 3, device=rays.device)
         it, active = shapes.intersect(rays, primary=self.training)
         if not active.any():

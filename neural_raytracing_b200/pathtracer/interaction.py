@@ -106,6 +106,49 @@ class MixedInteraction(SurfaceInteraction):
     with_logits: bool = True
     medium_mask = torch.tensor(False)
 
+    # ---- spatially varying BSDF weights (bsdfs.py:527-536 stores them on the interaction for ALL rays) ----
+    # The fused Direct path evaluates the sp_var MLP on the hits only; the misses are completed the first time either
+    # attribute is read (colocate.py:104-105 reads normalized_weights of all rays for its extra loss).
+    def _complete_weights(self):
+        lazy = self.__dict__.pop("_lazy_weights", None)
+        if lazy is None:
+            return
+        bsdf, logits_hit, idx, grad_mode = lazy
+        nb = logits_hit.shape[-1]
+        with torch.set_grad_enabled(grad_mode):          # the mode the shading ran in (e.g. no_grad renders)
+            flat_p = self.p.reshape(-1, 3)
+            miss = torch.ones(flat_p.shape[0], dtype=torch.bool, device=flat_p.device)
+            miss[idx] = False
+            midx = miss.nonzero().squeeze(-1)
+            full = torch.zeros(flat_p.shape[0], nb, device=flat_p.device)
+            if midx.numel() > 0:
+                full = full.index_copy(0, midx, bsdf.sp_var_fn(bsdf.preprocess(flat_p[midx].detach())).reshape(-1, nb))
+            full = full.index_copy(0, idx, logits_hit).reshape(self.p.shape[:-1] + (nb,))
+            self.__dict__["_nonnormalized_weights"] = full
+            self.__dict__["_normalized_weights"] = full.sigmoid()
+
+    @property
+    def normalized_weights(self):
+        self._complete_weights()
+        if "_normalized_weights" not in self.__dict__:
+            raise AttributeError("normalized_weights (set by ComposeSpatialVarying.eval_and_pdf; no ray hit)")
+        return self.__dict__["_normalized_weights"]
+
+    @normalized_weights.setter
+    def normalized_weights(self, v):
+        self.__dict__["_normalized_weights"] = v
+
+    @property
+    def nonnormalized_weights(self):
+        self._complete_weights()
+        if "_nonnormalized_weights" not in self.__dict__:
+            raise AttributeError("nonnormalized_weights (set by ComposeSpatialVarying.normalized_weights; no ray hit)")
+        return self.__dict__["_nonnormalized_weights"]
+
+    @nonnormalized_weights.setter
+    def nonnormalized_weights(self, v):
+        self.__dict__["_nonnormalized_weights"] = v
+
     def mark_mediums(self, medium_mask):
         self.medium_mask = medium_mask
 

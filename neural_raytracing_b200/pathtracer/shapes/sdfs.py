@@ -157,7 +157,11 @@ class SDF:
                 depths = torch.where(remaining.unsqueeze(-1), depths + d.unsqueeze(-1), depths)
         return depths, hit_any
 
-    def intersect(self, rays, max_t=10, active=True, primary: bool = True):
+    def intersect(self, rays, max_t=10, active=True, primary: bool = True, fused_hits: bool = False):
+        """sdfs.py:102-160.  fused_hits (not in the reference; used by the fused Direct integrator): the per-hit
+        quantities -- normal, offset point, local incoming direction -- are produced on the COMPACTED hits by one
+        kernel with a registered backward and handed over in `si._hits`; the full-size `si.n / si.frame / si.wi / si.p`
+        are then scattered copies without an autograd graph (gradients flow through `_hits` and `raw_normals`)."""
         r_o, r_d = rays.split(3, dim=-1)
         packed = self._fused()
         if packed is not None:
@@ -173,6 +177,25 @@ class SDF:
             throughput = -1000 * throughput
         si = MixedInteraction(p=p, t=depths.squeeze(), obj=self, throughput=throughput)
         normals = torch.zeros_like(p)
+        if fused_hits and rays.is_cuda:
+            from ..fused_shading import _ShadeGeom
+            idx = out_active.reshape(-1).nonzero().squeeze(-1)      # host sync: K = #hits (raw_normals is [K,3])
+            si._hits = None
+            if idx.numel() > 0:
+                rays_hit = rays.detach().reshape(-1, 6)[idx]
+                p_hit = p.detach().reshape(-1, 3)[idx]
+                raw = self.autograd_diff(p_hit)
+                setattr(si, "raw_normals", raw)
+                n_k, p_off, wi_k, frame_k = _ShadeGeom.apply(raw, p_hit, rays_hit, self.epsilon * 5)
+                si._hits = {"idx": idx, "raw": raw, "n": n_k, "p_off": p_off, "wi": wi_k, "rays": rays_hit}
+                with torch.no_grad():
+                    normals = normals.reshape(-1, 3).index_copy(0, idx, n_k.detach()).reshape(p.shape)
+                    p = p.detach().reshape(-1, 3).index_copy(0, idx, p_off.detach()).reshape(p.shape)
+                si.p = p
+            with torch.no_grad():
+                si.set_normals(normals)
+                si.wi = si.to_local(-r_d.detach())
+            return si, out_active
         if out_active.any():          # host sync, as in the reference: raw_normals is [K,3], K = #hits
             raw = self.autograd_diff(p[out_active])
             setattr(si, "raw_normals", raw)

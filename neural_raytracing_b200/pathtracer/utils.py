@@ -40,8 +40,8 @@ def param_rusin2(wo, wi):
         return ops.param_rusin2(wo, wi)
     wo = F.normalize(wo, dim=-1)
     wi = F.normalize(wi, dim=-1)
-    y_axis = torch.tensor([0., 1., 0.], device=wo.device).expand_as(wo)
-    z_axis = torch.tensor([0., 0., 1.], device=wo.device).expand_as(wo)
+    y_axis = torch.tensor([0., 1., 0.], device=wo.device, dtype=wo.dtype).expand_as(wo)
+    z_axis = torch.tensor([0., 0., 1.], device=wo.device, dtype=wo.dtype).expand_as(wo)
     half = F.normalize(wo + wi, dim=-1)
     hx, hy, hz = half[..., 0], half[..., 1], half[..., 2]
     r = nonzero_eps(hy).hypot(nonzero_eps(hx)).clamp(min=1e-6)

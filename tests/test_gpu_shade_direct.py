@@ -1,0 +1,88 @@
+"""GPU tests (-m gpu) of the fused Direct-lighting path (pathtracer/fused_shading.py + csrc/nrt_shade_direct.cu: compacted
+hits, three elementwise stages with hand-written backward kernels) against the unfused mirror of the reference's op
+sequence (integrators.py:156-206 through torch autograd), on the colocate-style scene (point light, learned-occlusion MLP,
+NeuralBSDF + Diffuse + Conductor) and on dtu.py's scene (LightField, 10 NeuralBSDF + 6 Diffuse).  The unfused mirror is
+itself pinned to the unmodified reference (test_gpu_pipeline.py, test_gpu_configs.py run through the fused path)."""
+import random
+
+import numpy as np
+import pytest
+
+import scenes
+import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def _run(kind, fused, w_isect_mode="scene"):
+    import torch
+    import neural_raytracing_b200.pathtracer as P
+    from neural_raytracing_b200.pathtracer.cameras import NeRFCamera
+    from neural_raytracing_b200.pathtracer.utils import eikonal_loss
+    random.random = lambda: 0.37
+    torch.manual_seed(0)
+    size = 24
+    if kind == "dtu16":
+        shape, sphere, bsdf, lights, integrator = scenes.build_dtu16(P, device="cuda")
+        w_isect = False
+    else:
+        shape, sphere, bsdf, lights, integrator, w_isect = scenes.build_pipeline(P, kind, device="cuda")
+        if w_isect_mode == "shadow":
+            w_isect = True
+        elif w_isect_mode == "none":
+            w_isect = False
+    direct = integrator.sub_integrator if hasattr(integrator, "sub_integrator") else integrator
+    direct.fused = fused
+    c2w, focal = synth.nerf_cameras(2, size, device="cuda")
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cuda")
+    got, mi = P.pathtrace_sample(shape, size=size, chunk_size=size, bundle_size=1, crop_size=size, uv=(0, 0), bsdf=bsdf,
+                                 integrator=integrator, lights=lights, cameras=cam, device="cuda", silent=True, background=0,
+                                 w_isect=w_isect, with_noise=False, addition=lambda it: it, squeeze_first=False)
+    w = torch.linspace(0.5, 1.5, got[..., :3].numel(), device="cuda").reshape(got[..., :3].shape)
+    loss = (got[..., :3] * w).sum() / 100 + 0.1 * eikonal_loss(mi.raw_normals) + 0.01 * mi.normalized_weights.std(dim=-1).mean()
+    loss.backward()
+    params = {}
+    for gname, mod in (("sdf", sphere), ("spvar", bsdf.sp_var_fn)):
+        for n_, p_ in mod.named_parameters():
+            params[gname + "." + n_] = p_.grad
+    for i, b in enumerate(bsdf.bsdfs):
+        for j, p_ in enumerate(b.parameters()):
+            params["bsdf%d.%d" % (i, j)] = p_.grad
+    lp = list(lights.parameters()) if kind != "colocate" else lights.spectrum_parameters()
+    for j, p_ in enumerate(lp):
+        params["light.%d" % j] = p_.grad
+    if isinstance(w_isect, torch.nn.Module):
+        for n_, p_ in w_isect.named_parameters():
+            params["occ." + n_] = p_.grad
+    return got.detach(), mi, float(loss.detach()), params
+
+
+@pytest.mark.parametrize("kind,mode", [("colocate", "scene"), ("colocate", "shadow"), ("colocate", "none"), ("dtu", "scene"),
+                                       ("dtu16", "scene")])
+def test_fused_direct_matches_unfused_mirror(kind, mode):
+    import torch
+    img_f, mi_f, loss_f, g_f = _run(kind, True, mode)
+    img_u, mi_u, loss_u, g_u = _run(kind, False, mode)
+    assert hasattr(mi_f, "_hits")
+    assert float((img_f - img_u).abs().max()) < 2e-5, float((img_f - img_u).abs().max())
+    assert abs(loss_f - loss_u) < 1e-5 * max(1.0, abs(loss_u))
+    assert float((mi_f.normalized_weights - mi_u.normalized_weights).detach().abs().max()) < 1e-5
+    assert float((mi_f.n - mi_u.n.detach()).abs().max()) < 1e-5 and float((mi_f.wi - mi_u.wi.detach()).abs().max()) < 1e-5
+    assert float((mi_f.p - mi_u.p.detach()).abs().max()) < 1e-6
+    checked = 0
+    for k in g_u:
+        a, b = g_f[k], g_u[k]
+        if b is None or float(b.abs().max()) == 0.0:
+            assert a is None or float(a.abs().max()) < 1e-12, k
+            continue
+        assert a is not None, k
+        c = _cos(a.cpu(), b.cpu())
+        assert c > 0.9999, (k, c)
+        assert abs(float(a.norm()) / float(b.norm()) - 1) < 5e-3, (k, float(a.norm()), float(b.norm()))
+        checked += 1
+    assert checked >= 20
