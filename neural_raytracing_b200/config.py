@@ -30,6 +30,12 @@ TRAIN_TC_NETS = {
     (3, 0, 16, 128, 5, 3, 65, 0),   # NeRFLE.first
     (70, 0, 16, 64, 8, 3, 3, 0),    # NeRFLE.second (point light)
     (115, 0, 16, 64, 8, 3, 3, 0),   # NeRFLE.second (environment-light code)
+    (3, 0, 64, 96, 6, 3, 3, 0),     # NeuralBSDF.mlp
+    (5, 0, 16, 64, 8, 3, 1, 0),     # occlusion MLP
+}
+# of those, the ones whose tensor-core backward also produces the INPUT gradient for 3..5-D (hi+lo split) inputs
+TRAIN_TC_GX_NETS = {
+    (3, 0, 64, 96, 6, 3, 3, 0), (5, 0, 16, 64, 8, 3, 1, 0),
 }
 
 

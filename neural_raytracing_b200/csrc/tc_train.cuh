@@ -1,0 +1,284 @@
+// Shared pieces of the tensor-core TRAINING path (nrt_tc_train.cu: networks whose weights are resident in shared memory;
+// nrt_tc_train_wide.cu: the 256-wide networks with streamed weights): the per-batch workspace of saved tiles, the
+// gradient IO policies with the device-side loss scale, and the weight-gradient kernel.  Internal header of libnrt_b200.
+#pragma once
+#include "tc_wide.cuh"
+
+namespace tc {
+
+// ---------------------------------------------------------------------------------------------
+// training workspace (one per MLP and batch): all sections 256-byte aligned
+// ---------------------------------------------------------------------------------------------
+struct TrainWs {
+  uint16_t* acts;      // [L+1][ntiles][(H+16) x 128]
+  uint16_t* enc_raw;   // [ntiles][(KE+16) x 128]
+  uint16_t* enc_act;   // [ntiles][(KE+16) x 128]
+  uint16_t* dz;        // [L+1][ntiles][H x 128]
+  uint16_t* gout;      // [ntiles][NOP x 128]
+  uint32_t* masks;     // [L+1][H/32][ntiles*128] sign bits of a_l
+  float* scale;        // [0]: max |g_out * out_act'| as float bits (atomicMax), [1]: loss scale S, [2]: 1/S
+  int64_t ntiles;
+  size_t bytes;
+};
+static TrainWs carve_ws(const Layout& y, int h, int L, int64_t M, void* base) {
+  TrainWs w{};
+  w.ntiles = (M + 127) / 128;
+  size_t off = 0;
+  auto take = [&](size_t n) { size_t o = off; off += (n + 255) / 256 * 256; return o; };
+  const size_t nt = (size_t)w.ntiles;
+  const size_t o_acts = take((size_t)(L + 1) * nt * (h + kTileRowsExtra) * 128 * 2);
+  const size_t o_er = take(nt * (y.KE + kTileRowsExtra) * 128 * 2);
+  const size_t o_ea = take(nt * (y.KE + kTileRowsExtra) * 128 * 2);
+  const size_t o_dz = take((size_t)(L + 1) * nt * h * 128 * 2);
+  const size_t o_go = take(nt * y.NOP * 128 * 2);
+  const size_t o_mk = take((size_t)(L + 1) * (h / 32) * nt * 128 * 4);
+  const size_t o_sc = take(256);
+  w.bytes = off;
+  uint8_t* b = reinterpret_cast<uint8_t*>(base);
+  if (b) {
+    w.acts = (uint16_t*)(b + o_acts); w.enc_raw = (uint16_t*)(b + o_er); w.enc_act = (uint16_t*)(b + o_ea);
+    w.dz = (uint16_t*)(b + o_dz); w.gout = (uint16_t*)(b + o_go);
+    w.scale = (float*)(b + o_sc); w.masks = (uint32_t*)(b + o_mk);
+  }
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// training-forward IO: materialised x in, activated output out
+// ---------------------------------------------------------------------------------------------
+template <int IN, int OUT>
+struct IoTrainFwd {
+  const float* x; float* out; int out_act;
+  __device__ __forceinline__ void load(int64_t m, float* v) const {
+#pragma unroll
+    for (int j = 0; j < IN; ++j) v[j] = __ldg(x + m * IN + j);
+  }
+  __device__ __forceinline__ void store(int64_t m, const float* o) const {
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) {
+      float v = o[j];
+      if (out_act == NRT_OUT_SIGMOID) v = 1.0f / (1.0f + __expf(-v));
+      else if (out_act == NRT_OUT_SOFTPLUS) v = v > 20.0f ? v : __logf(1.0f + __expf(v));
+      else if (out_act == NRT_OUT_TANH) v = tanhf(v);
+      out[m * OUT + j] = v;
+    }
+  }
+};
+
+// gradient IO: g_out (w.r.t. the ACTIVATED output `out`) in, g_x out
+template <int IN, int OUT>
+struct IoGrad {
+  const float* out; const float* g_out; float* g_x; int out_act; const float* scale;
+  // raw gradient w.r.t. the pre-activation output (no loss scale)
+  __device__ __forceinline__ float g_pre(int64_t m, int j) const {
+    float v = __ldg(g_out + m * OUT + j);
+    if (out_act != NRT_OUT_NONE) {
+      const float y = __ldg(out + m * OUT + j);
+      if (out_act == NRT_OUT_SIGMOID) v *= y * (1.0f - y);
+      else if (out_act == NRT_OUT_SOFTPLUS) v *= 1.0f - __expf(-y);
+      else if (out_act == NRT_OUT_TANH) v *= 1.0f - y * y;
+    }
+    return v;
+  }
+  __device__ __forceinline__ void load_g(int64_t m, float* g) const {
+    const float S = scale[1];
+#pragma unroll
+    for (int j = 0; j < OUT; ++j) g[j] = g_pre(m, j) * S;
+  }
+  __device__ __forceinline__ void store_gx1(int64_t m, int j, float v) const { g_x[m * IN + j] = v * scale[2]; }
+};
+
+// loss scale: S = 2^(5 - ceil(log2(max|g|))) so that the largest scaled gradient entering the chain is in [16, 32):
+// 2000x head-room below fp16's 65504 for layers that amplify the gradient, 5e5x above its smallest normal number
+// (IO policies whose gradient source is column-interleaved declare kColMajor: consecutive threads then take consecutive
+//  samples of one output column, which is the coalesced order for them)
+template <class IO, class = void> struct GradColMajor : std::false_type {};
+template <class IO> struct GradColMajor<IO, std::void_t<decltype(IO::kColMajor)>> : std::true_type {};
+template <class IO, int OUT>
+__global__ void k_grad_absmax(IO io, int64_t M, float* __restrict__ scale) {
+  float mx = 0.0f;
+  constexpr bool COL = GradColMajor<IO>::value;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < M * OUT; idx += (int64_t)gridDim.x * blockDim.x) {
+    const float v = fabsf(COL ? io.g_pre(idx % M, (int)(idx / M)) : io.g_pre(idx / OUT, (int)(idx % OUT)));
+    if (v < 3.0e38f) mx = fmaxf(mx, v);   // ignores inf / nan
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0 && mx > 0.0f) atomicMax(reinterpret_cast<unsigned int*>(scale), __float_as_uint(mx));
+}
+static __global__ void k_grad_scale(float* __restrict__ scale) {
+  const float mx = scale[0];
+  int e = 0;
+  if (mx > 0.0f) { frexpf(mx, &e); }          // mx = f * 2^e, f in [0.5, 1)
+  const int k = mx > 0.0f ? 5 - e : 0;
+  scale[1] = ldexpf(1.0f, k);
+  scale[2] = ldexpf(1.0f, -k);
+}
+
+// 32 fp32 gradient columns x leaky_relu'(sign bits in `mask`) -> 16 packed 16-bit pairs
+template <int FMT>
+__device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uint32_t mask, uint32_t* __restrict__ pk) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // saturate instead of overflowing to inf (fp16 operands: a network whose weights amplify the gradient by more
+      // than the 2000x head-room of the loss scale loses the largest entries, not the whole step)
+      const float d = fminf(fmaxf(__uint_as_float(acc[8 * g + i]), -60000.0f), 60000.0f);
+      v[i] = ((mask >> (8 * g + i)) & 1u) ? 0.01f * d : d;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(v[2 * i], v[2 * i + 1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// wgrad: D'[n_out (lanes)][cols] = sum over samples dZ[s][n_out] * src[s][col]
+// ---------------------------------------------------------------------------------------------
+struct WgradJob {
+  const uint16_t* a_tiles; int a_rows;     // dZ (or g_out) tiles: the M = 128 operand
+  const uint16_t* s0_tiles; int s0_rows;   // first source (activation tile or raw encoding), with the ones row
+  const uint16_t* s1_tiles; int s1_rows;   // second source (activated encoding of a skip layer) or null
+  int n_valid;                              // valid output units (lanes)
+  int N;                                    // fan-out of the linear layer (row stride of W^T [K][N])
+  int w_off, b_off;                         // float offsets in the packed-f32 gradient blob
+  int s0_kind;                              // 0: hidden activations (col c -> k = c), 1: encoding (col c -> enc_ref_index)
+  int s0_valid;                             // columns of source 0 before the ones row
+  int k_base1;                              // k offset of source 1 rows (hidden width)
+  int unit0;                                // first output unit of this job (256-wide layers: one job per 128 units)
+  int s0_kbase;                             // k offset of source 0 rows in W^T (jobs whose only source is the encoding of a skip layer)
+};
+constexpr int kMaxJobs = 64;
+struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; };
+
+template <int FMT>
+__global__ void __launch_bounds__(160, 1)
+k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int stage_bytes, int s0_off, int s1_off,
+               float* __restrict__ g_params, const float* __restrict__ scale) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[2];
+  __shared__ __align__(8) uint64_t bar_empty[2];
+  __shared__ __align__(8) uint64_t bar_done;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ WgradJob job;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    job = jobs_g.j[blockIdx.y];
+    mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
+    mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
+    mbar_init(&bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const int n = (int)(t_end - t_begin);
+  const uint32_t a_bytes = (uint32_t)job.a_rows * 256u, s0_bytes = (uint32_t)job.s0_rows * 256u;
+  const uint32_t s1_bytes = job.s1_tiles ? (uint32_t)job.s1_rows * 256u : 0u;
+
+  if (warp == 4) {
+    // producer + MMA issuer (whole warp convergent, one elected lane acts)
+    // both operands are MN-major tiles (feature-contiguous core-matrix rows): a_major (bit 15) = b_major (bit 16) = 1
+    constexpr uint32_t kMajorMN = (1u << 15) | (1u << 16);
+    const uint32_t idesc_base = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | kMajorMN | ((uint32_t)(128 >> 4) << 24);
+    for (int i = 0; i <= n; ++i) {
+      if (i < n) {
+        const int slot = i & 1;
+        if (i >= 2) mbar_wait(&bar_empty[slot], ((i >> 1) - 1) & 1);
+        if (elect_one()) {
+          uint8_t* sb = smem + (size_t)slot * stage_bytes;
+          const int64_t t = t_begin + i;
+          mbar_expect_tx(&bar_full[slot], a_bytes + s0_bytes + s1_bytes);
+          bulk_g2s(sb, job.a_tiles + t * (int64_t)(job.a_rows * 128), a_bytes, &bar_full[slot]);
+          for (uint32_t off = 0; off < s0_bytes; off += 32768u)
+            bulk_g2s(sb + s0_off + off, reinterpret_cast<const uint8_t*>(job.s0_tiles + t * (int64_t)(job.s0_rows * 128)) + off,
+                     min(32768u, s0_bytes - off), &bar_full[slot]);
+          for (uint32_t off = 0; off < s1_bytes; off += 32768u)
+            bulk_g2s(sb + s1_off + off, reinterpret_cast<const uint8_t*>(job.s1_tiles + t * (int64_t)(job.s1_rows * 128)) + off,
+                     min(32768u, s1_bytes - off), &bar_full[slot]);
+        }
+        __syncwarp();
+      }
+      if (i >= 1) {
+        const int j = i - 1, slot = j & 1;
+        mbar_wait(&bar_full[slot], (j >> 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sb = smem_u32(smem + (size_t)slot * stage_bytes);
+          const uint32_t lbo_a = (uint32_t)job.a_rows * 16u, lbo0 = (uint32_t)job.s0_rows * 16u, lbo1 = (uint32_t)job.s1_rows * 16u;
+          const uint64_t ad = make_desc(sb, lbo_a, 128), b0 = make_desc(sb + (uint32_t)s0_off, lbo0, 128), b1 = make_desc(sb + (uint32_t)s1_off, lbo1, 128);
+          for (int kc = 0; kc < 8; ++kc) {
+            const uint32_t acc = (j > 0 || kc > 0) ? 1u : 0u;
+            // D'[tmem] (+)= A''[smem] * B''[smem]^T; a source wider than the MMA's N limit (256) goes in N-chunks
+            for (int n0 = 0; n0 < job.s0_rows; n0 += 256) {
+              const uint32_t nn = (uint32_t)min(256, job.s0_rows - n0);
+              const uint32_t id = idesc_base | ((nn >> 3) << 17);
+              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                           ::"r"(tmem + (uint32_t)n0), "l"(ad + (uint64_t)((kc * 2 * lbo_a) >> 4)),
+                             "l"(b0 + (uint64_t)((kc * 2 * lbo0 + (uint32_t)(n0 / 8) * 128u) >> 4)), "r"(id), "r"(acc) : "memory");
+            }
+            if (s1_bytes)
+              for (int n0 = 0; n0 < job.s1_rows; n0 += 256) {
+                const uint32_t nn = (uint32_t)min(256, job.s1_rows - n0);
+                const uint32_t id = idesc_base | ((nn >> 3) << 17);
+                asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+                             "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+                             ::"r"(tmem + (uint32_t)job.s0_rows + (uint32_t)n0), "l"(ad + (uint64_t)((kc * 2 * lbo_a) >> 4)),
+                               "l"(b1 + (uint64_t)((kc * 2 * lbo1 + (uint32_t)(n0 / 8) * 128u) >> 4)), "r"(id), "r"(acc) : "memory");
+              }
+          }
+          tc_commit(&bar_empty[slot]);
+          if (j == n - 1) tc_commit(&bar_done);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (n > 0) {
+    // epilogue: lane = output unit; coalesced float atomics into the packed-f32 gradient blob
+    mbar_wait(&bar_done, 0);
+    tc_fence_after();
+    const int unit = tid;   // 0..127
+    const uint32_t trow = tmem + (((uint32_t)(warp * 32)) << 16);
+    const Layout& y = jobs_g.y;
+    const int in_size = jobs_g.in_size;
+    const int ncols = job.s0_rows + (job.s1_tiles ? job.s1_rows : 0);
+    const float inv_s = scale[2];
+    for (int c0 = 0; c0 < ncols; c0 += 16) {
+      uint32_t v[16];
+      TmemIO<16>::ld(trow + c0, v);
+      tc_wait_ld();
+      if (unit < job.n_valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int c = c0 + j;
+          int dst = -1;
+          if (c < job.s0_rows) {
+            if (c < job.s0_valid) {
+              const int k = job.s0_kind == 0 ? c : enc_ref_index(y, in_size, c);
+              if (k >= 0) dst = job.w_off + (job.s0_kbase + k) * job.N + job.unit0 + unit;
+            } else if (c == job.s0_valid && job.b_off >= 0) {
+              dst = job.b_off + job.unit0 + unit;
+            }
+          } else {
+            const int k = enc_ref_index(y, in_size, c - job.s0_rows);
+            if (k >= 0 && c - job.s0_rows < y.KE) dst = job.w_off + (job.k_base1 + k) * job.N + job.unit0 + unit;
+          }
+          if (dst >= 0) atomicAdd(g_params + dst, __uint_as_float(v[j]) * inv_s);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+}  // namespace tc

@@ -122,6 +122,11 @@ class SkipConnMLP(nn.Module):
         self._pack_key = None
         self._packed = None
 
+    def _shape_key(self):
+        m = self
+        return (m.in_size, m.latent_size, m.basis_p.shape[-1], m.init.out_features, len(m.layers), m.skip,
+                m.out.out_features, _activation_id(m.activation))
+
     def precision(self):
         """Arithmetic used for gradient-free evaluation."""
         if config.precision == "f32":
@@ -205,7 +210,7 @@ class _FusedMLP(torch.autograd.Function):
         ctx.need_in = p.requires_grad or (latent is not None and latent.requires_grad)
         ctx.tc_prec = module.train_precision()
         ctx.flat_grad = getattr(module, "_flat_grad", None)
-        if ctx.tc_prec != "f32" and (not ctx.need_in or pk.in_size > 5):
+        if ctx.tc_prec != "f32" and (not ctx.need_in or pk.in_size > 5 or module._shape_key() in config.TRAIN_TC_GX_NETS):
             # tensor-core training path: the workspace holds the saved activation tiles
             out, ws = ops.mlp_forward_train_tc(pk, x, out_act=out_act, prec=ctx.tc_prec)
             ctx.lead = p.shape[:-1]

