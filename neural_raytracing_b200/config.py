@@ -32,10 +32,15 @@ TRAIN_TC_NETS = {
     (115, 0, 16, 64, 8, 3, 3, 0),   # NeRFLE.second (environment-light code)
     (3, 0, 64, 96, 6, 3, 3, 0),     # NeuralBSDF.mlp
     (5, 0, 16, 64, 8, 3, 1, 0),     # occlusion MLP
+    # the 256-wide nets (nrt_tc_train_wide.cu; weights streamed)
+    (3, 0, 128, 256, 16, 3, 4, 0), (3, 0, 128, 256, 16, 3, 8, 0), (3, 0, 128, 256, 16, 3, 16, 0),   # sp_var_fn
+    (3, 0, 16, 256, 10, 3, 3, 0),                                                                      # LightField
 }
 # of those, the ones whose tensor-core backward also produces the INPUT gradient for 3..5-D (hi+lo split) inputs
 TRAIN_TC_GX_NETS = {
     (3, 0, 64, 96, 6, 3, 3, 0), (5, 0, 16, 64, 8, 3, 1, 0),
+    # 256-wide nets: the encoding rows of the chain as one more kernel over the saved dZ tiles (k_mlp_wide_denc_tc)
+    (3, 0, 128, 256, 16, 3, 4, 0), (3, 0, 128, 256, 16, 3, 8, 0), (3, 0, 128, 256, 16, 3, 16, 0), (3, 0, 16, 256, 10, 3, 3, 0),
 }
 
 

@@ -419,6 +419,7 @@ static int train_backward_io(const nrt_mlp_t* m, const MlpDev& d, IO io, int64_t
   for (int li = 0; li <= L + 1; ++li) {
     WgradJob& j = jobs.j[li];
     j.N = d.N[li]; j.w_off = d.w_off[li]; j.b_off = d.b_off[li]; j.k_base1 = H;
+    j.a_tile_rows = (li == L + 1) ? NOP : H;
     if (li == L + 1) {
       j.a_tiles = ws.gout; j.a_rows = NOP; j.n_valid = NET::OUT;
       j.s0_tiles = ws.acts + (int64_t)L * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
@@ -534,6 +535,15 @@ struct IoNerfGradFirst {       // [g_sigma | g_latent] in
 
 using namespace tc;
 
+// the 256-wide networks (streamed weights): nrt_tc_train_wide.cu
+int nrt_train_wide_id(const MlpDev& d);
+int64_t nrt_train_wide_dgrad_blob_bytes(const MlpDev& d, bool need_x);
+int nrt_train_wide_pack_dgrad(const MlpDev& d, int prec, bool need_x, void* blob_out, cudaStream_t st);
+int nrt_train_wide_forward(const nrt_mlp_t* m, const MlpDev& d, int prec, int out_act, const float* x, int64_t M, float* out,
+                           const TrainWs& ws, cudaStream_t st);
+int nrt_train_wide_backward(const MlpDev& d, int prec, int out_act, int64_t M, const float* out, const float* g_out,
+                            const void* dblob, const TrainWs& ws, float* g_params, float* g_x, cudaStream_t st);
+
 // which networks the training path instantiates, and whether their input gradient is available
 static int train_net_id(const MlpDev& d) {
   if (matches<NetNerfFirst>(d)) return 1;
@@ -548,7 +558,7 @@ extern "C" int64_t nrt_mlp_train_tc_workspace_bytes(const nrt_mlp_t* m, int64_t 
   MlpDev d;
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(train_net_id(d) != 0, "tensor-core training path: this MLP shape is not instantiated");
+  NRT_REQUIRE(train_net_id(d) != 0 || nrt_train_wide_id(d) != 0, "tensor-core training path: this MLP shape is not instantiated");
   const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
   return (int64_t)carve_ws(y, d.hidden, d.L, M, nullptr).bytes;
 }
@@ -557,6 +567,7 @@ extern "C" int64_t nrt_mlp_tc_dgrad_blob_bytes(const nrt_mlp_t* m, int need_x) {
   MlpDev d;
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
+  if (nrt_train_wide_id(d) != 0) return nrt_train_wide_dgrad_blob_bytes(d, need_x != 0);
   return (int64_t)make_dlayout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out, need_x != 0).bytes;
 }
 
@@ -565,6 +576,8 @@ extern "C" int nrt_mlp_pack_tc_dgrad(const nrt_mlp_t* m, int prec, int need_x, v
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
   NRT_REQUIRE(blob_out != nullptr && ((uintptr_t)blob_out & 15) == 0, "blob_out must be 16-byte aligned");
+  NRT_REQUIRE(prec == NRT_PREC_F16 || prec == NRT_PREC_BF16, "nrt_mlp_pack_tc_dgrad: prec must be F16 or BF16");
+  if (nrt_train_wide_id(d) != 0) return nrt_train_wide_pack_dgrad(d, prec, need_x != 0, blob_out, (cudaStream_t)stream);
   const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
   const DLayout dl = make_dlayout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out, need_x != 0);
   NrtProfScope _ps(TAG_TC_PACK, (cudaStream_t)stream);
@@ -589,6 +602,7 @@ extern "C" int nrt_mlp_forward_train_tc(const nrt_mlp_t* m, int prec, int out_ac
   const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
   const TrainWs ws = carve_ws(y, d.hidden, d.L, M, workspace);
   NRT_REQUIRE(workspace_bytes >= ws.bytes && ((uintptr_t)workspace & 255) == 0, "training workspace too small or not 256-byte aligned");
+  if (nrt_train_wide_id(d) != 0) return nrt_train_wide_forward(m, d, prec, out_act, x, M, out, ws, (cudaStream_t)stream);
   switch (train_net_id(d)) {
     case 1:
       if (prec == NRT_PREC_F16) return train_forward<NetNerfFirst, 0>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
@@ -625,6 +639,7 @@ extern "C" int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, in
   const TrainWs ws = carve_ws(y, d.hidden, d.L, M, workspace);
   NRT_REQUIRE(workspace_bytes >= ws.bytes, "training workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
+  if (nrt_train_wide_id(d) != 0) return nrt_train_wide_backward(d, prec, out_act, M, out, g_out, dgrad_blob, ws, g_params, g_x, st);
   switch (train_net_id(d)) {
     case 1:
       NRT_REQUIRE(g_x == nullptr, "NeRFLE.first on the tensor-core path has no input gradient (split-precision inputs)");

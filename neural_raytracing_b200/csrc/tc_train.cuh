@@ -114,9 +114,11 @@ static __global__ void k_grad_scale(float* __restrict__ scale) {
   scale[2] = ldexpf(1.0f, -k);
 }
 
-// 32 fp32 gradient columns x leaky_relu'(sign bits in `mask`) -> 16 packed 16-bit pairs
+// 32 fp32 gradient columns x leaky_relu'(sign bits in `mask`) x c (a power of two: the per-layer rescale of the deep
+// 256-wide chains, 1 elsewhere) -> 16 packed 16-bit pairs
 template <int FMT>
-__device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uint32_t mask, uint32_t* __restrict__ pk) {
+__device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uint32_t mask, uint32_t* __restrict__ pk, float c = 1.0f) {
+  const float c_neg = 0.01f * c;
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float v[8];
@@ -124,8 +126,8 @@ __device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uin
     for (int i = 0; i < 8; ++i) {
       // saturate instead of overflowing to inf (fp16 operands: a network whose weights amplify the gradient by more
       // than the 2000x head-room of the loss scale loses the largest entries, not the whole step)
-      const float d = fminf(fmaxf(__uint_as_float(acc[8 * g + i]), -60000.0f), 60000.0f);
-      v[i] = ((mask >> (8 * g + i)) & 1u) ? 0.01f * d : d;
+      const float d = __uint_as_float(acc[8 * g + i]) * (((mask >> (8 * g + i)) & 1u) ? c_neg : c);
+      v[i] = fminf(fmaxf(d, -60000.0f), 60000.0f);
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) pk[4 * g + i] = Elem<FMT>::pack(v[2 * i], v[2 * i + 1]);
@@ -136,7 +138,8 @@ __device__ __forceinline__ void dconvert32(const uint32_t* __restrict__ acc, uin
 // wgrad: D'[n_out (lanes)][cols] = sum over samples dZ[s][n_out] * src[s][col]
 // ---------------------------------------------------------------------------------------------
 struct WgradJob {
-  const uint16_t* a_tiles; int a_rows;     // dZ (or g_out) tiles: the M = 128 operand
+  const uint16_t* a_tiles; int a_rows;     // dZ (or g_out) tiles: the M = 128 operand (rows staged in shared memory)
+  int a_tile_rows;                          // rows of a whole dZ tile in HBM (> a_rows: this job stages rows unit0 .. unit0 + a_rows - 1)
   const uint16_t* s0_tiles; int s0_rows;   // first source (activation tile or raw encoding), with the ones row
   const uint16_t* s1_tiles; int s1_rows;   // second source (activated encoding of a skip layer) or null
   int n_valid;                              // valid output units (lanes)
@@ -147,9 +150,12 @@ struct WgradJob {
   int k_base1;                              // k offset of source 1 rows (hidden width)
   int unit0;                                // first output unit of this job (256-wide layers: one job per 128 units)
   int s0_kbase;                             // k offset of source 0 rows in W^T (jobs whose only source is the encoding of a skip layer)
+  int lexp_from;                            // dZ of this job carries the per-layer rescales lexp[lexp_from .. n_lexp-1] (see WgradJobs)
 };
 constexpr int kMaxJobs = 64;
-struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; };
+// lexp (optional): per-layer power-of-two exponents of the dgrad chain's rescale (256-wide nets): the dZ tiles of Linear li
+// hold S * 2^(lexp[li] + ... + lexp[n_lexp-1]) * dZ, which the flush divides out
+struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; const int* lexp; int n_lexp; };
 
 template <int FMT>
 __global__ void __launch_bounds__(160, 1)
@@ -196,7 +202,15 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
           uint8_t* sb = smem + (size_t)slot * stage_bytes;
           const int64_t t = t_begin + i;
           mbar_expect_tx(&bar_full[slot], a_bytes + s0_bytes + s1_bytes);
-          bulk_g2s(sb, job.a_tiles + t * (int64_t)(job.a_rows * 128), a_bytes, &bar_full[slot]);
+          const uint16_t* at = job.a_tiles + t * (int64_t)(job.a_tile_rows * 128);
+          if (job.a_tile_rows == job.a_rows) {
+            bulk_g2s(sb, at, a_bytes, &bar_full[slot]);
+          } else {
+            // a 128-unit half of a 256-row tile: per 8-sample group, a_rows features x 8 samples are contiguous
+            for (int g = 0; g < 16; ++g)
+              bulk_g2s(sb + (size_t)g * job.a_rows * 16, at + (size_t)g * job.a_tile_rows * 8 + (size_t)job.unit0 * 8,
+                       (uint32_t)job.a_rows * 16u, &bar_full[slot]);
+          }
           for (uint32_t off = 0; off < s0_bytes; off += 32768u)
             bulk_g2s(sb + s0_off + off, reinterpret_cast<const uint8_t*>(job.s0_tiles + t * (int64_t)(job.s0_rows * 128)) + off,
                      min(32768u, s0_bytes - off), &bar_full[slot]);
@@ -250,7 +264,12 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
     const Layout& y = jobs_g.y;
     const int in_size = jobs_g.in_size;
     const int ncols = job.s0_rows + (job.s1_tiles ? job.s1_rows : 0);
-    const float inv_s = scale[2];
+    float inv_s = scale[2];
+    if (jobs_g.lexp != nullptr) {
+      int e = 0;
+      for (int l = job.lexp_from; l < jobs_g.n_lexp; ++l) e += jobs_g.lexp[l];
+      inv_s = ldexpf(inv_s, -e);
+    }
     for (int c0 = 0; c0 < ncols; c0 += 16) {
       uint32_t v[16];
       TmemIO<16>::ld(trow + c0, v);

@@ -73,18 +73,27 @@ def _cos(a, b):
 LE_KW = dict(seed=33, in_size=115, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0)   # NeRFLE.second, envmap code
 
 
+# the 256-wide nets (nrt_tc_train_wide.cu): sp_var_fn with 4 / 16 bases (bsdfs.py:487-496), LightField (lights.py:159-164)
+WIDE_KW = {"sp_var4": dict(seed=41, in_size=3, out=4, num_layers=16, hidden=256, freqs=128, sigma=128.0),
+           "sp_var16": dict(seed=42, in_size=3, out=16, num_layers=16, hidden=256, freqs=128, sigma=128.0),
+           "light_field": dict(seed=43, in_size=3, out=3, num_layers=10, hidden=256, freqs=16, sigma=32.0)}
 OCC_KW = dict(seed=18, in_size=5, out=1, num_layers=8, hidden=64, freqs=16, sigma=32.0)      # occlusion MLP (colocate.py:82-85)
 
 
 @pytest.mark.parametrize("name,sig,need_x,gate_exact", [("nerf_first", False, False, 0.999), ("nerf_second", True, False, 0.999),
                                                         ("nerf_second", True, True, 0.999), ("nerf_second_le", True, True, 0.999),
                                                         ("neural_bsdf", True, True, 0.999), ("neural_bsdf", False, False, 0.999),
-                                                        ("occ", True, True, 0.999)])
+                                                        ("occ", True, True, 0.999),
+                                                        # 16 layers of 16-bit rounding and 4,096 leaky_relu kinks (default init, not the
+                                                        # reference's xavier): measured >= 0.9981 exact, >= 0.9993 quantised
+                                                        ("sp_var4", True, False, 0.998), ("sp_var16", False, True, 0.998),
+                                                        ("light_field", True, True, 0.999)])
 @pytest.mark.parametrize("M", [1, 129, 5000])
 def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     import torch
     from neural_raytracing_b200 import ops
-    kw = LE_KW if name == "nerf_second_le" else OCC_KW if name == "occ" else helpers.MLP_CASES[name][0]
+    kw = LE_KW if name == "nerf_second_le" else OCC_KW if name == "occ" else WIDE_KW[name] if name in WIDE_KW else \
+        helpers.MLP_CASES[name][0]
     w = synth.mlp_weights(**kw)
     m = helpers.cuda_mlp(w)
     out_act = ops.OUT_SIGMOID if sig else ops.OUT_NONE
@@ -95,7 +104,7 @@ def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     gp, gx = ops.mlp_backward_tc(m, M, out, gy, ws, out_act, need_input_grad=need_x, prec="f16")
     gW, gb = m.unpack(gp)
     assert torch.isfinite(gp).all()
-    for quantised, gate in ((True, 0.9995), (False, gate_exact)):
+    for quantised, gate in ((True, 0.999 if name.startswith("sp_var") else 0.9995), (False, gate_exact)):
         y, xr, Ws, bs = _ref(w, x, sig, quantised, split_inputs=kw["in_size"] <= 5)
         (y * gy.double()).sum().backward()
         assert float((out.double() - y.detach()).abs().max()) < (2e-4 if quantised else 1e-3)
@@ -108,7 +117,8 @@ def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
             assert _cos(b, rb.grad) > gate, (name, "b", i, quantised, _cos(b, rb.grad))
             if quantised:
                 scale = float(ra.grad.abs().max())
-                assert float((a.double() - ra.grad).abs().max()) <= 0.05 * scale + 1e-12
+                # (256-wide nets: a kink that flips on one of few samples shows in single entries; the cosine gates above hold)
+                assert float((a.double() - ra.grad).abs().max()) <= (0.15 if kw["hidden"] == 256 else 0.05) * scale + 1e-12
         if need_x:
             # d/dx of NeRFLE.second multiplies by the sigma = 32 basis (measured 0.9999)
             assert _cos(gx, xr.grad) > 0.999, (_cos(gx, xr.grad), quantised)
