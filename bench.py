@@ -254,6 +254,9 @@ def workload_config(precision):
             "sharding": "one frame per rank, no data-path collective"}
 
 
+NO_CPU = [False]
+
+
 def supplementary(dev, rank, world, steps=5, warmup=3):
     """Other BASELINE.json configs, measured after the headline run (reported under "also"; never part of `value`).
       cfg5_train: nerfle.py-style training step on 65,536 rays IN TOTAL (strong scaling: rank g takes 65,536/N rays),
@@ -270,6 +273,20 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
     from neural_raytracing_b200.pathtracer.shapes.nerf import NeRFLE
     from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
     out = {}
+    peak_tf, peak_gbs, peak_src = measured_peaks()
+
+    def roof(kernel, bound, work, ms, note=None):
+        """roofline entry of a supplementary config's dominant kernel: work = algorithmic TFLOP (tensor) or GB (hbm) done in
+        `ms` milliseconds of that kernel's CUDA-event time"""
+        if not ms or ms <= 0:
+            return None
+        ach = work / (ms * 1e-3)
+        peak = peak_tf if bound == "tensor" else peak_gbs
+        r = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+             "frac": ach / peak, "peak_source": peak_src, "kernel_ms": ms}
+        if note:
+            r["algorithmic_work"] = note
+        return r
 
     def sync():
         if world > 1:
@@ -320,7 +337,11 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
         ar_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ar) / steps)
         loss_val = float(loss)
         del loss
+        wg_ms = prof.get("mlp_tc_wgrad", (0.0, 0))[0] / steps
         return {"ms_per_step": ms, "rays_per_sec": total_rays / ms * 1e3, "mlp_samples_per_sec": total_rays * 64 / ms * 1e3,
+                "roofline": roof("k_mlp_wgrad_tc (tcgen05; the saved 16-bit activation / gradient tiles read once)", "hbm",
+                                 (hi - lo) * 64 * WGRAD_BYTES_PER_SAMPLE / 1e9, wg_ms,
+                                 "%d samples x %d B of saved tiles" % ((hi - lo) * 64, WGRAD_BYTES_PER_SAMPLE)),
 
                 "model_tflops_fwd_bwd": total_rays * 64 * (FLOP_FIRST + FLOP_SECOND) * 3 / ms / 1e9,
                 "grad_allreduce_ms": ar_ms, "grad_bucket_bytes": 4 * sum(p.numel() for p in net.parameters()),
@@ -399,7 +420,44 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
                 evals = int(cnt.item()) + R * 129
                 res[prec] = {"ms": ms, "rays_per_sec": R / ms * 1e3, "sdf_samples_per_sec": evals / ms * 1e3,
                              "tflops": evals * 331008 / ms / 1e9, "hit_fraction": float(h.float().mean())}
+            res["roofline"] = roof("k_mlp_tc<SphereSDF.shift 8x128 softplus; IoMarch + IoScanEval> (tcgen05, weights streamed)", "tensor",
+                                   res["f16"]["tflops"] * res["f16"]["ms"] * 1e-3, res["f16"]["ms"],
+                                   "live march evaluations + 129 scan evaluations per ray, 331,008 FLOP each")
             out["cfg1_sdf_march_512x512"] = res
+            # the same at cfg1's NAMED size (64x64 = 4,096 rays), next to the CPU: the reference's lock-step march (64
+            # evaluations of every ray) + scan (129) on the host cores (oracle/port.py, the reference's eager op sequence)
+            rays64 = torch.from_numpy(camera_rays(64, 0)).to(dev)
+            r64 = {}
+            for prec in ("f16", "f32"):
+                def fn64():
+                    ops.sphere_trace(packed, rays64, shape.epsilon, 64, 10.0, prec=prec)
+                    ops.min_scan(packed, rays64, 2.2 / 128, 128, prec=prec)
+                fn64(); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    fn64()
+                b.record(); torch.cuda.synchronize()
+                r64[prec] = {"ms": a.elapsed_time(b) / 5, "rays_per_sec": 4096 / (a.elapsed_time(b) / 5) * 1e3}
+            if rank == 0 and not NO_CPU[0]:
+                from oracle import port
+                lin = [sphere.shift.init] + list(sphere.shift.layers) + [sphere.shift.out]
+                wcpu = {"centers": sphere.centers.detach().cpu().numpy(), "radii": sphere.radii.detach().cpu().numpy(),
+                        "tfs": sphere.tfs.detach().cpu().numpy(),
+                        "shift": {"basis": sphere.shift.basis_p.detach().cpu().numpy(), "num_layers": len(sphere.shift.layers),
+                                  "skip": sphere.shift.skip, "W": [l.weight.detach().cpu().numpy() for l in lin],
+                                  "b": [l.bias.detach().cpu().numpy() for l in lin]}}
+                r_cpu = rays64.cpu().numpy()
+                port.torch_sdf_march_and_scan(wcpu, r_cpu[:256])     # warm-up
+                t0 = time.perf_counter()
+                _d, h_cpu, _i = port.torch_sdf_march_and_scan(wcpu, r_cpu)
+                cpu_ms = (time.perf_counter() - t0) * 1e3
+                d_gpu, h_gpu = ops.sphere_trace(packed, rays64, shape.epsilon, 64, 10.0, prec="f32")
+                r64["cpu_port"] = {"ms": cpu_ms, "rays_per_sec": 4096 / cpu_ms * 1e3, "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": "the whole 64x64 frame: 64 lock-step march + 129 scan evaluations of every ray (193 of the "
+                                             "~200 network evaluations per ray of the colocate pipeline), torch CPU, all host threads",
+                                   "hit_mask_xor_vs_gpu_f32": int((h_cpu.numpy() ^ h_gpu.cpu().numpy().astype(bool)).sum())}
+            out["cfg1_sdf_march_64x64"] = r64
         except Exception as e:   # noqa: BLE001
             out["cfg1_sdf_march_512x512"] = {"error": repr(e)[:300]}
     # cfg1: the whole colocate.py-style pipeline through the drop-in pathtrace() (sphere-trace + normals + 2 NeuralBSDF +
@@ -427,14 +485,22 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
                                            with_noise=False)
                 frame(); frame()
                 torch.cuda.synchronize()
+                ops.profile_collect(); ops.profile_enable(True)
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 n_it = 3 if prec == "f16" else 1
                 a.record()
                 for _ in range(n_it):
                     img = frame()
                 b.record(); torch.cuda.synchronize()
+                pr = ops.profile_collect(); ops.profile_enable(False)
                 ms = a.elapsed_time(b) / n_it
-                res[prec] = {"ms_per_frame": ms, "rays_per_sec": 512 * 512 / ms * 1e3}
+                res[prec] = {"ms_per_frame": ms, "rays_per_sec": 512 * 512 / ms * 1e3,
+                             "kernel_ms_per_frame": {k: round(v[0] / n_it, 3) for k, v in pr.items() if v[1]},
+                             "library_launches_per_frame": sum(v[1] for v in pr.values()) // n_it}
+                if prec == "f16":
+                    res["roofline"] = roof("k_mlp_tc<SphereSDF.shift; IoScanEval> (min-along-ray scan, tcgen05)", "tensor",
+                                           512 * 512 * 129 * 331008 / 1e12, pr.get("sdf_min_scan_tc", (0.0, 0))[0] / n_it,
+                                           "262,144 rays x 129 evaluations x 331,008 FLOP")
             config.set_precision(prev_p)
             out["cfg1_colocate_pipeline_512x512"] = res
         except Exception as e:   # noqa: BLE001
@@ -482,6 +548,90 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
             out["cfg2b_nerf_synthetic_pipeline_800x800"] = res
         except Exception as e:   # noqa: BLE001
             out["cfg2b_nerf_synthetic_pipeline_800x800"] = {"error": repr(e)[:300]}
+    # cfg4 (BASELINE.json configs[3]) at its NAMED size and model: dtu.py's scene (dtu.py:93-108: SDF(SphereSDF(n=64), 64 steps),
+    # ComposeSpatialVarying of 10 NeuralBSDF + 6 Diffuse under the 16-way 16x256 sp_var MLP, LightField, NeRFIntegrator(Direct),
+    # DTUCamera) trained on ONE 1600x1200 image = 1,920,000 rays per step, rendered as 12 crops of 400x400 through
+    # pathtrace_sample (gradients accumulate over the crops), masked_loss (no SSIM) + eikonal_loss on the analytic normals,
+    # ONE fused AdamW step on the flat parameter buffer.  Tensor-core inference AND training kernels (f16).
+    if world == 1:
+        try:
+            if os.path.join(ROOT, "tests", "golden") not in sys.path:
+                sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            import scenes
+            import neural_raytracing_b200.pathtracer as P
+            from neural_raytracing_b200 import training
+            from neural_raytracing_b200.pathtracer.cameras import DTUCamera
+            from neural_raytracing_b200.pathtracer.utils import eikonal_loss, masked_loss
+            prev_p, prev_t = config.precision, config.train_precision
+            config.set_precision("f16"); config.set_train_precision("f16")
+            random.seed(0)
+            torch.manual_seed(4)
+            shape_d, sphere_d, bsdf_d, lights_d, integ_d = scenes.build_dtu16(P, device=dev)
+            mlps = [sphere_d.shift, bsdf_d.sp_var_fn, lights_d.light_field_approx] + [k.mlp for k in bsdf_d.bsdfs if hasattr(k, "mlp")]
+            mlp_params = {id(q) for m in mlps for q in m.parameters()}
+            others = [q for q in list(sphere_d.parameters()) + list(bsdf_d.parameters()) + list(lights_d.parameters())
+                      if id(q) not in mlp_params]
+            flat = training.FlatParameters(mlps, others)
+            opt_d = torch.optim.AdamW([flat.param], lr=8e-5, weight_decay=0, fused=True)
+            pose, Kmat = scenes.dtu_cameras(1, device=dev)
+            cam_d = DTUCamera(pose=pose, intrinsic=Kmat, device=dev)
+            CROP, NX, NY = 400, 4, 3
+            exp_d, mask_d = scenes.dtu_targets(1, CROP, device=dev)
+            hits = [0]
+
+            def dtu_step():
+                flat.zero_grad()
+                tot = 0.0
+                for cx in range(NX):
+                    for cy in range(NY):
+                        got, mi = P.pathtrace_sample(shape_d, size=1600, chunk_size=CROP, bundle_size=1, crop_size=CROP, bsdf=bsdf_d,
+                                                     integrator=integ_d, cameras=cam_d, lights=lights_d, device=dev,
+                                                     uv=(cx * CROP, cy * CROP), background=0, addition=lambda mi: mi,
+                                                     squeeze_first=False, silent=True)
+                        loss = masked_loss(got[..., :3], exp_d, mi.throughput.squeeze(-1), mask_d, mask_weight=10,
+                                           with_logits=mi.with_logits, ssim_fn=None) / (NX * NY)
+                        if hasattr(mi, "raw_normals"):
+                            loss = loss + eikonal_loss(mi.raw_normals) / (NX * NY)
+                            hits[0] += mi.raw_normals.shape[0]
+                        loss.backward()
+                        tot = tot + loss.detach()
+                opt_d.step()
+                return tot
+            dtu_step()
+            torch.cuda.synchronize()
+            torch.cuda.reset_peak_memory_stats()
+            hits[0] = 0
+            ops.profile_collect(); ops.profile_enable(True)
+            n_it = 2
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            for _ in range(n_it):
+                l_d = dtu_step()
+            b.record(); torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3 / n_it
+            pr = ops.profile_collect(); ops.profile_enable(False)
+            ms = a.elapsed_time(b) / n_it
+            rays_d = CROP * CROP * NX * NY
+            kms = {k: round(v[0] / n_it, 3) for k, v in pr.items() if v[1]}
+            out["cfg4_dtu_step_1600x1200"] = {
+                "ms_per_step": ms, "wall_ms_per_step": wall, "rays_per_sec": rays_d / ms * 1e3, "rays_per_step": rays_d,
+                "hit_fraction": hits[0] / n_it / rays_d, "crops": "%d x %d crops of %dx%d" % (NX, NY, CROP, CROP),
+                "loss": float(l_d), "finite": bool(torch.isfinite(flat.grad).all()), "parameters": int(flat.flat.numel()),
+                "kernel_ms_per_step": kms, "library_launches_per_step": sum(v[1] for v in pr.values()) // n_it,
+                "library_kernel_ms_per_step": round(sum(kms.values()), 2),
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
+                "precision": "f16 operands / fp32 accumulate: march, min scan, training forward, dgrad, wgrad on tcgen05; normals "
+                             "(value + Jacobian and its reverse pass) and the SDF net's first-order backward on the fp32 kernels",
+                "roofline": roof("k_mlp_tc<SphereSDF.shift; IoScanEval> (min-along-ray scan of SDF.throughput, tcgen05)", "tensor",
+                                 rays_d * 129 * 331008 / 1e12, pr.get("sdf_min_scan_tc", (0.0, 0))[0] / n_it,
+                                 "1,920,000 rays x 129 evaluations x 331,008 FLOP")}
+            config.set_precision(prev_p); config.set_train_precision(prev_t)
+            del flat, opt_d, shape_d, sphere_d, bsdf_d, lights_d
+            torch.cuda.empty_cache()
+        except Exception as e:   # noqa: BLE001
+            out["cfg4_dtu_step_1600x1200"] = {"error": repr(e)[:400]}
+            config.set_precision("f32"); config.set_train_precision("f32")
     # cfg5 (i): ray-sharded 4K render (3840x2160 = 8,294,400 rays, the reference's single uniform pass of 64 samples,
     # nerf.py:175-214) on the tensor-core kernels: rank g renders its contiguous slice, no data-path collective
     try:
@@ -501,15 +651,21 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
         code = torch.tensor([[0.4, 1.0, 0.3]], device=dev)
         ops.nerfle_render(m1, m2, rays4k, ts, code, prec="f16")
         sync()
+        ops.profile_collect(); ops.profile_enable(True)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         img = ops.nerfle_render(m1, m2, rays4k, ts, code, prec="f16")
         b.record()
         sync()
+        prof4k = ops.profile_collect(); ops.profile_enable(False)
         ms = max_over_ranks(a.elapsed_time(b))
         out["cfg5_render_4k_64samples"] = {"ms_per_frame": ms, "rays_per_sec": total / ms * 1e3, "mlp_samples_per_sec": total * 64 / ms * 1e3,
                                            "model_tflops": total * 64 * (FLOP_FIRST + FLOP_SECOND) / ms / 1e9, "scaling": "strong",
-                                           "finite": bool(torch.isfinite(img).all())}
+                                           "finite": bool(torch.isfinite(img).all()),
+                                           "kernel_ms": {k: round(v[0], 3) for k, v in prof4k.items() if v[1]},
+                                           "roofline": roof("k_mlp_tc<NeRFLE.first> (tcgen05)", "tensor", (hi - lo) * 64 * FLOP_FIRST / 1e12,
+                                                            prof4k.get("mlp_tc_nerf_first", (0.0, 0))[0],
+                                                            "%d samples x %d FLOP (this rank's slice)" % ((hi - lo) * 64, FLOP_FIRST))}
         del rays4k, img, base
     except Exception as e:   # noqa: BLE001
         out["cfg5_render_4k_64samples"] = {"error": repr(e)[:300]}
@@ -934,6 +1090,7 @@ def main():
     e2e_value = world * R / (e2e_ms / 1e3)
 
     also = None
+    NO_CPU[0] = bool(args.no_cpu_baseline)
     if not args.no_also:
         del flush
         torch.cuda.empty_cache()

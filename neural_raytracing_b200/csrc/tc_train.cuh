@@ -194,6 +194,31 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
     // both operands are MN-major tiles (feature-contiguous core-matrix rows): a_major (bit 15) = b_major (bit 16) = 1
     constexpr uint32_t kMajorMN = (1u << 15) | (1u << 16);
     const uint32_t idesc_base = (1u << 4) | ((uint32_t)FMT << 7) | ((uint32_t)FMT << 10) | kMajorMN | ((uint32_t)(128 >> 4) << 24);
+    // the job lives in shared memory and every tcgen05.mma is a volatile asm with a memory clobber: keep what the issue
+    // loop needs in registers
+    const uint32_t lbo_a = (uint32_t)job.a_rows * 16u, lbo0 = (uint32_t)job.s0_rows * 16u, lbo1 = (uint32_t)job.s1_rows * 16u;
+    uint32_t e_col[4], e_id[4], e_src[4];
+    uint64_t e_boff[4];
+    int n_ent = 0;
+#pragma unroll
+    for (int src = 0; src < 2; ++src) {
+      const int rows = src == 0 ? job.s0_rows : (s1_bytes ? job.s1_rows : 0);
+      const uint32_t col0 = src == 0 ? 0u : (uint32_t)job.s0_rows;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int n0 = 256 * c;
+        if (n0 < rows) {
+          const uint32_t nn = (uint32_t)min(256, rows - n0);
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (e == n_ent) {
+              e_col[e] = col0 + (uint32_t)n0; e_id[e] = idesc_base | ((nn >> 3) << 17); e_src[e] = (uint32_t)src;
+              e_boff[e] = (uint64_t)(((uint32_t)(n0 / 8) * 128u) >> 4);
+            }
+          ++n_ent;
+        }
+      }
+    }
     for (int i = 0; i <= n; ++i) {
       if (i < n) {
         const int slot = i & 1;
@@ -226,28 +251,22 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sb = smem_u32(smem + (size_t)slot * stage_bytes);
-          const uint32_t lbo_a = (uint32_t)job.a_rows * 16u, lbo0 = (uint32_t)job.s0_rows * 16u, lbo1 = (uint32_t)job.s1_rows * 16u;
           const uint64_t ad = make_desc(sb, lbo_a, 128), b0 = make_desc(sb + (uint32_t)s0_off, lbo0, 128), b1 = make_desc(sb + (uint32_t)s1_off, lbo1, 128);
+#pragma unroll 1
           for (int kc = 0; kc < 8; ++kc) {
             const uint32_t acc = (j > 0 || kc > 0) ? 1u : 0u;
-            // D'[tmem] (+)= A''[smem] * B''[smem]^T; a source wider than the MMA's N limit (256) goes in N-chunks
-            for (int n0 = 0; n0 < job.s0_rows; n0 += 256) {
-              const uint32_t nn = (uint32_t)min(256, job.s0_rows - n0);
-              const uint32_t id = idesc_base | ((nn >> 3) << 17);
-              asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-                           "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                           ::"r"(tmem + (uint32_t)n0), "l"(ad + (uint64_t)((kc * 2 * lbo_a) >> 4)),
-                             "l"(b0 + (uint64_t)((kc * 2 * lbo0 + (uint32_t)(n0 / 8) * 128u) >> 4)), "r"(id), "r"(acc) : "memory");
-            }
-            if (s1_bytes)
-              for (int n0 = 0; n0 < job.s1_rows; n0 += 256) {
-                const uint32_t nn = (uint32_t)min(256, job.s1_rows - n0);
-                const uint32_t id = idesc_base | ((nn >> 3) << 17);
+            const uint64_t adk = ad + (uint64_t)((kc * 2 * lbo_a) >> 4);
+            // D'[tmem] (+)= A''[smem] * B''[smem]^T; a source wider than the MMA's N limit (256) goes in two N-chunks
+            // (the instruction operands were prepared once per job: e_col / e_id / e_boff / e_src, at most 4 entries)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e < n_ent) {
+                const uint64_t bd = (e_src[e] ? b1 + (uint64_t)((kc * 2 * lbo1) >> 4) : b0 + (uint64_t)((kc * 2 * lbo0) >> 4)) + e_boff[e];
                 asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                              "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-                             ::"r"(tmem + (uint32_t)job.s0_rows + (uint32_t)n0), "l"(ad + (uint64_t)((kc * 2 * lbo_a) >> 4)),
-                               "l"(b1 + (uint64_t)((kc * 2 * lbo1 + (uint32_t)(n0 / 8) * 128u) >> 4)), "r"(id), "r"(acc) : "memory");
+                             ::"r"(tmem + e_col[e]), "l"(adk), "l"(bd), "r"(e_id[e]), "r"(acc) : "memory");
               }
+            }
           }
           tc_commit(&bar_empty[slot]);
           if (j == n - 1) tc_commit(&bar_done);

@@ -165,6 +165,47 @@ def torch_nerfle_render(w1, w2, rays, light_code, n_coarse, n_fine, t_near, t_fa
     return composite_ray_major(sig, rgb, t_all[rows, order])
 
 
+def torch_sphere_sdf(w, p):
+    """SphereSDF.forward (shapes/sdfs.py:37-46, utils.py:385-387) with synth-format weights: w['centers'] [n,3],
+    w['radii'] [n], w['tfs'] [n,3,3], w['shift'] (8x128 softplus SkipConnMLP)."""
+    import torch
+    c, r, tf = torch.as_tensor(w["centers"]), torch.as_tensor(w["radii"]), torch.as_tensor(w["tfs"])
+    tfs = tf + torch.eye(3).unsqueeze(0)
+    q = torch.einsum("ijk,ibk->ibj", tfs, p.reshape(1, -1, 3).expand(tfs.shape[0], -1, -1)) - c.unsqueeze(1)
+    sd = q.norm(p=2, dim=-1) - r.unsqueeze(-1)
+    out = -torch.exp(-32.0 * sd).sum(0).clamp(min=1e-4).log() / 32.0
+    return out + torch_mlp(w["shift"], p.reshape(-1, 3), act="softplus").reshape_as(out)
+
+
+def torch_sdf_march_and_scan(w, rays, eps=1e-3, max_steps=64, max_t=10.0, scan_n=128, scan_dist=2.2):
+    """The SDF evaluations of one colocate.py-style frame on the CPU, as the reference issues them: the lock-step
+    sphere-trace march (shapes/sdfs.py:111-131: max_steps evaluations of EVERY ray, no early exit) and the
+    min-along-ray scan of SDF.throughput (:232-249: scan_n + 1 evaluations of every ray).  Returns (depth [R], hit [R],
+    argmin index [R]).  193 of the ~200 network evaluations per ray of the cfg1 pipeline are these."""
+    import torch
+    rays = torch.as_tensor(rays).reshape(-1, 6)
+    r_o, r_d = rays[:, :3], rays[:, 3:]
+    with torch.no_grad():
+        depths = torch.zeros(rays.shape[0], 1)
+        remaining = torch.ones(rays.shape[0], dtype=torch.bool)
+        hit = torch.zeros_like(remaining)
+        for _ in range(max_steps):
+            remaining = remaining & (depths < max_t).squeeze(-1)
+            d = torch_sphere_sdf(w, r_o + r_d * depths)
+            hits = remaining & (d <= eps)
+            hit = hit | hits
+            remaining = remaining & ~hits
+            depths = torch.where(remaining.unsqueeze(-1), depths + d.unsqueeze(-1), depths)
+        step = scan_dist / scan_n
+        cur = torch_sphere_sdf(w, r_o)
+        idx = torch.zeros_like(cur, dtype=torch.long)
+        for i in range(scan_n):
+            sd = torch_sphere_sdf(w, r_o + (step * (i + 1)) * r_d)
+            idx = torch.where(sd < cur, i + 1, idx)
+            cur = torch.minimum(cur, sd)
+    return depths.squeeze(-1), hit, idx
+
+
 class TorchNerfleTrainer:
     """nerfle.py:104-120 on the CPU with torch autograd: NeRFLE.forward (nerf.py:175-214) -> F.mse_loss-style loss ->
     backward -> AdamW(lr 8e-5, wd 0) (nerfle.py:55-57).  Same op sequence as the reference's eager step; used as the
