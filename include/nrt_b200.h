@@ -138,7 +138,9 @@ int nrt_mlp_backward(const nrt_mlp_t* m, int out_act, const float* x, const floa
  * training_utils.py:211-260), as three tcgen05 kernels: a forward that saves its activations as 16-bit tiles,
  * the fused data-gradient chain, and the weight-gradient kernel.  prec = NRT_PREC_F16 (default; gradients are
  * loss-scaled on the device by a power of two taken from max|g_out|) or NRT_PREC_BF16; fp32 accumulation.
- * Instantiated for NeRFLE.first (3->65, 5x128) and the point-light NeRFLE.second (70->3, 8x64).
+ * Instantiated for NeRFLE.first (3->65, 5x128), NeRFLE.second (70 / 115 -> 3, 8x64), NeuralBSDF.mlp (3->3, 6x96), the
+ * occlusion MLP (5->1, 8x64), SphereSDF.shift (3->1, 8x128 softplus; no g_x) and the 256-wide nets (sp_var_fn 4 / 8 / 16
+ * bases, LightField; streamed weights).
  *   workspace: nrt_mlp_train_tc_workspace_bytes(m, M) bytes, 256-byte aligned, must stay untouched between the
  *              forward and the backward call of the same batch;
  *   m->params_tc: the nrt_mlp_pack_tc blob of the same prec;
@@ -193,6 +195,19 @@ int nrt_mlp_value_jac_forward(const nrt_mlp_t* m, const float* p, int64_t M, flo
 int nrt_mlp_value_jac_backward(const nrt_mlp_t* m, const float* p, int64_t M, const float* acts,
                                const float* g_value, const float* g_jac, const float* params_nk,
                                float* g_params, void* stream);
+/* The same pair on the tensor cores (tcgen05, 16-bit operands, fp32 accumulation), for SphereSDF.shift (3 -> 1, 8 x 128,
+ * softplus, 32 frequencies; sdfs.py:23-31): four rows per point (value, d/dp_0..2) through the streamed-weight forward
+ * with the coupled activation a_v = softplus(z_v), a_t = sigmoid(z_v) z_t, saved as 16-bit tiles; the reverse pass is
+ * a dgrad chain with g_z_v = s g_a_v + (1 - s) sum_t g_a_t a_t, g_z_t = s g_a_t and the shared weight-gradient kernel.
+ *   K points; p [K,3] -> value [K], jac [K,3];  workspace: nrt_mlp_value_jac_tc_workspace_bytes(m, K) bytes, 256-byte
+ *   aligned, untouched between the two calls;  m->params_tc / dgrad_blob (need_x = 0): as for nrt_mlp_forward_train_tc;
+ *   g_value [K] or NULL, g_jac [K,3] -> g_params (packed-f32 layout, ACCUMULATED into). */
+int64_t nrt_mlp_value_jac_tc_workspace_bytes(const nrt_mlp_t* m, int64_t K);
+int nrt_mlp_value_jac_forward_tc(const nrt_mlp_t* m, int prec, const float* p, int64_t K, float* value, float* jac,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int nrt_mlp_value_jac_backward_tc(const nrt_mlp_t* m, int prec, int64_t K, const float* g_value, const float* g_jac,
+                                  const void* dgrad_blob, void* workspace, size_t workspace_bytes, float* g_params,
+                                  void* stream);
 
 /* ---- a4: SDF.intersect march loop (sdfs.py:111-131) ---------------------------------- */
 /* depth [R] (final `depths`), hit [R] uint8 (`out_active`).  `active` (optional, [R]

@@ -80,6 +80,9 @@ SIGNATURES = {
     "nrt_sdf_value_grad": (c_int, [_PS, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nrt_mlp_value_jac_forward": (c_int, [_PM, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "nrt_mlp_value_jac_backward": (c_int, [_PM, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nrt_mlp_value_jac_tc_workspace_bytes": (c_i64, [_PM, c_i64]),
+    "nrt_mlp_value_jac_forward_tc": (c_int, [_PM, c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "nrt_mlp_value_jac_backward_tc": (c_int, [_PM, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp, c_vp]),
     "nrt_sdf_sphere_trace": (c_int, [_PS, c_int, c_vp, c_vp, c_i64, c_f32, c_int, c_f32, c_vp, c_vp, c_vp, c_vp]),
     "nrt_sdf_shadow_test": (c_int, [_PS, c_int, c_vp, c_vp, c_vp, c_i64, c_f32, c_int, c_vp, c_vp, c_vp]),
     "nrt_sdf_min_scan": (c_int, [_PS, c_int, c_vp, c_i64, c_f64, c_int, c_vp, c_vp, c_vp, c_vp]),

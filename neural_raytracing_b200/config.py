@@ -35,6 +35,7 @@ TRAIN_TC_NETS = {
     # the 256-wide nets (nrt_tc_train_wide.cu; weights streamed)
     (3, 0, 128, 256, 16, 3, 4, 0), (3, 0, 128, 256, 16, 3, 8, 0), (3, 0, 128, 256, 16, 3, 16, 0),   # sp_var_fn
     (3, 0, 16, 256, 10, 3, 3, 0),                                                                      # LightField
+    (3, 0, 32, 128, 8, 3, 1, 1),    # SphereSDF.shift (softplus; nrt_tc_train_sdf.cu: first order and value + Jacobian; no g_x)
 }
 # of those, the ones whose tensor-core backward also produces the INPUT gradient for 3..5-D (hi+lo split) inputs
 TRAIN_TC_GX_NETS = {

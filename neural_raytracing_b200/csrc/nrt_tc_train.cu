@@ -21,36 +21,6 @@
 
 namespace tc {
 
-// ---------------------------------------------------------------------------------------------
-// dgrad blob: the weights with the roles of K and N swapped, UMMA canonical K-major, backward op order
-//   op 0        : output layer   B'[n' = hidden unit][k' = output]
-//   op 1+j      : hidden layer l = L-1-j   B'[n' = input of the layer (h | enc if NEEDX and skip)][k' = unit]
-//   op L+1 (X)  : init layer     B'[n' = encoding column][k' = unit]
-//   op L+2 (X)  : Fourier basis  B'[n' = input j][k' = frequency f] = basis[j][f]
-// ---------------------------------------------------------------------------------------------
-struct DLayout {
-  int n_ops;
-  int opN[kMaxOps], opK[kMaxOps], op_off[kMaxOps];
-  int w_elems, bytes;
-};
-__host__ __device__ constexpr DLayout make_dlayout(int in, int lat, int f, int h, int L, int skip, int out, bool needx) {
-  const Layout y = make_layout(in, lat, f, h, L, skip, out);
-  DLayout d{};
-  d.n_ops = 1 + L + (needx ? 2 : 0);
-  int off = 0;
-  for (int o = 0; o < d.n_ops; ++o) {
-    int N = 0, K = 0;
-    if (o == 0) { N = h; K = y.NOP; }
-    else if (o <= L) { const int l = L - o; N = h + ((needx && is_skip(l, skip, L)) ? y.KE : 0); K = h; }
-    else if (o == L + 1) { N = y.KE; K = h; }
-    else { N = y.XR; K = y.FP; }
-    d.opN[o] = N; d.opK[o] = K; d.op_off[o] = off; off += N * K;
-  }
-  d.w_elems = off;
-  d.bytes = off * 2;
-  return d;
-}
-
 template <int FMT>
 __global__ void k_pack_dgrad(MlpDev m, Layout y, DLayout d, int needx, uint8_t* __restrict__ blob) {
   uint16_t* w = reinterpret_cast<uint16_t*>(blob);
@@ -410,48 +380,8 @@ static int train_backward_io(const nrt_mlp_t* m, const MlpDev& d, IO io, int64_t
     kern<<<grid, kEpiThreads * 2 + 32 * DN::NSLOT, bytes, st>>>(reinterpret_cast<const uint8_t*>(dblob), io, M, ws);
     NRT_CUDA(cudaGetLastError());
   }
-  // ---- weight gradients: one job per linear layer ----
-  constexpr int H = NET::H, L = NET::L, KE = NET::KE, NOP = NET::NOP;
-  constexpr int FRA = H + kTileRowsExtra, FRE = KE + kTileRowsExtra;
-  WgradJobs jobs{};
-  jobs.y = NET::Y; jobs.in_size = NET::IN; jobs.n = L + 2;
-  const int64_t nt = ws.ntiles;
-  for (int li = 0; li <= L + 1; ++li) {
-    WgradJob& j = jobs.j[li];
-    j.N = d.N[li]; j.w_off = d.w_off[li]; j.b_off = d.b_off[li]; j.k_base1 = H;
-    j.a_tile_rows = (li == L + 1) ? NOP : H;
-    if (li == L + 1) {
-      j.a_tiles = ws.gout; j.a_rows = NOP; j.n_valid = NET::OUT;
-      j.s0_tiles = ws.acts + (int64_t)L * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
-    } else if (li == 0) {
-      j.a_tiles = ws.dz; j.a_rows = H; j.n_valid = H;
-      j.s0_tiles = ws.enc_raw; j.s0_rows = FRE; j.s0_kind = 1; j.s0_valid = KE;
-    } else {
-      j.a_tiles = ws.dz + (int64_t)li * nt * H * 128; j.a_rows = H; j.n_valid = H;
-      j.s0_tiles = ws.acts + (int64_t)(li - 1) * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
-      if (is_skip(li - 1, NET::SKIP, L)) { j.s1_tiles = ws.enc_act; j.s1_rows = FRE; }
-    }
-  }
-  // stage: [A'' | source 0 | source 1].  The M = 128 operand reads 128 rows per sample group whatever a_rows is, so its
-  // region spans (15 * a_rows + 128) * 16 bytes; the garbage rows only reach accumulator lanes >= a_rows (ignored)
-  constexpr int A_ROWS = H > NOP ? H : NOP;
-  constexpr int S0_OFF = ((15 * A_ROWS + 128) * 16 + 1023) / 1024 * 1024;
-  constexpr int S0_BYTES = (FRA > FRE ? FRA : FRE) * 256;
-  constexpr int S1_OFF = S0_OFF + S0_BYTES;
-  const int stage_bytes = S1_OFF + FRE * 256;
-  const size_t bytes = 2 * (size_t)stage_bytes + 8192;
-  static_assert(2 * (S1_OFF + FRE * 256) + 8192 + 1024 <= 227 * 1024, "wgrad stages do not fit in shared memory");
-  static_assert(FRA + FRE <= 512 && FRA <= 256 && FRE <= 256, "wgrad accumulator / MMA N limits");
-  auto kern = k_mlp_wgrad_tc<FMT>;
-  NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jobs.n - 1) / jobs.n));
-  {
-    NrtProfScope _ps(TAG_TC_WGRAD, st);
-    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(jobs, nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);   // job table by value (2 KB of kernel parameters): no copy, graph-capturable
-  }
-  NRT_CUDA(cudaGetLastError());
   (void)m;
-  return NRT_OK;
+  return launch_wgrad_std<NET, FMT>(d, ws, g_params, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -544,6 +474,15 @@ int nrt_train_wide_forward(const nrt_mlp_t* m, const MlpDev& d, int prec, int ou
 int nrt_train_wide_backward(const MlpDev& d, int prec, int out_act, int64_t M, const float* out, const float* g_out,
                             const void* dblob, const TrainWs& ws, float* g_params, float* g_x, cudaStream_t st);
 
+// SphereSDF.shift (softplus, streamed weights): nrt_tc_train_sdf.cu
+bool nrt_train_is_sdf(const MlpDev& d);
+int64_t nrt_train_sdf_dgrad_tail_bytes(const MlpDev& d);
+int nrt_train_sdf_pack_tail(const MlpDev& d, void* tail, cudaStream_t st);
+int nrt_train_sdf_forward(const nrt_mlp_t* m, int prec, int out_act, const float* x, int64_t M, float* out, const TrainWs& ws,
+                          cudaStream_t st);
+int nrt_train_sdf_backward(const MlpDev& d, int prec, int out_act, int64_t M, const float* out, const float* g_out,
+                           const void* dblob, const TrainWs& ws, float* g_params, cudaStream_t st);
+
 // which networks the training path instantiates, and whether their input gradient is available
 static int train_net_id(const MlpDev& d) {
   if (matches<NetNerfFirst>(d)) return 1;
@@ -558,7 +497,7 @@ extern "C" int64_t nrt_mlp_train_tc_workspace_bytes(const nrt_mlp_t* m, int64_t 
   MlpDev d;
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
-  NRT_REQUIRE(train_net_id(d) != 0 || nrt_train_wide_id(d) != 0, "tensor-core training path: this MLP shape is not instantiated");
+  NRT_REQUIRE(train_net_id(d) != 0 || nrt_train_wide_id(d) != 0 || nrt_train_is_sdf(d), "tensor-core training path: this MLP shape is not instantiated");
   const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
   return (int64_t)carve_ws(y, d.hidden, d.L, M, nullptr).bytes;
 }
@@ -568,7 +507,8 @@ extern "C" int64_t nrt_mlp_tc_dgrad_blob_bytes(const nrt_mlp_t* m, int need_x) {
   int rc = nrt_build_mlp_dev(m, &d);
   if (rc != NRT_OK) return rc;
   if (nrt_train_wide_id(d) != 0) return nrt_train_wide_dgrad_blob_bytes(d, need_x != 0);
-  return (int64_t)make_dlayout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out, need_x != 0).bytes;
+  return (int64_t)make_dlayout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out, need_x != 0).bytes +
+         (nrt_train_is_sdf(d) ? nrt_train_sdf_dgrad_tail_bytes(d) : 0);
 }
 
 extern "C" int nrt_mlp_pack_tc_dgrad(const nrt_mlp_t* m, int prec, int need_x, void* blob_out, void* stream) {
@@ -586,6 +526,7 @@ extern "C" int nrt_mlp_pack_tc_dgrad(const nrt_mlp_t* m, int prec, int need_x, v
   if (prec == NRT_PREC_F16) k_pack_dgrad<0><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, dl, need_x, (uint8_t*)blob_out);
   else k_pack_dgrad<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d, y, dl, need_x, (uint8_t*)blob_out);
   NRT_CUDA(cudaGetLastError());
+  if (nrt_train_is_sdf(d)) return nrt_train_sdf_pack_tail(d, (uint8_t*)blob_out + dl.bytes, (cudaStream_t)stream);
   return NRT_OK;
 }
 
@@ -603,6 +544,7 @@ extern "C" int nrt_mlp_forward_train_tc(const nrt_mlp_t* m, int prec, int out_ac
   const TrainWs ws = carve_ws(y, d.hidden, d.L, M, workspace);
   NRT_REQUIRE(workspace_bytes >= ws.bytes && ((uintptr_t)workspace & 255) == 0, "training workspace too small or not 256-byte aligned");
   if (nrt_train_wide_id(d) != 0) return nrt_train_wide_forward(m, d, prec, out_act, x, M, out, ws, (cudaStream_t)stream);
+  if (nrt_train_is_sdf(d)) return nrt_train_sdf_forward(m, prec, out_act, x, M, out, ws, (cudaStream_t)stream);
   switch (train_net_id(d)) {
     case 1:
       if (prec == NRT_PREC_F16) return train_forward<NetNerfFirst, 0>(m, out_act, x, M, out, ws, (cudaStream_t)stream);
@@ -640,6 +582,10 @@ extern "C" int nrt_mlp_backward_tc(const nrt_mlp_t* m, int prec, int out_act, in
   NRT_REQUIRE(workspace_bytes >= ws.bytes, "training workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   if (nrt_train_wide_id(d) != 0) return nrt_train_wide_backward(d, prec, out_act, M, out, g_out, dgrad_blob, ws, g_params, g_x, st);
+  if (nrt_train_is_sdf(d)) {
+    NRT_REQUIRE(g_x == nullptr, "tensor-core training path: SphereSDF.shift has no input gradient (its points come out of a no_grad march)");
+    return nrt_train_sdf_backward(d, prec, out_act, M, out, g_out, dgrad_blob, ws, g_params, st);
+  }
   switch (train_net_id(d)) {
     case 1:
       NRT_REQUIRE(g_x == nullptr, "NeRFLE.first on the tensor-core path has no input gradient (split-precision inputs)");

@@ -34,30 +34,6 @@ __host__ __device__ constexpr int wide_dgrad_elems(int L, int nop) { return 256 
 // 6e-7 over 16 layers; the loss scale alone leaves 5e5x below its target)
 __host__ __device__ constexpr int wide_dgrad_bytes(int L, int nop) { return wide_dgrad_elems(L, nop) * 2 + (L + 1 + 3) / 4 * 16; }
 
-__global__ void k_wide_dgrad_scales(MlpDev m, int* __restrict__ lexp) {
-  // block l: Linear li = l + 1 (the one that consumes a_l); hidden rows only (the encoding rows carry no gradient here)
-  const int l = blockIdx.x, li = l + 1, h = m.hidden;
-  const int n_out = li == m.n_lin - 1 ? m.out : h;
-  const float* w = m.params + m.w_off[li];
-  float ss = 0.0f;
-  for (int i = threadIdx.x; i < h * n_out; i += blockDim.x) { const float v = w[i]; ss = fmaf(v, v, ss); }
-  __shared__ float red[32];
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float t = 0.0f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
-    const float gain = 0.7071f * sqrtf(t / (float)h);
-    int e = 0;
-    if (gain > 0.0f && gain < 3.0e38f) e = -(int)lrintf(log2f(gain));
-    lexp[l] = max(-8, min(8, e));
-  }
-}
-
-// blob: chunks in consumption order.  op 0 (output layer): halves nh = 0, 1 of B'[n = hidden unit][k = output];
-// op o = 1..L (hidden layer l = L - o, Linear li = l + 1): quarters q = 2 * nh + kh of B'[n = input unit][k = output unit];
-// every chunk UMMA canonical K-major with N = 128: element (n, k) at ((k / 8) * 128 + n) * 8 + k % 8
 template <int FMT>
 __global__ void k_pack_dgrad_wide(MlpDev m, int nop, uint8_t* __restrict__ blob) {
   uint16_t* w = reinterpret_cast<uint16_t*>(blob);
@@ -614,7 +590,7 @@ int nrt_train_wide_pack_dgrad(const MlpDev& d, int prec, bool need_x, void* blob
   if (prec == NRT_PREC_F16) k_pack_dgrad_wide<0><<<grid, 256, 0, st>>>(d, c16(d.out), (uint8_t*)blob_out);
   else k_pack_dgrad_wide<1><<<grid, 256, 0, st>>>(d, c16(d.out), (uint8_t*)blob_out);
   int* lexp = reinterpret_cast<int*>((uint8_t*)blob_out + (size_t)total * 2);
-  k_wide_dgrad_scales<<<d.L + 1, 256, 0, st>>>(d, lexp);
+  k_dgrad_layer_scales<<<d.L + 1, 256, 0, st>>>(d, lexp);
   if (need_x) {
     const Layout y = make_layout(d.in_size, d.latent, d.freqs, d.hidden, d.L, d.skip, d.out);
     uint8_t* eb = (uint8_t*)blob_out + wide_dgrad_bytes(d.L, c16(d.out));

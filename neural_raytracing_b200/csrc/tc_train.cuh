@@ -7,6 +7,36 @@
 namespace tc {
 
 // ---------------------------------------------------------------------------------------------
+// dgrad blob: the weights with the roles of K and N swapped, UMMA canonical K-major, backward op order
+//   op 0        : output layer   B'[n' = hidden unit][k' = output]
+//   op 1+j      : hidden layer l = L-1-j   B'[n' = input of the layer (h | enc if NEEDX and skip)][k' = unit]
+//   op L+1 (X)  : init layer     B'[n' = encoding column][k' = unit]
+//   op L+2 (X)  : Fourier basis  B'[n' = input j][k' = frequency f] = basis[j][f]
+// ---------------------------------------------------------------------------------------------
+struct DLayout {
+  int n_ops;
+  int opN[kMaxOps], opK[kMaxOps], op_off[kMaxOps];
+  int w_elems, bytes;
+};
+__host__ __device__ constexpr DLayout make_dlayout(int in, int lat, int f, int h, int L, int skip, int out, bool needx) {
+  const Layout y = make_layout(in, lat, f, h, L, skip, out);
+  DLayout d{};
+  d.n_ops = 1 + L + (needx ? 2 : 0);
+  int off = 0;
+  for (int o = 0; o < d.n_ops; ++o) {
+    int N = 0, K = 0;
+    if (o == 0) { N = h; K = y.NOP; }
+    else if (o <= L) { const int l = L - o; N = h + ((needx && is_skip(l, skip, L)) ? y.KE : 0); K = h; }
+    else if (o == L + 1) { N = y.KE; K = h; }
+    else { N = y.XR; K = y.FP; }
+    d.opN[o] = N; d.opK[o] = K; d.op_off[o] = off; off += N * K;
+  }
+  d.w_elems = off;
+  d.bytes = off * 2;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
 // training workspace (one per MLP and batch): all sections 256-byte aligned
 // ---------------------------------------------------------------------------------------------
 struct TrainWs {
@@ -317,6 +347,86 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
   tc_fence_before();
   __syncthreads();
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+
+// per-layer power-of-two rescale of a deep dgrad chain (lexp[l], l = 0..L: dZ_l is multiplied by 2^lexp[l] when it leaves
+// the accumulator, and the weight-gradient flush divides the accumulated product out): 2^-lexp[l] ~ the gain of the step
+// dZ_{l+1} -> dZ_l estimated from the weights, |dA| ~ |dZ| * ||W||_F / sqrt(hidden rows), times ~0.7 for the activation's
+// derivative.  Without it a chain whose layers shrink the gradient (default-initialised 256-wide layers: 0.41 per layer; a
+// freshly initialised SDF residual net: 0.1) leaves fp16's range after a few layers, whatever the loss scale.
+static __global__ void k_dgrad_layer_scales(MlpDev m, int* __restrict__ lexp) {
+  // block l: Linear li = l + 1 (the one that consumes a_l); hidden rows only (the encoding rows carry no gradient here)
+  const int l = blockIdx.x, li = l + 1, h = m.hidden;
+  const int n_out = li == m.n_lin - 1 ? m.out : h;
+  const float* w = m.params + m.w_off[li];
+  float ss = 0.0f;
+  for (int i = threadIdx.x; i < h * n_out; i += blockDim.x) { const float v = w[i]; ss = fmaf(v, v, ss); }
+  __shared__ float red[32];
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    const float gain = 0.7071f * sqrtf(t / (float)h);
+    int e = 0;
+    if (gain > 0.0f && gain < 3.0e38f) e = -(int)lrintf(log2f(gain));
+    lexp[l] = max(-8, min(8, e));
+  }
+}
+
+// blob: chunks in consumption order.  op 0 (output layer): halves nh = 0, 1 of B'[n = hidden unit][k = output];
+// op o = 1..L (hidden layer l = L - o, Linear li = l + 1): quarters q = 2 * nh + kh of B'[n = input unit][k = output unit];
+// every chunk UMMA canonical K-major with N = 128: element (n, k) at ((k / 8) * 128 + n) * 8 + k % 8
+
+// weight gradients of a network whose layers are at most 128 wide: one job per Linear (skip layers: hidden activations and
+// the activated encoding as two sources of one job)
+template <class NET, int FMT>
+static int launch_wgrad_std(const MlpDev& d, const TrainWs& ws, float* g_params, cudaStream_t st, const int* lexp = nullptr) {
+  // ---- weight gradients: one job per linear layer ----
+  constexpr int H = NET::H, L = NET::L, KE = NET::KE, NOP = NET::NOP;
+  constexpr int FRA = H + kTileRowsExtra, FRE = KE + kTileRowsExtra;
+  WgradJobs jobs{};
+  jobs.y = NET::Y; jobs.in_size = NET::IN; jobs.n = L + 2;
+  jobs.lexp = lexp; jobs.n_lexp = lexp ? L + 1 : 0;
+  const int64_t nt = ws.ntiles;
+  for (int li = 0; li <= L + 1; ++li) {
+    WgradJob& j = jobs.j[li];
+    j.N = d.N[li]; j.w_off = d.w_off[li]; j.b_off = d.b_off[li]; j.k_base1 = H;
+    j.a_tile_rows = (li == L + 1) ? NOP : H;
+    j.lexp_from = li;
+    if (li == L + 1) {
+      j.a_tiles = ws.gout; j.a_rows = NOP; j.n_valid = NET::OUT;
+      j.s0_tiles = ws.acts + (int64_t)L * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
+    } else if (li == 0) {
+      j.a_tiles = ws.dz; j.a_rows = H; j.n_valid = H;
+      j.s0_tiles = ws.enc_raw; j.s0_rows = FRE; j.s0_kind = 1; j.s0_valid = KE;
+    } else {
+      j.a_tiles = ws.dz + (int64_t)li * nt * H * 128; j.a_rows = H; j.n_valid = H;
+      j.s0_tiles = ws.acts + (int64_t)(li - 1) * nt * FRA * 128; j.s0_rows = FRA; j.s0_kind = 0; j.s0_valid = H;
+      if (is_skip(li - 1, NET::SKIP, L)) { j.s1_tiles = ws.enc_act; j.s1_rows = FRE; }
+    }
+  }
+  // stage: [A'' | source 0 | source 1].  The M = 128 operand reads 128 rows per sample group whatever a_rows is, so its
+  // region spans (15 * a_rows + 128) * 16 bytes; the garbage rows only reach accumulator lanes >= a_rows (ignored)
+  constexpr int A_ROWS = H > NOP ? H : NOP;
+  constexpr int S0_OFF = ((15 * A_ROWS + 128) * 16 + 1023) / 1024 * 1024;
+  constexpr int S0_BYTES = (FRA > FRE ? FRA : FRE) * 256;
+  constexpr int S1_OFF = S0_OFF + S0_BYTES;
+  const int stage_bytes = S1_OFF + FRE * 256;
+  const size_t bytes = 2 * (size_t)stage_bytes + 8192;
+  static_assert(2 * (S1_OFF + FRE * 256) + 8192 + 1024 <= 227 * 1024, "wgrad stages do not fit in shared memory");
+  static_assert(FRA + FRE <= 512 && FRA <= 256 && FRE <= 256, "wgrad accumulator / MMA N limits");
+  auto kern = k_mlp_wgrad_tc<FMT>;
+  NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jobs.n - 1) / jobs.n));
+  {
+    NrtProfScope _ps(TAG_TC_WGRAD, st);
+    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(jobs, nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);   // job table by value (2 KB of kernel parameters): no copy, graph-capturable
+  }
+  NRT_CUDA(cudaGetLastError());
+  return NRT_OK;
 }
 
 }  // namespace tc

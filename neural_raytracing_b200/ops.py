@@ -334,6 +334,40 @@ def mlp_value_jac_backward(m: PackedMLP, p: torch.Tensor, acts: torch.Tensor, g_
     return g_params
 
 
+def mlp_value_jac_forward_tc(m: PackedMLP, p: torch.Tensor, prec=PREC_F16):
+    """Tensor-core (value, d value / d p) of SphereSDF.shift: p [K,3] -> value [K,1], jac [K,1,3] and the workspace of
+    saved activation tiles for mlp_value_jac_backward_tc (nrt_mlp_value_jac_forward_tc)."""
+    prec = prec_id(prec)
+    p2 = _chk(p, "p").reshape(-1, 3)
+    K = p2.shape[0]
+    val = torch.empty((K, 1), dtype=torch.float32, device=p.device)
+    jac = torch.empty((K, 1, 3), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        c = m.c_struct(prec)
+        nbytes = N.lib().nrt_mlp_value_jac_tc_workspace_bytes(ctypes.byref(c), K)
+        if nbytes < 0:
+            N.check(int(nbytes))
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=p.device)
+        N.check(N.lib().nrt_mlp_value_jac_forward_tc(ctypes.byref(c), prec, _ptr(p2), K, _ptr(val), _ptr(jac), _ptr(ws), ws.numel(),
+                                                     _stream()))
+    return val, jac, ws
+
+
+def mlp_value_jac_backward_tc(m: PackedMLP, K: int, ws: torch.Tensor, g_value: Optional[torch.Tensor], g_jac: torch.Tensor,
+                              prec=PREC_F16, g_params=None):
+    """Reverse pass of mlp_value_jac_forward_tc into the packed-f32 parameter gradient."""
+    prec = prec_id(prec)
+    gv = None if g_value is None else _chk(g_value, "g_value").reshape(K)
+    gj = _chk(g_jac, "g_jac").reshape(K, 3)
+    g_params = _grad_out(m, g_params)
+    with torch.cuda.device(gj.device):
+        c = m.c_struct(prec)
+        blob = m.dgrad_blob(False, prec)
+        N.check(N.lib().nrt_mlp_value_jac_backward_tc(ctypes.byref(c), prec, K, _ptr(gv), _ptr(gj), _ptr(blob), _ptr(ws), ws.numel(),
+                                                      _ptr(g_params), _stream()))
+    return g_params
+
+
 def sphere_trace(s: PackedSDF, rays: torch.Tensor, epsilon=1e-3, max_steps=64, max_t=10.0,
                  active: Optional[torch.Tensor] = None, prec=PREC_F32, steps_counter: Optional[torch.Tensor] = None):
     """SDF.intersect march loop (sdfs.py:111-131).  rays [...,6] -> depth [...], hit [...] (bool)."""

@@ -32,16 +32,31 @@ class _MlpValueJac(torch.autograd.Function):
     def forward(ctx, module, p, *params):
         pk = module.packed()
         x = p.detach().float().reshape(-1, 3).contiguous()
-        val, jac, acts = ops.mlp_value_jac_forward(pk, x, save_acts=True)
         ctx.pk = pk
+        ctx.tc_prec = module.train_precision()
+        ctx.flat_grad = getattr(module, "_flat_grad", None)
+        if ctx.tc_prec != "f32":
+            # tensor cores: four rows per point through the streamed-weight forward, activations saved as 16-bit tiles
+            val, jac, ws = ops.mlp_value_jac_forward_tc(pk, x, prec=ctx.tc_prec)
+            ctx.K = x.shape[0]
+            ctx.save_for_backward(ws)
+            return val, jac
+        val, jac, acts = ops.mlp_value_jac_forward(pk, x, save_acts=True)
         ctx.save_for_backward(x, acts)
         return val, jac
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_val, g_jac):
-        x, acts = ctx.saved_tensors
-        g_params = ops.mlp_value_jac_backward(ctx.pk, x, acts, g_val.contiguous().float(), g_jac.contiguous().float())
+        if ctx.tc_prec != "f32":
+            ws, = ctx.saved_tensors
+            g_params = ops.mlp_value_jac_backward_tc(ctx.pk, ctx.K, ws, g_val.contiguous().float(), g_jac.contiguous().float(),
+                                                     prec=ctx.tc_prec, g_params=ctx.flat_grad)
+            if ctx.flat_grad is not None:       # accumulated straight into training.FlatParameters' gradient buffer
+                return (None, None) + (None,) * (2 * len(ctx.pk.dims))
+        else:
+            x, acts = ctx.saved_tensors
+            g_params = ops.mlp_value_jac_backward(ctx.pk, x, acts, g_val.contiguous().float(), g_jac.contiguous().float())
         gW, gb = ctx.pk.unpack(g_params)
         flat = []
         for w, b in zip(gW, gb):

@@ -25,7 +25,7 @@ def _q(v):
     return v + (v.detach().half().double() - v.detach())
 
 
-def _ref(w, x, out_act_sigmoid, quantised, split_inputs):
+def _ref(w, x, out_act_sigmoid, quantised, split_inputs, softplus=False):
     import torch
     Ws = [torch.tensor(a, dtype=torch.float64, device="cuda") for a in w["W"]]
     bs = [torch.tensor(a, dtype=torch.float64, device="cuda", requires_grad=True) for a in w["b"]]
@@ -35,7 +35,7 @@ def _ref(w, x, out_act_sigmoid, quantised, split_inputs):
         a.requires_grad_()
     B = torch.tensor(w["basis"], dtype=torch.float64, device="cuda")
     x = x.double().requires_grad_()
-    act = torch.nn.functional.leaky_relu
+    act = torch.nn.functional.softplus if softplus else torch.nn.functional.leaky_relu
     # Fourier phases keep ~fp32 accuracy for every network (fp32 FMAs for 3..5-D inputs, hi+lo split phase GEMM
     # otherwise); the raw inputs enter the init / skip layers as hi + lo columns (<= 5-D) or rounded once (wider)
     xq = _q(x) if (quantised and not split_inputs) else x
@@ -87,7 +87,9 @@ OCC_KW = dict(seed=18, in_size=5, out=1, num_layers=8, hidden=64, freqs=16, sigm
                                                         # 16 layers of 16-bit rounding and 4,096 leaky_relu kinks (default init, not the
                                                         # reference's xavier): measured >= 0.9981 exact, >= 0.9993 quantised
                                                         ("sp_var4", True, False, 0.998), ("sp_var16", False, True, 0.998),
-                                                        ("light_field", True, True, 0.999)])
+                                                        ("light_field", True, True, 0.999),
+                                                        # SphereSDF.shift (softplus, no kinks): first-order path of sdf(best_pos)
+                                                        ("sdf_shift", False, False, 0.9999)])
 @pytest.mark.parametrize("M", [1, 129, 5000])
 def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     import torch
@@ -95,7 +97,7 @@ def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     kw = LE_KW if name == "nerf_second_le" else OCC_KW if name == "occ" else WIDE_KW[name] if name in WIDE_KW else \
         helpers.MLP_CASES[name][0]
     w = synth.mlp_weights(**kw)
-    m = helpers.cuda_mlp(w)
+    m = helpers.cuda_mlp(w, "softplus" if name == "sdf_shift" else None)
     out_act = ops.OUT_SIGMOID if sig else ops.OUT_NONE
     g = torch.Generator(device="cuda").manual_seed(M + 5)
     x = (0.6 if kw["in_size"] <= 5 else 0.1) * torch.randn(M, kw["in_size"], device="cuda", generator=g)
@@ -105,9 +107,10 @@ def test_tc_train_gradients(name, sig, need_x, gate_exact, M):
     gW, gb = m.unpack(gp)
     assert torch.isfinite(gp).all()
     for quantised, gate in ((True, 0.999 if name.startswith("sp_var") else 0.9995), (False, gate_exact)):
-        y, xr, Ws, bs = _ref(w, x, sig, quantised, split_inputs=kw["in_size"] <= 5)
+        y, xr, Ws, bs = _ref(w, x, sig, quantised, split_inputs=kw["in_size"] <= 5, softplus=name == "sdf_shift")
         (y * gy.double()).sum().backward()
-        assert float((out.double() - y.detach()).abs().max()) < (2e-4 if quantised else 1e-3)
+        # (sdf_shift: the kernel's fp32 output layer sees the unrounded last activations, the quantised reference rounds them)
+        assert float((out.double() - y.detach()).abs().max()) < (2e-4 if quantised and name != "sdf_shift" else 1e-3)
         if M < 100 and not quantised:
             continue   # a single sample: one flipped kink moves the cosine; the quantised gate still applies
         if M < 1000 and not quantised:
@@ -317,3 +320,42 @@ def test_tc_train_large_weights_do_not_overflow():
     (y * gy.double()).sum().backward()
     gW, gb = m.unpack(gp)
     assert min(_cos(a, r.grad) for a, r in zip(gW, Ws)) > 0.995
+
+
+@pytest.mark.parametrize("K", [1, 32, 203, 3000])
+def test_tc_value_jacobian_matches_double_backward(K):
+    """nrt_mlp_value_jac_forward_tc / _backward_tc (SphereSDF.shift on the tensor cores: four rows per point, coupled
+    softplus / sigmoid activation, shuffle-coupled reverse pass) vs FLOAT64 torch autograd: jac = autograd.grad(y, p,
+    create_graph=True) and a loss on (y, jac) back-propagated into the weights -- the double backward the reference runs
+    through SDF.autograd_diff (sdfs.py:184-197) for eikonal_loss (utils.py:294) and the shading normals."""
+    import copy
+    import torch
+    import torch.nn.functional as F
+    from neural_raytracing_b200 import ops
+    from neural_raytracing_b200.pathtracer import neural_blocks as nb
+    torch.manual_seed(0)
+    mlp = nb.SkipConnMLP(device="cuda", in_size=3, out=1, num_layers=8, hidden_size=128, freqs=32, activation=F.softplus).to("cuda")
+    synth.fill_module(mlp, 11)
+    g = torch.Generator("cuda").manual_seed(K + 1)
+    p = 0.5 * torch.randn(K, 3, device="cuda", generator=g)
+    gv = torch.randn(K, 1, device="cuda", generator=g) * 1e-3
+    gj = torch.randn(K, 1, 3, device="cuda", generator=g) * 1e-3
+    pk = mlp.packed()
+    val, jac, ws = ops.mlp_value_jac_forward_tc(pk, p, prec="f16")
+    g_params = ops.mlp_value_jac_backward_tc(pk, K, ws, gv, gj, prec="f16")
+    assert torch.isfinite(g_params).all()
+    gW, gb = pk.unpack(g_params)
+    m64 = copy.deepcopy(mlp).cpu().double()
+    m64.basis_p = mlp.basis_p.detach().cpu().double()
+    p64 = p.detach().cpu().double().requires_grad_()
+    y64 = m64.forward_reference_ops(p64)
+    j64, = torch.autograd.grad(y64[:, 0].sum(), p64, create_graph=True)
+    scale_v, scale_j = y64.abs().max().item() + 1e-6, j64.abs().max().item() + 1e-6
+    assert (val.cpu().double() - y64.detach()).abs().max().item() < 1e-3 * max(1.0, scale_v)
+    assert (jac.cpu().double()[:, 0] - j64.detach()).abs().max().item() < 3e-3 * max(1.0, scale_j)
+    assert _cos(jac[:, 0], j64.detach().cuda()) > 0.99999
+    ((y64 * gv.cpu().double()).sum() + (j64 * gj.cpu().double()[:, 0]).sum()).backward()
+    lin64 = [m64.init] + list(m64.layers) + [m64.out]
+    for i, (w, b, l64) in enumerate(zip(gW, gb, lin64)):
+        assert _cos(w, l64.weight.grad.cuda()) > 0.9995, ("W", i, _cos(w, l64.weight.grad.cuda()))
+        assert _cos(b, l64.bias.grad.cuda()) > 0.9995, ("b", i, _cos(b, l64.bias.grad.cuda()))
