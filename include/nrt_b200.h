@@ -182,6 +182,16 @@ int nrt_sdf_eval(const nrt_sphere_sdf_t* s, int prec, const float* p, int64_t M,
 /* a6: value and analytic d(sdf)/dp (replaces SDF.autograd_diff, sdfs.py:184-197). */
 int nrt_sdf_value_grad(const nrt_sphere_sdf_t* s, const float* p, int64_t M, float* value,
                        float* grad, void* stream);
+/* a6 + a22 (training): the sphere set of SphereSDF alone (sdfs.py:37-45 without `shift`): value [K] and its gradient
+ * grad [K,3] = d value / d p (grad may be NULL), and the reverse pass of both outputs into centers [n,3] / radii [n] /
+ * tfs [n,3,3] (g_* ACCUMULATED into: zero them first; g_value [K] or NULL, g_grad [K,3] or NULL).  Replaces the torch
+ * expression + autograd.grad(create_graph=True) + double backward of SDF.autograd_diff (sdfs.py:184-197) for this part
+ * of the SDF; p carries no gradient. */
+int nrt_sphere_set_forward(int n, const float* centers, const float* radii, const float* tfs, const float* p, int64_t K,
+                           float* value, float* grad, void* stream);
+int nrt_sphere_set_backward(int n, const float* centers, const float* radii, const float* tfs, const float* p, int64_t K,
+                            const float* g_value, const float* g_grad, float* g_centers, float* g_radii, float* g_tfs,
+                            void* stream);
 /* a6 + a22 (training): the same forward-mode evaluation for a bare SkipConnMLP with in_size 3 (SphereSDF.shift),
  * keeping what the reverse pass needs, and that reverse pass.  Together they replace the create_graph autograd of
  * SDF.autograd_diff (sdfs.py:184-197) and the double backward that loss.backward() runs through it for

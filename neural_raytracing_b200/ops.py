@@ -334,6 +334,32 @@ def mlp_value_jac_backward(m: PackedMLP, p: torch.Tensor, acts: torch.Tensor, g_
     return g_params
 
 
+def sphere_set_forward(centers, radii, tfs, p: torch.Tensor, want_grad=True):
+    """Smooth-min of the warped spheres (sdfs.py:37-45) at p [K,3]: value [K] and d value / d p [K,3]."""
+    p2 = _chk(p, "p").reshape(-1, 3)
+    K = p2.shape[0]
+    c, r, t = _chk(centers.detach(), "centers"), _chk(radii.detach(), "radii"), _chk(tfs.detach(), "tfs")
+    val = torch.empty(K, dtype=torch.float32, device=p.device)
+    grad = torch.empty((K, 3), dtype=torch.float32, device=p.device) if want_grad else None
+    with torch.cuda.device(p.device):
+        N.check(N.lib().nrt_sphere_set_forward(int(c.shape[0]), _ptr(c), _ptr(r), _ptr(t), _ptr(p2), K, _ptr(val), _ptr(grad), _stream()))
+    return val, grad
+
+
+def sphere_set_backward(centers, radii, tfs, p: torch.Tensor, g_value, g_grad):
+    """Reverse pass of sphere_set_forward's two outputs into (g_centers, g_radii, g_tfs)."""
+    p2 = _chk(p, "p").reshape(-1, 3)
+    K = p2.shape[0]
+    c, r, t = _chk(centers.detach(), "centers"), _chk(radii.detach(), "radii"), _chk(tfs.detach(), "tfs")
+    gv = None if g_value is None else _chk(g_value, "g_value").reshape(K)
+    gg = None if g_grad is None else _chk(g_grad, "g_grad").reshape(K, 3)
+    gc, gr, gt = torch.zeros_like(c), torch.zeros_like(r), torch.zeros_like(t)
+    with torch.cuda.device(p.device):
+        N.check(N.lib().nrt_sphere_set_backward(int(c.shape[0]), _ptr(c), _ptr(r), _ptr(t), _ptr(p2), K, _ptr(gv), _ptr(gg), _ptr(gc),
+                                                _ptr(gr), _ptr(gt), _stream()))
+    return gc, gr, gt
+
+
 def mlp_value_jac_forward_tc(m: PackedMLP, p: torch.Tensor, prec=PREC_F16):
     """Tensor-core (value, d value / d p) of SphereSDF.shift: p [K,3] -> value [K,1], jac [K,1,3] and the workspace of
     saved activation tiles for mlp_value_jac_backward_tc (nrt_mlp_value_jac_forward_tc)."""

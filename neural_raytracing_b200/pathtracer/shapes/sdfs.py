@@ -64,6 +64,31 @@ class _MlpValueJac(torch.autograd.Function):
         return (None, None) + tuple(flat)
 
 
+class _SphereSet(torch.autograd.Function):
+    """(value, d value / d p) of the sphere set at leaf points p, with the hand-written reverse pass of both outputs
+    into centers / radii / tfs (nrt_sphere_set_forward / _backward): the reference's torch expression, its
+    autograd.grad(create_graph=True) and the double backward through it (sdfs.py:37-45, 184-197) as two kernels."""
+
+    @staticmethod
+    def forward(ctx, centers, radii, tfs, p, want_grad):
+        x = p.detach().float().reshape(-1, 3).contiguous()
+        val, grad = ops.sphere_set_forward(centers, radii, tfs, x, want_grad=want_grad)
+        ctx.save_for_backward(centers, radii, tfs, x)
+        ctx.want_grad = want_grad
+        if not want_grad:
+            grad = val.new_zeros(0)
+            ctx.mark_non_differentiable(grad)
+        return val, grad
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_val, g_grad):
+        centers, radii, tfs, x = ctx.saved_tensors
+        gc, gr, gt = ops.sphere_set_backward(centers, radii, tfs, x, g_val.contiguous().float(),
+                                             g_grad.contiguous().float() if ctx.want_grad else None)
+        return gc, gr, gt, None, None
+
+
 class SphereSDF(nn.Module):
     """Smooth-min of n affinely warped spheres plus a residual MLP (sdfs.py:16-46)."""
 
@@ -109,13 +134,12 @@ class SphereSDF(nn.Module):
 
     def value_and_normal(self, p):
         """sdf(p) and d sdf / d p for leaf points p [K,3], both carrying the graph to the parameters: the residual MLP
-        through the analytic-Jacobian kernels, the sphere set through torch's create_graph autograd."""
-        pl = p.detach().reshape(-1, 3).requires_grad_()
+        through the analytic-Jacobian kernels, the sphere set through its value + gradient kernel and that kernel's
+        hand-written reverse pass (_SphereSet)."""
+        pl = p.detach().reshape(-1, 3)
         with torch.enable_grad():
-            s = self.sphere_set(pl)
-            n_s, = torch.autograd.grad(inputs=pl, outputs=s, grad_outputs=torch.ones_like(s), create_graph=True,
-                                       retain_graph=True, only_inputs=True)
-            v_m, j_m = _MlpValueJac.apply(self.shift, pl.detach(), *self.shift._flat_params())
+            s, n_s = _SphereSet.apply(self.centers, self.radii, self.tfs, pl, True)
+            v_m, j_m = _MlpValueJac.apply(self.shift, pl, *self.shift._flat_params())
         return s + v_m[:, 0], n_s + j_m[:, 0, :]
 
     def precision(self):
@@ -127,8 +151,12 @@ class SphereSDF(nn.Module):
         if p.is_cuda and not self._needs_grad(p):
             return ops.sdf_eval(self.packed(), p.detach().float(), prec=self.precision())
         if p.is_cuda:
-            # first-order graph: the residual MLP through the fused forward / backward kernels (_FusedMLP)
-            out = self.sphere_set(p)
+            # first-order graph: the residual MLP through the fused forward / backward kernels (_FusedMLP), the sphere
+            # set through its own kernel pair when the points are leaves without gradient (SDF.throughput, sdfs.py:249)
+            if not p.requires_grad and self.centers.is_cuda:
+                out = _SphereSet.apply(self.centers, self.radii, self.tfs, p, False)[0].reshape(p.shape[:-1])
+            else:
+                out = self.sphere_set(p)
             return out + self.shift(p).reshape_as(out)
         return self.forward_reference_ops(p)
 

@@ -318,3 +318,51 @@ def test_wide_backward_without_input_gradient_uses_32_sample_tiles(M):
     (y64 * go.cpu().double()).sum().backward()
     for (pname, p32), p64 in zip(mlp.named_parameters(), m64.parameters()):
         _close(p32.grad, p64.grad, pname)
+
+
+@pytest.mark.parametrize("K,n", [(1, 64), (77, 64), (4000, 128)])
+def test_sphere_set_kernels_match_double_backward(K, n):
+    """nrt_sphere_set_forward / _backward (value + gradient of the smooth-min of warped spheres and the reverse pass of
+    both outputs) vs FLOAT64 torch autograd of the reference expression (sdfs.py:37-45, utils.py:385-387) with
+    autograd.grad(create_graph=True) and a loss on (value, gradient): the double backward of SDF.autograd_diff."""
+    import torch
+    from neural_raytracing_b200.pathtracer.shapes import sdfs
+    torch.manual_seed(K)
+    s = sdfs.SphereSDF(n=n, device="cuda")
+    with torch.no_grad():
+        s.tfs.add_(0.1 * torch.randn_like(s.tfs))
+        s.radii.abs_()
+    g = torch.Generator("cuda").manual_seed(K + 3)
+    p = 0.15 * torch.randn(K, 3, device="cuda", generator=g)
+    if K > 1:
+        p[K // 2] = 5.0                   # far away: the 1e-4 clamp of smooth_min is active there (zero gradients)
+    gv = torch.randn(K, device="cuda", generator=g)
+    gn = torch.randn(K, 3, device="cuda", generator=g)
+    val, grad = sdfs._SphereSet.apply(s.centers, s.radii, s.tfs, p, True)
+    ((val * gv).sum() + (grad * gn).sum()).backward()
+    got = [q.grad.clone() for q in (s.centers, s.radii, s.tfs)]
+    c64, r64, t64 = (q.detach().double().requires_grad_() for q in (s.centers, s.radii, s.tfs))
+    p64 = p.double().requires_grad_()
+    tf = t64 + torch.eye(3, device="cuda", dtype=torch.float64).unsqueeze(0)
+    q = torch.einsum("ijk,ibk->ibj", tf, p64.unsqueeze(0).expand(n, -1, -1)) - c64.unsqueeze(1)
+    sd = q.norm(p=2, dim=-1) - r64.unsqueeze(-1)
+    v64 = -torch.exp(-32.0 * sd).sum(0).clamp(min=1e-4).log() / 32.0
+    n64, = torch.autograd.grad(v64.sum(), p64, create_graph=True)
+    assert (val.double() - v64.detach()).abs().max().item() < 2e-6
+    assert (grad.double() - n64.detach()).abs().max().item() < 2e-5
+    assert K == 1 or grad[K // 2].abs().max().item() == 0.0
+    ((v64 * gv.double()).sum() + (n64 * gn.double()).sum()).backward()
+    for a, b, name in zip(got, (c64.grad, r64.grad, t64.grad), ("centers", "radii", "tfs")):
+        _close(a, b, name, rtol=2e-4, min_cos=0.99999)
+    # first order only (SDF.throughput's sdf(best_pos))
+    for q_ in (s.centers, s.radii, s.tfs):
+        q_.grad = None
+    v1 = sdfs._SphereSet.apply(s.centers, s.radii, s.tfs, p, False)[0]
+    (v1 * gv).sum().backward()
+    c64.grad = r64.grad = t64.grad = None
+    q = torch.einsum("ijk,ibk->ibj", t64 + torch.eye(3, device="cuda", dtype=torch.float64).unsqueeze(0),
+                     p.double().unsqueeze(0).expand(n, -1, -1)) - c64.unsqueeze(1)
+    v = -torch.exp(-32.0 * (q.norm(p=2, dim=-1) - r64.unsqueeze(-1))).sum(0).clamp(min=1e-4).log() / 32.0
+    (v * gv.double()).sum().backward()
+    for a, b, name in zip((s.centers.grad, s.radii.grad, s.tfs.grad), (c64.grad, r64.grad, t64.grad), ("centers", "radii", "tfs")):
+        _close(a, b, name + " (first order)", rtol=2e-4, min_cos=0.99999)
