@@ -5,7 +5,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libnrt_b200.so")
+_TAG = os.environ.get("NRT_LIB_TAG", "")   # development: a kernel variant built with NRT_BUILD_TAG (build_native.py)
+LIB_PATH = os.path.join(_HERE, "lib", "libnrt_b200%s.so" % ("_" + _TAG if _TAG else ""))
 
 OK, E_INVALID, E_CUDA, E_UNSUPPORTED = 0, -1, -2, -3
 ACT_LEAKY_RELU, ACT_SOFTPLUS = 0, 1

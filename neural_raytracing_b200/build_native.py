@@ -10,8 +10,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(ROOT, "build", "nrt_obj")
-LIB = os.path.join(HERE, "lib", "libnrt_b200.so")
+# NRT_BUILD_TAG (development): kernel variants (NRT_EXTRA_NVCC_FLAGS=-D...) built side by side as
+# lib/libnrt_b200_<tag>.so; NRT_LIB_TAG selects one at load time (_native.py).  The product is the untagged build.
+TAG = os.environ.get("NRT_BUILD_TAG", "")
+OBJ = os.path.join(ROOT, "build", "nrt_obj" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "lib", "libnrt_b200%s.so" % ("_" + TAG if TAG else ""))
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),

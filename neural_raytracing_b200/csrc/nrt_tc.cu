@@ -190,6 +190,11 @@ enum { TC_MARCH_PRIMARY = 0, TC_MARCH_SHADOW = 1 };
 // state machine as k_sdf_march (nrt_f32.cu); the SDF value comes from the 16-bit tensor-core evaluation.
 template <int MODE>
 struct IoMarch {
+  // softplus form of the hidden layers (tc_core.cuh, SoftplusOf).  The primary march keeps the two-MUFU form: depths and
+  // hit masks stay bit-identical to the kernels the goldens were accepted with (a grazing pixel of the 16-basis DTU
+  // golden flips with ANY change of the 16-bit rounding sequence: 36.9 instead of > 50 dB on 4,096 pixels).  The shadow
+  // march takes the one-MUFU fp32 polynomial (|error| <= 1e-5).
+  static constexpr int kSoftplusForm = MODE == TC_MARCH_PRIMARY ? 0 : 1;
   SdfDev sd;
   const float* rays; const float* max_t_per_ray; const uint8_t* active; int64_t R;
   float eps; int max_steps; float max_t; float t_start;
@@ -254,6 +259,7 @@ struct IoMarch {
 // every MMA row busy whatever the ray count; the per-thread state machine of the march would serialise the n+1
 // evaluations of a ray: 129 x ~25 us for a small ray batch) followed by a warp-per-ray argmin.
 struct IoScanEval {
+  static constexpr int kSoftplusForm = 3;   // packed-half polynomial (tc_core.cuh, SoftplusOf): the scan only picks a position
   SdfDev sd;
   const float* rays; double step; int n1; float* val;
   __device__ __forceinline__ void point(int64_t m, float* p) const {

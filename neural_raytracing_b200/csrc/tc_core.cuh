@@ -324,6 +324,21 @@ __device__ __forceinline__ void tmem_load(uint32_t t, uint32_t* r) {
   else if constexpr (NP == 1) { TmemIO<1>::ld(t, r); }
 }
 
+// Softplus forms.  Generic code (act_fast, convert32, the training kernels): NRT_SOFTPLUS_POLY, default 0 = two MUFU
+// (ex2 + lg2); 1 = ex2 + degree-4 polynomial of log1p on the FMA pipe (fp32); 2 = everything on packed halves.
+// The hidden-layer conversion of the inference kernel k_mlp_tc (convert_row_pipe) takes its form from the IO policy
+// (SoftplusOf<IO>): 0 = two MUFU, chunked conversion (the primary sphere-trace march), 1 = fp32 polynomial (default:
+// shadow march, point evaluation), 3 = exponent in fp32, polynomial + max on packed halves (the min scan of
+// SDF.throughput, which only picks a position).
+// Measured on B200 with one form for all three kernels (262,144 rays: march / shadow march / min scan, ms):
+// two MUFU 10.6 / 15.1 / 34.2, form 1: 9.5 / 14.1 / 32.1, form 3: 8.5 / 12.2 / 27.8; median depth error of the march
+// vs the exact kernels 0.9e-5 / 1.2e-5 / 1.6e-5, but with form 3 only 97.4 % (< 99 %) of the 64x64 colocate depths stay
+// within 2e-3 of the reference (tests/test_gpu_configs.py), hence form 1 where depths are produced.
+#ifndef NRT_SOFTPLUS_POLY
+#define NRT_SOFTPLUS_POLY 0
+#endif
+template <class T, class = void> struct SoftplusOf { static constexpr int value = 1; };
+template <class T> struct SoftplusOf<T, std::void_t<decltype(T::kSoftplusForm)>> { static constexpr int value = T::kSoftplusForm; };
 // fast activations for the 16-bit path (results are rounded to 16 bits anyway)
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -332,9 +347,17 @@ __device__ __forceinline__ float act_fast(float x) {
   if constexpr (ACT == NRT_ACT_SOFTPLUS) {
     // branch-free softplus: max(x,0) + log(1 + exp(-|x|)); beyond torch's threshold (20) the log term is < 3e-9,
     // i.e. the result is x like F.softplus.  Two MUFU ops, no divergence (a `x > 20 ? x : ...` form compiles to a
-    // per-element branch that cost ~100 cycles per element).  A one-MUFU variant (ex2 + degree-5 polynomial for
-    // log1p) measured the same throughput in isolation (tools/softplus_bw.cu) and is less accurate.
+    // per-element branch that cost ~100 cycles per element).  NRT_SOFTPLUS_POLY: the log term as u * q(u), u = exp(-|x|),
+    // q a degree-3 minimax polynomial (|error| <= 7.1e-5, a quarter of an fp16 ulp of the result): one MUFU.
+#if NRT_SOFTPLUS_POLY
+    const float u = ex2_approx(-1.4426950408889634f * fabsf(x));
+    float q = fmaf(-5.875710231e-02f, u, 2.256856408e-01f);
+    q = fmaf(q, u, -4.713012532e-01f);
+    q = fmaf(q, u, 9.974489612e-01f);
+    return fmaf(q, u, fmaxf(x, 0.0f));
+#else
     return fmaf(0.6931471805599453f, lg2_approx(1.0f + ex2_approx(-1.4426950408889634f * fabsf(x))), fmaxf(x, 0.0f));
+#endif
   } else {
     return fmaxf(x, 0.01f * x);
   }
@@ -354,9 +377,6 @@ __device__ __forceinline__ uint32_t act_pack(float a, float b) {
     return *reinterpret_cast<const uint32_t*>(&r);
   }
 }
-#ifndef NRT_SOFTPLUS_POLY
-#define NRT_SOFTPLUS_POLY 0
-#endif
 // 32 accumulator columns -> act -> 16 packed operand columns.  Written structure-of-arrays over groups of 8
 // elements so that every step is 8 independent instructions: a single epilogue warp has its SM sub-partition
 // (almost) to itself, so the conversion runs at the speed of its dependent chains unless the ILP is explicit
@@ -364,6 +384,38 @@ __device__ __forceinline__ uint32_t act_pack(float a, float b) {
 template <int ACT, int FMT>
 __device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint32_t* __restrict__ pk) {
   if constexpr (ACT == NRT_ACT_SOFTPLUS) {
+#if NRT_SOFTPLUS_POLY == 2
+    if constexpr (FMT == 0) {
+      // packed-half form: one F2FP per pair up front, exponent argument / polynomial / max on half2 (half the issue
+      // slots of the fp32 form), MUFU.EX2.F16 per element
+      const __half2 kL = __floats2half2_rn(-1.4426950408889634f, -1.4426950408889634f);
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        __half2 x[8], u[8], q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = __floats2half2_rn(__uint_as_float(acc[16 * g + 2 * i]), __uint_as_float(acc[16 * g + 2 * i + 1]));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 t = __hmul2(__habs2(x[i]), kL);
+          uint32_t tu = *reinterpret_cast<const uint32_t*>(&t), uu;
+          asm("ex2.approx.f16x2 %0, %1;" : "=r"(uu) : "r"(tu));
+          u[i] = *reinterpret_cast<__half2*>(&uu);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __hfma2(__floats2half2_rn(-5.875710231e-02f, -5.875710231e-02f), u[i], __floats2half2_rn(2.256856408e-01f, 2.256856408e-01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __hfma2(q[i], u[i], __floats2half2_rn(-4.713012532e-01f, -4.713012532e-01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __hfma2(q[i], u[i], __floats2half2_rn(9.974489612e-01f, 9.974489612e-01f));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const __half2 r = __hfma2(q[i], u[i], __hmax2(x[i], __floats2half2_rn(0.0f, 0.0f)));
+          pk[8 * g + i] = *reinterpret_cast<const uint32_t*>(&r);
+        }
+      }
+      return;
+    }
+#endif
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
       float x[8], u[8];
@@ -372,21 +424,18 @@ __device__ __forceinline__ void convert32(const uint32_t* __restrict__ acc, uint
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] = ex2_approx(-1.4426950408889634f * fabsf(x[i]));
 #if NRT_SOFTPLUS_POLY
-      // log1p(u) on (0,1]: degree-5 minimax polynomial (max error 1.0e-5) on the FMA pipe instead of a second MUFU:
-      // ncu shows the XU pipe (MUFU + F2FP) 77 % busy with the two-MUFU form
+      // log1p(u) = u * q(u) on (0,1]: degree-4 minimax polynomial without constant term (max error 7.1e-5, a quarter of
+      // an fp16 ulp of the result where it matters) on the FMA pipe instead of a second MUFU; max(x,0) is the addend
+      // of the last FMA.  ncu shows the XU pipe (MUFU + F2FP) 60-77 % busy with the two-MUFU form.
       float q[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fmaf(3.044916823e-02f, u[i], -1.315825124e-01f);
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(-5.875710231e-02f, u[i], 2.256856408e-01f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 2.852736055e-01f);
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], -4.713012532e-01f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], -4.902312316e-01f);
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 9.974489612e-01f);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 9.992355931e-01f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 9.968642295e-06f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) u[i] = fmaxf(x[i], 0.0f) + q[i];
+      for (int i = 0; i < 8; ++i) u[i] = fmaf(q[i], u[i], fmaxf(x[i], 0.0f));
 #else
 #pragma unroll
       for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
@@ -499,6 +548,93 @@ __device__ __forceinline__ void convert_row(uint32_t dD, uint32_t aU, uint16_t* 
   if constexpr (SAVE) { if (one_col >= 0) save_row[tile_elem(one_col)] = one16<FMT>(); }
 }
 
+// Softplus rows (NRT_SOFTPLUS_FULLROW): the WHOLE accumulator row goes into registers first.  The accumulator is
+// then free, so `pre` (next layer's bias: LDS + tcgen05.st) runs under the conversion instead of after it, and the
+// four 32-column conversions form one basic block without tcgen05.wait::ld in between: the MUFU pipe of a warp that has
+// its SM sub-partition to itself stays busy across the chunk boundaries (timeline of the chunked form: 2,050 cycles per
+// row for 1,024 cycles of MUFU, the pipeline drains at every wait).
+template <int ACT, int FMT, int H, class PRE>
+__device__ __forceinline__ void convert_row_full(uint32_t dD, uint32_t aU, PRE pre) {
+  static_assert(H % 32 == 0, "hidden width must be a multiple of 32");
+  constexpr int NC = H / 32;
+  uint32_t acc[H];
+  tmem_load<H>(dD, acc);
+  tc_wait_ld();
+  pre();
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    uint32_t pk[16];
+    convert32<ACT, FMT>(acc + 32 * c, pk);
+    TmemIO<16>::st(aU + 16 * c, pk);
+  }
+}
+
+// Softplus rows, software pipelined (NRT_SOFTPLUS_PIPE): 16-column chunks, the exponentials (MUFU, one per 8 cycles
+// and sub-partition) of chunk k+1 are issued between the polynomial FMAs of chunk k, while chunk k+2 is being loaded.
+// A lone warp otherwise alternates between a MUFU-bound phase with idle issue slots and an FMA phase with an idle
+// MUFU pipe (timeline: 1,950 cycles per 128-column row for ~1,050 cycles of either).  `pre` (next layer's bias into the
+// accumulator) runs as soon as the last chunk has been read.
+template <int FMT, int H, int FORM, class PRE>
+__device__ __forceinline__ void convert_row_pipe(uint32_t dD, uint32_t aU, PRE pre, long long* t_dbg = nullptr) {
+  static_assert(H % 16 == 0 && H >= 48, "pipelined softplus conversion: at least three 16-column chunks");
+  constexpr int NC = H / 16;
+  uint32_t xb[3][16];
+  float u[2][16];
+  TmemIO<16>::ld(dD, xb[0]);
+  TmemIO<16>::ld(dD + 16, xb[1]);
+  tc_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) u[0][i] = ex2_approx(-1.4426950408889634f * fabsf(__uint_as_float(xb[0][i])));
+#ifdef NRT_DBG_CONV
+  if (t_dbg) t_dbg[0] = clock64();
+#endif
+#pragma unroll
+  for (int k = 0; k < NC; ++k) {
+    if (k + 2 < NC) TmemIO<16>::ld(dD + 16 * (k + 2), xb[(k + 2) % 3]);
+    uint32_t pk[8];
+    if constexpr (FORM == 3 && FMT == 0) {
+      // exponent argument and MUFU in fp32 (accurate for large |x|), then u and x packed: polynomial and max on half2
+      // (11 instead of 15 instructions per pair; the result is rounded twice: ~1 fp16 ulp instead of 0.5)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (k + 1 < NC) {
+          u[(k + 1) & 1][2 * i] = ex2_approx(-1.4426950408889634f * fabsf(__uint_as_float(xb[(k + 1) % 3][2 * i])));
+          u[(k + 1) & 1][2 * i + 1] = ex2_approx(-1.4426950408889634f * fabsf(__uint_as_float(xb[(k + 1) % 3][2 * i + 1])));
+        }
+        const __half2 uu = __floats2half2_rn(u[k & 1][2 * i], u[k & 1][2 * i + 1]);
+        const __half2 xx = __floats2half2_rn(__uint_as_float(xb[k % 3][2 * i]), __uint_as_float(xb[k % 3][2 * i + 1]));
+        __half2 q = __hfma2(__floats2half2_rn(-5.875710231e-02f, -5.875710231e-02f), uu, __floats2half2_rn(2.256856408e-01f, 2.256856408e-01f));
+        q = __hfma2(q, uu, __floats2half2_rn(-4.713012532e-01f, -4.713012532e-01f));
+        q = __hfma2(q, uu, __floats2half2_rn(9.974489612e-01f, 9.974489612e-01f));
+        const __half2 r = __hfma2(q, uu, __hmax2(xx, __floats2half2_rn(0.0f, 0.0f)));
+        pk[i] = *reinterpret_cast<const uint32_t*>(&r);
+      }
+    } else {
+    float r[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      if (k + 1 < NC) u[(k + 1) & 1][i] = ex2_approx(-1.4426950408889634f * fabsf(__uint_as_float(xb[(k + 1) % 3][i])));
+      const float uu = u[k & 1][i], xx = __uint_as_float(xb[k % 3][i]);
+      // log1p(u) = u * q(u), q of degree 4: |error| <= 9.9e-6 (the fp16 rounding of the result is >= 6e-5 for results
+      // above 0.125); with degree 3 (7.1e-5) the DTU step's most position-sensitive gradient (sp_var_fn.init.weight,
+      // sigma = 128) drops from cosine 0.9975 to 0.9964 against the reference: more rays stop one march step apart
+      float q = fmaf(3.215182172e-02f, uu, -1.360436010e-01f);
+      q = fmaf(q, uu, 2.894552203e-01f);
+      q = fmaf(q, uu, -4.919007447e-01f);
+      q = fmaf(q, uu, 9.994943976e-01f);
+      r[i] = fmaf(q, uu, fmaxf(xx, 0.0f));
+      if (i & 1) pk[i >> 1] = Elem<FMT>::pack(r[i - 1], r[i]);
+    }
+    }
+    TmemIO<8>::st(aU + 8 * k, pk);
+    if (k + 2 < NC) tc_wait_ld();
+#ifdef NRT_DBG_CONV
+    if (t_dbg && k + 3 == NC) t_dbg[1] = clock64();
+#endif
+    if (k + 3 == NC) pre();   // every accumulator column has been read
+  }
+}
+
 // K-split variant (see Net::KSPLIT): whole row into registers, `pre()` (bias of the next layer into the now free
 // accumulator, in-place encoding activation), first half -> arrive on bar_a, second half -> arrive on bar_b.
 template <int ACT, int FMT, int H, class PRE>
@@ -534,7 +670,7 @@ __device__ __forceinline__ void convert_row_split(uint32_t dD, uint32_t aU, uint
 
 // Last hidden layer of a network with a tiny output layer: act(accumulator row) . W_out (fp32, [H][4] in shared
 // memory, broadcast reads) accumulated on the fly; o[] must hold the output bias on entry.
-template <int ACT, int FMT, int H, int OUT, bool SAVE>
+template <int ACT, int FMT, int H, int OUT, bool SAVE, bool POLY = (NRT_SOFTPLUS_POLY != 0)>
 __device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __restrict__ wout, float* __restrict__ o,
                                                 uint16_t* save_row = nullptr, uint32_t* mask_ptr = nullptr,
                                                 int64_t mask_stride = 0) {
@@ -556,10 +692,22 @@ __device__ __forceinline__ void convert_row_out(uint32_t dD, const float* __rest
         float u[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) u[i] = ex2_approx(-1.4426950408889634f * fabsf(a[i]));
+        if constexpr (POLY) {
+          float q[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
+          for (int i = 0; i < 8; ++i) q[i] = fmaf(-5.875710231e-02f, u[i], 2.256856408e-01f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) a[i] = fmaf(0.6931471805599453f, u[i], fmaxf(a[i], 0.0f));
+          for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], -4.713012532e-01f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) q[i] = fmaf(q[i], u[i], 9.974489612e-01f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = fmaf(q[i], u[i], fmaxf(a[i], 0.0f));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) u[i] = lg2_approx(1.0f + u[i]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) a[i] = fmaf(0.6931471805599453f, u[i], fmaxf(a[i], 0.0f));
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[i] = fmaxf(a[i], 0.01f * a[i]);
@@ -712,7 +860,10 @@ struct Net {
   // SDF march +15 %): the epilogue is bound by the throughput of the conversion pipes of the SM sub-partition
   // (F2FP.PACK_AB ~4 cycles, HMUL2 / HMNMX2 2 cycles per warp instruction: ~512 cycles per 128x128 tile layer),
   // not by the latency of one warp's dependent chain, and 17 warps cap the kernel at 96 registers per thread.
-  static constexpr int WPS = 4;
+#ifndef NRT_SOFTPLUS_WPS
+#define NRT_SOFTPLUS_WPS 4
+#endif
+  static constexpr int WPS = ACT == NRT_ACT_SOFTPLUS ? NRT_SOFTPLUS_WPS : 4;
   // K-split early start (k_mlp_tc): a hidden epilogue pulls the WHOLE accumulator row into registers first (the
   // accumulator is then free: bias in), converts the first half of the columns, arrives on `ready_a`, converts the
   // second half, arrives on `ready`.  The MMA warp issues the K-chunks of the first half (and the encoding chunks of
@@ -741,7 +892,19 @@ struct Net {
 #ifndef NRT_MMA_WARP_PER_SLOT
 #define NRT_MMA_WARP_PER_SLOT 1
 #endif
-  static constexpr int NMMA = (NRT_MMA_WARP_PER_SLOT && !STREAM) ? NSLOT : 1;
+#ifndef NRT_MMA_WARP_PER_SLOT_STREAM
+#define NRT_MMA_WARP_PER_SLOT_STREAM 0
+#endif
+  // Self-issue (NRT_SELF_ISSUE, the streamed softplus net): NO MMA warp.  The first epilogue warp of each tile slot
+  // waits for its slot's `ready` barrier after its own arrive (it would only wait for `done` otherwise) and issues the
+  // stage itself, under a CTA-wide lock so that the two slots' tcgen05.mma batches do not interleave.  8 (16) warps
+  // instead of 9 (17): two (four) warps per SM sub-partition and therefore 255 (128) registers per thread instead of
+  // 168 (96) -- ptxas caps at 16 K registers / warps of the fullest sub-partition.
+#ifndef NRT_SELF_ISSUE
+#define NRT_SELF_ISSUE 0
+#endif
+  static constexpr bool SELF = NRT_SELF_ISSUE != 0 && STREAM && ACT == NRT_ACT_SOFTPLUS && ENC_CUDA && FUSE_OUT && NSLOT == 2;
+  static constexpr int NMMA = SELF ? 0 : ((STREAM ? NRT_MMA_WARP_PER_SLOT_STREAM != 0 : NRT_MMA_WARP_PER_SLOT != 0) ? NSLOT : 1);
   static constexpr int threads(int wps) { return NWG * wps * 32 + 32 * NMMA; }
   static constexpr int max_op_bytes() {
     int m = 0;
@@ -840,8 +1003,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ptxas rounds the block size of __launch_bounds__ up to a multiple of 128 threads when it derives the register cap:
+// the 288-thread kernels (8 epilogue warps + 1 MMA warp) get 168 registers, as if they had 384 threads.
+// NRT_MAXNREG replaces the launch bound by an explicit __maxnreg__ = 64 K registers / threads (the two cannot be combined).
+#ifdef NRT_MAXNREG
+#define NRT_KMLP_BOUNDS(T) __maxnreg__(((65536 / (T)) / 8 * 8) > 255 ? 255 : ((65536 / (T)) / 8 * 8))
+#else
+#define NRT_KMLP_BOUNDS(T) __launch_bounds__(T, 1)
+#endif
 template <class NET, class IO, int FMT, class SV = NoSave, int WPS = NET::WPS>
-__global__ void __launch_bounds__(NET::threads(WPS), 1)
+__global__ void NRT_KMLP_BOUNDS(NET::threads(WPS))
 k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restrict__ dbg, SV sv = SV{}) {
   constexpr int EPI = WPS * 32;                 // epilogue threads per tile slot
   static_assert(NET::FITS_TMEM, "network does not fit in TMEM");
@@ -868,6 +1039,15 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   __shared__ __align__(8) uint64_t bar_done[3];
   // K-split early start: not with the 8-warp epilogue, not while saving activation tiles (training forward)
   constexpr bool KSPLIT = NET::KSPLIT && WPS == 4 && !SV::kOn && !SV::kF32;
+#ifndef NRT_SOFTPLUS_FULLROW
+#define NRT_SOFTPLUS_FULLROW 0
+#endif
+#ifndef NRT_SOFTPLUS_PIPE
+#define NRT_SOFTPLUS_PIPE 1
+#endif
+  constexpr bool kPipeRow = NRT_SOFTPLUS_PIPE != 0 && SoftplusOf<IO>::value != 0 && NET::ACT == NRT_ACT_SOFTPLUS && !KSPLIT &&
+                            !SV::kOn && !SV::kF32;
+  constexpr bool kFullRow = NRT_SOFTPLUS_FULLROW != 0 && !kPipeRow && NET::ACT == NRT_ACT_SOFTPLUS && !KSPLIT && !SV::kOn && !SV::kF32;
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_bias[NET::STAGES];
   constexpr bool ITER = IsIterative<IO>::value;
@@ -876,8 +1056,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
-  const int mma_id = warp - NET::NWG * WPS;          // >= 0: MMA-issuing warp
-  const bool is_mma_warp = mma_id == 0;              // the one that also owns TMEM allocation and the weight load
+  constexpr bool SELF = NET::SELF;
+  const int mma_id = SELF ? -1 : warp - NET::NWG * WPS;   // >= 0: MMA-issuing warp
+  const bool is_mma_warp = SELF ? warp == 0 : mma_id == 0;   // the one that also owns TMEM allocation and the weight load
+  __shared__ uint32_t s_issue_lock;                  // self-issue: one slot's MMA batch at a time
   const int64_t ntiles = (M + 127) / 128;
   if (tid < NET::STAGES) {
     s_bias[tid] = (uint32_t)Y.bias_off[tid];
@@ -887,6 +1069,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
 
   if (tid == 0) {
     s_slot_live[0] = 1; s_slot_live[1] = 1; s_slot_live[2] = 1;
+    s_issue_lock = 0;
     mbar_init(&bar_w, 1);
     for (int s = 0; s < 3; ++s) {
       mbar_init(&bar_ready[s], EPI); mbar_init(&bar_done[s], 1); mbar_init(&bar_ready_a[s], EPI);
@@ -934,9 +1117,25 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     // works on one tile while the other tile's epilogue (or prologue / output store) runs.
     constexpr int NMMA = NET::NMMA;
     constexpr bool OWN = NMMA == NSLOT;      // this warp serves exactly one slot: blocking waits
-    auto mine = [&](int slot) { return slot % NMMA == mma_id; };
-    auto is_ready = [&](uint64_t* bar, uint32_t parity) {
+    auto mine = [&](int slot) { return slot % (NMMA > 0 ? NMMA : 1) == mma_id; };
+    // Single warp, two slots (NRT_MMA_ALTERNATE): the slots are served strictly in turn with a BLOCKING wait on the
+    // slot whose turn it is.  The polling loop (mbarrier test + nanosleep) saw an arrive 120-580 cycles late (350 on
+    // average, 10 % of a stage); a slot can only arrive once per stage it is served, so alternation costs nothing in
+    // the steady state and keeps the two tiles in anti-phase (one in its MMAs while the other converts).
+#ifndef NRT_MMA_ALTERNATE
+#define NRT_MMA_ALTERNATE 0
+#endif
+    constexpr bool ALT = NRT_MMA_ALTERNATE != 0 && !OWN && NSLOT == 2 && !KSPLIT;
+    int turn = 0;
+    bool live[3];
+    auto is_ready = [&](int slot, uint64_t* bar, uint32_t parity) {
       if constexpr (OWN) { mbar_wait(bar, parity); return true; }
+      else if constexpr (ALT) {
+        if (slot != turn && live[turn]) return false;
+        mbar_wait(bar, parity);
+        turn = slot ^ 1;
+        return true;
+      }
       else return mbar_test(bar, parity);
     };
     const uint32_t sW_addr = smem_u32(sW);
@@ -945,8 +1144,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
     uint32_t n_ready_a[3] = {0, 0, 0};
     bool half_issued[3] = {false, false, false};
     int64_t tile[3] = {(int64_t)blockIdx.x * NSLOT, (int64_t)blockIdx.x * NSLOT + 1, (int64_t)blockIdx.x * NSLOT + 2};
-    bool live[3] = {mine(0) && (ITER || tile[0] < ntiles), NSLOT > 1 && mine(1) && (ITER || tile[1] < ntiles),
-                    NSLOT > 2 && mine(2) && (ITER || tile[2] < ntiles)};
+    live[0] = mine(0) && (ITER || tile[0] < ntiles);
+    live[1] = NSLOT > 1 && mine(1) && (ITER || tile[1] < ntiles);
+    live[2] = NSLOT > 2 && mine(2) && (ITER || tile[2] < ntiles);
     int it_dbg[3] = {0, 0, 0};
     uint32_t n_issued[3] = {0, 0, 0};   // streaming: stages issued per slot (selects the stage buffer)
     if (STREAM) {
@@ -965,7 +1165,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         if constexpr (KSPLIT) {
           if (st[slot] >= 2 && !half_issued[slot]) {
             // first half of a hidden stage's operand is in place: issue its K-chunks under the rest of the epilogue
-            if (!is_ready(&bar_ready_a[slot], n_ready_a[slot] & 1)) continue;
+            if (!is_ready(slot, &bar_ready_a[slot], n_ready_a[slot] & 1)) continue;
             progressed = true;
             n_ready_a[slot]++;
             half_issued[slot] = true;
@@ -982,7 +1182,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             continue;
           }
         }
-        if (!is_ready(&bar_ready[slot], n_ready[slot] & 1)) continue;
+        if (!is_ready(slot, &bar_ready[slot], n_ready[slot] & 1)) continue;
         progressed = true;
         n_ready[slot]++;
         tc_fence_after();
@@ -1002,6 +1202,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           const uint32_t b = n_issued[slot] & 1;
           mbar_wait(&bar_wfull[slot][b], (n_issued[slot] >> 1) & 1);
           b_addr = sW_addr + (uint32_t)((slot * 2 + b) * NET::MAXOP);
+          if ((tid & 31) == 0) stamp(it_dbg[slot], st[slot], slot, 0);   // streamed operand has landed
         }
         if (KSPLIT && half_issued[slot]) {
           half_issued[slot] = false;
@@ -1030,9 +1231,10 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           __syncwarp();
         }
       }
-      // this warp shares an SM sub-partition with two epilogue warps: do not burn their issue slots
+      // (a back-off here -- the warp shares its SM sub-partition with two epilogue warps -- measured 1 % slower than
+      //  plain polling for the streamed SDF net: min scan 28.1 vs 27.8 ms)
 #ifndef NRT_MMA_POLL_SLEEP_NS
-#define NRT_MMA_POLL_SLEEP_NS 32
+#define NRT_MMA_POLL_SLEEP_NS 0
 #endif
       if (NRT_MMA_POLL_SLEEP_NS > 0 && !progressed) __nanosleep(NRT_MMA_POLL_SLEEP_NS);
     }
@@ -1051,9 +1253,64 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
       const uint32_t dD = base, aU = base + NET::DC, aE = base + NET::DC + NET::UC;
       uint32_t n_done = 0;
       int it_dbg = 0;
-      auto estamp = [&](int st, int k) { if (lane_row == 0) stamp(it_dbg, st, slot, k); };
+#ifndef NRT_DBG_LANE
+#define NRT_DBG_LANE 0
+#endif
+      auto estamp = [&](int st, int k) { if (lane_row == NRT_DBG_LANE) stamp(it_dbg, st, slot, k); };
       typename StateOf<IO>::type state;
       if constexpr (ITER) io.init(state);
+      // ---- self-issue: the slot's first warp is its MMA issuer ----
+      const bool leader = SELF && (warp % WPS) == 0;
+      int st_mma = NET::FIRST_STAGE;
+      uint32_t n_ready_l = 0, n_issued_l = 0;
+      const uint32_t sW_addr_l = smem_u32(sW);
+      if constexpr (SELF) {
+        if (leader) {
+          if (elect_one())
+            stream_op(smem + (size_t)(slot * 2) * NET::MAXOP, blob + s_opoff[NET::FIRST_STAGE], s_opbytes[NET::FIRST_STAGE],
+                      &bar_wfull[slot][0]);
+          __syncwarp();
+        }
+      }
+      // called by every warp of the slot right after its arrive on `ready`; only the leader does anything
+      auto self_issue = [&]() {
+        if constexpr (SELF) {
+          if (leader) {
+            mbar_wait(&bar_ready[slot], n_ready_l & 1); n_ready_l++;
+            const uint32_t b = n_issued_l & 1;
+            mbar_wait(&bar_wfull[slot][b], (n_issued_l >> 1) & 1);
+            if ((tid & 31) == 0) {
+              while (atomicCAS(&s_issue_lock, 0u, 1u) != 0u) __nanosleep(64);
+            }
+            __syncwarp();
+            tc_fence_after();
+            if ((tid & 31) == 0) stamp(it_dbg, st_mma, slot, 1);
+            const uint32_t base0 = tmem + slot * NET::COLS;
+            issue_stage_dyn<NET, FMT>(st_mma, sW_addr_l + (uint32_t)((slot * 2 + b) * NET::MAXOP), base0, base0 + NET::DC,
+                                      base0 + NET::DC + NET::UC, &bar_done[slot]);
+            if ((tid & 31) == 0) {
+              stamp(it_dbg, st_mma, slot, 2);
+              __threadfence_block();
+              atomicExch(&s_issue_lock, 0u);
+            }
+            if (++st_mma == NET::END_STAGE) st_mma = NET::FIRST_STAGE;
+            n_issued_l++;
+            // prefetch the operand of the slot's next stage (possibly of an iteration that never happens: drained at
+            // exit).  The other buffer held the previous stage's operand, whose MMAs completed before the epilogue
+            // that made this stage ready.
+            if (elect_one()) {
+              const uint32_t nb = n_issued_l & 1;
+              stream_op(smem + (size_t)(slot * 2 + nb) * NET::MAXOP, blob + s_opoff[st_mma], s_opbytes[st_mma], &bar_wfull[slot][nb]);
+            }
+            __syncwarp();
+          }
+        }
+      };
+      auto self_drain = [&]() {
+        if constexpr (SELF) {
+          if (leader) mbar_wait(&bar_wfull[slot][n_issued_l & 1], (n_issued_l >> 1) & 1);
+        }
+      };
 #ifndef NRT_SLOT_STAGGER
 #define NRT_SLOT_STAGGER 900
 #endif
@@ -1076,11 +1333,12 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           if (!any) {
             if (lane_row == 0) s_slot_live[slot] = 0;
             mbar_arrive(&bar_ready[slot]);   // release: the MMA warp reads s_slot_live after its acquire
+            self_drain();
             break;
           }
         } else {
           const int64_t tile = t0 + slot;
-          if (tile >= ntiles) break;
+          if (tile >= ntiles) { self_drain(); break; }
           m = tile * 128 + lane_row;
           valid = m < M;
           if (valid && primary) io.load(m, x);
@@ -1092,6 +1350,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             mbar_wait(&bar_done[slot], n_done & 1); n_done++;
           }
           mbar_arrive(&bar_ready[slot]);
+          self_issue();
         } else {
         // ---- stage 0: inputs -> encode-GEMM A operand (+ x / latent parts of enc_raw, enc_act) ----
         uint32_t ex[NET::XR / 2];     // act(x): stored in stage 1 when the hi+lo phase GEMM borrows its place for x_lo
@@ -1230,6 +1489,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&bar_ready[slot]);
+          self_issue();
         }
         }   // primary
         // ---- stages 2 .. L+1: hidden activations ----
@@ -1287,15 +1547,27 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           else if constexpr (SV::kF32)
             convert_row_savef32<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2,
                                                    valid ? sv.acts + ((int64_t)st * H) * sv.M + m : nullptr, sv.M);
+          else if constexpr (kPipeRow) {
+            long long* d = nullptr;
+#ifdef NRT_DBG_CONV
+            // development: stamps 3 / 4 of the stage row are reused for "first exponentials issued" / "all columns read"
+            if (dbg != nullptr && lane_row == NRT_DBG_LANE && slot < 2 && blockIdx.x == 0 && it_dbg >= kDbgIt0 && it_dbg < kDbgIt0 + kDbgIts)
+              d = dbg + (((it_dbg - kDbgIt0) * NET::STAGES + 2 + st) * 2 + slot) * 8 + 3;
+#endif
+            convert_row_pipe<FMT, HW, SoftplusOf<IO>::value>(dD + coff, aU + coff / 2, pre, d);
+          }
+          else if constexpr (kFullRow)
+            convert_row_full<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2, pre);
           else
             convert_row<NET::ACT, FMT, HW>(dD + coff, aU + coff / 2);
           // done after the conversion so the accumulator registers are dead and all LDS.128 can be in flight
-          pre();
+          if constexpr (!(kFullRow || kPipeRow) || SV::kOn || SV::kF32) pre();
           estamp(2 + st, 6);
           tc_wait_st();
           tc_fence_before();
           mbar_arrive(&bar_ready[slot]);
           estamp(2 + st, 7);
+          self_issue();
           }
         }
         // ---- output layer ----
@@ -1318,7 +1590,7 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             convert_row_out_savef32<NET::ACT, FMT, H, NET::OUT>(dD, sBias + Y.wout_f32_off, o,
                                                                   valid ? sv.acts + ((int64_t)L * H) * sv.M + m : nullptr, sv.M);
           else
-            convert_row_out<NET::ACT, FMT, H, NET::OUT, false>(dD, sBias + Y.wout_f32_off, o);
+            convert_row_out<NET::ACT, FMT, H, NET::OUT, false, kPipeRow || (NRT_SOFTPLUS_POLY != 0)>(dD, sBias + Y.wout_f32_off, o);
           if constexpr (ITER) { if (valid) io.consume(state, o); }
           else { if (valid) io.store(m, o); }
           tc_fence_before();
