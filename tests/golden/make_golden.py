@@ -265,6 +265,65 @@ def gen_shading():
     print("shading.npz ok")
 
 
+def gen_lights_bsdf():
+    """a9 / a14: PointLights.sample_direction (lights.py:89-110), Diffuse.eval_and_pdf (bsdfs.py:108-118) with the three
+    preprocess functions the scripts use, Conductor.eval_and_pdf (bsdfs.py:364-388), each with the gradients of a fixed
+    scalar loss to every leaf the scripts optimise (PYTORCH_JIT=0 in the shim: Conductor.eta DOES receive a gradient)."""
+    from types import SimpleNamespace
+    from pytorch3d.pathtracer.bsdf.bsdfs import identity_div_pi
+    rs = np.random.RandomState(77)
+    out = {}
+    N, W, H = 2, 6, 5
+    p = (0.6 * rs.standard_normal((N, W, H, 1, 3))).astype(np.float32)
+    active = rs.uniform(size=(N, W, H, 1)) > 0.3
+    wgt = rs.standard_normal((N, W, H, 1, 3)).astype(np.float32)           # dL/dspectrum
+    wgt_d = rs.standard_normal((N, W, H, 1, 3)).astype(np.float32)         # dL/dd
+    out.update(p=p, active=active, wgt=wgt, wgt_d=wgt_d)
+    loc = np.array([[0.3, 1.2, 0.4], [-0.8, 0.5, 1.1]], np.float32)
+    lights = PointLights(device="cpu", scale=5.0, intensity=[0.9, 0.7, 0.8], location=loc.tolist(), const=0.3, linear=0.05, square=0.7)
+    lights.location = T(loc).clone().requires_grad_(True)
+    pt_ = T(p).clone().requires_grad_(True)
+    ds, spec = lights.sample_direction(SimpleNamespace(p=pt_), None, T(active))
+    loss = (spec * T(wgt)).sum() + (ds.d * T(wgt_d)).sum() + 0.1 * ds.dist.sum()
+    loss.backward()
+    out.update(light_loc=loc, pl_d=ds.d.detach().numpy(), pl_dist=ds.dist.detach().numpy(), pl_spectrum=spec.detach().numpy(),
+               pl_g_p=pt_.grad.numpy(), pl_g_location=lights.location.grad.numpy(), pl_g_intensity=lights.intensity.grad.numpy(),
+               pl_g_scale=lights.scale.grad.numpy(), pl_g_const=lights.const.grad.numpy(), pl_g_linear=lights.linear.grad.numpy(),
+               pl_g_square=lights.square.grad.numpy())
+    # local directions
+    wi = rs.standard_normal((N, W, H, 1, 3)).astype(np.float32); wi /= np.linalg.norm(wi, axis=-1, keepdims=True)
+    wo = rs.standard_normal((N, W, H, 1, 3)).astype(np.float32); wo /= np.linalg.norm(wo, axis=-1, keepdims=True)
+    # a few mirror configurations so that the conductor lobe (reflect(wi) . wo > 0.94) is hit
+    for j in range(8):
+        wo[0, j % W, j % H, 0] = wi[0, j % W, j % H, 0] * np.array([-1, -1, 1], np.float32)
+    out.update(wi=wi, wo=wo)
+    refl = rs.uniform(0.05, 0.95, 3).astype(np.float32)
+    out["reflectance"] = refl
+    for name, pre in (("div_pi", identity_div_pi), ("softplus", torch.nn.Softplus()), ("sigmoid", torch.sigmoid)):
+        d = Diffuse(reflectance=refl.tolist(), preprocess=pre, device="cpu")
+        wo_t = T(wo).clone().requires_grad_(True)
+        spec, pdf = d.eval_and_pdf(SimpleNamespace(wi=T(wi), p=T(p)), wo_t, T(active))
+        ((spec * T(wgt)).sum() + pdf.sum()).backward()
+        out["df_%s_spectrum" % name] = spec.detach().numpy(); out["df_%s_pdf" % name] = pdf.detach().numpy()
+        out["df_%s_g_reflectance" % name] = d.reflectance.grad.numpy(); out["df_%s_g_wo" % name] = wo_t.grad.numpy()
+    spc = rs.uniform(-1, 1, 3).astype(np.float32)
+    out["specular"] = spc
+    for name, act in (("sigmoid", torch.sigmoid), ("softplus", torch.nn.Softplus())):
+        c = Conductor(specular=spc.tolist(), eta=1.3, k=1.0, device="cpu", activation=act)
+        wi_t = T(wi).clone().requires_grad_(True)
+        spec, pdf = c.eval_and_pdf(SimpleNamespace(wi=wi_t, p=T(p)), T(wo), T(active))
+        (spec * T(wgt)).sum().backward()
+        out["cd_%s_spectrum" % name] = spec.detach().numpy(); out["cd_%s_pdf" % name] = pdf.detach().numpy()
+        out["cd_%s_g_specular" % name] = c.specular.grad.numpy(); out["cd_%s_g_wi" % name] = wi_t.grad.numpy()
+        out["cd_%s_g_eta" % name] = np.float32(0.0) if c.eta.grad is None else c.eta.grad.numpy()
+        out["cd_%s_eta_has_grad" % name] = np.bool_(c.eta.grad is not None)
+        out["cd_%s_k_has_grad" % name] = np.bool_(c.k.grad is not None)
+    out["lobe_pixels"] = np.int64(int((out["cd_sigmoid_pdf"] > 0).sum()))
+    out["src"] = np.array("lights.py:89-110; bsdfs.py:108-118, 327-341, 364-388 (PYTORCH_JIT=0)")
+    np.savez_compressed(os.path.join(HERE, "lights_bsdf.npz"), **out)
+    print("lights_bsdf.npz ok, conductor lobe pixels:", int(out["lobe_pixels"]), "eta grad:", bool(out["cd_sigmoid_eta_has_grad"]))
+
+
 from scenes import build_pipeline  # noqa: E402
 
 
@@ -571,7 +630,7 @@ def gen_path():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16"]
+                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()

@@ -15,8 +15,17 @@ random.random = lambda: 0.37
 config.set_precision(prec); config.set_train_precision(prec)
 shape, sphere, bsdf, lights, integrator = scenes.build_dtu16(P, device="cuda")
 params = list(sphere.parameters()) + list(bsdf.parameters()) + list(lights.parameters())
-opt = torch.optim.AdamW([{"params": list(sphere.parameters())}, {"params": list(bsdf.parameters())}, {"params": list(lights.parameters())}],
-                        lr=8e-5, weight_decay=0)
+FLAT = os.environ.get("NRT_FLAT") == "1"    # flat parameter / gradient buffers + one fused AdamW kernel (training.FlatParameters)
+if FLAT:
+    from neural_raytracing_b200 import training
+    mlps = [sphere.shift, bsdf.sp_var_fn, lights.light_field_approx] + [k.mlp for k in bsdf.bsdfs if hasattr(k, "mlp")]
+    mlp_params = {id(q) for m in mlps for q in m.parameters()}
+    flat = training.FlatParameters(mlps, [q for q in params if id(q) not in mlp_params])
+    opt = torch.optim.AdamW([flat.param], lr=8e-5, weight_decay=0, fused=True)
+    opt.zero_grad = lambda *a, **k: flat.zero_grad()
+else:
+    opt = torch.optim.AdamW([{"params": list(sphere.parameters())}, {"params": list(bsdf.parameters())}, {"params": list(lights.parameters())}],
+                            lr=8e-5, weight_decay=0)
 size = crop
 pose, K = scenes.dtu_cameras(1, device="cuda")
 cam = DTUCamera(pose=pose, intrinsic=K, device="cuda")
@@ -51,3 +60,9 @@ rows = sorted([(e.self_device_time_total / 3e3, e.count // 3, e.key[:100]) for e
 tot = sum(r[0] for r in rows)
 print("GPU busy ms/step %.2f in %d launches" % (tot, sum(r[1] for r in rows)))
 for r in rows[:22]: print("%8.3f ms %5d x  %s" % r)
+if os.environ.get("NRT_PROF_BY_COUNT"):
+    print("--- by launch count")
+    for r in sorted(rows, key=lambda r: -r[1])[:45]: print("%8.3f ms %5d x  %s" % r)
+    cpu = sorted([(e.self_cpu_time_total / 3e3, e.count // 3, e.key[:90]) for e in ka], reverse=True)
+    print("--- host side (self CPU ms per step)")
+    for r in cpu[:40]: print("%8.3f ms %5d x  %s" % r)
