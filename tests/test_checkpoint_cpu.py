@@ -1,0 +1,57 @@
+"""SURVEY 8f rank 3 (dtu.py:93-94, 159): TorchScript SDF archives.  The archive written by save_sdf_archive carries a scriptable
+restatement of the reference's SphereSDF; its output is checked against the reference's own values (tests/golden/sdf.npz:
+SphereSDF.forward of the unmodified reference on the same weights), and load_sdf_archive brings the tensors back into this
+package's SphereSDF.  CPU only: archives are host-side interchange."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+
+
+def _sphere_sdf_from(w, device="cpu"):
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SphereSDF
+    s = SphereSDF(n=w["n"], device=device)
+    with torch.no_grad():
+        s.centers.copy_(torch.from_numpy(w["centers"])); s.radii.copy_(torch.from_numpy(w["radii"])); s.tfs.copy_(torch.from_numpy(w["tfs"]))
+        m = w["shift"]
+        lins = [s.shift.init] + list(s.shift.layers) + [s.shift.out]
+        for lin, W, b in zip(lins, m["W"], m["b"]):
+            lin.weight.copy_(torch.from_numpy(W)); lin.bias.copy_(torch.from_numpy(b))
+    s.shift.basis_p = torch.from_numpy(m["basis"]).clone()
+    return s
+
+
+def test_sdf_archive_round_trip_and_reference_values(tmp_path):
+    from neural_raytracing_b200.pathtracer import checkpoint
+    g = helpers.golden("sdf")
+    s = _sphere_sdf_from(helpers.golden_sdf_weights())
+    path = str(tmp_path / "dtu_sdf.pt")
+    checkpoint.save_sdf_archive(s, path)
+    # what the reference's script does with the file (dtu.py:93): torch.jit.load -> a callable with parameters
+    m = torch.jit.load(path, "cpu")
+    pts = torch.from_numpy(g["pts"])
+    got = m(pts).detach().numpy()
+    assert got.shape == g["sdf_vals"].shape
+    assert np.abs(got - g["sdf_vals"]).max() < 2e-6, np.abs(got - g["sdf_vals"]).max()      # the unmodified reference's values
+    assert m(pts.reshape(10, 30, 3)).shape == (10, 30)                                      # batch dims like SphereSDF.forward
+    names = {k for k, _ in m.named_parameters()}
+    assert {"centers", "radii", "tfs", "shift.init.weight", "shift.layers.7.bias", "shift.out.weight"} <= names
+    assert len(list(m.parameters())) == len(list(s.parameters())) == 23
+    # gradients flow to the archive's parameters (the reference optimises density_field.parameters(), dtu.py:125)
+    m(pts).sum().backward()
+    assert all(p.grad is not None for p in m.parameters())
+    # and back into this package
+    s2 = checkpoint.load_sdf_archive(path, device="cpu")
+    for (k, a), (k2, b) in zip(s.state_dict().items(), s2.state_dict().items()):
+        assert k == k2 and torch.equal(a, b), k
+    assert torch.equal(s2.shift.basis_p, s.shift.basis_p)
+    assert np.abs(s2(pts).detach().numpy() - g["sdf_vals"]).max() < 2e-6
+
+
+def test_sdf_archive_of_another_module_is_rejected(tmp_path):
+    from neural_raytracing_b200.pathtracer import checkpoint
+    path = str(tmp_path / "other.pt")
+    torch.jit.save(torch.jit.script(torch.nn.Linear(3, 1)), path)
+    with pytest.raises(ValueError, match="not a SphereSDF archive"):
+        checkpoint.load_sdf_archive(path, device="cpu")
