@@ -90,8 +90,8 @@ def _(x, latent, out, acts, g_out, params, basis, arch, out_act):
 def _mlp_setup(ctx, inputs, output):
     x, latent, params, basis, arch, out_act, prec = inputs
     if prec != ops.PREC_F32:
-        raise ops.NrtError("nrt_b200::mlp_forward is differentiable in fp32 only (use the class layer's tensor-core "
-                           "training path, config.set_train_precision, for 16-bit training)")
+        raise ops.NrtError("nrt_b200::mlp_forward is differentiable in fp32 only; 16-bit training: "
+                           "torch.ops.nrt_b200.mlp_forward_train_tc (forward and backward on the tensor cores)")
     out, acts = output
     ctx.save_for_backward(x, latent if latent is not None else x.new_empty(0), out, acts, params, basis)
     ctx.arch, ctx.out_act, ctx.has_latent = list(arch), out_act, latent is not None
@@ -105,6 +105,56 @@ def _mlp_bwd(ctx, g_out, g_acts):
 
 
 mlp_forward.register_autograd(_mlp_bwd, setup_context=_mlp_setup)
+
+
+# ---- a2 under autograd on the tensor cores (north_star: forward and backward registered) ---------------------------------
+@torch.library.custom_op(NS + "::mlp_forward_train_tc", mutates_args=())
+def mlp_forward_train_tc(x: Tensor, params: Tensor, basis: Tensor, arch: List[int], out_act: int, prec: int) -> Tuple[Tensor, Tensor]:
+    """Tensor-core training forward (tcgen05, 16-bit operands / fp32 accumulate): x [M,in] -> (out [M,out] with `out_act`
+    applied, workspace of saved activation tiles for mlp_backward_tc).  The shapes the library instantiates: NeRFLE.first /
+    .second, NeuralBSDF.mlp, the occlusion MLP, SphereSDF.shift, sp_var_fn (4 / 8 / 16 bases), LightField; others raise."""
+    m = _mlp(params, basis, arch)
+    out, ws = ops.mlp_forward_train_tc(m, x, out_act, prec=prec)
+    return out, ws
+
+
+@mlp_forward_train_tc.register_fake
+def _(x, params, basis, arch, out_act, prec):
+    M = x.reshape(-1, arch[0]).shape[0]
+    ws = torch.empty(torch.library.get_ctx().new_dynamic_size(), dtype=torch.uint8, device=x.device)
+    return x.new_empty((M, arch[6])), ws
+
+
+@torch.library.custom_op(NS + "::mlp_backward_tc", mutates_args=())
+def mlp_backward_tc(x: Tensor, out: Tensor, ws: Tensor, g_out: Tensor, params: Tensor, basis: Tensor, arch: List[int],
+                    out_act: int, prec: int) -> Tuple[Tensor, Tensor]:
+    """Reverse mode of mlp_forward_train_tc: streamed dgrad + wgrad on the tensor cores -> (g_params [P], g_x [M,in])."""
+    m = _mlp(params, basis, arch)
+    M = x.reshape(-1, arch[0]).shape[0]
+    g_params, g_x = ops.mlp_backward_tc(m, M, out, g_out.contiguous(), ws, out_act, need_input_grad=True, prec=prec)
+    return g_params, g_x
+
+
+@mlp_backward_tc.register_fake
+def _(x, out, ws, g_out, params, basis, arch, out_act, prec):
+    M = x.reshape(-1, arch[0]).shape[0]
+    return params.new_empty(params.shape), x.new_empty((M, arch[0]))
+
+
+def _mlp_tc_setup(ctx, inputs, output):
+    x, params, basis, arch, out_act, prec = inputs
+    out, ws = output
+    ctx.save_for_backward(x, out, ws, params, basis)
+    ctx.arch, ctx.out_act, ctx.prec = list(arch), out_act, prec
+
+
+def _mlp_tc_bwd(ctx, g_out, g_ws):
+    x, out, ws, params, basis = ctx.saved_tensors
+    g_params, g_x = torch.ops.nrt_b200.mlp_backward_tc(x, out, ws, g_out, params, basis, ctx.arch, ctx.out_act, ctx.prec)
+    return g_x.reshape(x.shape), g_params, None, None, None, None
+
+
+mlp_forward_train_tc.register_autograd(_mlp_tc_bwd, setup_context=_mlp_tc_setup)
 
 
 # ---- a19: compositing ------------------------------------------------------------------------------------------
@@ -250,5 +300,5 @@ def _(rays, ts, light_code, params1, basis1, arch1, params2, basis2, arch2, prec
     return rays.new_empty((rays.reshape(-1, 6).shape[0], 3))
 
 
-OPERATORS = ["mlp_forward", "mlp_backward", "composite", "composite_backward", "mlp_value_jac", "mlp_value_jac_backward",
+OPERATORS = ["mlp_forward", "mlp_backward", "mlp_forward_train_tc", "mlp_backward_tc", "composite", "composite_backward", "mlp_value_jac", "mlp_value_jac_backward",
              "sdf_eval", "sdf_sphere_trace", "sdf_shadow_test", "sdf_min_scan", "nerfle_render"]

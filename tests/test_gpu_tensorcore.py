@@ -130,13 +130,12 @@ def test_tc_nerfle_golden_views():
     assert np.abs(rgb - g["pt_rgb"].reshape(-1, 3)).max() < 1e-3
 
 
-@pytest.mark.parametrize("prec,tol", [("f32", 2e-5), ("f16", 1e-3)])
+@pytest.mark.parametrize("prec,tol,min_psnr", [("f32", 2e-6, 120.0), ("f16", 5e-4, 85.0)])
 @pytest.mark.parametrize("seed", [0, 7])
-def test_hierarchical_render_vs_restatement(prec, tol, seed):
+def test_hierarchical_render_vs_restatement(prec, tol, min_psnr, seed):
     """64 coarse + 128 fine (BASELINE config 2).  Not in the reference: pinned by the numpy
-    restatement in oracle/port.py (MLPs through the C oracle).  A resampled distance sitting on a
-    bin edge may land in the neighbouring bin when sigma differs in the last bit, so a tiny fraction
-    of rays is allowed to deviate."""
+    restatement in oracle/port.py (MLPs through the C oracle).  EVERY ray within the tolerance (measured on B200: fp32
+    max 4.8e-7 / 139 dB, f16 max 1.1e-4 / 93 dB; the fp32 kernels use the deterministic exp of nrt_detmath.h)."""
     from neural_raytracing_b200 import ops
     w1, w2 = helpers.nerfle_weights(False)
     rays = synth.camera_rays(55, 192)
@@ -146,8 +145,8 @@ def test_hierarchical_render_vs_restatement(prec, tol, seed):
     rgb = ops.nerfle_render(helpers.cuda_mlp(w1), helpers.cuda_mlp(w2), _t(rays), None, _t(code), prec=prec, n_coarse=64,
                             n_fine=128, t_near=0.0, t_far=2.05, jitter_seed=seed).cpu().numpy()
     err = np.abs(rgb - ref).max(axis=-1)
-    assert (err < tol).mean() > 0.97, (err.max(), (err < tol).mean())
-    assert helpers.psnr(rgb, ref) > 55
+    assert err.max() < tol, (err.max(), (err < tol).mean())
+    assert helpers.psnr(rgb, ref) > min_psnr
 
 
 def test_hierarchical_zero_fine_equals_reference_mode():
