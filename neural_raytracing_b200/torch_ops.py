@@ -127,18 +127,19 @@ def _(x, params, basis, arch, out_act, prec):
 
 @torch.library.custom_op(NS + "::mlp_backward_tc", mutates_args=())
 def mlp_backward_tc(x: Tensor, out: Tensor, ws: Tensor, g_out: Tensor, params: Tensor, basis: Tensor, arch: List[int],
-                    out_act: int, prec: int) -> Tuple[Tensor, Tensor]:
-    """Reverse mode of mlp_forward_train_tc: streamed dgrad + wgrad on the tensor cores -> (g_params [P], g_x [M,in])."""
+                    out_act: int, prec: int, need_input_grad: bool) -> Tuple[Tensor, Tensor]:
+    """Reverse mode of mlp_forward_train_tc: streamed dgrad + wgrad on the tensor cores -> (g_params [P], g_x [M,in] or
+    empty).  NeRFLE.first has no input gradient on this path (its inputs are ray samples; split-precision encoding)."""
     m = _mlp(params, basis, arch)
     M = x.reshape(-1, arch[0]).shape[0]
-    g_params, g_x = ops.mlp_backward_tc(m, M, out, g_out.contiguous(), ws, out_act, need_input_grad=True, prec=prec)
-    return g_params, g_x
+    g_params, g_x = ops.mlp_backward_tc(m, M, out, g_out.contiguous(), ws, out_act, need_input_grad=need_input_grad, prec=prec)
+    return g_params, g_x if g_x is not None else x.new_empty(0)
 
 
 @mlp_backward_tc.register_fake
-def _(x, out, ws, g_out, params, basis, arch, out_act, prec):
+def _(x, out, ws, g_out, params, basis, arch, out_act, prec, need_input_grad):
     M = x.reshape(-1, arch[0]).shape[0]
-    return params.new_empty(params.shape), x.new_empty((M, arch[0]))
+    return params.new_empty(params.shape), x.new_empty((M, arch[0]) if need_input_grad else (0,))
 
 
 def _mlp_tc_setup(ctx, inputs, output):
@@ -150,8 +151,9 @@ def _mlp_tc_setup(ctx, inputs, output):
 
 def _mlp_tc_bwd(ctx, g_out, g_ws):
     x, out, ws, params, basis = ctx.saved_tensors
-    g_params, g_x = torch.ops.nrt_b200.mlp_backward_tc(x, out, ws, g_out, params, basis, ctx.arch, ctx.out_act, ctx.prec)
-    return g_x.reshape(x.shape), g_params, None, None, None, None
+    need = bool(ctx.needs_input_grad[0])
+    g_params, g_x = torch.ops.nrt_b200.mlp_backward_tc(x, out, ws, g_out, params, basis, ctx.arch, ctx.out_act, ctx.prec, need)
+    return (g_x.reshape(x.shape) if need else None), g_params, None, None, None, None
 
 
 mlp_forward_train_tc.register_autograd(_mlp_tc_bwd, setup_context=_mlp_tc_setup)

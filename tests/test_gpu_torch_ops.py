@@ -45,9 +45,9 @@ def test_mlp_operator_forward_and_registered_backward():
     assert a16.numel() == 0 and (o16 - m.forward_reference_ops(x.detach())).abs().max().item() < 5e-3
 
 
-@pytest.mark.parametrize("kw,out_act", [(dict(in_size=3, out=3, num_layers=6, hidden_size=96, freqs=64), 1),
-                                        (dict(in_size=3, out=65, num_layers=5, hidden_size=128, freqs=16), 0)])
-def test_tensor_core_training_operator_has_forward_and_backward_registered(kw, out_act):
+@pytest.mark.parametrize("kw,out_act,need_x", [(dict(in_size=3, out=3, num_layers=6, hidden_size=96, freqs=64), 1, True),
+                                               (dict(in_size=3, out=65, num_layers=5, hidden_size=128, freqs=16), 0, False)])
+def test_tensor_core_training_operator_has_forward_and_backward_registered(kw, out_act, need_x):
     """nrt_b200::mlp_forward_train_tc under autograd (tcgen05 forward with saved tiles, streamed dgrad + wgrad) against the
     fp32 operator on the same weights: outputs within 1e-3, every parameter gradient and the input gradient cosine >= 0.999."""
     import torch
@@ -59,17 +59,18 @@ def test_tensor_core_training_operator_has_forward_and_backward_registered(kw, o
     res = {}
     for name, prec in (("f32", ops.PREC_F32), ("f16", ops.PREC_F16)):
         m.zero_grad()
-        x = x0.clone().requires_grad_()
+        x = x0.clone().requires_grad_(need_x)      # NeRFLE.first: ray samples, no input gradient on the tensor-core path
         if prec == ops.PREC_F32:
             out, _ = torch.ops.nrt_b200.mlp_forward(x, None, T.pack_module(m), m.basis_p, T.arch_of(m), out_act, prec)
         else:
             out, ws = torch.ops.nrt_b200.mlp_forward_train_tc(x, T.pack_module(m), m.basis_p, T.arch_of(m), out_act, prec)
             assert ws.dtype == torch.uint8 and ws.numel() > 0
         (out * go).sum().backward()
-        res[name] = (out.detach(), x.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters()})
+        res[name] = (out.detach(), x.grad.clone() if need_x else None, {k: p.grad.clone() for k, p in m.named_parameters()})
     assert (res["f16"][0] - res["f32"][0]).abs().max().item() < 1e-3
     cos = lambda a, b: float((a.double().flatten() @ b.double().flatten()) / (a.double().norm() * b.double().norm() + 1e-300))
-    assert cos(res["f16"][1], res["f32"][1]) > 0.999
+    if need_x:
+        assert cos(res["f16"][1], res["f32"][1]) > 0.999
     for k in res["f32"][2]:
         assert cos(res["f16"][2][k], res["f32"][2][k]) > 0.999, k
 
