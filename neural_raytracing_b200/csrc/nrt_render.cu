@@ -30,20 +30,34 @@ static int nerf_pass(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, 
 // ---- stratified sample distances -------------------------------------------------------------
 // ts[r][s] = near + (s + u)/S * (far-near), u = hash(seed, r, s) in [0,1)  (extension; the
 // reference uses the same ts for every ray, nerf.py:178).
+// (32-bit arithmetic: the 64-bit splitmix of round 1 cost ~25 integer instructions per sample in kernels that should
+//  be HBM-bound; oracle/port.py restates the same recipe)
 __device__ __forceinline__ float hash_u01(uint64_t seed, uint64_t a, uint64_t b) {
-  uint64_t x = seed ^ (a * 0x9E3779B97F4A7C15ull) ^ (b * 0xC2B2AE3D27D4EB4Full);
-  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
-  return (float)(x >> 40) * (1.0f / 16777216.0f);
+  uint32_t h = (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0x9E3779B1u);
+  h = (h ^ (uint32_t)a) * 0x85EBCA77u;
+  h = (h ^ (uint32_t)b) * 0xC2B2AE3Du;
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
 }
 
+// four consecutive samples of one ray per thread (S % 4 == 0: one 16-byte store per thread, coalesced), else one
+template <int V>
 __global__ void k_stratified_ts(int64_t R, int64_t r_off, int S, float t_near, float t_far, uint64_t seed,
                                 float* __restrict__ ts) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= R * S) return;
-  const int64_t r = i / S;
-  const int s = (int)(i - r * S);
-  const float u = seed ? hash_u01(seed, (uint64_t)(r + r_off), (uint64_t)s) : 0.5f;
-  ts[i] = t_near + ((float)s + u) / (float)S * (t_far - t_near);
+  const int SV = S / V;
+  if (i >= R * SV) return;
+  const int64_t r = i / SV;
+  const int s0 = (int)(i - r * SV) * V;
+  const float span = t_far - t_near;
+  float t[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) {
+    const float u = seed ? hash_u01(seed, (uint64_t)(r + r_off), (uint64_t)(s0 + k)) : 0.5f;
+    t[k] = t_near + ((float)(s0 + k) + u) / (float)S * span;
+  }
+  if (V == 4) *reinterpret_cast<float4*>(ts + r * S + s0) = make_float4(t[0], t[1], t[2], t[3]);
+  else ts[r * S + s0] = t[0];
 }
 
 // ---- importance resampling (standard NeRF sample_pdf, inverse CDF over the coarse bins) ----------
@@ -145,30 +159,36 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
   const int warps = blockDim.x >> 5;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = Sc + Sf;
-  float* m_t = sm + (size_t)wid * 5 * S;
-  float* m_sig = m_t + S;
-  float* m_rgb = m_sig + S;
+  // per warp: the two sorted distance lists (searched below: in shared memory, not through dependent global loads --
+  // ncu of the round-1 kernel: long_scoreboard 12.2 warps per issue), then alpha and rgb in merged order
+  float* s_tc = sm + (size_t)wid * 5 * S;
+  float* s_tf = s_tc + Sc;
+  float* m_a = s_tc + S;
+  float* m_rgb = m_a + S;
   const int64_t r = (int64_t)blockIdx.x * warps + wid;
   if (r >= R) return;
   const float* tc = ts_c_per_ray ? ts_c_per_ray + r * Sc : ts_c_shared;
   const float* tf = Sf > 0 ? ts_f + r * Sf : nullptr;
+  for (int i = lane; i < Sc; i += 32) s_tc[i] = tc[i];
+  for (int j = lane; j < Sf; j += 32) s_tf[j] = tf[j];
+  __syncwarp();
   // rank of each element in the merged order: coarse element i goes to i + #(fine < tc[i]),
-  // fine element j to j + #(coarse <= tf[j])  (stable: coarse first on ties)
+  // fine element j to j + #(coarse <= tf[j])  (stable: coarse first on ties); alpha is computed once, here
   for (int i = lane; i < Sc; i += 32) {
-    const float t = tc[i];
+    const float t = s_tc[i];
     int lo = 0, hi = Sf;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < t) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tf[mid] < t) lo = mid + 1; else hi = mid; }
     const int p = i + lo;
-    m_t[p] = t; m_sig[p] = sig_c[r * Sc + i];
+    m_a[p] = 1.0f - exp_w<EXACT>(-fmaxf(sig_c[r * Sc + i], 0.0f) * t);
     m_rgb[p * 3] = rgb_c[(r * Sc + i) * 3]; m_rgb[p * 3 + 1] = rgb_c[(r * Sc + i) * 3 + 1];
     m_rgb[p * 3 + 2] = rgb_c[(r * Sc + i) * 3 + 2];
   }
   for (int j = lane; j < Sf; j += 32) {
-    const float t = tf[j];
+    const float t = s_tf[j];
     int lo = 0, hi = Sc;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[mid] <= t) lo = mid + 1; else hi = mid; }
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (s_tc[mid] <= t) lo = mid + 1; else hi = mid; }
     const int p = j + lo;
-    m_t[p] = t; m_sig[p] = sig_f[r * Sf + j];
+    m_a[p] = 1.0f - exp_w<EXACT>(-fmaxf(sig_f[r * Sf + j], 0.0f) * t);
     m_rgb[p * 3] = rgb_f[(r * Sf + j) * 3]; m_rgb[p * 3 + 1] = rgb_f[(r * Sf + j) * 3 + 1];
     m_rgb[p * 3 + 2] = rgb_f[(r * Sf + j) * 3 + 2];
   }
@@ -177,10 +197,7 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
   const int per = (S + 31) / 32;
   const int s0 = lane * per, s1 = min(S, s0 + per);
   float prod = 1.0f;
-  for (int s = s0; s < s1; ++s) {
-    const float a = 1.0f - exp_w<EXACT>(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
-    prod *= fmaxf(1.0f - a, 1e-10f);
-  }
+  for (int s = s0; s < s1; ++s) prod *= fmaxf(1.0f - m_a[s], 1e-10f);
   float incl = prod;
   for (int o = 1; o < 32; o <<= 1) {
     const float v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -191,7 +208,7 @@ __global__ void k_merge_composite(const float* __restrict__ sig_c, const float* 
   const float total = __shfl_sync(0xffffffffu, incl, 31);
   float cp = excl, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
   for (int s = s0; s < s1; ++s) {
-    const float a = 1.0f - exp_w<EXACT>(-fmaxf(m_sig[s], 0.0f) * m_t[s]);
+    const float a = m_a[s];
     float w;
     if (s == 0) w = a * (S == 1 ? 1.0f : total);   // roll quirk: sample 0 gets the total product
     else if (s == S - 1) w = a;                      // last transmittance forced to 1
@@ -275,8 +292,12 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
     if (jitter || ts == nullptr) {
       // per-ray (stratified) distances; without jitter this is the bin-centre grid
       NrtProfScope _ps(TAG_STRATIFIED_TS, st);
-      k_stratified_ts<<<nrt_cdiv(n * Sc, 256), 256, 0, st>>>(n, r0, Sc, sampling->t_near, sampling->t_far,
-                                                            sampling->jitter_seed, ts_c);
+      if (Sc % 4 == 0)
+        k_stratified_ts<4><<<nrt_cdiv(n * (Sc / 4), 256), 256, 0, st>>>(n, r0, Sc, sampling->t_near, sampling->t_far,
+                                                                       sampling->jitter_seed, ts_c);
+      else
+        k_stratified_ts<1><<<nrt_cdiv(n * Sc, 256), 256, 0, st>>>(n, r0, Sc, sampling->t_near, sampling->t_far,
+                                                                 sampling->jitter_seed, ts_c);
       NRT_CUDA(cudaGetLastError());
       ts_shared = nullptr; ts_pr = ts_c;
     }

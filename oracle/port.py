@@ -17,14 +17,17 @@ M64 = np.uint64(0xFFFFFFFFFFFFFFFF)
 
 
 def hash_u01(seed, a, b):
-    """splitmix-style hash -> [0,1) with 24 bits (same integer recipe as the kernels)."""
+    """32-bit integer hash -> [0,1) with 24 bits (same integer recipe as the kernels: nrt_render.cu, hash_u01)."""
+    M = np.uint64(0xFFFFFFFF)
+    seed = np.uint64(seed)
     with np.errstate(over="ignore"):
-        x = np.uint64(seed) ^ (a.astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)) ^ \
-            (b.astype(np.uint64) * np.uint64(0xC2B2AE3D27D4EB4F))
-        x ^= x >> np.uint64(33); x *= np.uint64(0xff51afd7ed558ccd)
-        x ^= x >> np.uint64(33); x *= np.uint64(0xc4ceb9fe1a85ec53)
-        x ^= x >> np.uint64(33)
-    return (x >> np.uint64(40)).astype(F32) * F32(1.0 / 16777216.0)
+        h = ((seed & M) ^ (((seed >> np.uint64(32)) * np.uint64(0x9E3779B1)) & M)) & M
+        h = ((h ^ (a.astype(np.uint64) & M)) * np.uint64(0x85EBCA77)) & M
+        h = ((h ^ (b.astype(np.uint64) & M)) * np.uint64(0xC2B2AE3D)) & M
+        h ^= h >> np.uint64(16); h = (h * np.uint64(0x7FEB352D)) & M
+        h ^= h >> np.uint64(15); h = (h * np.uint64(0x846CA68B)) & M
+        h ^= h >> np.uint64(16)
+    return (h >> np.uint64(8)).astype(F32) * F32(1.0 / 16777216.0)
 
 
 def stratified_ts(R, S, t_near, t_far, seed, r_off=0):
