@@ -621,8 +621,9 @@ def supplementary(dev, rank, world, steps=5, warmup=3):
                 "kernel_ms_per_step": kms, "library_launches_per_step": sum(v[1] for v in pr.values()) // n_it,
                 "library_kernel_ms_per_step": round(sum(kms.values()), 2),
                 "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1),
-                "precision": "f16 operands / fp32 accumulate: march, min scan, training forward, dgrad, wgrad on tcgen05; normals "
-                             "(value + Jacobian and its reverse pass) and the SDF net's first-order backward on the fp32 kernels",
+                "precision": "f16 operands / fp32 accumulate: march, min scan, training forward, dgrad, wgrad of every network on "
+                             "tcgen05, incl. the normals (value + Jacobian of SphereSDF.shift and its reverse pass); the sphere set "
+                             "and the shading stages in fp32",
                 "roofline": roof("k_mlp_tc<SphereSDF.shift; IoScanEval> (min-along-ray scan of SDF.throughput, tcgen05)", "tensor",
                                  rays_d * 129 * 331008 / 1e12, pr.get("sdf_min_scan_tc", (0.0, 0))[0] / n_it,
                                  "1,920,000 rays x 129 evaluations x 331,008 FLOP")}
