@@ -556,10 +556,10 @@ static int wide_train_backward(const MlpDev& d, int out_act, int64_t M, const fl
   static_assert(FRA <= 512 && FRE <= 512, "wgrad accumulator columns");
   auto kern = k_mlp_wgrad_tc<FMT>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jb.n - 1) / jb.n));
+  const int ctas = wgrad_assign_splits(jb, nt, nrt_sm_count());
   {
     NrtProfScope _ps(TAG_TC_WGRAD, st);
-    kern<<<dim3(splits, jb.n), 160, bytes, st>>>(jb, nt, stage_bytes, S0_OFF, S0_OFF + S0_BYTES, g_params, ws.scale);
+    kern<<<ctas, 160, bytes, st>>>(jb, nt, stage_bytes, S0_OFF, S0_OFF + S0_BYTES, g_params, ws.scale);
   }
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;

@@ -181,11 +181,49 @@ struct WgradJob {
   int unit0;                                // first output unit of this job (256-wide layers: one job per 128 units)
   int s0_kbase;                             // k offset of source 0 rows in W^T (jobs whose only source is the encoding of a skip layer)
   int lexp_from;                            // dZ of this job carries the per-layer rescales lexp[lexp_from .. n_lexp-1] (see WgradJobs)
+  int split0, nsplit;                       // CTAs split0 .. split0 + nsplit - 1 share this job's sample range (wgrad_assign_splits)
 };
 constexpr int kMaxJobs = 64;
 // lexp (optional): per-layer power-of-two exponents of the dgrad chain's rescale (256-wide nets): the dZ tiles of Linear li
 // hold S * 2^(lexp[li] + ... + lexp[n_lexp-1]) * dZ, which the flush divides out
 struct WgradJobs { WgradJob j[kMaxJobs]; int n; Layout y; int in_size; const int* lexp; int n_lexp; };
+
+// One CTA per SM (512 TMEM columns, ~200 KB of stages).  The jobs share EXACTLY one or two waves of CTAs (round 1: the same
+// number of splits for every job on a ceil(2 x SMs / jobs) x jobs grid = 301 CTAs for 7 jobs on 148 SMs: a third wave of 5
+// CTAs, 6.3 instead of 5.0 ms for the 65,536-ray NeRFLE step).  A CTA's time per tile is a fixed part (barrier round trips of
+// the 2-stage ring) plus the bytes it streams (dZ + sources): splits in proportion to  fixed + rows.  Measured on B200
+// (tools/train_scaling.py, wgrad ms at 4,096 / 16,384 / 65,536 rays; profiles/r02_wgrad_sweep.log):
+//   bytes only, one wave 0.49 / 1.78 / 6.96   fixed = 256 rows, one wave 0.39 / 1.34 / 5.16   equal splits, two waves 0.45 / 1.34 / 4.97
+static inline int wgrad_assign_splits(WgradJobs& jb, int64_t nt, int ctas) {
+  double w[kMaxJobs], tot = 0.0;
+  const bool large = nt >= 8192;                 // >= ~28 tiles per CTA and job in two waves
+  static const char* env_c = getenv("NRT_WGRAD_C");          // development knobs
+  static const char* env_w = getenv("NRT_WGRAD_WAVES");
+  const double kFixed = env_c ? atof(env_c) : (large ? 1.0e5 : 256.0);
+  const double kWaves = env_w ? atof(env_w) : (large ? 2.0 : 1.0);
+  ctas = (int)(ctas * kWaves);
+  for (int i = 0; i < jb.n; ++i) {
+    const WgradJob& j = jb.j[i];
+    w[i] = kFixed + (double)j.a_rows + j.s0_rows + (j.s1_tiles ? j.s1_rows : 0);
+    tot += w[i];
+  }
+  int used = 0;
+  for (int i = 0; i < jb.n; ++i) {
+    int k = (int)(ctas * w[i] / tot);            // floor; the remainder goes to the largest jobs below
+    k = (int)std::max<int64_t>(1, std::min<int64_t>(nt, k));
+    jb.j[i].nsplit = k; used += k;
+  }
+  for (bool more = true; more && used < ctas;) {  // hand out what the floors left, heaviest tiles-per-CTA first
+    more = false;
+    int best = -1; double load = 0.0;
+    for (int i = 0; i < jb.n; ++i)
+      if (jb.j[i].nsplit < nt && w[i] / jb.j[i].nsplit > load) { load = w[i] / jb.j[i].nsplit; best = i; }
+    if (best >= 0) { jb.j[best].nsplit++; used++; more = true; }
+  }
+  int at = 0;
+  for (int i = 0; i < jb.n; ++i) { jb.j[i].split0 = at; at += jb.j[i].nsplit; }
+  return at;
+}
 
 template <int FMT>
 __global__ void __launch_bounds__(160, 1)
@@ -199,7 +237,9 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
   __shared__ WgradJob job;
   const int tid = threadIdx.x, warp = tid >> 5;
   if (tid == 0) {
-    job = jobs_g.j[blockIdx.y];
+    int ji = 0;
+    while (ji + 1 < jobs_g.n && (int)blockIdx.x >= jobs_g.j[ji + 1].split0) ++ji;
+    job = jobs_g.j[ji];
     mbar_init(&bar_full[0], 1); mbar_init(&bar_full[1], 1);
     mbar_init(&bar_empty[0], 1); mbar_init(&bar_empty[1], 1);
     mbar_init(&bar_done, 1);
@@ -214,7 +254,8 @@ k_mlp_wgrad_tc(const __grid_constant__ WgradJobs jobs_g, int64_t ntiles, int sta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const int64_t t_begin = ntiles * blockIdx.x / gridDim.x, t_end = ntiles * (blockIdx.x + 1) / gridDim.x;
+  const int64_t sp = (int64_t)blockIdx.x - job.split0;
+  const int64_t t_begin = ntiles * sp / job.nsplit, t_end = ntiles * (sp + 1) / job.nsplit;
   const int n = (int)(t_end - t_begin);
   const uint32_t a_bytes = (uint32_t)job.a_rows * 256u, s0_bytes = (uint32_t)job.s0_rows * 256u;
   const uint32_t s1_bytes = job.s1_tiles ? (uint32_t)job.s1_rows * 256u : 0u;
@@ -420,10 +461,10 @@ static int launch_wgrad_std(const MlpDev& d, const TrainWs& ws, float* g_params,
   static_assert(FRA + FRE <= 512 && FRA <= 256 && FRE <= 256, "wgrad accumulator / MMA N limits");
   auto kern = k_mlp_wgrad_tc<FMT>;
   NRT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  const int splits = (int)std::max<int64_t>(1, std::min<int64_t>(nt, (2 * nrt_sm_count() + jobs.n - 1) / jobs.n));
+  const int ctas = wgrad_assign_splits(jobs, nt, nrt_sm_count());
   {
     NrtProfScope _ps(TAG_TC_WGRAD, st);
-    kern<<<dim3(splits, jobs.n), 160, bytes, st>>>(jobs, nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);   // job table by value (2 KB of kernel parameters): no copy, graph-capturable
+    kern<<<ctas, 160, bytes, st>>>(jobs, nt, stage_bytes, S0_OFF, S1_OFF, g_params, ws.scale);   // job table by value (kernel parameters): no copy, graph-capturable
   }
   NRT_CUDA(cudaGetLastError());
   return NRT_OK;
