@@ -993,6 +993,8 @@ __device__ __forceinline__ void stream_op(uint8_t* dst, const uint8_t* src, uint
 //     new one from a global queue (warp-aggregated atomic) and produces the next evaluation point; consume()
 //     takes the network output.  The tile slot keeps cycling while any of its 128 threads is live, so every MMA
 //     row is (up to the queue tail) spent on a live ray: this is the compaction of the sphere-trace march.
+template <class T, class = void> struct HasCtaInit : std::false_type {};
+template <class T> struct HasCtaInit<T, std::void_t<decltype(&T::cta_init)>> : std::true_type {};
 template <class T, class = void> struct IsIterative : std::false_type {};
 template <class T> struct IsIterative<T, std::void_t<typename T::State>> : std::true_type {};
 struct NoState {};
@@ -1061,6 +1063,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
   const bool is_mma_warp = SELF ? warp == 0 : mma_id == 0;   // the one that also owns TMEM allocation and the weight load
   __shared__ uint32_t s_issue_lock;                  // self-issue: one slot's MMA batch at a time
   const int64_t ntiles = (M + 127) / 128;
+  // IO policies that keep per-CTA tables in shared memory (the sphere set of the SDF policies) fill them here; the
+  // __syncthreads() below publishes them
+  if constexpr (HasCtaInit<IO>::value) io.cta_init();
   if (tid < NET::STAGES) {
     s_bias[tid] = (uint32_t)Y.bias_off[tid];
     s_opoff[tid] = (uint32_t)Y.op_off[tid] * 2;
