@@ -275,6 +275,15 @@ class SDF:
         wants_graph = torch.is_grad_enabled() and (not isinstance(s, SphereSDF) or
                                                    any(q.requires_grad for q in s.parameters()))
         if isinstance(s, SphereSDF) and p.is_cuda and not wants_graph and ops.HAS_SDF_VALUE_GRAD:
+            prec = s.precision()
+            if prec != "f32":
+                # 16-bit inference: the residual MLP's Jacobian on the tensor cores (four rows per point through the
+                # streamed-weight kernel the training path uses), the sphere set's gradient from its own kernel; the
+                # fp32 analytic-Jacobian kernel was 3.0 of 40 ms of the 512x512 colocate frame
+                x = p.detach().float().reshape(-1, 3).contiguous()
+                _v, g_s = ops.sphere_set_forward(s.centers, s.radii, s.tfs, x, want_grad=True)
+                _vm, jac, _ws = ops.mlp_value_jac_forward_tc(s.shift.packed(), x, prec=prec)
+                return (g_s + jac[:, 0, :]).reshape(p.shape)
             return ops.sdf_value_grad(s.packed(), p.detach())[1]
         if isinstance(s, SphereSDF) and s._fusable_grad(p):
             return s.value_and_normal(p)[1].reshape(p.shape)
