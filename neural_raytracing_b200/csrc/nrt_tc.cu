@@ -91,7 +91,7 @@ struct IoNerfFirst {
 };
 
 // NeRFLE.second: [latent | r_d | light code] in, sigmoid(rgb) out.  nerf.py:199-203
-template <int NLAT, int LD>
+template <int NLAT, int LD, bool PACKED = false>
 struct IoNerfSecond {
   const float* rays; const void* latent; const float* light_code; const int32_t* view_of_ray; int S;
   float* rgb; int fmt; int out_act; int lat32;
@@ -119,6 +119,25 @@ struct IoNerfSecond {
           }
         }
       }
+    }
+    const float* r = rays + ray * 6;
+    v[NLAT] = __ldg(r + 3); v[NLAT + 1] = __ldg(r + 4); v[NLAT + 2] = __ldg(r + 5);
+    const int view = view_of_ray ? __ldg(view_of_ray + ray) : 0;
+#pragma unroll
+    for (int j = 0; j < LD; ++j) v[NLAT + 3 + j] = __ldg(light_code + (int64_t)view * LD + j);
+  }
+  // The latent arrives as 16-bit values in the kernel's own operand format: its NLAT / 2 packed pairs ARE the x_hi operand
+  // of the phase GEMM and of the init / skip layers, and x_lo is zero.  load_packed hands the words through (the generic
+  // path unpacks them to fp32, re-packs and computes x - x_hi = 0: ~10 instructions per pair, a tenth of the kernel's
+  // instructions).  x[] receives only the view direction and the light code.
+  static constexpr int kPackedPairs = PACKED ? NLAT / 2 : 0;     // PACKED: launched only with a 16-bit latent (lat32 == 0)
+  __device__ __forceinline__ void load_packed(int64_t m, uint32_t* w, float* v) const {
+    const int64_t ray = m / S;
+    const uint4* src = reinterpret_cast<const uint4*>(latent) + (m >> 7) * (int64_t)(NLAT / 8 * 128) + (m & 127);
+#pragma unroll
+    for (int j = 0; j < NLAT / 8; ++j) {
+      const uint4 q = __ldg(src + j * 128);
+      w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
     }
     const float* r = rays + ray * 6;
     v[NLAT] = __ldg(r + 3); v[NLAT + 1] = __ldg(r + 4); v[NLAT + 2] = __ldg(r + 5);
@@ -591,6 +610,11 @@ int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
   rc = fmt == 0 ? launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST)
                 : launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);
   if (rc != NRT_OK) return rc;
+  if (pt && !lat32) {
+    IoNerfSecond<64, 3, true> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
+    return fmt == 0 ? launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
+                    : launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
+  }
   if (pt) {
     IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
     return fmt == 0 ? launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)

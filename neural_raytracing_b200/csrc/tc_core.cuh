@@ -993,6 +993,8 @@ __device__ __forceinline__ void stream_op(uint8_t* dst, const uint8_t* src, uint
 //     new one from a global queue (warp-aggregated atomic) and produces the next evaluation point; consume()
 //     takes the network output.  The tile slot keeps cycling while any of its 128 threads is live, so every MMA
 //     row is (up to the queue tail) spent on a live ray: this is the compaction of the sphere-trace march.
+template <class T, class = void> struct PackedPairsOf { static constexpr int value = 0; };
+template <class T> struct PackedPairsOf<T, std::void_t<decltype(T::kPackedPairs)>> { static constexpr int value = T::kPackedPairs; };
 template <class T, class = void> struct HasCtaInit : std::false_type {};
 template <class T> struct HasCtaInit<T, std::void_t<decltype(&T::cta_init)>> : std::true_type {};
 template <class T, class = void> struct IsIterative : std::false_type {};
@@ -1329,6 +1331,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
         int64_t m = 0;
         bool valid;
         float x[IN + LAT];
+        // leading input pairs that the IO policy can hand over already packed in the operand format (IoNerfSecond)
+        constexpr int kPP = (!ITER && !NET::SPLIT && !SV::kOn && !SV::kF32 && LAT == 0 && NET::ACT == NRT_ACT_LEAKY_RELU) ? PackedPairsOf<IO>::value : 0;
+        uint32_t pw[kPP > 0 ? kPP : 1];
         if constexpr (ITER) {
           valid = primary ? io.next(state, x) : false;
           const unsigned bal = __ballot_sync(0xffffffffu, valid);
@@ -1346,7 +1351,11 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
           if (tile >= ntiles) { self_drain(); break; }
           m = tile * 128 + lane_row;
           valid = m < M;
-          if (valid && primary) io.load(m, x);
+          if constexpr (kPP > 0) {
+            if (valid && primary) io.load_packed(m, pw, x);
+          } else {
+            if (valid && primary) io.load(m, x);
+          }
         }
         if (!primary) {
           // the helper half has no work before the first hidden layer: keep in phase with the barriers only
@@ -1395,6 +1404,11 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             for (int j = 0; j < NET::XR / 2; ++j) lx[j] = 0;
 #pragma unroll
             for (int j = 0; j < (IN + 1) / 2; ++j) {
+              if (kPP > 0 && j < kPP) {
+                ax[j] = valid ? pw[j] : 0u;      // x_hi as stored; x_lo = 0 (lx stays zero); NET::INPLACE: act(x) is made in place later
+                if constexpr (!NET::INPLACE) ex[j] = leaky_packed<FMT>(ax[j]);
+                continue;
+              }
               const float xa = x[2 * j], xb = (2 * j + 1 < IN) ? x[2 * j + 1 < IN ? 2 * j + 1 : 0] : 0.0f;   // odd in: zero pad
               ax[j] = E::pack(xa, xb);
               const float ha = E::back((uint16_t)(ax[j] & 0xffffu)), hb = E::back((uint16_t)(ax[j] >> 16));
