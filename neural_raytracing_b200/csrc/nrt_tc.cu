@@ -53,12 +53,17 @@ struct IoPlain {   // materialised x [M,IN] (+ latent [M,LAT]) -> out [M,OUT] wi
 // consumed by the thread of the same tile / lane (m / 128, m % 128), so the scratch is TILE-INTERLEAVED:
 // 16-byte group g of sample m lives at ((m / 128) * G + g) * 128 + m % 128 (in 16-byte units, G groups per sample):
 // one warp-wide 16-byte store or load covers 512 contiguous bytes (4 lines instead of 32).
+// ray of sample m (samples-per-ray S): a shift when S is a power of two (64, 128: every script), else the 64-bit division
+// (~50 integer instructions per sample in kernels whose epilogue warps are bound by their instruction count)
+static inline int pow2_shift(int S) { int k = 0; while ((1 << k) < S) ++k; return (1 << k) == S ? k : -1; }
+__device__ __forceinline__ int64_t ray_of(int64_t m, int S, int shift) { return shift >= 0 ? (m >> shift) : m / S; }
+
 template <int NLAT>
 struct IoNerfFirst {
   const float* rays; const float* ts; const float* ts_per_ray; int S;
-  float* sigma; void* latent; int fmt; int lat32;
+  float* sigma; void* latent; int fmt; int lat32; int s_shift;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
-    const int64_t ray = m / S;
+    const int64_t ray = ray_of(m, S, s_shift);
     const int s = (int)(m - ray * S);
     const float t = ts_per_ray ? __ldg(ts_per_ray + m) : __ldg(ts + s);
     const float* r = rays + ray * 6;
@@ -94,9 +99,9 @@ struct IoNerfFirst {
 template <int NLAT, int LD, bool PACKED = false>
 struct IoNerfSecond {
   const float* rays; const void* latent; const float* light_code; const int32_t* view_of_ray; int S;
-  float* rgb; int fmt; int out_act; int lat32;
+  float* rgb; int fmt; int out_act; int lat32; int s_shift;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
-    const int64_t ray = m / S;
+    const int64_t ray = ray_of(m, S, s_shift);
     if (lat32) {
       const float4* src = reinterpret_cast<const float4*>(latent) + (m >> 7) * (int64_t)(NLAT / 4 * 128) + (m & 127);
 #pragma unroll
@@ -132,7 +137,7 @@ struct IoNerfSecond {
   // instructions).  x[] receives only the view direction and the light code.
   static constexpr int kPackedPairs = PACKED ? NLAT / 2 : 0;     // PACKED: launched only with a 16-bit latent (lat32 == 0)
   __device__ __forceinline__ void load_packed(int64_t m, uint32_t* w, float* v) const {
-    const int64_t ray = m / S;
+    const int64_t ray = ray_of(m, S, s_shift);
     const uint4* src = reinterpret_cast<const uint4*>(latent) + (m >> 7) * (int64_t)(NLAT / 8 * 128) + (m & 127);
 #pragma unroll
     for (int j = 0; j < NLAT / 8; ++j) {
@@ -606,21 +611,22 @@ int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
   NRT_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)((M + 127) / 128 * 128) * 64 * (lat32 ? 4 : 2), "workspace too small");
   void* lat = workspace;
   const int fmt = fmt_of(prec);
-  IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt, lat32};
+  const int s_shift = pow2_shift(S);
+  IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt, lat32, s_shift};
   rc = fmt == 0 ? launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST)
                 : launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);
   if (rc != NRT_OK) return rc;
   if (pt && !lat32) {
-    IoNerfSecond<64, 3, true> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
+    IoNerfSecond<64, 3, true> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32, s_shift};
     return fmt == 0 ? launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
                     : launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
   }
   if (pt) {
-    IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
+    IoNerfSecond<64, 3> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32, s_shift};
     return fmt == 0 ? launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
                     : launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
   }
-  IoNerfSecond<64, 48> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32};
+  IoNerfSecond<64, 48> io2{rays, lat, light_code, view_of_ray, S, out_srgb, fmt, second_out_act, lat32, s_shift};
   return fmt == 0 ? launch<NetNerfSecondLE, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
                   : launch<NetNerfSecondLE, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
 }
