@@ -267,8 +267,8 @@ struct IoMarch {
   // softplus form of the hidden layers (tc_core.cuh, SoftplusOf).  The primary march keeps the two-MUFU form: depths and
   // hit masks stay bit-identical to the kernels the goldens were accepted with (a grazing pixel of the 16-basis DTU
   // golden flips with ANY change of the 16-bit rounding sequence: 36.9 instead of > 50 dB on 4,096 pixels).  The shadow
-  // march takes the one-MUFU fp32 polynomial (|error| <= 1e-5).
-  static constexpr int kSoftplusForm = MODE == TC_MARCH_PRIMARY ? 0 : 1;
+  // march (a boolean comes out) takes the fp32 exponent + packed-half polynomial like the min scan.
+  static constexpr int kSoftplusForm = MODE == TC_MARCH_PRIMARY ? 0 : 3;
   __device__ __forceinline__ void cta_init() const { sph_fill(sd); }
   SdfDev sd;
   const float* rays; const float* max_t_per_ray; const uint8_t* active; int64_t R;

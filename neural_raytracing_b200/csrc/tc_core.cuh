@@ -328,8 +328,8 @@ __device__ __forceinline__ void tmem_load(uint32_t t, uint32_t* r) {
 // (ex2 + lg2); 1 = ex2 + degree-4 polynomial of log1p on the FMA pipe (fp32); 2 = everything on packed halves.
 // The hidden-layer conversion of the inference kernel k_mlp_tc (convert_row_pipe) takes its form from the IO policy
 // (SoftplusOf<IO>): 0 = two MUFU, chunked conversion (the primary sphere-trace march), 1 = fp32 polynomial (default:
-// shadow march, point evaluation), 3 = exponent in fp32, polynomial + max on packed halves (the min scan of
-// SDF.throughput, which only picks a position).
+// point evaluation), 3 = exponent in fp32, polynomial + max on packed halves (the min scan of SDF.throughput, which only
+// picks a position, and the shadow march, which returns a boolean).
 // Measured on B200 with one form for all three kernels (262,144 rays: march / shadow march / min scan, ms):
 // two MUFU 10.6 / 15.1 / 34.2, form 1: 9.5 / 14.1 / 32.1, form 3: 8.5 / 12.2 / 27.8; median depth error of the march
 // vs the exact kernels 0.9e-5 / 1.2e-5 / 1.6e-5, but with form 3 only 97.4 % (< 99 %) of the 64x64 colocate depths stay
