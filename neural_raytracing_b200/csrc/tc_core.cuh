@@ -602,11 +602,14 @@ __device__ __forceinline__ void convert_row_pipe(uint32_t dD, uint32_t aU, PRE p
           u[(k + 1) & 1][2 * i + 1] = ex2_approx(-1.4426950408889634f * fabsf(__uint_as_float(xb[(k + 1) % 3][2 * i + 1])));
         }
         const __half2 uu = __floats2half2_rn(u[k & 1][2 * i], u[k & 1][2 * i + 1]);
-        const __half2 xx = __floats2half2_rn(__uint_as_float(xb[k % 3][2 * i]), __uint_as_float(xb[k % 3][2 * i + 1]));
+        // max(x, 0) of the pair in the conversion itself (cvt.rn.relu: one instruction instead of F2FP + HMNMX2; the
+        // epilogue warp is bound by its instruction count)
+        uint32_t rx;
+        asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(rx) : "f"(__uint_as_float(xb[k % 3][2 * i + 1])), "f"(__uint_as_float(xb[k % 3][2 * i])));
         __half2 q = __hfma2(__floats2half2_rn(-5.875710231e-02f, -5.875710231e-02f), uu, __floats2half2_rn(2.256856408e-01f, 2.256856408e-01f));
         q = __hfma2(q, uu, __floats2half2_rn(-4.713012532e-01f, -4.713012532e-01f));
         q = __hfma2(q, uu, __floats2half2_rn(9.974489612e-01f, 9.974489612e-01f));
-        const __half2 r = __hfma2(q, uu, __hmax2(xx, __floats2half2_rn(0.0f, 0.0f)));
+        const __half2 r = __hfma2(q, uu, *reinterpret_cast<const __half2*>(&rx));
         pk[i] = *reinterpret_cast<const uint32_t*>(&r);
       }
     } else {
