@@ -103,6 +103,19 @@ def camera_rays(size, view):
     return np.concatenate([o, d], -1).reshape(-1, 6).astype(np.float32)
 
 
+def camera_matrix(view):
+    """cam_to_world [1,4,4] (NeRF convention, -z forward) of the camera camera_rays() looks through."""
+    az = 0.7 * view + 0.3
+    el = 0.4
+    c = np.array([np.cos(el) * np.sin(az), np.sin(el), np.cos(el) * np.cos(az)], np.float64)
+    fwd = -c / np.linalg.norm(c)
+    right = np.cross(fwd, [0, 1, 0]); right /= np.linalg.norm(right)
+    up = np.cross(right, fwd)
+    m = np.eye(4)
+    m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, c
+    return m[None].astype(np.float32)
+
+
 class ClockSampler:
     """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -1090,6 +1103,23 @@ def main():
     e2e_ms = float(t.item())
     e2e_value = world * R / (e2e_ms / 1e3)
 
+    # ---- the same frame from its camera: rays generated on the device inside the call, nothing but the
+    #      camera descriptor goes in, the image comes back to pinned host memory ----
+    cam = ops.CameraDesc(ops.CAM_NERF, torch.from_numpy(camera_matrix(rank)).to(dev), None,
+                         focal=0.5 * IMG / np.tan(np.radians(30)), size=IMG, nx=IMG, ny=IMG)
+    ops.nerfle_render_camera_host(m1, m2, cam, None, code, out_host, **kw)
+    cam_finite = bool(torch.isfinite(out_host).all())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ops.nerfle_render_camera_host(m1, m2, cam, None, code, out_host, **kw)
+    torch.cuda.synchronize()
+    cam_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t = torch.tensor([cam_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cam_ms = float(t.item())
+
     also = None
     NO_CPU[0] = bool(args.no_cpu_baseline)
     if not args.no_also:
@@ -1153,7 +1183,11 @@ def main():
             "model_tflops": value * (N_COARSE + N_FINE) * (FLOP_FIRST + FLOP_SECOND) / 1e12,
             "config": workload_config(args.precision),
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": R * 24, "d2h_bytes_per_step": R * 12,
-                    "ms_per_step": e2e_ms},
+                    "ms_per_step": e2e_ms,
+                    "from_camera": {"value": world * R / (cam_ms / 1e3), "unit": "rays/s", "ms_per_step": cam_ms,
+                                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": R * 12, "finite": cam_finite,
+                                    "note": "nrt_nerfle_render_camera_host: pixel -> ray inside the library "
+                                            "(k_camera_rays per 262,144-ray chunk), no ray array crosses PCIe"}},
             "gpu_launches": launches,
             "kernel_ms": {k: round(v[0], 3) for k, v in prof.items() if v[1]},
             "clocks": clocks,

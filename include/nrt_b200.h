@@ -278,6 +278,56 @@ int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int 
                            const nrt_nerf_sampling_t* sampling, const float* light_code,
                            int light_dim, float* out_rgb_host, void* stream);
 
+/* ---- a21 / f4: ray generators on the device, and the camera-driven whole-frame render ------------------------------
+ * Pixel -> ray [origin(3) | unit direction(3)] for the three cameras the scripts use:
+ *   NRT_CAM_NERF  NeRFCamera.sample_positions            pathtracer/cameras/cameras.py:23-54
+ *   NRT_CAM_DTU   DTUCamera.sample_positions (+ lift)    pathtracer/cameras/cameras.py:132-147, 156-192
+ *   NRT_CAM_FOV   FoVPerspectiveCameras.sample_positions renderer/cameras.py:539-575
+ * The rays of one call form the reference's [n_views, nx, ny, bundle, 6] block: ray
+ * r = ((view * nx + i) * ny + j) * bundle + b looks through pixel position (u, v) = (y0 + j, x0 + i), which is how
+ * pathtrace lays out a tile (main.py:67-74: positions = stack([grid_y, grid_x])).  `positions`, when not NULL, replaces
+ * that grid with explicit pixel positions [nx * ny * pos_per_pixel, 2] (the caller's jittered samples; pos_per_pixel is 1
+ * or `bundle`); otherwise `jitter` > 0 perturbs the grid by (U - 0.5) * jitter with the library's counter hash (the
+ * reference draws the same perturbation from torch's generator, cameras.py:35-37 / renderer/cameras.py:553-556).
+ * All matrices are fp32 DEVICE pointers, so no host synchronisation is needed to render from a camera that lives on the GPU. */
+#define NRT_CAM_NERF 0
+#define NRT_CAM_DTU 1
+#define NRT_CAM_FOV 2
+typedef struct nrt_camera {
+  int32_t kind;             /* NRT_CAM_*                                                                              */
+  int32_t n_views;
+  const float* a;           /* NERF: cam_to_world; DTU: pose; FOV: inverse of the full projection matrix (row vectors)   */
+  const float* b;           /* DTU: intrinsics; FOV: camera centres [n_views,3] (row stride 3); NERF: unused (NULL)      */
+  int32_t a_view_stride, a_row_stride;   /* in floats: 16 / 4 for [n,4,4], 12 / 4 for [n,3,4]                          */
+  int32_t b_view_stride, b_row_stride;
+  float focal;              /* NERF                                                                                  */
+  float size;               /* the `size` pixel positions are normalised by (all three)                              */
+  int32_t x0, y0, nx, ny;   /* pixel window                                                                          */
+  int32_t bundle;           /* rays per pixel (NERF: 1)                                                              */
+  int32_t pos_per_pixel;    /* rows of `positions` per pixel: 1 or bundle                                            */
+  const float* positions;   /* optional explicit pixel positions, see above                                          */
+  float jitter;             /* window-grid jitter amplitude in pixels (0 = pixel positions as they are)              */
+  uint64_t jitter_seed;
+} nrt_camera_t;
+/* Rays r0 .. r0 + n - 1 of the block -> out_rays [n,6]; out_view [n] int32 = view of each ray, or NULL. */
+int nrt_camera_rays(const nrt_camera_t* cam, int64_t r0, int64_t n, float* out_rays, int32_t* out_view,
+                    void* stream);
+/* f4: nrt_nerfle_render with the rays generated on the device inside the call (per 262,144-ray chunk, into the
+ * workspace): replaces pathtrace's Python tile loop + sample_positions + integrator call for a volumetric shape
+ * (main.py:57-88) by one library call per frame.  R = n_views * nx * ny * bundle; light_code row = the ray's view.
+ * out_rgb [R,3] in the block order above, i.e. already the reference's [n_views, nx, ny(, bundle), 3] image. */
+size_t nrt_nerfle_render_camera_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                          const nrt_camera_t* cam, const nrt_nerf_sampling_t* sampling);
+int nrt_nerfle_render_camera(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                             const nrt_camera_t* cam, const float* ts, const nrt_nerf_sampling_t* sampling,
+                             const float* light_code, int light_dim, float* out_rgb, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* Host-image variant: nothing but the camera goes in, the image comes back to (pinned) host memory; synchronises. */
+int nrt_nerfle_render_camera_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                  const nrt_camera_t* cam, const float* ts_host, int S,
+                                  const nrt_nerf_sampling_t* sampling, const float* light_code, int light_dim,
+                                  float* out_rgb_host, void* stream);
+
 /* ---- a8/a9/a12/a14/a15/a16: shading glue as fused elementwise kernels ---------------- */
 /* coordinate_system + to_local(-r_d) (interaction.py:9-27,38-41; sdfs.py:158-159).
  * normals [R,3] -> frame [R,3,3] (columns s,t,n as torch.stack(dim=-1)), wi [R,3]. */

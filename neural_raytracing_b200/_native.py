@@ -34,6 +34,16 @@ class NrtNerfSampling(ctypes.Structure):
                 ("jitter_seed", ctypes.c_uint64)]
 
 
+class NrtCamera(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("n_views", ctypes.c_int32), ("a", c_vp), ("b", c_vp),
+                ("a_view_stride", ctypes.c_int32), ("a_row_stride", ctypes.c_int32),
+                ("b_view_stride", ctypes.c_int32), ("b_row_stride", ctypes.c_int32),
+                ("focal", c_f32), ("size", c_f32), ("x0", ctypes.c_int32), ("y0", ctypes.c_int32),
+                ("nx", ctypes.c_int32), ("ny", ctypes.c_int32), ("bundle", ctypes.c_int32),
+                ("pos_per_pixel", ctypes.c_int32), ("positions", c_vp), ("jitter", c_f32),
+                ("jitter_seed", ctypes.c_uint64)]
+
+
 MAX_BSDFS = 16
 
 
@@ -53,6 +63,7 @@ class NrtError(RuntimeError):
 
 _PM, _PS, _PN = ctypes.POINTER(NrtMlp), ctypes.POINTER(NrtSphereSdf), ctypes.POINTER(NrtNerfSampling)
 _PL, _PB = ctypes.POINTER(NrtLight), ctypes.POINTER(NrtBlend)
+_PC = ctypes.POINTER(NrtCamera)
 
 # every symbol declared in include/nrt_b200.h: name -> (restype, argtypes)
 SIGNATURES = {
@@ -94,6 +105,10 @@ SIGNATURES = {
     "nrt_nerfle_render": (c_int, [_PM, _PM, c_int, c_vp, c_i64, c_vp, _PN, c_vp, c_int, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "nrt_nerfle_render_workspace": (c_sz, [_PM, _PM, c_int, c_i64, _PN]),
     "nrt_nerfle_render_host": (c_int, [_PM, _PM, c_int, c_vp, c_i64, c_vp, c_int, _PN, c_vp, c_int, c_vp, c_vp]),
+    "nrt_camera_rays": (c_int, [_PC, c_i64, c_i64, c_vp, c_vp, c_vp]),
+    "nrt_nerfle_render_camera_workspace": (c_sz, [_PM, _PM, c_int, _PC, _PN]),
+    "nrt_nerfle_render_camera": (c_int, [_PM, _PM, c_int, _PC, c_vp, _PN, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
+    "nrt_nerfle_render_camera_host": (c_int, [_PM, _PM, c_int, _PC, c_vp, c_int, _PN, c_vp, c_int, c_vp, c_vp]),
     "nrt_shading_frame": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "nrt_to_local": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "nrt_param_rusin2": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -28,6 +28,7 @@ EXTRA = {
     "nrt_sdf_grad.cu": ["-fmad=false"],
     "nrt_shade.cu": ["-fmad=false"],
     "nrt_shade_direct.cu": ["-fmad=false"],
+    "nrt_camera.cu": ["-fmad=false"],
 }
 
 

@@ -262,6 +262,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // rays are rendered in chunks of this many so that the scratch (per-sample sigma / rgb / latent: ~150 B x 192 per ray)
 // stays a few GB regardless of the image size (65,536-ray chunks measured 2 % slower: 3.3x the launches)
 static const int64_t kRayChunk = 262144;
+static size_t cam_scratch_bytes(int64_t C) { return align256((size_t)C * 24) + align256((size_t)C * 4); }
 
 extern "C" size_t nrt_nerfle_render_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
                                               int64_t R, const nrt_nerf_sampling_t* sampling) {
@@ -278,24 +279,35 @@ extern "C" size_t nrt_nerfle_render_workspace(const nrt_mlp_t* first, const nrt_
   return total;
 }
 
-extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays,
-                                 int64_t R, const float* ts, const nrt_nerf_sampling_t* sampling,
-                                 const float* light_code, int light_dim, const int32_t* view_of_ray,
-                                 float* out_rgb, void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+int nrt_check_camera(const nrt_camera_t* cam, int64_t* total);
+int nrt_camera_rays_dev(const nrt_camera_t* cam, int64_t r0, int64_t n, float* out_rays, int32_t* out_view,
+                        cudaStream_t st);
+
+// the render of R rays given either as an array (rays) or as a camera (cam: every chunk's rays are generated into the
+// tail of the workspace right before its first pass)
+static int render_impl(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays,
+                       const nrt_camera_t* cam, int64_t R, const float* ts, const nrt_nerf_sampling_t* sampling,
+                       const float* light_code, int light_dim, const int32_t* view_of_ray,
+                       float* out_rgb, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   NRT_REQUIRE(R >= 0, "nrt_nerfle_render: negative R");
   if (R == 0) return NRT_OK;
-  NRT_REQUIRE(rays != nullptr && out_rgb != nullptr, "nrt_nerfle_render: null rays/out");
+  NRT_REQUIRE((rays != nullptr || cam != nullptr) && out_rgb != nullptr, "nrt_nerfle_render: null rays/out");
   NRT_REQUIRE(sampling != nullptr, "nrt_nerfle_render: sampling descriptor is NULL");
   const int Sc = sampling->n_coarse, Sf = sampling->n_fine;
   const bool jitter = sampling->jitter_seed != 0;
   NRT_REQUIRE(Sc >= 1 && Sf >= 0, "nrt_nerfle_render: bad sample counts %d/%d", Sc, Sf);
   NRT_REQUIRE(ts != nullptr || sampling->t_far > sampling->t_near, "nrt_nerfle_render: need ts or t_near<t_far");
   NRT_REQUIRE(Sf == 0 || Sc >= 3, "hierarchical sampling needs n_coarse >= 3");
-  const size_t need = nrt_nerfle_render_workspace(first, second, prec, R, sampling);
+  const int64_t C = std::min<int64_t>(R, kRayChunk);
+  const size_t need = nrt_nerfle_render_workspace(first, second, prec, R, sampling) + (cam ? cam_scratch_bytes(C) : 0);
   NRT_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "nrt_nerfle_render: workspace of %zu bytes required, got %zu", need, workspace_bytes);
-  const int64_t C = std::min<int64_t>(R, kRayChunk);
+  float* cam_rays = nullptr; int32_t* cam_view = nullptr;
+  if (cam) {
+    char* tail = (char*)workspace + (need - cam_scratch_bytes(C));
+    cam_rays = (float*)tail;
+    if (cam->n_views > 1) cam_view = (int32_t*)(tail + align256((size_t)C * 24));
+  }
   char* wp = (char*)workspace;
   auto take = [&](size_t bytes) { char* p = wp; wp += align256(bytes); return (void*)p; };
   const bool store_c = Sf > 0 || prec != NRT_PREC_F32;
@@ -317,8 +329,12 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
 
   for (int64_t r0 = 0; r0 < R; r0 += C) {
     const int64_t n = std::min<int64_t>(C, R - r0);
-    const float* c_rays = rays + r0 * 6;
-    const int32_t* c_view = view_of_ray ? view_of_ray + r0 : nullptr;
+    const float* c_rays = cam ? cam_rays : rays + r0 * 6;
+    const int32_t* c_view = cam ? cam_view : view_of_ray ? view_of_ray + r0 : nullptr;
+    if (cam) {
+      const int rcc = nrt_camera_rays_dev(cam, r0, n, cam_rays, cam_view, st);
+      if (rcc != NRT_OK) return rcc;
+    }
     float* c_out = out_rgb + r0 * 3;
     const float* ts_shared = ts;
     const float* ts_pr = nullptr;
@@ -371,6 +387,34 @@ extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second
   return NRT_OK;
 }
 
+extern "C" int nrt_nerfle_render(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays,
+                                 int64_t R, const float* ts, const nrt_nerf_sampling_t* sampling,
+                                 const float* light_code, int light_dim, const int32_t* view_of_ray,
+                                 float* out_rgb, void* workspace, size_t workspace_bytes, void* stream) {
+  NRT_REQUIRE(R <= 0 || rays != nullptr, "nrt_nerfle_render: null rays");
+  return render_impl(first, second, prec, rays, nullptr, R, ts, sampling, light_code, light_dim, view_of_ray, out_rgb,
+                     workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- f4: the frame from a camera (main.py:57-88 for a volumetric shape as one call) ------------------------------
+extern "C" size_t nrt_nerfle_render_camera_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                                     const nrt_camera_t* cam, const nrt_nerf_sampling_t* sampling) {
+  int64_t R = 0;
+  if (nrt_check_camera(cam, &R) != NRT_OK) return 0;
+  return nrt_nerfle_render_workspace(first, second, prec, R, sampling) + cam_scratch_bytes(std::min<int64_t>(R, kRayChunk));
+}
+
+extern "C" int nrt_nerfle_render_camera(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                        const nrt_camera_t* cam, const float* ts, const nrt_nerf_sampling_t* sampling,
+                                        const float* light_code, int light_dim, float* out_rgb, void* workspace,
+                                        size_t workspace_bytes, void* stream) {
+  int64_t R = 0;
+  const int rc = nrt_check_camera(cam, &R);
+  if (rc != NRT_OK) return rc;
+  return render_impl(first, second, prec, nullptr, cam, R, ts, sampling, light_code, light_dim, nullptr, out_rgb,
+                     workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 // The host-buffer entry point keeps grow-only device scratch PER DEVICE (a stream-ordered pool would hand the memory
 // back at every synchronisation and re-allocate >1 GB per call); calls on the same device are serialised by the
 // record's host_mu, calls on different devices are independent.
@@ -398,6 +442,35 @@ extern "C" int nrt_nerfle_render_host(const nrt_mlp_t* first, const nrt_mlp_t* s
   NRT_CUDA(cudaMemcpyAsync(d_rays, rays_host, (size_t)R * 24, cudaMemcpyHostToDevice, st));
   rc = nrt_nerfle_render(first, second, prec, (const float*)d_rays, R, (const float*)d_ts, sampling, light_code, light_dim,
                          nullptr, (float*)d_out, ws, wsb, st);
+  if (rc != NRT_OK) return rc;
+  NRT_CUDA(cudaMemcpyAsync(out_rgb_host, d_out, (size_t)R * 12, cudaMemcpyDeviceToHost, st));
+  NRT_CUDA(cudaStreamSynchronize(st));
+  return NRT_OK;
+}
+
+extern "C" int nrt_nerfle_render_camera_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
+                                             const nrt_camera_t* cam, const float* ts_host, int S,
+                                             const nrt_nerf_sampling_t* sampling, const float* light_code,
+                                             int light_dim, float* out_rgb_host, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  NRT_REQUIRE(out_rgb_host && sampling, "nrt_nerfle_render_camera_host: bad arguments");
+  int64_t R = 0;
+  int rc = nrt_check_camera(cam, &R);
+  if (rc != NRT_OK) return rc;
+  if (R == 0) return NRT_OK;
+  void *d_ts = nullptr, *d_out = nullptr, *ws = nullptr;
+  NrtDeviceState* ds = nrt_device_state();
+  NRT_REQUIRE(ds != nullptr, "nrt_nerfle_render_camera_host: no current CUDA device");
+  std::lock_guard<std::mutex> host_lock(ds->host_mu);
+  const size_t wsb = nrt_nerfle_render_camera_workspace(first, second, prec, cam, sampling);
+  rc = nrt_host_scratch(ds, 1, (size_t)R * 12, &d_out); if (rc != NRT_OK) return rc;
+  rc = nrt_host_scratch(ds, 2, wsb, &ws); if (rc != NRT_OK) return rc;
+  if (ts_host) {
+    rc = nrt_host_scratch(ds, 3, (size_t)S * 4, &d_ts); if (rc != NRT_OK) return rc;
+    NRT_CUDA(cudaMemcpyAsync(d_ts, ts_host, (size_t)S * 4, cudaMemcpyHostToDevice, st));
+  }
+  rc = render_impl(first, second, prec, nullptr, cam, R, (const float*)d_ts, sampling, light_code, light_dim, nullptr,
+                   (float*)d_out, ws, wsb, st);
   if (rc != NRT_OK) return rc;
   NRT_CUDA(cudaMemcpyAsync(out_rgb_host, d_out, (size_t)R * 12, cudaMemcpyDeviceToHost, st));
   NRT_CUDA(cudaStreamSynchronize(st));

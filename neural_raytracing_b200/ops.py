@@ -672,6 +672,114 @@ def nerfle_render_host(first: PackedMLP, second: PackedMLP, rays_host: torch.Ten
     return out_host
 
 
+# ---- a21 / f4: ray generators on the device, camera-driven render --------------------------------
+CAM_NERF, CAM_DTU, CAM_FOV = 0, 1, 2
+
+
+class CameraDesc:
+    """nrt_camera_t plus the tensors its device pointers borrow (kept alive for the duration of the call).
+
+    kind: CAM_NERF (a = cam_to_world [n,3|4,4], focal), CAM_DTU (a = pose [n,4,4], b = intrinsics [n,3|4,3|4]) or
+    CAM_FOV (a = inverse full projection [n,4,4] in the row-vector convention, b = camera centres [n,3]).  The block
+    of rays is the reference's [n_views, nx, ny, bundle, 6]: pixel position (u, v) = (y0 + j, x0 + i) as in
+    pathtrace (main.py:67-74), or `positions` [nx, ny(, bundle), 2] when given."""
+
+    def __init__(self, kind, a, b=None, focal=1.0, size=1.0, x0=0, y0=0, nx=0, ny=0, bundle=1, positions=None,
+                 jitter=0.0, jitter_seed=0):
+        a = _chk(a, "camera matrix a")
+        if a.dim() != 3:
+            raise NrtError("camera matrix a must be [n_views, rows, cols], got %s" % (tuple(a.shape),))
+        self.device = a.device
+        self.n_views = a.shape[0]
+        if b is not None:
+            b = _chk(b, "camera matrix b")
+            if b.dim() == 2:
+                b = b.reshape(b.shape[0], 1, b.shape[1])
+            if b.shape[0] != self.n_views:
+                raise NrtError("camera matrices a and b disagree on the number of views")
+        elif kind != CAM_NERF:
+            raise NrtError("this camera kind needs the second matrix (intrinsics / centres)")
+        ppp = 1
+        if positions is not None:
+            positions = _chk(positions, "positions")
+            if positions.shape[-1] != 2 or positions.numel() not in (nx * ny * 2, nx * ny * bundle * 2):
+                raise NrtError("positions must be [nx, ny(, bundle), 2]")
+            ppp = positions.numel() // (nx * ny * 2) if nx * ny else 1
+        self._keep = (a, b, positions)
+        self.nx, self.ny, self.bundle = int(nx), int(ny), int(bundle)
+        self.struct = N.NrtCamera(
+            int(kind), int(self.n_views), _ptr(a), _ptr(b), a.shape[1] * a.shape[2], a.shape[2],
+            (b.shape[1] * b.shape[2]) if b is not None else 0, b.shape[2] if b is not None else 0,
+            float(focal), float(size), int(x0), int(y0), int(nx), int(ny), int(bundle), int(ppp), _ptr(positions),
+            float(jitter), int(jitter_seed))
+
+    @property
+    def n_rays(self):
+        return self.n_views * self.nx * self.ny * self.bundle
+
+
+def camera_rays(cam: CameraDesc, want_view=False):
+    """sample_positions of the three cameras as one kernel: rays [n_views, nx, ny, bundle, 6] (fp32, device)."""
+    R = cam.n_rays
+    out = torch.empty((cam.n_views, cam.nx, cam.ny, cam.bundle, 6), dtype=torch.float32, device=cam.device)
+    view = torch.empty((R,), dtype=torch.int32, device=cam.device) if want_view else None
+    with torch.cuda.device(cam.device):
+        N.check(N.lib().nrt_camera_rays(ctypes.byref(cam.struct), 0, R, _ptr(out), _ptr(view), _stream()))
+    return (out, view) if want_view else out
+
+
+def nerfle_render_camera(first: PackedMLP, second: PackedMLP, cam: CameraDesc, ts: Optional[torch.Tensor],
+                         light_code: torch.Tensor, prec=PREC_F32, n_coarse: Optional[int] = None, n_fine=0,
+                         t_near=0.0, t_far=0.0, jitter_seed=0) -> torch.Tensor:
+    """The frame of a volumetric shape from its camera in one call: rays are generated on the device inside the
+    library (f4; replaces the tile loop of pathtrace, main.py:57-88).  -> rgb [n_views, nx, ny, bundle, 3]."""
+    prec = prec_id(prec)
+    t = _chk(ts, "ts").reshape(-1) if ts is not None else None
+    if n_coarse is None:
+        if t is None:
+            raise NrtError("either ts or n_coarse must be given")
+        n_coarse = t.numel()
+    lc = _chk(light_code, "light_code")
+    lc = lc.reshape(-1, lc.shape[-1])
+    if lc.shape[0] < cam.n_views:
+        raise NrtError("light_code has %d rows for %d views" % (lc.shape[0], cam.n_views))
+    out = torch.empty((cam.n_views, cam.nx, cam.ny, cam.bundle, 3), dtype=torch.float32, device=cam.device)
+    samp = N.NrtNerfSampling(int(n_coarse), int(n_fine), float(t_near), float(t_far), int(jitter_seed))
+    with torch.cuda.device(cam.device):
+        c1, c2 = first.c_struct(prec), second.c_struct(prec)
+        nbytes = N.lib().nrt_nerfle_render_camera_workspace(ctypes.byref(c1), ctypes.byref(c2), prec,
+                                                            ctypes.byref(cam.struct), ctypes.byref(samp))
+        key = (cam.device.index, torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=cam.device)
+            _ws_cache[key] = ws
+        N.check(N.lib().nrt_nerfle_render_camera(ctypes.byref(c1), ctypes.byref(c2), prec, ctypes.byref(cam.struct),
+                                                 _ptr(t), ctypes.byref(samp), _ptr(lc), lc.shape[-1], _ptr(out),
+                                                 _ptr(ws), ws.numel(), _stream()))
+    return out
+
+
+def nerfle_render_camera_host(first: PackedMLP, second: PackedMLP, cam: CameraDesc, ts_host: Optional[torch.Tensor],
+                              light_code: torch.Tensor, out_host: torch.Tensor, prec=PREC_F32, n_coarse=None,
+                              n_fine=0, t_near=0.0, t_far=0.0, jitter_seed=0):
+    """End-to-end leg of the camera-driven render: only the camera goes in, the image comes back to HOST memory."""
+    prec = prec_id(prec)
+    assert not out_host.is_cuda and out_host.numel() == cam.n_rays * 3
+    S = ts_host.numel() if ts_host is not None else 0
+    if n_coarse is None:
+        n_coarse = S
+    lc = _chk(light_code, "light_code")
+    samp = N.NrtNerfSampling(int(n_coarse), int(n_fine), float(t_near), float(t_far), int(jitter_seed))
+    with torch.cuda.device(cam.device):
+        c1, c2 = first.c_struct(prec), second.c_struct(prec)
+        N.check(N.lib().nrt_nerfle_render_camera_host(
+            ctypes.byref(c1), ctypes.byref(c2), prec, ctypes.byref(cam.struct),
+            ctypes.c_void_p(ts_host.data_ptr()) if ts_host is not None else None, S, ctypes.byref(samp), _ptr(lc),
+            lc.shape[-1], ctypes.c_void_p(out_host.data_ptr()), _stream()))
+    return out_host
+
+
 # ---- launch accounting / per-kernel timing ----------------------------------------------------
 def profile_enable(on: bool):
     N.check(N.lib().nrt_profile_enable(1 if on else 0))

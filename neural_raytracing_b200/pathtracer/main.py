@@ -1,6 +1,7 @@
 """Render entry points with the reference's signatures (pytorch3d/pathtracer/main.py:13-179)."""
 import torch
 
+from .. import ops
 from .samplers import Sampler
 from .utils import rand_uv
 
@@ -15,14 +16,48 @@ def _pixel_grid(x0, y0, nx, ny, device):
     return torch.stack([gy, gx], dim=-1)      # the reference stacks (y, x)
 
 
-def _render_tile(shapes, lights, cameras, integrator, bsdf, positions, sampler, bundle_size, size, batch_dims,
-                 with_noise, w_isect, background):
-    rays = cameras.sample_positions(positions, sampler, bundle_size, size=size, N=batch_dims, with_noise=with_noise)
+def _tile_rays(cameras, window, sampler, bundle_size, size, batch_dims, with_noise, device):
+    """Rays [N, nx, ny, bundle, 6] of the pixel window (x0, y0, nx, ny).  Without pixel jitter and with a CUDA camera
+    the window goes to the ray-generation kernel as four integers (no position tensor); with jitter the positions are
+    built and perturbed with torch's generator exactly as the reference does (main.py:67-80)."""
+    x0, y0, nx, ny = window
+    if not with_noise and str(device).startswith("cuda") and hasattr(cameras, "device_desc"):
+        desc = cameras.device_desc(size, x0=x0, y0=y0, nx=nx, ny=ny, bundle_size=bundle_size)
+        if desc is not None:
+            return ops.camera_rays(desc)
+    positions = _pixel_grid(x0, y0, nx, ny, device)
+    return cameras.sample_positions(positions, sampler, bundle_size, size=size, N=batch_dims, with_noise=with_noise)
+
+
+def _render_tile(shapes, lights, cameras, integrator, bsdf, window, sampler, bundle_size, size, batch_dims,
+                 with_noise, w_isect, background, device):
+    rays = _tile_rays(cameras, window, sampler, bundle_size, size, batch_dims, with_noise, device)
     values, mask, it = integrator.sample(shapes, rays, bsdf=bsdf, lights=lights, sampler=sampler, w_isect=w_isect)
     valid = mask.any(dim=-1)
     v = torch.mean(values, dim=-2)
     v[~valid] = background
     return v, it
+
+
+def _camera_frame(shapes, lights, cameras, integrator, size, x0, y0, nx, ny, bundle_size, with_noise, background):
+    """f4: a volumetric shape under NeRFReproduce on a CUDA camera renders its whole window in ONE library call, the
+    rays generated on the device inside it (shapes.render_camera -> nrt_nerfle_render_camera) -- no tile loop, no ray
+    tensor, no per-tile launches.  Returns None when that does not apply (surface integrators, training, CPU cameras).
+    Rays are independent, so the image equals the tiled one for any chunk_size / trim; pixel jitter comes from the
+    library's counter hash instead of torch's generator (same distribution: (U - 0.5) * with_noise pixels)."""
+    from .integrators import NeRFReproduce
+    if type(integrator) is not NeRFReproduce or not hasattr(shapes, "render_camera") \
+            or not hasattr(cameras, "device_desc"):
+        return None
+    if torch.is_grad_enabled() and any(p.requires_grad for p in shapes.parameters()):
+        return None
+    seed = int(torch.randint(1, 2 ** 31 - 1, (1,)).item()) if with_noise else 0      # CPU generator: no device sync
+    cam = cameras.device_desc(size, x0=x0, y0=y0, nx=nx, ny=ny, bundle_size=bundle_size,
+                              jitter=float(with_noise or 0.0), jitter_seed=seed)
+    if cam is None:
+        return None
+    values = shapes.render_camera(cam, lights)
+    return torch.mean(values, dim=-2)       # every pixel is valid under NeRFReproduce (integrators.py:260-267)
 
 
 def pathtrace(shapes, lights, cameras, integrator, bsdf=None, size=512, width=None, height=None, chunk_size=32,
@@ -33,15 +68,20 @@ def pathtrace(shapes, lights, cameras, integrator, bsdf=None, size=512, width=No
     batch_dims = len(cameras)
     width = size if width is None else width
     height = size if height is None else height
-    out = torch.full([batch_dims, width, height, integrator.dims()], background, device=device, dtype=torch.float)
     assert (size % chunk_size) == 0, \
         f"Can only specify chunk sizes which evenly divide size, {size} % {chunk_size}"
     it = None
+    if addition is nothing and str(device).startswith("cuda"):
+        frame = _camera_frame(shapes, lights, cameras, integrator, size, 0, 0, width, height, bundle_size, with_noise,
+                              background)
+        if frame is not None:
+            return (frame.squeeze(0) if squeeze_first and batch_dims == 1 else frame), None
+    out = torch.full([batch_dims, width, height, integrator.dims()], background, device=device, dtype=torch.float)
     for x0 in range(0, width, chunk_size):
         for y0 in range(0, height, chunk_size):
-            pos = _pixel_grid(x0 - trim, y0 - trim, chunk_size + 2 * trim, chunk_size + 2 * trim, device)
-            v, it = _render_tile(shapes, lights, cameras, integrator, bsdf, pos, sampler, bundle_size, size, batch_dims,
-                                 with_noise, w_isect, background)
+            win = (x0 - trim, y0 - trim, chunk_size + 2 * trim, chunk_size + 2 * trim)
+            v, it = _render_tile(shapes, lights, cameras, integrator, bsdf, win, sampler, bundle_size, size, batch_dims,
+                                 with_noise, w_isect, background, device)
             if trim != 0:
                 v = v[:, trim:-trim, trim:-trim]
             out[:, x0:x0 + chunk_size, y0:y0 + chunk_size, :] = v
@@ -69,9 +109,8 @@ def pathtrace_sample(shapes, lights, cameras, integrator, bsdf=None, size=512, c
     it = None
     for x0 in range(u, u + crop_size, chunk_size):
         for y0 in range(v, v + crop_size, chunk_size):
-            pos = _pixel_grid(x0, y0, chunk_size, chunk_size, device)
-            vals, it = _render_tile(shapes, lights, cameras, integrator, bsdf, pos, sampler, bundle_size, size,
-                                    batch_dims, with_noise, w_isect, background)
+            vals, it = _render_tile(shapes, lights, cameras, integrator, bsdf, (x0, y0, chunk_size, chunk_size), sampler,
+                                    bundle_size, size, batch_dims, with_noise, w_isect, background, device)
             if mode == "crop":
                 out[:, x0 - u:x0 - u + chunk_size, y0 - v:y0 - v + chunk_size] = vals
             else:

@@ -120,6 +120,18 @@ class NeRFLE(nn.Module):
     def _needs_grad(self, rays):
         return torch.is_grad_enabled() and (rays.requires_grad or any(p.requires_grad for p in self.parameters()))
 
+    def render_camera(self, cam, lights):
+        """The frame of `cam` (ops.CameraDesc) in one library call, rays generated on the device inside it (f4):
+        what pathtrace's tile loop + sample_positions + forward compute for an inference render (main.py:57-88,
+        nerf.py:175-214), with ONE far-plane draw (nerf.py:178) per frame instead of one per tile.
+        -> rgb [n_views, nx, ny, bundle, 3]."""
+        device = cam.device
+        ts = self._sample_ts(device)
+        code = self._light_code(lights, device)
+        prec = config.precision if self.first.precision() != "f32" and self.second.precision() != "f32" else "f32"
+        return ops.nerfle_render_camera(self.first.packed(), self.second.packed(), cam, ts, code.detach().float(),
+                                        prec=prec)
+
     def forward(self, rays, lights):
         r_o, r_d = rays.split([3, 3], dim=-1)
         device = r_o.device

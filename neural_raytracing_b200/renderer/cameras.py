@@ -5,14 +5,17 @@ training_utils.py:198 construct them (`OpenGLPerspectiveCameras(device=, R=, T=)
 
 Written from the conventions, not from the upstream class hierarchy: PyTorch3D transforms ROW vectors,
     x_view = x_world @ R + T,        x_clip = [x_view, 1] @ P^T,        x_ndc = x_clip[:3] / x_clip[3],
-so a camera here is just the batch of 4x4 matrices `world -> clip`; rays come from its inverse.  Pure torch (a few
-4x4 products per call): ray generation is 24 B/ray of output and not worth a kernel of its own.
+so a camera here is just the batch of 4x4 matrices `world -> clip`; rays come from its inverse.  The matrices are
+a few 4x4 torch products per call; on a CUDA device the per-pixel unprojection is one launch of the library's ray
+generator (`nrt_camera_rays`, csrc/nrt_camera.cu), which the camera-driven render also runs inside the library (f4).
 """
 import math
 from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
+
+from .. import ops
 
 
 def _as_batch(x, device, width=None):
@@ -134,6 +137,16 @@ class FoVPerspectiveCameras:
     def get_camera_center(self) -> torch.Tensor:
         return torch.inverse(self.world_to_view_matrix())[:, 3, :3]
 
+    def device_desc(self, size, x0=0, y0=0, nx=0, ny=0, bundle_size=1, positions=None, jitter=0.0, jitter_seed=0):
+        """nrt_camera_t of these cameras (ops.CameraDesc): the inverse full projection and the camera centres stay
+        device tensors (two small torch ops per call, no host synchronisation).  None when the kernel does not apply
+        (CPU cameras, or R / T that require grad)."""
+        if self.device.type != "cuda" or (torch.is_grad_enabled() and (self.R.requires_grad or self.T.requires_grad)):
+            return None
+        inv = torch.inverse(self.full_projection_matrix()).float()
+        return ops.CameraDesc(ops.CAM_FOV, inv, self.get_camera_center().float(), size=size, x0=x0, y0=y0, nx=nx, ny=ny,
+                              bundle=bundle_size, positions=positions, jitter=jitter, jitter_seed=jitter_seed)
+
     # ---- ray generator (the fork's addition, renderer/cameras.py:539-575) ----------------------------
     def sample_positions(self, position_samples, sampler, bundle_size=8, size=512, with_noise=False, N=1) -> torch.Tensor:
         """position_samples [W,H,2] (pixels) -> rays [N,W,H,bundle,6].  Kept from the reference: the jitter is
@@ -144,6 +157,12 @@ class FoVPerspectiveCameras:
         if with_noise:
             d = with_noise
             p = p + (d * sampler.sample(p.shape, device=device) - d / 2)
+        if position_samples.dim() == 3 and position_samples.is_cuda and position_samples.dtype == torch.float32:
+            # one kernel for the unprojection (nrt_camera_rays); the jitter above keeps the caller's sampler
+            desc = self.device_desc(size, nx=position_samples.shape[0], ny=position_samples.shape[1],
+                                    bundle_size=bundle_size, positions=p if with_noise else position_samples)
+            if desc is not None:
+                return ops.camera_rays(desc)
         p = -2 * (p / size) + 1
         pts = torch.cat([p, torch.ones(p.shape[:-1] + (2,), device=device)], dim=-1)      # homogeneous, ndc z = 1
         inv = torch.inverse(self.full_projection_matrix())                                  # [N,4,4]

@@ -408,6 +408,55 @@ def gen_cameras():
     print("cameras.npz: rays", out["rays"].shape, "dir norm", np.linalg.norm(out["rays"][..., 3:], axis=-1).mean())
 
 
+def gen_camera_rays():
+    """f4 fixtures: rays of NeRFCamera / DTUCamera on a pixel window (cameras.py:23-54, 132-192), and the reference's
+    own pathtrace of a NeRFLE under NeRFReproduce through a NeRFCamera and through OpenGLPerspectiveCameras
+    (main.py:13-93; nerfle.py:130-135 is this call) -- what the camera-driven whole-frame render must reproduce."""
+    import scenes
+    from pytorch3d.pathtracer.cameras import NeRFCamera, DTUCamera
+    from pytorch3d.pathtracer.integrators import NeRFReproduce
+    from pytorch3d.pathtracer.samplers import Sampler
+    from pytorch3d.renderer import OpenGLPerspectiveCameras, look_at_view_transform
+    import pytorch3d.pathtracer as P
+    out = {}
+    size = 16
+    gx, gy = torch.meshgrid(torch.arange(3, 13, dtype=torch.float), torch.arange(2, 8, dtype=torch.float))
+    pos = torch.stack([gy, gx], dim=-1)                      # window x0 = 3, y0 = 2, nx = 10, ny = 6
+    out["window"] = np.array([3, 2, 10, 6], np.int32)
+    c2w, focal = synth.nerf_cameras(3, size)
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cpu")
+    out["nerf_rays"] = cam.sample_positions(pos, Sampler(device="cpu"), bundle_size=1, size=size, N=3, with_noise=False).numpy()
+    pose, K = scenes.dtu_cameras(2, device="cpu")
+    dcam = DTUCamera(pose=pose, intrinsic=K, device="cpu")
+    out["dtu_rays"] = dcam.sample_positions(pos, Sampler(device="cpu"), bundle_size=2, size=size, N=2, with_noise=False).numpy()
+    # whole frames of a NeRFLE
+    random.random = lambda: FIXED_RANDOM
+    n = NeRFLE(envmap=False, device="cpu")
+    w1 = synth.mlp_weights(seed=31, in_size=3, out=65, num_layers=5, hidden=128, freqs=16, sigma=32.0)
+    w2 = synth.mlp_weights(seed=32, in_size=70, out=3, num_layers=8, hidden=64, freqs=16, sigma=32.0)
+    w1["b"][-1][0] = 0.8
+    load_mlp(n.first, w1)
+    load_mlp(n.second, w2)
+    loc = np.array([[0.4, 1.0, 0.3], [-0.8, 0.5, 0.6]], np.float32)
+    lights = PointLights(device="cpu", location=T(loc), scale=10)
+    cam2 = NeRFCamera(cam_to_world=c2w[:2], focal=focal, device="cpu")
+    with torch.no_grad():
+        img, _ = P.pathtrace(n, size=size, chunk_size=8, bundle_size=1, bsdf=None, integrator=NeRFReproduce(),
+                             lights=lights, cameras=cam2, device="cpu", silent=True, with_noise=False)
+        R, Tt = look_at_view_transform(dist=1.6, elev=torch.tensor([20.0, 35.0]), azim=torch.tensor([-40.0, 70.0]))
+        fcam = OpenGLPerspectiveCameras(device="cpu", R=R, T=Tt)
+        img_f, _ = P.pathtrace(n, size=size, chunk_size=8, bundle_size=2, bsdf=None, integrator=NeRFReproduce(),
+                               lights=lights, cameras=fcam, device="cpu", silent=True, with_noise=False)
+    out["light_loc"] = loc
+    out["frame_nerf"], out["frame_fov"] = img.numpy(), img_f.numpy()
+    out["fov_R"], out["fov_T"] = R.numpy(), Tt.numpy()
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("pathtracer/cameras/cameras.py:23-54, 132-192; pathtracer/main.py:13-93; shapes/nerf.py:175-214")
+    np.savez_compressed(os.path.join(HERE, "camera_rays.npz"), **out)
+    print("camera_rays.npz:", out["nerf_rays"].shape, out["dtu_rays"].shape, out["frame_nerf"].shape, out["frame_fov"].shape,
+          "frame means %.4f %.4f" % (img.mean(), img_f.mean()))
+
+
 def train_loop_case(P, train_nerf, device):
     """The tiny nerf_synthetic.py-style problem both the reference and the mirror train on (shared by the test)."""
     import scenes
@@ -630,7 +679,7 @@ def gen_path():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf"]
+                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()

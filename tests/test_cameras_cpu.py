@@ -13,7 +13,9 @@ sys.path.insert(0, os.path.dirname(HERE))
 from neural_raytracing_b200.renderer import (FoVPerspectiveCameras, OpenGLPerspectiveCameras,  # noqa: E402
                                               look_at_view_transform)
 
+sys.path.insert(0, os.path.join(HERE, "golden"))
 G = np.load(os.path.join(HERE, "golden", "cameras.npz"))
+GR = np.load(os.path.join(HERE, "golden", "camera_rays.npz"))
 
 
 class _Sampler:
@@ -57,3 +59,21 @@ def test_sample_positions_jitter_is_bounded_and_seeded():
     clean = cams.sample_positions(pos, _Sampler(), bundle_size=4, size=16, N=1, with_noise=False)
     assert (a[..., 3:] - clean[..., 3:]).abs().max().item() < 2e-3      # +-0.005 pixel of a 16-pixel image
     assert (a[..., :3] - clean[..., :3]).abs().max().item() == 0.0
+
+
+def test_nerf_and_dtu_cameras_match_reference_rays():
+    """The torch expressions of NeRFCamera / DTUCamera (the path CPU tensors and learned poses take) against rays of the
+    unmodified reference on a 10 x 6 pixel window (tests/golden/make_golden.py::gen_camera_rays)."""
+    import scenes
+    import synth
+    from neural_raytracing_b200.pathtracer.cameras import DTUCamera, NeRFCamera
+    x0, y0, nx, ny = (int(v) for v in GR["window"])
+    gx, gy = torch.meshgrid(torch.arange(x0, x0 + nx, dtype=torch.float), torch.arange(y0, y0 + ny, dtype=torch.float),
+                            indexing="ij")
+    pos = torch.stack([gy, gx], dim=-1)
+    c2w, focal = synth.nerf_cameras(3, 16)
+    rays = NeRFCamera(cam_to_world=c2w, focal=focal, device="cpu").sample_positions(pos, _Sampler(), bundle_size=1, size=16, N=3)
+    assert tuple(rays.shape) == GR["nerf_rays"].shape and np.abs(rays.numpy() - GR["nerf_rays"]).max() < 1e-6
+    pose, K = scenes.dtu_cameras(2, device="cpu")
+    rays = DTUCamera(pose=pose, intrinsic=K, device="cpu").sample_positions(pos, _Sampler(), bundle_size=2, size=16, N=2)
+    assert tuple(rays.shape) == GR["dtu_rays"].shape and np.abs(rays.numpy() - GR["dtu_rays"]).max() < 1e-6
