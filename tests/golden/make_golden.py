@@ -457,6 +457,38 @@ def gen_camera_rays():
           "frame means %.4f %.4f" % (img.mean(), img_f.mean()))
 
 
+def gen_vis():
+    """The visualisation integrators of dtu_vis.py / nerv_vis.py / visualize.py on the pipeline test scenes
+    (integrators.py:25-136): BasisBRDF weight map, Debug normals, Depth, Illumination, Luminance."""
+    import pytorch3d.pathtracer as P
+    from pytorch3d.pathtracer.cameras import NeRFCamera
+    from pytorch3d.pathtracer.integrators import BasisBRDF, Debug, Depth, Illumination, Luminance, Mask
+    from scenes import build_pipeline
+    out = {}
+    random.random = lambda: FIXED_RANDOM
+    size = 16
+    c2w, focal = synth.nerf_cameras(1, size)
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cpu")
+
+    def render(scene, integrator):
+        shape, sphere, bsdf, lights, _integ, _w = build_pipeline(P, scene)
+        integ = integrator(bsdf)
+        with torch.no_grad():
+            img, _ = P.pathtrace(shape, size=size, chunk_size=size, bundle_size=1, bsdf=bsdf, integrator=integ,
+                                 lights=lights, cameras=cam, device="cpu", silent=True, background=0, with_noise=False)
+        return img.numpy()
+    out["dtu_basis"] = render("dtu", lambda b: BasisBRDF(b))
+    out["dtu_debug_mask"] = render("dtu", lambda b: Mask(Debug()))
+    out["dtu_depth"] = render("dtu", lambda b: Depth())
+    out["colocate_basis"] = render("colocate", lambda b: BasisBRDF(b))
+    out["colocate_illumination"] = render("colocate", lambda b: Illumination())
+    out["colocate_luminance"] = render("colocate", lambda b: Luminance())
+    out["fixed_random"] = np.array(FIXED_RANDOM, np.float64)
+    out["src"] = np.array("pytorch3d/pathtracer/integrators/integrators.py:25-136")
+    np.savez_compressed(os.path.join(HERE, "vis.npz"), **out)
+    print("vis.npz:", {k: (v.shape, float(np.mean(v))) for k, v in out.items() if hasattr(v, "shape") and v.ndim > 1})
+
+
 def train_loop_case(P, train_nerf, device):
     """The tiny nerf_synthetic.py-style problem both the reference and the mirror train on (shared by the test)."""
     import scenes
@@ -679,7 +711,7 @@ def gen_path():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays"]
+                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays", "vis"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
