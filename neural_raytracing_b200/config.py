@@ -18,6 +18,8 @@ TC_NETS = {
     (3, 0, 128, 256, 16, 3, 8, 0),  # ... 8 bases (nerf_synthetic.py)
     (3, 0, 128, 256, 16, 3, 16, 0), # ... 16 bases (dtu.py)
     (3, 0, 16, 256, 10, 3, 3, 0),   # LightField.light_field_approx (K-chunk streamed)
+    (3, 32, 16, 32, 5, 3, 33, 0),   # PlainNeRF.first (per-image latent as part of the encoding operand)
+    (2, 64, 16, 32, 5, 3, 3, 0),    # PlainNeRF.second
 }
 
 # arithmetic of the differentiable (training) MLP evaluations:

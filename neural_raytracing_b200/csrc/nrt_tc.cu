@@ -397,6 +397,8 @@ using NetNerfSecondPT = Net<70, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;    // N
 using NetNerfSecondLE = Net<115, 0, 16, 64, 8, 3, 3, NRT_ACT_LEAKY_RELU>;   // NeRFLE.second, envmap code (64+3+48)
 using NetNeuralBsdf = Net<3, 0, 64, 96, 6, 3, 3, NRT_ACT_LEAKY_RELU>;       // NeuralBSDF.mlp bsdfs.py:616-621
 using NetOcc = Net<5, 0, 16, 64, 8, 3, 1, NRT_ACT_LEAKY_RELU>;              // occlusion MLP  colocate.py:82-85
+using NetPlainFirst = Net<3, 32, 16, 32, 5, 3, 33, NRT_ACT_LEAKY_RELU>;      // PlainNeRF.first  nerf.py:17-22 (per-image latent)
+using NetPlainSecond = Net<2, 64, 16, 32, 5, 3, 3, NRT_ACT_LEAKY_RELU>;      // PlainNeRF.second nerf.py:24-28
 using NetSdfShift = Net<3, 0, 32, 128, 8, 3, 1, NRT_ACT_SOFTPLUS>;         // SphereSDF.shift sdfs.py:23-31 (streamed)
 
 template <class NET>
@@ -480,6 +482,8 @@ int nrt_mlp_forward_tc(const nrt_mlp_t* m, int prec, int out_act, const float* x
   if (matches<NetNeuralBsdf>(d)) return forward_plain<NetNeuralBsdf>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetOcc>(d)) return forward_plain<NetOcc>(m, prec, out_act, x, latent, M, out, st);
   if (matches<NetSdfShift>(d)) return forward_plain<NetSdfShift>(m, prec, out_act, x, latent, M, out, st);
+  if (matches<NetPlainFirst>(d)) return forward_plain<NetPlainFirst>(m, prec, out_act, x, latent, M, out, st);
+  if (matches<NetPlainSecond>(d)) return forward_plain<NetPlainSecond>(m, prec, out_act, x, latent, M, out, st);
   {
     bool handled = false;   // the 256-wide networks (weights streamed in K-chunks, nrt_tc_wide.cu)
     rc = nrt_mlp_forward_tc_wide(m, d, prec, out_act, x, M, out, nullptr, st, &handled);

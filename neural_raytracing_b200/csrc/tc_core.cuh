@@ -1548,7 +1548,9 @@ k_mlp_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, long long* __restri
             if (st < L) preload_bias<HW>(dD + coff, sBias + s_bias[2 + st] + coff);
             else {
               // output-layer bias: every half writes only the accumulator columns it has just read
-              constexpr int N0 = NET::NOP < HW ? NET::NOP : HW, N1 = NET::NOP > HW ? NET::NOP - HW : 0;
+              // (one warp per lane quarter: the primary writes all of them, also those beyond the hidden width -- an
+              //  output wider than the hidden layers, PlainNeRF.first 32 -> 33)
+              constexpr int N0 = (WPS != 8 || NET::NOP < HW) ? NET::NOP : HW, N1 = (WPS == 8 && NET::NOP > HW) ? NET::NOP - HW : 0;
               if (primary) preload_bias<N0>(dD, sBias + s_bias[NET::STAGES - 1]);
               else if constexpr (N1 > 0) preload_bias<N1>(dD + HW, sBias + s_bias[NET::STAGES - 1] + HW);
             }

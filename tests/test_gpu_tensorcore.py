@@ -45,6 +45,30 @@ def test_tc_mlp_forward_vs_oracle(name, M):
         assert np.abs(y - yo).max() < tol, (prec, np.abs(y - yo).max())
 
 
+LATENT_CASES = {
+    # PlainNeRF (nerf.py:17-28): 5x32 networks whose per-image latent rides in the encoding operand next to x
+    "plain_first": dict(seed=61, in_size=3, out=33, num_layers=5, hidden=32, freqs=16, sigma=32.0, latent=32),
+    "plain_second": dict(seed=62, in_size=2, out=3, num_layers=5, hidden=32, freqs=16, sigma=32.0, latent=64),
+}
+
+
+@pytest.mark.parametrize("name", list(LATENT_CASES))
+@pytest.mark.parametrize("M", [1, 129, 3000])
+def test_tc_latent_mlp_forward_vs_oracle(name, M):
+    from neural_raytracing_b200 import ops
+    kw = LATENT_CASES[name]
+    w = synth.mlp_weights(**kw)
+    rs = np.random.RandomState(M)
+    x = (0.6 * rs.standard_normal((M, kw["in_size"]))).astype(np.float32)
+    lat = (0.5 * rs.standard_normal((M, kw["latent"]))).astype(np.float32)
+    yo = c_oracle.mlp_forward(helpers.oracle_mlp(w), x, lat)
+    m = helpers.cuda_mlp(w)
+    for prec, tol in (("f16", 1e-3), ("bf16", 5e-3)):
+        y = ops.mlp_forward(m, _t(x), _t(lat), prec=prec).cpu().numpy()
+        assert y.shape == yo.shape and np.isfinite(y).all()
+        assert np.abs(y - yo).max() < tol, (prec, np.abs(y - yo).max())
+
+
 WIDE_CASES = {
     # ComposeSpatialVarying.sp_var_fn (bsdfs.py:487-496, 4 bases) and LightField.light_field_approx (lights.py:159-164):
     # 256-wide, weights streamed in K-chunks, encoding operand in shared memory (csrc/nrt_tc_wide.cu)
