@@ -930,6 +930,43 @@ def run_multi_gpu(args, rank, world, local_rank):
                   "nrank_vs_1rank_bit_identical": bool(chk[1]) if rank == 0 else None,
                   "compared": "%d pixels of rank %d's slice re-rendered by rank 0" % (n_cmp, other)}
         del rays4k, img, base
+        # the same 4K frame from its camera: rank g renders its pixel rows, generating the rays on its own
+        # device inside the library call -- no ray array is built, sharded or copied anywhere
+        try:
+            c2w = torch.from_numpy(camera_matrix(0)).to(dev)
+            xlo, xhi = D.shard_range(3840, rank, world)
+
+            def rows(x0, n):
+                cam = ops.CameraDesc(ops.CAM_NERF, c2w, None, focal=0.5 * 3840 / np.tan(np.radians(30)), size=3840, x0=x0,
+                                     y0=840, nx=n, ny=2160)
+                return ops.nerfle_render_camera(m1, m2, cam, ts, code, prec="f16")
+            rows(xlo, xhi - xlo)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            mine_rows = rows(xlo, xhi - xlo)
+            b.record()
+            barrier()
+            cms = max_over_ranks(a.elapsed_time(b))
+            same = torch.zeros(1, device=dev, dtype=torch.float64)
+            n_cmp = min(16, xhi - xlo)
+            if rank == world - 1 and world > 1:
+                dist.send(mine_rows[:, :n_cmp].contiguous(), dst=0)
+            if rank == 0:
+                olo, _ = D.shard_range(3840, world - 1, world)
+                theirs = torch.empty((1, n_cmp, 2160, 1, 3), device=dev)
+                if world > 1:
+                    dist.recv(theirs, src=world - 1)
+                else:
+                    theirs.copy_(mine_rows[:, :n_cmp])
+                same[0] = float(torch.equal(rows(olo, n_cmp), theirs))
+            render["from_camera"] = {"ms_per_frame": cms, "rays_per_sec": total / cms * 1e3,
+                                     "nrank_vs_1rank_bit_identical": bool(same[0]) if rank == 0 else None,
+                                     "note": "rank g renders pixel rows shard_range(3840, g, N) of the 3840x2160 window through "
+                                             "nrt_nerfle_render_camera (rays generated on its own device)"}
+            del mine_rows
+        except Exception as e:   # noqa: BLE001
+            render["from_camera"] = {"error": repr(e)[:300]}
     except Exception as e:   # noqa: BLE001
         render = {"error": repr(e)[:300]}
 

@@ -47,6 +47,31 @@ def render_sharded(render_fn: Callable[[torch.Tensor], torch.Tensor], rays: torc
     return torch.cat(pieces, dim=0)
 
 
+def render_camera_sharded(render_rows_fn: Callable[[int, int], torch.Tensor], nx: int, gather: bool = True,
+                          group=None) -> torch.Tensor:
+    """Camera-driven multi-GPU frame (f4): rank g renders the pixel ROWS [lo, hi) of the frame's first image axis with
+    `render_rows_fn(lo, hi - lo) -> [n_views, hi - lo, ny, C]` (e.g. `ops.nerfle_render_camera` on a window of the camera
+    descriptor: every rank generates its own rays on its own device, no ray array exists anywhere) and, if gather, all
+    ranks receive the whole [n_views, nx, ny, C] image.  Rays are independent: the result equals the 1-rank frame."""
+    rank, world = _world(group)
+    lo, hi = shard_range(nx, rank, world)
+    local = render_rows_fn(lo, hi - lo)
+    if world == 1 or not gather:
+        return local
+    per = (nx + world - 1) // world
+    n_views = local.shape[0]
+    tail = tuple(local.shape[2:])
+    padded = torch.zeros((per, n_views) + tail, dtype=local.dtype, device=local.device)     # rows first: contiguous shards
+    padded[: hi - lo] = local.transpose(0, 1)
+    out = torch.empty((world * per, n_views) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    pieces = []
+    for g in range(world):
+        glo, ghi = shard_range(nx, g, world)
+        pieces.append(out[g * per: g * per + (ghi - glo)])
+    return torch.cat(pieces, dim=0).transpose(0, 1).contiguous()
+
+
 def allreduce_gradients(params: Iterable[torch.Tensor], average: bool = True, group=None) -> Optional[torch.Tensor]:
     """One flat-bucket all-reduce of every .grad (missing grads count as zero); writes the reduced
     gradients back.  Returns the bucket (for inspection)."""

@@ -40,6 +40,15 @@ def _worker(rank, world, port, R, q):
         rays = torch.randn(R, 6, generator=g)
         img = D.render_sharded(_fake_render, rays)
         ok_img = torch.equal(img, _fake_render(rays))
+        # camera-driven frame: every rank renders its rows of the window, the gathered image equals the whole frame
+        nx, ny = (R % 37) + 3, 5
+
+        def rows(x0, n):
+            i = torch.arange(x0, x0 + n, dtype=torch.float)[None, :, None, None]
+            j = torch.arange(ny, dtype=torch.float)[None, None, :, None]
+            v = torch.arange(2, dtype=torch.float)[:, None, None, None]
+            return torch.cat([i * 100 + j + 0 * v, v + 0 * i + 0 * j, i * j + v], dim=-1)
+        ok_img = ok_img and torch.equal(D.render_camera_sharded(rows, nx), rows(0, nx))
         # gradients: each rank contributes the gradient of ITS slice of a sum-loss; the all-reduced
         # (summed) bucket must equal the single-process gradient over all rays
         lin = torch.nn.Linear(6, 3)

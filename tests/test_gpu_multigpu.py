@@ -52,6 +52,14 @@ def _worker(rank, world, port, q):
         img = D.render_sharded(lambda r: ops.nerfle_render(m1, m2, r, ts, code, prec="f16"), rays)
         whole = ops.nerfle_render(m1, m2, rays, ts, code, prec="f16")
         ok_img = bool(torch.equal(img, whole))
+        # ---- the same from a camera (f4): every rank generates the rays of ITS rows on its own device ----
+        c2w, focal = synth.nerf_cameras(2, 75, device=dev)
+
+        def rows(x0, n):
+            cam = ops.CameraDesc(ops.CAM_NERF, c2w, None, focal=focal, size=75, x0=x0, y0=0, nx=n, ny=75)
+            return ops.nerfle_render_camera(m1, m2, cam, ts, code.expand(2, 3).contiguous(), prec="f16")
+        frame = D.render_camera_sharded(rows, 75)              # 75 rows over the ranks: uneven
+        ok_img = ok_img and bool(torch.equal(frame, rows(0, 75))) and tuple(frame.shape) == (2, 75, 75, 1, 3)
         # ---- training step: flat gradient, all-reduced over the ranks, vs the whole batch on one rank ----
         res = {}
         for tprec in ("f32", "f16"):
