@@ -183,12 +183,23 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// NRT_TRYWAIT_HINT (ns, 0 = none): suspend-time hint of mbarrier.try_wait.  Without it a waiting warp's try_wait returns after
+// a short implementation-defined time and the loop re-issues it (ncu source page of NeRFLE.second: SYNCS + BRA + YIELD of the
+// wait loops = 18 % of all warp instructions executed, ~7 polls per wait).
+#ifndef NRT_TRYWAIT_HINT
+#define NRT_TRYWAIT_HINT 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   uint32_t ok = 0;
   while (!ok) {
+#if NRT_TRYWAIT_HINT > 0
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(ok) : "r"(a), "r"(parity), "r"((uint32_t)NRT_TRYWAIT_HINT) : "memory");
+#else
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
                  : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#endif
   }
 }
 // non-blocking phase test (all lanes of the warp call it; the result is warp-uniform)
