@@ -125,6 +125,16 @@ int nrt_check_camera(const nrt_camera_t* cam, int64_t* total) {
   NRT_REQUIRE(cam->kind != NRT_CAM_NERF || cam->bundle == 1, "NeRF camera: one ray per pixel (cameras.py:50)");
   NRT_REQUIRE(cam->positions == nullptr || cam->pos_per_pixel == 1 || cam->pos_per_pixel == cam->bundle,
               "camera: pos_per_pixel must be 1 or bundle");
+  // strides must cover the elements the kernel reads: 3 rows x 4 columns of a (4 x 4 for the FoV inverse), the first two
+  // rows / three columns of the DTU intrinsics, three floats of a FoV centre
+  const int a_rows = cam->kind == NRT_CAM_FOV ? 4 : 3;
+  NRT_REQUIRE(cam->a_row_stride >= 4 && cam->a_view_stride >= (a_rows - 1) * cam->a_row_stride + 4,
+              "camera: matrix a needs %d rows of 4 columns per view (strides %d / %d)", a_rows, cam->a_view_stride,
+              cam->a_row_stride);
+  NRT_REQUIRE(cam->kind != NRT_CAM_DTU || (cam->b_row_stride >= 3 && cam->b_view_stride >= cam->b_row_stride + 3),
+              "DTU camera: intrinsics need two rows of three columns per view (strides %d / %d)", cam->b_view_stride,
+              cam->b_row_stride);
+  NRT_REQUIRE(cam->kind != NRT_CAM_FOV || cam->b_view_stride >= 3, "FoV camera: centres need three floats per view");
   *total = (int64_t)cam->n_views * cam->nx * cam->ny * cam->bundle;
   return NRT_OK;
 }

@@ -132,6 +132,9 @@ def test_camera_errors():
         ops.CameraDesc(ops.CAM_DTU, cam.cam_to_world, None, size=16, nx=4, ny=4)
     with pytest.raises(ops.NrtError):       # CPU matrices: there is no CPU path
         ops.CameraDesc(ops.CAM_NERF, cam.cam_to_world.cpu(), None, focal=1.0, size=16, nx=4, ny=4)
+    with pytest.raises(ops.NrtError):       # a rotation without the translation column is not a camera-to-world matrix
+        ops.camera_rays(ops.CameraDesc(ops.CAM_NERF, cam.cam_to_world[:, :3, :3].contiguous(), None, focal=1.0, size=16,
+                                       nx=4, ny=4))
     # empty window
     assert ops.camera_rays(cam.device_desc(16, nx=0, ny=4)).numel() == 0
 
