@@ -1,2 +1,2 @@
-from .integrators import (BasisBRDF, Debug, Depth, Direct, Illumination, Integrator, Luminance, Mask, NeRFIntegrator,
-                          NeRFReproduce, Path, Silhouette)
+from .integrators import Debug, Direct, Integrator, Mask, NeRFIntegrator, NeRFReproduce, Path, Silhouette
+from .vis import BasisBRDF, Depth, Illumination, Luminance

@@ -56,78 +56,6 @@ class Mask(Integrator):
         return result, torch.ones_like(active), si
 
 
-class Depth(Integrator):
-    """Hit distance along the ray, `empty_val` where nothing was hit (integrators.py:57-67; the optional rescale by the
-    maximum is the reference's, including its exclusion of exact zeros)."""
-
-    def __init__(self, scale=False, empty_val=-1, **kwargs):
-        super().__init__(**kwargs)
-        self.empty_val = empty_val
-        self.scale = scale
-
-    def dims(self):
-        return 1
-
-    def sample(self, shapes, rays, bsdf, **kwargs):
-        it, active = shapes.intersect(rays)
-        results = torch.where(active, it.t, torch.full_like(it.t, self.empty_val))
-        if self.scale:
-            nz = results != 0
-            results[nz] = results[nz] / results[nz].max()
-        return results.unsqueeze(-1), active, it
-
-
-class BasisBRDF(Integrator):
-    """Weight map of a spatially varying BSDF: sigmoid(sp_var_fn(p)) at the hits (integrators.py:79-90; dtu_vis.py:125,
-    nerv_vis.py:119, visualize.py:95).  The 256-wide sp_var network runs on the compacted hits only."""
-
-    def __init__(self, multi_basis_bsdf):
-        super().__init__()
-        self.bsdf = multi_basis_bsdf
-
-    def dims(self):
-        return len(self.bsdf.bsdfs)
-
-    def sample(self, shapes, rays, bsdf, **kwargs):
-        results = torch.zeros(*rays.shape[:-1], self.dims(), device=rays.device)
-        it, active = shapes.intersect(rays)
-        if not active.any():
-            return results, active, it
-        results[active] = self.bsdf.normalized_weights(it.p[active], it)
-        return results, active, it
-
-
-class Illumination(Integrator):
-    """Local direction to the sampled emitter at every hit, as a colour (integrators.py:93-111)."""
-
-    def dims(self):
-        return 3
-
-    def sample(self, shapes, rays, lights, sampler, **kwargs):
-        sample_emitter = kwargs.get("sample_emitter_fn", sample_emitter_dir_wo_isect)
-        it, active = shapes.intersect(rays)
-        ds, _ = sample_emitter(it, shapes, lights=lights, sampler=sampler, active=active)
-        local = torch.nn.functional.normalize(it.to_local(ds.d), dim=-1)
-        results = torch.where(active.unsqueeze(-1), (local + 1) / 2, torch.zeros_like(ds.d))
-        return (1 + results) / 2, active, it
-
-
-class Luminance(Integrator):
-    """Luminance of the sampled emitter at every hit (integrators.py:114-136).  Kept from the reference: the weights
-    are `0.2126 r + 0.7152 * 0.0722 b` (green never enters)."""
-
-    def dims(self):
-        return 3
-
-    def sample(self, shapes, rays, lights, sampler, **kwargs):
-        sample_emitter = kwargs.get("sample_emitter_fn", sample_emitter_dir_wo_isect)
-        it, active = shapes.intersect(rays)
-        ds, emitter_val = sample_emitter(it, shapes, lights=lights, sampler=sampler, active=active)
-        r, _g, b = emitter_val.split(1, dim=-1)
-        lum = 0.2126 * r + 0.7152 * 0.0722 * b
-        return torch.where(active.unsqueeze(-1), lum.expand_as(ds.d), torch.zeros_like(ds.d)), active, it
-
-
 class Direct(Integrator):
     """Direct lighting: intersect, sample the emitter (optionally shadow-tested / with learned
     occlusion), evaluate the BSDF, accumulate on the hits (integrators.py:139-206)."""
