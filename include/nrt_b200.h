@@ -322,6 +322,10 @@ int nrt_nerfle_render_camera(const nrt_mlp_t* first, const nrt_mlp_t* second, in
                              const nrt_camera_t* cam, const float* ts, const nrt_nerf_sampling_t* sampling,
                              const float* light_code, int light_dim, float* out_rgb, void* workspace,
                              size_t workspace_bytes, void* stream);
+/* Where nrt_nerfle_render_camera takes the rays of the 16-bit (tensor-core) passes from: 0 (default) = k_camera_rays writes each
+ * chunk's rays into the workspace before the chunk's first pass; 1 = the MLP kernels compute every sample's ray from the camera
+ * in their prologues (no ray array; bit-identical image; measured 2.5-3 % slower on B200).  Process-wide. */
+int nrt_set_camera_rays_mode(int fused);
 /* Host-image variant: nothing but the camera goes in, the image comes back to (pinned) host memory; synchronises. */
 int nrt_nerfle_render_camera_host(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec,
                                   const nrt_camera_t* cam, const float* ts_host, int S,

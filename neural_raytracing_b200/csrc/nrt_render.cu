@@ -2,6 +2,7 @@
 // coarse -> importance resample -> fine -> merged compositing), plus the HBM-bound
 // sampling / compositing kernels of the hierarchical path.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "nrt_common.cuh"
 
@@ -13,18 +14,43 @@ int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
                        const float* ts, const float* ts_per_ray, int S, const float* light_code,
                        int light_dim, const int32_t* view_of_ray, int second_out_act, float* out_rgb,
                        float* out_sigma, float* out_srgb, void* workspace, size_t workspace_bytes,
-                       cudaStream_t st);
+                       cudaStream_t st, const nrt_camera_t* cam = nullptr, int64_t cam_r0 = 0);
+bool nrt_nerfle_pass_tc_camera_ok(const nrt_mlp_t* first, const nrt_mlp_t* second, int light_dim);
 size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t* second, int64_t R, int S);
 
 static int nerf_pass(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
                      const float* ts, const float* ts_per_ray, int S, const float* light_code, int light_dim,
                      const int32_t* view_of_ray, float* out_rgb, float* out_sigma, float* out_srgb,
-                     void* ws, size_t ws_bytes, cudaStream_t st) {
+                     void* ws, size_t ws_bytes, cudaStream_t st, const nrt_camera_t* cam = nullptr, int64_t cam_r0 = 0) {
   if (prec == NRT_PREC_F32)
     return nrt_nerfle_pass_f32(first, second, rays, R, ts, ts_per_ray, S, light_code, light_dim, view_of_ray,
                                NRT_OUT_SIGMOID, out_rgb, out_sigma, out_srgb, st);
   return nrt_nerfle_pass_tc(first, second, prec, rays, R, ts, ts_per_ray, S, light_code, light_dim, view_of_ray,
-                            NRT_OUT_SIGMOID, out_rgb, out_sigma, out_srgb, ws, ws_bytes, st);
+                            NRT_OUT_SIGMOID, out_rgb, out_sigma, out_srgb, ws, ws_bytes, st, cam, cam_r0);
+}
+
+// Where a camera-driven frame gets its rays.  Mode 0 (default): k_camera_rays generates each chunk's rays into the
+// workspace (24 B per ray) right before the chunk's first pass.  Mode 1 (nrt_set_camera_rays_mode(1), or NRT_CAMERA_RAYS=fused
+// in the environment): the two tensor-core kernels compute the ray of every sample in their per-sample prologues from the
+// camera (IoNerfFirst / IoNerfSecond with CAM; bit-identical rays, no ray array at all).  Measured on B200, cfg2 frame from the
+// camera, alternating runs on one box: 53.6 / 54.1 / 53.9 ms (mode 0) against 54.8 / 55.8 / 55.1 ms (mode 1) -- recomputing a ray
+// 64-192 times per ray in kernels whose epilogue warps are bound by the instructions they issue costs 2.5-3 %, to save 24 B of
+// the 27 KB of per-ray traffic; hence mode 0 (profiles/r02i_camera_fused.md).
+#include <atomic>
+static std::atomic<int> g_camera_mode{-1};
+static bool camera_fused_default() {
+  int m = g_camera_mode.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("NRT_CAMERA_RAYS");
+    m = (e && e[0] == 'f') ? 1 : 0;
+    g_camera_mode.store(m, std::memory_order_relaxed);
+  }
+  return m == 1;
+}
+extern "C" int nrt_set_camera_rays_mode(int fused) {
+  NRT_REQUIRE(fused == 0 || fused == 1, "nrt_set_camera_rays_mode: 0 (prologue kernel) or 1 (inside the MLP kernels)");
+  g_camera_mode.store(fused, std::memory_order_relaxed);
+  return NRT_OK;
 }
 
 // ---- stratified sample distances -------------------------------------------------------------
@@ -303,6 +329,8 @@ static int render_impl(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
   NRT_REQUIRE(workspace != nullptr && workspace_bytes >= need,
               "nrt_nerfle_render: workspace of %zu bytes required, got %zu", need, workspace_bytes);
   float* cam_rays = nullptr; int32_t* cam_view = nullptr;
+  const bool fused = cam && prec != NRT_PREC_F32 && camera_fused_default() &&
+                     nrt_nerfle_pass_tc_camera_ok(first, second, light_dim);
   if (cam) {
     char* tail = (char*)workspace + (need - cam_scratch_bytes(C));
     cam_rays = (float*)tail;
@@ -331,7 +359,9 @@ static int render_impl(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
     const int64_t n = std::min<int64_t>(C, R - r0);
     const float* c_rays = cam ? cam_rays : rays + r0 * 6;
     const int32_t* c_view = cam ? cam_view : view_of_ray ? view_of_ray + r0 : nullptr;
-    if (cam) {
+    // camera-fed kernels: the tensor-core pass computes the rays itself, nothing to generate
+    const nrt_camera_t* kcam = (cam && fused) ? cam : nullptr;
+    if (cam && !fused) {
       const int rcc = nrt_camera_rays_dev(cam, r0, n, cam_rays, cam_view, st);
       if (rcc != NRT_OK) return rcc;
     }
@@ -353,13 +383,13 @@ static int render_impl(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
     int rc;
     if (!store_c) {
       rc = nerf_pass(first, second, prec, c_rays, n, ts_shared, ts_pr, Sc, light_code, light_dim, c_view, c_out,
-                     nullptr, nullptr, tcws, tcws_bytes, st);
+                     nullptr, nullptr, tcws, tcws_bytes, st, kcam, r0);
       if (rc != NRT_OK) return rc;
       continue;
     }
     // coarse pass keeps per-sample sigma / rgb
     rc = nerf_pass(first, second, prec, c_rays, n, ts_shared, ts_pr, Sc, light_code, light_dim, c_view, nullptr,
-                   sig_c, rgb_c, tcws, tcws_bytes, st);
+                   sig_c, rgb_c, tcws, tcws_bytes, st, kcam, r0);
     if (rc != NRT_OK) return rc;
     if (Sf > 0) {
       { NrtProfScope _ps(TAG_SAMPLE_PDF, st);
@@ -372,7 +402,7 @@ static int render_impl(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
             sig_c, ts_shared, ts_pr, Sc, Sf, n, r0, sampling->jitter_seed, ts_f); }
       NRT_CUDA(cudaGetLastError());
       rc = nerf_pass(first, second, prec, c_rays, n, nullptr, ts_f, Sf, light_code, light_dim, c_view, nullptr,
-                     sig_f, rgb_f, tcws, tcws_bytes, st);
+                     sig_f, rgb_f, tcws, tcws_bytes, st, kcam, r0);
       if (rc != NRT_OK) return rc;
     }
     { NrtProfScope _ps(TAG_MERGE_COMPOSITE, st);

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "tc_core.cuh"
+#include "camera_math.cuh"
 
 namespace tc {
 
@@ -58,18 +59,33 @@ struct IoPlain {   // materialised x [M,IN] (+ latent [M,LAT]) -> out [M,OUT] wi
 static inline int pow2_shift(int S) { int k = 0; while ((1 << k) < S) ++k; return (1 << k) == S ? k : -1; }
 __device__ __forceinline__ int64_t ray_of(int64_t m, int S, int shift) { return shift >= 0 ? (m >> shift) : m / S; }
 
-template <int NLAT>
+// CAM: the ray of a sample is not read from an array but computed from the pixel it belongs to -- ray index
+// r_off + m / S of the camera's [n_views, nx, ny, bundle] block, camera_math.cuh, bit-identical to k_camera_rays -- so a
+// camera-driven frame has no ray array at all (12 uniform loads of the camera matrix + ~45 arithmetic instructions per sample
+// against 6 broadcast loads; measured in profiles/r02i_camera_fused.md).
+struct NoCam {};
+struct WithCam { nrtcam::CamDev cam; int64_t r_off; };
+
+template <int NLAT, bool CAM = false>
 struct IoNerfFirst {
   const float* rays; const float* ts; const float* ts_per_ray; int S;
   float* sigma; void* latent; int fmt; int lat32; int s_shift;
+  std::conditional_t<CAM, WithCam, NoCam> c;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
     const int64_t ray = ray_of(m, S, s_shift);
     const int s = (int)(m - ray * S);
     const float t = ts_per_ray ? __ldg(ts_per_ray + m) : __ldg(ts + s);
-    const float* r = rays + ray * 6;
-    v[0] = __ldg(r) + t * __ldg(r + 3);
-    v[1] = __ldg(r + 1) + t * __ldg(r + 4);
-    v[2] = __ldg(r + 2) + t * __ldg(r + 5);
+    if constexpr (CAM) {
+      float o[3], d[3];
+      int view;
+      nrtcam::cam_ray(c.cam, c.r_off + ray, o, d, &view);
+      v[0] = o[0] + t * d[0]; v[1] = o[1] + t * d[1]; v[2] = o[2] + t * d[2];
+    } else {
+      const float* r = rays + ray * 6;
+      v[0] = __ldg(r) + t * __ldg(r + 3);
+      v[1] = __ldg(r + 1) + t * __ldg(r + 4);
+      v[2] = __ldg(r + 2) + t * __ldg(r + 5);
+    }
   }
   __device__ __forceinline__ void store(int64_t m, const float* o) const {
     sigma[m] = o[0];
@@ -96,10 +112,24 @@ struct IoNerfFirst {
 };
 
 // NeRFLE.second: [latent | r_d | light code] in, sigmoid(rgb) out.  nerf.py:199-203
-template <int NLAT, int LD, bool PACKED = false>
+template <int NLAT, int LD, bool PACKED = false, bool CAM = false>
 struct IoNerfSecond {
   const float* rays; const void* latent; const float* light_code; const int32_t* view_of_ray; int S;
   float* rgb; int fmt; int out_act; int lat32; int s_shift;
+  std::conditional_t<CAM, WithCam, NoCam> c;
+  // view direction and light-code row of a ray: from the ray array, or from the camera (CAM)
+  __device__ __forceinline__ int dir_and_view(int64_t ray, float* d) const {
+    if constexpr (CAM) {
+      float o[3];
+      int view;
+      nrtcam::cam_ray(c.cam, c.r_off + ray, o, d, &view);
+      return view;
+    } else {
+      const float* r = rays + ray * 6;
+      d[0] = __ldg(r + 3); d[1] = __ldg(r + 4); d[2] = __ldg(r + 5);
+      return view_of_ray ? __ldg(view_of_ray + ray) : 0;
+    }
+  }
   __device__ __forceinline__ void load(int64_t m, float* v) const {
     const int64_t ray = ray_of(m, S, s_shift);
     if (lat32) {
@@ -125,9 +155,7 @@ struct IoNerfSecond {
         }
       }
     }
-    const float* r = rays + ray * 6;
-    v[NLAT] = __ldg(r + 3); v[NLAT + 1] = __ldg(r + 4); v[NLAT + 2] = __ldg(r + 5);
-    const int view = view_of_ray ? __ldg(view_of_ray + ray) : 0;
+    const int view = dir_and_view(ray, v + NLAT);
 #pragma unroll
     for (int j = 0; j < LD; ++j) v[NLAT + 3 + j] = __ldg(light_code + (int64_t)view * LD + j);
   }
@@ -144,9 +172,7 @@ struct IoNerfSecond {
       const uint4 q = __ldg(src + j * 128);
       w[4 * j] = q.x; w[4 * j + 1] = q.y; w[4 * j + 2] = q.z; w[4 * j + 3] = q.w;
     }
-    const float* r = rays + ray * 6;
-    v[NLAT] = __ldg(r + 3); v[NLAT + 1] = __ldg(r + 4); v[NLAT + 2] = __ldg(r + 5);
-    const int view = view_of_ray ? __ldg(view_of_ray + ray) : 0;
+    const int view = dir_and_view(ray, v + NLAT);
 #pragma unroll
     for (int j = 0; j < LD; ++j) v[NLAT + 3 + j] = __ldg(light_code + (int64_t)view * LD + j);
   }
@@ -592,10 +618,19 @@ size_t nrt_nerfle_pass_tc_workspace(const nrt_mlp_t* first, const nrt_mlp_t*, in
   return mpad * nlat * (nerf_latent32() ? 4 : 2) + 256;           // latent scratch between the two kernels
 }
 
+// whether the camera-fed kernels (IoNerfFirst / IoNerfSecond with CAM) exist for this pair of networks: the point-light net
+// with the 16-bit packed latent hand-off (every script's configuration; the others take their rays from k_camera_rays)
+bool nrt_nerfle_pass_tc_camera_ok(const nrt_mlp_t* first, const nrt_mlp_t* second, int light_dim) {
+  MlpDev d1, d2;
+  if (nrt_build_mlp_dev(first, &d1) != NRT_OK || nrt_build_mlp_dev(second, &d2) != NRT_OK) return false;
+  return matches<NetNerfFirst>(d1) && matches<NetNerfSecondPT>(d2) && light_dim == 3 && !nerf_latent32();
+}
+
 int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec, const float* rays, int64_t R,
                        const float* ts, const float* ts_per_ray, int S, const float* light_code, int light_dim,
                        const int32_t* view_of_ray, int second_out_act, float* out_rgb, float* out_sigma,
-                       float* out_srgb, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                       float* out_srgb, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                       const nrt_camera_t* cam, int64_t cam_r0) {
   MlpDev d1, d2;
   int rc = nrt_build_mlp_dev(first, &d1);
   if (rc != NRT_OK) return rc;
@@ -616,6 +651,18 @@ int nrt_nerfle_pass_tc(const nrt_mlp_t* first, const nrt_mlp_t* second, int prec
   void* lat = workspace;
   const int fmt = fmt_of(prec);
   const int s_shift = pow2_shift(S);
+  if (cam != nullptr) {
+    // rays computed inside the kernels from the camera (f4): no ray array
+    NRT_REQUIRE(pt && !lat32, "camera-fed tensor-core NeRF pass: point-light net with the 16-bit latent only");
+    const WithCam wc{nrtcam::make_cam_dev(cam), cam_r0};
+    IoNerfFirst<64, true> io1{nullptr, ts, ts_per_ray, S, out_sigma, lat, fmt, lat32, s_shift, wc};
+    rc = fmt == 0 ? launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST)
+                  : launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);
+    if (rc != NRT_OK) return rc;
+    IoNerfSecond<64, 3, true, true> io2{nullptr, lat, light_code, nullptr, S, out_srgb, fmt, second_out_act, lat32, s_shift, wc};
+    return fmt == 0 ? launch<NetNerfSecondPT, decltype(io2), 0>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND)
+                    : launch<NetNerfSecondPT, decltype(io2), 1>(second->params_tc, io2, M, st, TAG_TC_NERF_SECOND);
+  }
   IoNerfFirst<64> io1{rays, ts, ts_per_ray, S, out_sigma, lat, fmt, lat32, s_shift};
   rc = fmt == 0 ? launch<NetNerfFirst, decltype(io1), 0>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST)
                 : launch<NetNerfFirst, decltype(io1), 1>(first->params_tc, io1, M, st, TAG_TC_NERF_FIRST);

@@ -728,6 +728,12 @@ def camera_rays(cam: CameraDesc, want_view=False):
     return (out, view) if want_view else out
 
 
+def set_camera_rays_mode(fused: bool):
+    """False (default): every chunk's rays come from k_camera_rays; True: the tensor-core NeRF kernels compute each sample's
+    ray from the camera themselves (no ray array; same image bit for bit; measured 2.5-3 % slower on B200)."""
+    N.check(N.lib().nrt_set_camera_rays_mode(1 if fused else 0))
+
+
 def nerfle_render_camera(first: PackedMLP, second: PackedMLP, cam: CameraDesc, ts: Optional[torch.Tensor],
                          light_code: torch.Tensor, prec=PREC_F32, n_coarse: Optional[int] = None, n_fine=0,
                          t_near=0.0, t_far=0.0, jitter_seed=0) -> torch.Tensor:

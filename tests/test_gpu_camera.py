@@ -218,6 +218,21 @@ def test_render_camera_equals_render_of_generated_rays(prec):
         assert tuple(a.shape) == (2, c["nx"], c["ny"], 1, 3)
         assert torch.equal(a, b)
         assert (a[0] - a[1]).abs().max().item() > 0          # the two views differ (pose and light)
+    # the camera-fed kernels (rays computed in the MLP kernels' prologues, no ray array): same image bit for bit, and no
+    # ray-generation launch
+    if prec != "f32":
+        desc = cam.device_desc(400, x0=3, y0=5, nx=24, ny=20)
+        kw = dict(n_coarse=16, n_fine=32, t_near=0.1, t_far=2.0, jitter_seed=9)
+        a = ops.nerfle_render_camera(first, second, desc, None, code, prec=prec, **kw)
+        try:
+            ops.set_camera_rays_mode(True)
+            ops.profile_collect()
+            b = ops.nerfle_render_camera(first, second, desc, None, code, prec=prec, **kw)
+            counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+        finally:
+            ops.set_camera_rays_mode(False)
+        assert torch.equal(a, b)
+        assert "camera_rays" not in counts and counts["mlp_tc_nerf_first"] == 2, counts
     # host-image variant: same pixels in pinned memory
     desc = cam.device_desc(400, x0=3, y0=5, nx=24, ny=20)
     host = torch.empty((2, 24, 20, 1, 3), dtype=torch.float32).pin_memory()
