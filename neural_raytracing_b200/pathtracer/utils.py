@@ -164,3 +164,32 @@ def masked_loss(got, exp, throughput, exp_mask, eps: float = 1e-10, trim: int = 
         fn = F.binary_cross_entropy_with_logits if with_logits else F.binary_cross_entropy
         mask_loss = fn(throughput[misses].reshape(-1, 1), exp_mask[misses].reshape(-1, 1))
     return mask_weight * mask_loss + 10 * color_loss
+
+
+# ---- helpers of the vis scripts (utils.py:409-445) --------------------------------------------------------------
+def sphere_examples(bsdf, device="cuda", size=256, chunk_size=128, scale=100):
+    """One Direct-lit render of the unit sphere per basis of a spatially varying BSDF (utils.py:409-431; dtu_vis.py:108,
+    nerv_vis.py, visualize.py): analytic sphere, look-at camera at distance 2, one point light at (0, 1, 4)."""
+    from . import integrators
+    from .main import pathtrace
+    from .shapes import Sphere
+    from ..renderer import OpenGLPerspectiveCameras, PointLights, look_at_view_transform
+    ball = Sphere([0, 0, 0], 1, device=device)
+    R, T = look_at_view_transform(dist=2.0, elev=0, azim=0)
+    cameras = OpenGLPerspectiveCameras(device=device, R=R, T=T)
+    lights = PointLights(device=device, location=[[0.0, 1.0, 4.0]], scale=scale)
+    return [pathtrace(ball, cameras=cameras, lights=lights, chunk_size=chunk_size, size=size, bsdf=basis,
+                      integrator=integrators.Direct(), device=device, silent=True)[0] for basis in bsdf.bsdfs]
+
+
+def heightmap(warp, size=256, device="cuda"):
+    """pdf of a warp over the unit square (utils.py:434-439)."""
+    u, v = torch.meshgrid(torch.linspace(0, 1, size, device=device), torch.linspace(0, 1, size, device=device), indexing="ij")
+    return warp.pdf(torch.stack([u, v], dim=-1))
+
+
+def depth_image(img):
+    """[depth | mask] -> grey RGBA with the depth scaled by its maximum (utils.py:441-445; colocate.py, nerfle.py)."""
+    depth, mask = img.split(1, dim=-1)
+    depth = depth / depth.max()
+    return torch.cat([depth, depth, depth, mask], dim=-1)

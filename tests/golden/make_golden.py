@@ -489,6 +489,34 @@ def gen_vis():
     print("vis.npz:", {k: (v.shape, float(np.mean(v))) for k, v in out.items() if hasattr(v, "shape") and v.ndim > 1})
 
 
+def gen_sphere_examples():
+    """utils.sphere_examples (utils.py:409-431) as dtu_vis.py:108 / nerv_vis.py / visualize.py call it: every basis of the
+    spatially varying BSDF on the analytic unit sphere (shapes/shapes.py:31-68) under the fork's renderer.PointLights
+    (renderer/lighting.py:289-305), Direct lighting; plus depth_image (utils.py:441-445).  pathtrace's default pixel jitter
+    (1e-3 pixel) stays on, as in the scripts: the fixture is compared with a tolerance that covers it."""
+    import pytorch3d.pathtracer as P
+    from pytorch3d.pathtracer.utils import sphere_examples, depth_image
+    from pytorch3d.pathtracer.shapes.shapes import Sphere
+    from scenes import build_pipeline
+    out = {}
+    _shape, _sphere, bsdf, _lights, _integ, _w = build_pipeline(P, "dtu")
+    with torch.no_grad():
+        imgs = sphere_examples(bsdf, device="cpu", size=24, chunk_size=12, scale=100)
+    out["bases"] = np.stack([i.numpy() for i in imgs])
+    rays = T(synth.camera_rays(91, 300))
+    rays[:, :3] *= 2.5
+    ball = Sphere([0.1, -0.2, 0.05], 0.8, device="cpu")
+    si, hit = ball.intersect(rays.clone())
+    out["rays"], out["hit"], out["t"], out["p"], out["n"], out["wi"] = rays.numpy(), hit.numpy(), si.t.numpy(), si.p.numpy(), si.n.numpy(), si.wi.numpy()
+    lo, hi, m = ball.intersect_limits(rays.clone())
+    out["lo"], out["hi"] = lo.numpy(), hi.numpy()
+    d = torch.rand(5, 7, 2) + 0.1
+    out["depth_in"], out["depth_out"] = d.numpy(), depth_image(d).numpy()
+    out["src"] = np.array("pytorch3d/pathtracer/utils.py:409-445; shapes/shapes.py:9-97; renderer/lighting.py:220-305")
+    np.savez_compressed(os.path.join(HERE, "sphere_examples.npz"), **out)
+    print("sphere_examples.npz:", out["bases"].shape, out["bases"].mean(axis=(1, 2, 3)), "hits", int(hit.sum()), "of", len(hit))
+
+
 def train_loop_case(P, train_nerf, device):
     """The tiny nerf_synthetic.py-style problem both the reference and the mirror train on (shared by the test)."""
     import scenes
@@ -711,7 +739,7 @@ def gen_path():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays", "vis"]
+                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays", "vis", "sphere_examples"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
