@@ -288,3 +288,52 @@ def test_dtu(density_field, integrator, bsdf, lights, poses, intrinsics, exp_img
 test.__test__ = False
 test_nerf.__test__ = False
 test_dtu.__test__ = False
+
+
+# ---- dataset layouts the scripts load their targets from (training_utils.py:538-595) ------------------------------
+def test_nerf_resources(directory, size=128, kind="test", device="cuda"):
+    """NeRF-synthetic layout (nerf_synthetic.py:125): `directory + transforms_<kind>.json` with `camera_angle_x` and
+    per-frame `file_path` / `transform_matrix`.  -> (cam_to_worlds [3,4] each, camera centre pulled onto the unit
+    sphere; focal = 0.5 size / tan(fov_x / 2); RGB targets; masks = ceil(alpha - 1e-5))."""
+    import json
+    from .utils import load_image
+    assert kind in ("train", "test")
+    with open(directory + "transforms_%s.json" % kind) as f:
+        meta = json.load(f)
+    focal = 0.5 * size / np.tan(0.5 * float(meta["camera_angle_x"]))
+    poses, images, masks = [], [], []
+    for frame in meta["frames"]:
+        rgba = load_image(os.path.join(directory, frame["file_path"] + ".png"), resize=(size, size)).to(device)
+        images.append(rgba[..., :3])
+        masks.append((rgba[..., 3] - 1e-5).ceil())
+        pose = torch.tensor(frame["transform_matrix"], dtype=torch.float, device=device)[:3, :4]
+        pose[:3, 3] = F.normalize(pose[:3, 3], dim=-1)
+        poses.append(pose)
+    return poses, focal, images, masks
+
+
+def test_colocate_resources(kind, size=128, dist=1, device="cuda", root="mitsuba_scenes/cbox_relight"):
+    """The relighting set of colocate.py:162 / nerfle.py:177: 4 x 4 camera poses (elevation 0..45, azimuth -90..90), each
+    with 3 x 3 light positions on the sphere of radius 1.05 dist; images `gt_<kind>_<i>_<j>_<k>_<l>.png` under `root`.
+    -> (Rs, Ts, RGB targets, alpha masks, light positions), 144 entries each."""
+    from .utils import load_image
+    from ..renderer.cameras import look_at_view_transform
+
+    def on_sphere(elev, azim, rad):
+        elev, azim = torch.deg2rad(elev), torch.deg2rad(azim)
+        return torch.stack([rad * elev.cos() * azim.sin(), rad * elev.cos() * azim.cos(), rad * elev.sin()], dim=0)
+
+    Rs, Ts, images, masks, light_xyz = [], [], [], [], []
+    for i, elev in enumerate(torch.linspace(0, 45, 4, device=device)):
+        for j, azim in enumerate(torch.linspace(-90, 90, 4, device=device)):
+            R, T = look_at_view_transform(dist=dist, elev=elev, azim=azim, device=device)
+            for k, light_elev in enumerate(torch.linspace(0, 45, 3, device=device)):
+                for l, light_azim in enumerate(torch.linspace(-90, 90, 3, device=device)):
+                    rgba = load_image(os.path.join(root, "gt_%s_%03d_%03d_%03d_%03d.png" % (kind, i, j, k, l)),
+                                      (size, size)).to(device)
+                    Rs.append(R)
+                    Ts.append(T)
+                    images.append(rgba[..., :3])
+                    masks.append(rgba[..., 3])
+                    light_xyz.append(on_sphere(light_elev, light_azim, dist * 1.05))
+    return Rs, Ts, images, masks, light_xyz

@@ -517,6 +517,33 @@ def gen_sphere_examples():
     print("sphere_examples.npz:", out["bases"].shape, out["bases"].mean(axis=(1, 2, 3)), "hits", int(hit.sum()), "of", len(hit))
 
 
+def gen_dataset_loaders():
+    """training_utils.test_nerf_resources / test_colocate_resources (training_utils.py:538-595) on the miniature datasets of
+    tests/golden/tiny_datasets.py: what the reference's loaders return for them."""
+    import tempfile
+    import tiny_datasets
+    from pytorch3d.pathtracer.training_utils import test_nerf_resources, test_colocate_resources
+    out = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        d = tiny_datasets.write_nerf_synthetic(os.path.join(tmp, "lego")) + os.sep
+        c2w, focal, imgs, masks = test_nerf_resources(d, size=8, kind="test", device="cpu")
+        out["nerf_c2w"], out["nerf_focal"] = torch.stack(c2w).numpy(), np.array(focal, np.float64)
+        out["nerf_imgs"], out["nerf_masks"] = torch.stack(imgs).numpy(), torch.stack(masks).numpy()
+        cwd = os.getcwd()
+        os.chdir(tmp)
+        try:
+            tiny_datasets.write_colocate(os.path.join("mitsuba_scenes", "cbox_relight"), "bunny")
+            Rs, Ts, imgs, masks, xyzs = test_colocate_resources("bunny", size=4, dist=1.3, device="cpu")
+        finally:
+            os.chdir(cwd)
+        out["col_R"], out["col_T"] = torch.cat(Rs).numpy(), torch.cat(Ts).numpy()
+        out["col_imgs"], out["col_masks"], out["col_xyz"] = torch.stack(imgs).numpy(), torch.stack(masks).numpy(), torch.stack(xyzs).numpy()
+    out["src"] = np.array("pytorch3d/pathtracer/training_utils.py:538-595; utils.py:365-369")
+    np.savez_compressed(os.path.join(HERE, "dataset_loaders.npz"), **out)
+    print("dataset_loaders.npz:", out["nerf_c2w"].shape, float(out["nerf_focal"]), out["col_R"].shape, out["col_xyz"].shape,
+          "mask values", np.unique(out["nerf_masks"]))
+
+
 def train_loop_case(P, train_nerf, device):
     """The tiny nerf_synthetic.py-style problem both the reference and the mirror train on (shared by the test)."""
     import scenes
@@ -739,7 +766,7 @@ def gen_path():
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["mlp", "sdf", "nerfle", "nerfle_train", "composite", "shading", "pipeline", "cameras",
-                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays", "vis", "sphere_examples"]
+                             "train_loop", "plain_nerf", "path", "colocate64", "dtu16", "lights_bsdf", "camera_rays", "vis", "sphere_examples", "dataset_loaders"]
     for w in which:
         torch.manual_seed(0); random.seed(0); np.random.seed(0)
         globals()["gen_" + w]()
