@@ -217,7 +217,8 @@ __device__ __forceinline__ void sph_fill(const SdfDev& sd) {
 }
 // APPROX (shadow march, min scan: a boolean / an argmin come out): norm as d2 * rsqrt(d2) and the exponential as one
 // ex2.approx on a pre-scaled argument, 2 + 2 instead of 8 + 6 instructions per sphere (sqrtf carries a Newton step and a
-// slow-path branch, __expf a range check); the primary march and the point evaluation keep the round-1 arithmetic.
+// slow-path branch, __expf a range check); since the end of round 2 the primary march as well (NRT_MARCH_FAST bit 1: 9.4 ->
+// 8.7 ms per 262,144 rays with every golden unchanged); the point evaluation keeps the round-1 arithmetic.
 template <bool APPROX = false>
 __device__ __forceinline__ float sphere_smin_fast(const SdfDev& sd, float px, float py, float pz) {
   float sum = 0.0f;
@@ -290,11 +291,16 @@ enum { TC_MARCH_PRIMARY = 0, TC_MARCH_SHADOW = 1 };
 // state machine as k_sdf_march (nrt_f32.cu); the SDF value comes from the 16-bit tensor-core evaluation.
 template <int MODE>
 struct IoMarch {
-  // softplus form of the hidden layers (tc_core.cuh, SoftplusOf).  The primary march keeps the two-MUFU form: depths and
-  // hit masks stay bit-identical to the kernels the goldens were accepted with (a grazing pixel of the 16-basis DTU
-  // golden flips with ANY change of the 16-bit rounding sequence: 36.9 instead of > 50 dB on 4,096 pixels).  The shadow
+  // softplus form of the hidden layers (tc_core.cuh, SoftplusOf).  The primary march keeps the two-MUFU form: with the fp32
+  // polynomial (NRT_MARCH_FAST bit 0; march 9.4 -> 9.1 ms per 262,144 rays, 8.1 ms together with bit 1) one grazing pixel of the
+  // 16-basis DTU golden flips from hit to miss (36.9 instead of 94 dB on 8,192 pixels, g_spvar.init.weight cosine 0.9966 < 0.997).
+  // The sphere set of the primary march takes the approximate norm / exponential of the shadow march and the scan
+  // (NRT_MARCH_FAST bit 1, default): 9.4 -> 8.7 ms, every golden unchanged (hits 5,401 / 5,401, image 94.4 dB).  The shadow
   // march (a boolean comes out) takes the fp32 exponent + packed-half polynomial like the min scan.
-  static constexpr int kSoftplusForm = MODE == TC_MARCH_PRIMARY ? 0 : 3;
+#ifndef NRT_MARCH_FAST
+#define NRT_MARCH_FAST 2
+#endif
+  static constexpr int kSoftplusForm = MODE == TC_MARCH_PRIMARY ? ((NRT_MARCH_FAST & 1) ? 1 : 0) : 3;
   __device__ __forceinline__ void cta_init() const { sph_fill(sd); }
   SdfDev sd;
   const float* rays; const float* max_t_per_ray; const uint8_t* active; int64_t R;
@@ -337,7 +343,7 @@ struct IoMarch {
     return true;
   }
   __device__ __forceinline__ void consume(State& s, const float* o) const {
-    const float d = sphere_smin_fast<MODE != TC_MARCH_PRIMARY>(sd, s.p[0], s.p[1], s.p[2]) + o[0];
+    const float d = sphere_smin_fast<MODE != TC_MARCH_PRIMARY || ((NRT_MARCH_FAST & 2) != 0)>(sd, s.p[0], s.p[1], s.p[2]) + o[0];
     s.steps++;
     if (MODE == TC_MARCH_PRIMARY) {
       if (d <= eps) { depth[s.r] = s.t; flag[s.r] = 1; s.r = -1; }   // depth is NOT advanced on the hit step
