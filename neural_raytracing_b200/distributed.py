@@ -52,7 +52,10 @@ def render_camera_sharded(render_rows_fn: Callable[[int, int], torch.Tensor], nx
     """Camera-driven multi-GPU frame (f4): rank g renders the pixel ROWS [lo, hi) of the frame's first image axis with
     `render_rows_fn(lo, hi - lo) -> [n_views, hi - lo, ny, C]` (e.g. `ops.nerfle_render_camera` on a window of the camera
     descriptor: every rank generates its own rays on its own device, no ray array exists anywhere) and, if gather, all
-    ranks receive the whole [n_views, nx, ny, C] image.  Rays are independent: the result equals the 1-rank frame."""
+    ranks receive the whole [n_views, nx, ny, C] image.  Rays are independent: the result equals the 1-rank frame bit for
+    bit when the sample distances are deterministic (the reference's shared `ts`, or stratified / hierarchical sampling with
+    jitter_seed = 0); the library's stratified and pixel jitter are keyed by a ray's index inside its CALL, so with a
+    non-zero seed an N-rank frame is a different (equally distributed) draw than the 1-rank frame."""
     rank, world = _world(group)
     lo, hi = shard_range(nx, rank, world)
     local = render_rows_fn(lo, hi - lo)

