@@ -195,8 +195,12 @@ extern "C" void nrtdbg_set_timeline(long long* dev_buf) { g_dbg_timeline = dev_b
 // (sph_fill, once per CTA through the policies' cta_init): per sample and sphere three broadcast LDS.128 + one LDS instead
 // of 13 dependent global loads in a loop that could not be unrolled.  Round 2 measured the sphere set at a quarter of the
 // min-scan kernel (35.1 ms for sdf_eval against 23.5 ms for the bare MLP on 33.8 M samples).  Same operation order as
-// before: values are bit-identical.  More than kSphMax spheres (nerf_synthetic.py uses 128) take the global-memory loop.
-constexpr int kSphMax = 64;
+// before: values are bit-identical.  The table holds up to kSphMax = 128 spheres (nerf_synthetic.py's SphereSDF(n=2<<6); 6.5 KB
+// next to the 220 KB of streamed-weight buffers); more than that take the global-memory loop.
+#ifndef NRT_SPH_MAX
+#define NRT_SPH_MAX 128
+#endif
+constexpr int kSphMax = NRT_SPH_MAX;
 __device__ __forceinline__ float* sph_table() {
   __shared__ __align__(16) float tab[kSphMax * 13];
   return tab;

@@ -269,6 +269,46 @@ def test_tc_shadow_and_min_scan_vs_fp32(R):
     assert float((v_at_16 - m32).abs().max()) < 1e-3   # the position found is (within tolerance) a minimiser
 
 
+@pytest.mark.parametrize("n_spheres", [128, 130])
+def test_tc_sdf_kernels_with_many_spheres(n_spheres):
+    """nerf_synthetic.py builds SphereSDF(n=2<<6): 128 spheres fill the shared-memory sphere table of the tensor-core SDF
+    kernels exactly; 130 take the global-memory loop.  Point evaluation, march, shadow march and min scan against the
+    exact fp32 kernels (which are bit-identical to the oracle for any sphere count, test_gpu_parity.py)."""
+    import torch
+    from neural_raytracing_b200 import ops
+    w = synth.sdf_weights(seed=23, n=n_spheres)
+    sdf = helpers.cuda_sdf(w)
+    R = 20000
+    rays = _t(synth.camera_rays(9, R))
+    pts = _t((0.7 * np.random.RandomState(4).standard_normal((4000, 3))).astype(np.float32))
+    vo = c_oracle.sdf_eval(helpers.oracle_sdf(w), pts.cpu().numpy())
+    v32 = ops.sdf_eval(sdf, pts, prec="f32").cpu().numpy()
+    assert np.array_equal(v32.view(np.uint32), vo.view(np.uint32))
+    v16 = ops.sdf_eval(sdf, pts, prec="f16").cpu().numpy()
+    assert np.abs(v16 - vo).max() < 1e-3
+    d32, h32 = ops.sphere_trace(sdf, rays, 1e-3, 64, 10.0, prec="f32")
+    d16, h16 = ops.sphere_trace(sdf, rays, 1e-3, 64, 10.0, prec="f16")
+    assert 0 < int(h32.sum()) < R
+    assert int((h32 ^ h16).sum()) <= max(1, int(1e-3 * R))
+    both = (h32 & h16)
+    err = (d32 - d16).abs()[both]
+    assert int((err > 1.3e-3).sum()) <= max(2, int(0.01 * err.numel())) and err.median().item() < 3e-4
+    p = rays[:, :3] + d32[:, None] * rays[:, 3:]
+    dirv = torch.tensor([0.3, 1.2, 0.4], device="cuda") - p
+    dist = dirv.norm(dim=-1)
+    srays = torch.cat([p, dirv / dist[:, None]], -1).contiguous()
+    nb32 = ops.shadow_test(sdf, srays, dist, 1e-3, 64, prec="f32")
+    nb16 = ops.shadow_test(sdf, srays, dist, 1e-3, 64, prec="f16")
+    assert int((nb32 ^ nb16).sum()) <= max(1, int(2e-3 * R))
+    step = 2.2 / 128
+    i32, p32, m32 = ops.min_scan(sdf, rays, step, 128, prec="f32")
+    i16, p16, m16 = ops.min_scan(sdf, rays, step, 128, prec="f16")
+    assert (m32 - m16).abs().max().item() < 1e-3
+    assert int(i16.min()) >= 0 and int(i16.max()) <= 128
+    v_at_16 = ops.sdf_eval(sdf, p16.contiguous(), prec="f32")
+    assert float((v_at_16 - m32).abs().max()) < 1e-3   # the position found is (within tolerance) a minimiser
+
+
 def test_tc_march_is_order_invariant():
     """Compaction on the tensor-core path: a ray's result depends only on its own state."""
     import torch
