@@ -68,3 +68,15 @@ def set_precision(p):
     global precision
     assert p in ("f32", "f16", "bf16"), p
     precision = p
+
+
+# pathtrace (main.py:13-93) renders gradient-free frames in row blocks of up to this many rays per integrator call instead of
+# the caller's chunk_size tiles (the kernels are latency-bound on the reference's default 32 x 32 = 1,024-ray tiles: a 64-step
+# march takes 1.8 ms for 4,096 rays and 8.7 ms for 262,144).  0 keeps the caller's tiles.  Rays are independent, so the image
+# is the same; 524,288 rays of a Direct-lit SDF frame need < 4 GB of intermediates.
+max_tile_rays = 524288
+
+
+def set_max_tile_rays(n):
+    global max_tile_rays
+    max_tile_rays = int(n)

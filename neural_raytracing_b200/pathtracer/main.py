@@ -60,6 +60,19 @@ def _camera_frame(shapes, lights, cameras, integrator, size, x0, y0, nx, ny, bun
     return torch.mean(values, dim=-2)       # every pixel is valid under NeRFReproduce (integrators.py:260-267)
 
 
+def _row_block(width, height, rays_per_pixel, chunk_size, addition, device):
+    """Rows per integrator call for a gradient-free GPU frame, or 0 to keep the caller's chunk_size tiles (training, CPU, a
+    caller that reads the last tile's interaction through `addition`, or tiles that are already larger)."""
+    from .. import config
+    budget = config.max_tile_rays
+    if budget <= 0 or torch.is_grad_enabled() or addition is not nothing or not str(device).startswith("cuda"):
+        return 0
+    rows = max(1, budget // max(1, height * rays_per_pixel))
+    if rows * height <= chunk_size * chunk_size:
+        return 0
+    return min(rows, width)
+
+
 def pathtrace(shapes, lights, cameras, integrator, bsdf=None, size=512, width=None, height=None, chunk_size=32,
               bundle_size=4, background=1, addition=nothing, sampler=None, silent=False, trim=0, device="cuda",
               squeeze_first=True, w_isect=False, with_noise=1e-3):
@@ -77,6 +90,18 @@ def pathtrace(shapes, lights, cameras, integrator, bsdf=None, size=512, width=No
         if frame is not None:
             return (frame.squeeze(0) if squeeze_first and batch_dims == 1 else frame), None
     out = torch.full([batch_dims, width, height, integrator.dims()], background, device=device, dtype=torch.float)
+    rows = _row_block(width, height, batch_dims * bundle_size, chunk_size, addition, device)
+    if rows:
+        # gradient-free frame on the GPU: row blocks of up to config.max_tile_rays rays instead of chunk_size tiles (the
+        # per-ray results do not depend on the tiling; `trim` only widens tiles whose border is then cut off again)
+        for x0 in range(0, width, rows):
+            nx = min(rows, width - x0)
+            v, it = _render_tile(shapes, lights, cameras, integrator, bsdf, (x0, 0, nx, height), sampler, bundle_size, size,
+                                 batch_dims, with_noise, w_isect, background, device)
+            out[:, x0:x0 + nx, :, :] = v
+        if squeeze_first and batch_dims == 1:
+            out = out.squeeze(0)
+        return out, addition(it)
     for x0 in range(0, width, chunk_size):
         for y0 in range(0, height, chunk_size):
             win = (x0 - trim, y0 - trim, chunk_size + 2 * trim, chunk_size + 2 * trim)

@@ -182,3 +182,41 @@ def test_nerfle_module_tensor_core_precision():
     assert np.abs(rgb2.detach().cpu().numpy() - ref).max() < 1e-3
     assert torch.isfinite(n.first.init.weight.grad).all() and n.first.init.weight.grad.abs().sum() > 0
     assert n.second.out.weight.grad.abs().sum() > 0
+
+
+def test_gradient_free_frames_render_in_row_blocks():
+    """pathtrace under no_grad ignores a small chunk_size and renders row blocks of up to config.max_tile_rays rays: the same
+    image as the caller's tiles (rays are independent), one march launch instead of sixteen."""
+    torch, P, g = _setup()
+    from neural_raytracing_b200 import config, ops
+    from neural_raytracing_b200.pathtracer.cameras import NeRFCamera
+    size = 16
+    shape, sphere, bsdf, lights, integrator, w_isect = scenes.build_pipeline(P, "colocate", device="cuda")
+    c2w, focal = synth.nerf_cameras(1, size, device="cuda")
+    cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cuda")
+
+    def frame(chunk, trim=0):
+        ops.profile_collect()
+        with torch.no_grad():
+            img, _ = P.pathtrace(shape, size=size, chunk_size=chunk, bundle_size=1, bsdf=bsdf, integrator=integrator,
+                                 lights=lights, cameras=cam, device="cuda", silent=True, background=0, w_isect=w_isect,
+                                 with_noise=False, trim=trim)
+        counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+        return img, counts.get("sdf_march_f32", 0) + counts.get("sdf_march_tc", 0)
+    whole, n_whole = frame(16)
+    blocks, n_blocks = frame(4)
+    assert n_whole == 1 and n_blocks == 1
+    assert torch.equal(blocks, whole)
+    assert torch.equal(frame(4, trim=2)[0], whole)
+    prev = config.max_tile_rays
+    try:
+        config.set_max_tile_rays(0)                       # the caller's tiles, as in the reference
+        tiles, n_tiles = frame(4)
+        config.set_max_tile_rays(100)                     # 6 rows of 16 pixels per call: uneven last block
+        uneven, n_uneven = frame(4)
+    finally:
+        config.set_max_tile_rays(prev)
+    assert n_tiles == 16 and n_uneven == 3
+    assert (tiles - whole).abs().max().item() < 1e-6 and (uneven - whole).abs().max().item() < 1e-6
+    ref = g["colocate_img"]
+    assert helpers.psnr(whole.cpu().numpy(), ref) > 50
