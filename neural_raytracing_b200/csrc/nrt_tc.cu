@@ -375,9 +375,11 @@ struct IoScanEval {
   SdfDev sd;
   const float* rays; double step; int n1; float* val;
   __device__ __forceinline__ void point(int64_t m, float* p) const {
-    const int64_t ray = m / n1;
-    const int k = (int)(m - ray * n1);
-    const float* rp = rays + ray * 6;
+    // (a launch covers at most 262,144 rays x (n + 1) samples: 32-bit index arithmetic; the 64-bit division costs ~50
+    //  integer instructions and point() runs twice per sample, in load and in store)
+    const uint32_t ray = (uint32_t)m / (uint32_t)n1;
+    const int k = (int)((uint32_t)m - ray * (uint32_t)n1);
+    const float* rp = rays + (int64_t)ray * 6;
     const float t = (float)(step * (double)k);   // python float (double) product, rounded to fp32 when it scales d
 #pragma unroll
     for (int j = 0; j < 3; ++j) p[j] = (k == 0) ? __ldg(rp + j) : __fadd_rn(__ldg(rp + j), __fmul_rn(t, __ldg(rp + 3 + j)));
@@ -578,6 +580,7 @@ int nrt_sdf_min_scan_tc(const nrt_sphere_sdf_t* s, int prec, const float* rays, 
   NRT_REQUIRE(matches<NetSdfShift>(d.mlp), "tensor-core SDF path: shift must be the 8x128 softplus MLP with 32 frequencies");
   (void)counter;
   const int n1 = n_steps + 1;
+  NRT_REQUIRE(n_steps >= 0 && n1 <= 8192, "tensor-core min scan: 0..8191 steps (32-bit sample index per 262,144-ray pass)");
   const int64_t kChunk = 262144;                       // rays per pass: bounds the scratch to 135 MB at n = 128
   const int64_t C = std::min<int64_t>(R, kChunk);
   // stream-ordered scratch from the device's default memory pool; without a release threshold the pool hands the
