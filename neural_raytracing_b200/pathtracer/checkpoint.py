@@ -124,3 +124,42 @@ def save_sdf_archive(sphere_sdf, path):
     scripted = torch.jit.script(m)
     torch.jit.save(scripted, path)
     return path
+
+
+def adopt_script_sphere_sdf(scripted):
+    """A TorchScript SphereSDF archive as the scripts hold it (`shape = torch.jit.load(path, device); SDF(sdf=shape)`,
+    dtu.py:93-94, nerf_synthetic.py:63-64, colocate.py:65-66) -> a SphereSDF of this package whose parameters ARE the
+    archive's parameter tensors (same objects: an optimizer step or a load_state_dict on either side is seen by both, and
+    `torch.jit.save(density_field.sdf, ...)` later writes the trained weights), so that SDF runs the fused march / scan /
+    normals kernels on it.  None when `scripted` is not a SphereSDF archive (SDF then marches the callable generically)."""
+    from .shapes.sdfs import SphereSDF
+    if not isinstance(scripted, torch.jit.ScriptModule):
+        return None
+    params = dict(scripted.named_parameters())
+    need = {"centers", "radii", "tfs", "shift.init.weight", "shift.init.bias", "shift.out.weight", "shift.out.bias"}
+    if not need.issubset(params.keys()) or not hasattr(scripted, "shift") or not hasattr(scripted.shift, "basis_p"):
+        return None
+    basis_p = scripted.shift.basis_p
+    try:
+        n, in_size, dim_p, hidden, num_layers = _shape_of(params, basis_p)
+    except ValueError:
+        return None
+    device = params["centers"].device
+    out = SphereSDF(n=n, device=device)
+    ref = out.shift
+    if (ref.in_size, ref.init.in_features, ref.init.out_features, len(ref.layers)) != (in_size, dim_p, hidden, num_layers):
+        return None
+    own = dict(out.named_parameters())
+    if set(own.keys()) != set(params.keys()):
+        return None
+    for name, tensor in params.items():
+        if tuple(own[name].shape) != tuple(tensor.shape):
+            return None
+        mod = out
+        *path, leaf = name.split(".")
+        for part in path:
+            mod = getattr(mod, part)
+        mod._parameters[leaf] = tensor                 # share, do not copy
+    out.shift.basis_p = basis_p.detach().to(device=device, dtype=torch.float32)
+    out.invalidate_packed()
+    return out

@@ -174,13 +174,32 @@ class SDF:
     def __len__(self):
         return 1
 
+    # `sdf` is what the caller handed over (and what `torch.jit.save(density_field.sdf, ...)` writes back, dtu.py:159);
+    # `_impl` is what is evaluated: the same object, except for a TorchScript SphereSDF archive -- the way the scripts hold
+    # their shape (`SDF(sdf=torch.jit.load(path, device))`, dtu.py:93-94) -- which is adopted as a SphereSDF of this package
+    # sharing the archive's parameter tensors (checkpoint.adopt_script_sphere_sdf), so that it runs on the fused kernels
+    # instead of the generic march over a scripted callable.
+    @property
+    def sdf(self):
+        return self._sdf
+
+    @sdf.setter
+    def sdf(self, model):
+        self._sdf = model
+        self._impl = model
+        if isinstance(model, torch.jit.ScriptModule):
+            from ..checkpoint import adopt_script_sphere_sdf
+            adopted = adopt_script_sphere_sdf(model)
+            if adopted is not None:
+                self._impl = adopted
+
     def parameters(self):
-        return self.sdf.parameters()
+        return self._impl.parameters()
 
     # ---- fused / unfused dispatch -----------------------------------------------------------
     def _fused(self):
-        """PackedSDF if self.sdf is (or wraps) a SphereSDF the kernels can evaluate, else None."""
-        s = self.sdf
+        """PackedSDF if self._impl is (or wraps) a SphereSDF the kernels can evaluate, else None."""
+        s = self._impl
         if isinstance(s, SphereSDF) and s.centers.is_cuda:
             return s.packed()
         return None
@@ -193,7 +212,7 @@ class SDF:
         with torch.no_grad():
             for _ in range(self.max_steps):
                 remaining = remaining & (depths < max_t).squeeze(-1)
-                d = self.sdf(r_o + r_d * depths)
+                d = self._impl(r_o + r_d * depths)
                 hits = remaining & (d <= self.epsilon)
                 hit_any = hit_any | hits
                 remaining = remaining & ~hits
@@ -209,7 +228,7 @@ class SDF:
         packed = self._fused()
         if packed is not None:
             d, out_active = ops.sphere_trace(packed, rays.detach(), self.epsilon, self.max_steps, float(max_t),
-                                             prec=self.sdf.precision())
+                                             prec=self._impl.precision())
             depths = d.unsqueeze(-1)
         else:
             depths, out_active = self._march_generic(r_o, r_d, max_t)
@@ -254,13 +273,13 @@ class SDF:
             mt = max_t if torch.is_tensor(max_t) else torch.full(rays.shape[:-1], float(max_t), device=rays.device)
             act = active if torch.is_tensor(active) else None
             return ops.shadow_test(packed, rays.detach(), mt.detach().float().reshape(rays.shape[:-1]), self.epsilon,
-                                   self.max_steps, active=act, prec=self.sdf.precision())
+                                   self.max_steps, active=act, prec=self._impl.precision())
         r_o, r_d = rays.split(3, dim=-1)
         depths = torch.zeros(r_o.shape[:-1] + (1,), device=rays.device) + 1e2 * self.epsilon
         remaining = torch.ones(depths.shape[:-1], dtype=torch.bool, device=rays.device)
         with torch.no_grad():
             for _ in range(self.max_steps):
-                d = self.sdf(r_o + r_d * depths)
+                d = self._impl(r_o + r_d * depths)
                 hits = remaining & (d < self.epsilon)
                 depths = torch.where(remaining.unsqueeze(-1), depths + d.unsqueeze(-1), depths)
                 remaining = remaining & ~hits
@@ -271,7 +290,7 @@ class SDF:
         enabled: the same forward-mode kernel for the residual MLP with its hand-written reverse pass (so eikonal /
         shading losses reach the SDF weights), the sphere set through create_graph autograd.  Callables other than
         SphereSDF (and points that themselves require grad) take the reference's create_graph autograd."""
-        s = self.sdf
+        s = self._impl
         wants_graph = torch.is_grad_enabled() and (not isinstance(s, SphereSDF) or
                                                    any(q.requires_grad for q in s.parameters()))
         if isinstance(s, SphereSDF) and p.is_cuda and not wants_graph and ops.HAS_SDF_VALUE_GRAD:
@@ -304,14 +323,14 @@ class SDF:
         packed = self._fused()
         if packed is not None:
             rays = torch.cat([r_o_local.expand_as(d), d], dim=-1).detach()
-            _idx, best_pos, _mv = ops.min_scan(packed, rays, step, n, prec=self.sdf.precision())
+            _idx, best_pos, _mv = ops.min_scan(packed, rays, step, n, prec=self._impl.precision())
         else:
             with torch.no_grad():
-                sd = self.sdf(r_o_local).squeeze(-1)
+                sd = self._impl(r_o_local).squeeze(-1)
                 cur, idxs = sd, torch.zeros_like(sd, dtype=torch.long)
                 for i in range(n):
-                    sd = self.sdf(r_o_local + (step * (i + 1)) * d).squeeze(-1)
+                    sd = self._impl(r_o_local + (step * (i + 1)) * d).squeeze(-1)
                     idxs = torch.where(sd < cur, i + 1, idxs)
                     cur = torch.minimum(cur, sd)
             best_pos = r_o_local + idxs.unsqueeze(-1).unsqueeze(-1) * step * d
-        return self.sdf(best_pos), best_pos
+        return self._impl(best_pos), best_pos

@@ -55,3 +55,42 @@ def test_sdf_archive_of_another_module_is_rejected(tmp_path):
     torch.jit.save(torch.jit.script(torch.nn.Linear(3, 1)), path)
     with pytest.raises(ValueError, match="not a SphereSDF archive"):
         checkpoint.load_sdf_archive(path, device="cpu")
+
+
+def test_script_archive_is_adopted_with_shared_parameters(tmp_path):
+    """What the scripts literally do -- `shape = torch.jit.load(path, device); density_field = SDF(sdf=shape)` (dtu.py:93-94),
+    optimise `density_field.parameters()`, `torch.jit.save(density_field.sdf, ...)` (dtu.py:159): the archive is evaluated as a
+    SphereSDF of this package that SHARES its parameter tensors, `.sdf` stays the archive."""
+    from neural_raytracing_b200.pathtracer import checkpoint
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    g = helpers.golden("sdf")
+    path = str(tmp_path / "dtu_sdf.pt")
+    checkpoint.save_sdf_archive(_sphere_sdf_from(helpers.golden_sdf_weights()), path)
+    shape = torch.jit.load(path, "cpu")
+    field = SDF(sdf=shape, device="cpu")
+    assert field.sdf is shape and isinstance(field._impl, SphereSDF)
+    mine, theirs = dict(field._impl.named_parameters()), dict(shape.named_parameters())
+    assert mine.keys() == theirs.keys()
+    assert all(mine[k].data_ptr() == theirs[k].data_ptr() for k in mine)
+    assert {p.data_ptr() for p in field.parameters()} == {p.data_ptr() for p in shape.parameters()}
+    pts = torch.from_numpy(g["pts"])
+    assert np.abs(field._impl(pts).detach().numpy() - g["sdf_vals"]).max() < 2e-6
+    # an optimizer step on density_field.parameters() changes what the archive computes and what torch.jit.save writes
+    opt = torch.optim.SGD(field.parameters(), lr=0.1)
+    field._impl(pts).sum().backward()
+    assert all(p.grad is not None for p in shape.parameters())          # the gradient lands on the archive's tensors
+    before = shape(pts).detach().clone()
+    opt.step()
+    after = shape(pts).detach()
+    assert (after - before).abs().max().item() > 1e-3
+    assert torch.allclose(field._impl(pts).detach(), after, atol=2e-6)
+    out = str(tmp_path / "trained.pt")
+    torch.jit.save(field.sdf, out)
+    assert torch.allclose(torch.jit.load(out, "cpu")(pts).detach(), after, atol=1e-7)
+    # something that is not a SphereSDF archive stays a generic callable
+    other = torch.jit.script(torch.nn.Sequential(torch.nn.Linear(3, 1)))
+    generic = SDF(sdf=other, device="cpu")
+    assert generic._impl is other and generic._fused() is None
+    # plain assignment after construction goes through the same adoption
+    generic.sdf = shape
+    assert isinstance(generic._impl, SphereSDF)

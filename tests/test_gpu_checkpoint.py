@@ -33,3 +33,40 @@ def test_loaded_archive_runs_on_the_fused_march(tmp_path):
     same = hit == g["hit"].astype(bool)
     depth = it.t.reshape(-1).cpu().numpy()
     assert np.abs(depth[same] - g["depth"][same]).max() < 5e-4
+
+
+def test_script_archive_held_by_sdf_runs_on_the_fused_kernels(tmp_path):
+    """The scripts' own lines (dtu.py:93-94): `shape = torch.jit.load(path, device); density_field = SDF(sdf=shape)`.  The march,
+    the scan and the normals run on the library's kernels (not on the generic loop over a scripted callable), the result equals
+    the load_sdf_archive route bit for bit, and gradients of a loss on the normals land on the ARCHIVE's parameters."""
+    import torch
+    from neural_raytracing_b200 import ops
+    from neural_raytracing_b200.pathtracer import checkpoint
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    g = helpers.golden("sdf")
+    path = str(tmp_path / "dtu_sdf.pt")
+    checkpoint.save_sdf_archive(_sphere_sdf_from(helpers.golden_sdf_weights()), path)
+    random.random = lambda: float(g["fixed_random"])
+    shape = torch.jit.load(path, "cuda")
+    field = SDF(sdf=shape, device="cuda")
+    field.max_steps = 64
+    assert field.sdf is shape and isinstance(field._impl, SphereSDF) and field._fused() is not None
+    other = SDF(sdf=checkpoint.load_sdf_archive(path, device="cuda"), device="cuda")
+    other.max_steps = 64
+    rays = torch.from_numpy(g["rays"]).cuda().reshape(1, -1, 1, 1, 6)
+    ops.profile_collect()
+    with torch.no_grad():
+        it, active = field.intersect(rays)
+    counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+    assert counts.get("sdf_march_f32", 0) == 1 and counts.get("sdf_min_scan_f32", 0) >= 1, counts
+    with torch.no_grad():
+        it2, active2 = other.intersect(rays)
+    assert torch.equal(active, active2) and torch.equal(it.t, it2.t) and torch.equal(it.throughput, it2.throughput)
+    hit = active.reshape(-1).cpu().numpy()
+    assert int((hit != g["hit"].astype(bool)).sum()) <= 2
+    # a differentiable pass: eikonal-style loss on the raw normals -> gradients on the archive's own tensors
+    it3, active3 = field.intersect(rays)
+    assert active3.any()
+    ((it3.raw_normals.norm(dim=-1) - 1) ** 2).mean().backward()
+    grads = [p.grad for p in shape.parameters()]
+    assert all(gr is not None for gr in grads) and sum(float(gr.abs().sum()) for gr in grads) > 0
