@@ -163,3 +163,22 @@ def adopt_script_sphere_sdf(scripted):
     out.shift.basis_p = basis_p.detach().to(device=device, dtype=torch.float32)
     out.invalidate_packed()
     return out
+
+
+def scriptable_view(sphere_sdf):
+    """`torch.jit.script(SphereSDF(n=...))` (colocate.py:63, dtu.py:95, nerf_synthetic.py:65): the module torch.jit.script
+    compiles instead of this package's SphereSDF (whose forward dispatches to the library and is not TorchScript) -- the
+    scriptable restatement of sdfs.py:37-46 over the SAME parameter tensors.  `SDF(sdf=<the scripted module>)` adopts it back
+    (adopt_script_sphere_sdf), so the script's line runs on the fused kernels and trains the tensors it was given."""
+    params = dict(sphere_sdf.named_parameters())
+    basis_p = sphere_sdf.shift.basis_p.detach()
+    n, in_size, dim_p, hidden, num_layers = _shape_of(params, basis_p)
+    m = ScriptSphereSDF(n, in_size, dim_p, hidden, num_layers, int(sphere_sdf.shift.skip))
+    for name, tensor in params.items():
+        mod = m
+        *path, leaf = name.split(".")
+        for part in path:
+            mod = getattr(mod, part)
+        mod._parameters[leaf] = tensor
+    m.shift.basis_p = basis_p.to(torch.float32)
+    return m

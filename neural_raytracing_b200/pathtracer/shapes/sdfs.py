@@ -100,6 +100,11 @@ class SphereSDF(nn.Module):
         self.shift = SkipConnMLP(num_layers=8, hidden_size=128, in_size=3, out=1, device=device, freqs=32,
                                  activation=F.softplus, zero_init=True).to(device)
 
+    def __prepare_scriptable__(self):
+        # torch.jit.script(SphereSDF(...)) compiles the TorchScript restatement over the same parameter tensors
+        from ..checkpoint import scriptable_view
+        return scriptable_view(self)
+
     def set_center(self, at):
         self.centers = nn.Parameter(at.expand_as(self.centers).clone().detach())
 

@@ -94,3 +94,21 @@ def test_script_archive_is_adopted_with_shared_parameters(tmp_path):
     # plain assignment after construction goes through the same adoption
     generic.sdf = shape
     assert isinstance(generic._impl, SphereSDF)
+
+
+def test_torch_jit_script_of_sphere_sdf_shares_parameters():
+    """colocate.py:63 / dtu.py:95 / nerf_synthetic.py:65: `SDF(sdf=torch.jit.script(SphereSDF(n=...)))`.  torch.jit.script
+    compiles the TorchScript restatement over the module's own tensors; SDF adopts it back as a SphereSDF on the same tensors."""
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    s = SphereSDF(n=2 << 5, device="cpu")
+    with torch.no_grad():
+        for q in s.shift.parameters():
+            q.normal_(0, 0.05)
+    js = torch.jit.script(s)
+    assert isinstance(js, torch.jit.ScriptModule)
+    assert all(a.data_ptr() == b.data_ptr() for a, b in zip(s.parameters(), js.parameters()))
+    pts = torch.randn(40, 3) * 0.5
+    assert (js(pts) - s.forward_reference_ops(pts)).abs().max().item() < 2e-6
+    field = SDF(sdf=js, device="cpu")
+    assert field.sdf is js and isinstance(field._impl, SphereSDF)
+    assert all(a.data_ptr() == b.data_ptr() for a, b in zip(field.parameters(), s.parameters()))
