@@ -112,3 +112,31 @@ def test_torch_jit_script_of_sphere_sdf_shares_parameters():
     field = SDF(sdf=js, device="cpu")
     assert field.sdf is js and isinstance(field._impl, SphereSDF)
     assert all(a.data_ptr() == b.data_ptr() for a, b in zip(field.parameters(), s.parameters()))
+
+
+def test_bsdf_and_light_objects_pickle_like_the_scripts_do():
+    """dtu.py:99-113, 163-170: `torch.save(learned_bsdf, path)` / `torch.load(path)` of whole objects, `setattr(bsdf, "act",
+    nn.Sigmoid())` on the children.  (The reference as shipped cannot write these files -- lambda activation, INTEGRATION 2b --
+    but the scripts' lines must work on this package's classes.)"""
+    import io
+    import torch.nn as nn
+    from neural_raytracing_b200.pathtracer.bsdf import ComposeSpatialVarying, Diffuse, NeuralBSDF
+    from neural_raytracing_b200.pathtracer.lights import LightField
+    bsdf = ComposeSpatialVarying([NeuralBSDF(device="cpu") for _ in range(2)] +
+                                 [Diffuse(preprocess=torch.sigmoid, device="cpu").random()], device="cpu")
+    for child in bsdf.bsdfs[:2]:
+        setattr(child, "act", nn.Sigmoid())
+    lights = LightField(device="cpu")
+    for obj in (bsdf, lights):
+        buf = io.BytesIO()
+        torch.save(obj, buf)
+        buf.seek(0)
+        back = torch.load(buf, weights_only=False)
+        assert type(back) is type(obj)
+        for (k, a), (k2, b) in zip(obj.state_dict().items(), back.state_dict().items()):
+            assert k == k2 and torch.equal(a, b), k
+    pts = torch.randn(7, 3)
+    buf = io.BytesIO(); torch.save(bsdf, buf); buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert isinstance(back.bsdfs[0].act, nn.Sigmoid)
+    assert torch.equal(back.sp_var_fn(pts), bsdf.sp_var_fn(pts))
