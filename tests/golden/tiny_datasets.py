@@ -18,13 +18,17 @@ def _rgba(seed, n=12):
 def write_nerf_synthetic(directory, n_frames=3):
     from PIL import Image
     os.makedirs(os.path.join(directory, "test"), exist_ok=True)
-    rs = np.random.RandomState(5)
     frames = []
     for i in range(n_frames):
         Image.fromarray(_rgba(100 + i), "RGBA").save(os.path.join(directory, "test", "r_%d.png" % i))
+        # NeRF-convention camera-to-world (-z forward) on a sphere of radius 4 looking at the origin, like the real dataset
+        az, el = 0.5 + 0.9 * i, 0.35 + 0.1 * i
+        c = np.array([np.cos(el) * np.sin(az), np.sin(el), np.cos(el) * np.cos(az)])
+        fwd = -c
+        right = np.cross(fwd, [0, 1, 0]); right /= np.linalg.norm(right)
+        up = np.cross(right, fwd)
         m = np.eye(4)
-        m[:3, :3] = np.linalg.qr(rs.standard_normal((3, 3)))[0]
-        m[:3, 3] = rs.standard_normal(3) * 4.0
+        m[:3, 0], m[:3, 1], m[:3, 2], m[:3, 3] = right, up, -fwd, 4.0 * c
         frames.append({"file_path": "./test/r_%d" % i, "transform_matrix": m.tolist()})
     with open(os.path.join(directory, "transforms_test.json"), "w") as f:
         json.dump({"camera_angle_x": 0.6911112070083618, "frames": frames}, f)
