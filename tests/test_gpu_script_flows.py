@@ -103,3 +103,100 @@ def test_nerf_synthetic_script_flow(tmp_path):
             assert np.allclose(a, b, rtol=1e-2, atol=1e-4), (k, a, b)
     finally:
         config.set_precision("f32"); config.set_train_precision("f32")
+
+
+def test_colocate_script_flow(tmp_path):
+    """scripts/colocate.py:26-175 on this package at toy size: the cbox relighting layout from disk, `SDF(sdf=torch.jit.load(...))`,
+    the script's 2 NeuralBSDF + Diffuse(Softplus) + Conductor(Softplus) BSDF, PointLights(scale=5) with `intensity_parameters()` in
+    the optimizer, the learned occlusion MLP passed as `w_isect`, `light_update` moving the light with the camera, `train_sample`
+    with the eikonal + weight-spread extra loss, `torch.jit.save` / `torch.save`, then `test(..., w_isect=True)` (shadow rays)."""
+    import torch
+    import torch.nn as nn
+    from neural_raytracing_b200 import config, ops
+    from neural_raytracing_b200.pathtracer import checkpoint
+    from neural_raytracing_b200.pathtracer.bsdf import ComposeSpatialVarying, Conductor, Diffuse, NeuralBSDF
+    from neural_raytracing_b200.pathtracer.integrators import Direct
+    from neural_raytracing_b200.pathtracer.lights import PointLights
+    from neural_raytracing_b200.pathtracer.neural_blocks import SkipConnMLP
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    from neural_raytracing_b200.pathtracer.training_utils import test, test_colocate_resources, train_sample
+    from neural_raytracing_b200.pathtracer.utils import eikonal_loss, rand_uv
+    device, SIZE, DIST, k = "cuda", 16, 1.0, "bunny"
+    random.seed(1); np.random.seed(1); torch.manual_seed(1)
+    root = tiny_datasets.write_colocate(str(tmp_path / "mitsuba_scenes" / "cbox_relight"), k)
+    os.makedirs(tmp_path / "models"); os.makedirs(tmp_path / "outputs")
+    sdf_path = str(tmp_path / "models" / ("col_%s_sdf.pt" % k))
+    # the archive an earlier run left (colocate.py:141 saves from the GPU, :65 loads it back without a device argument);
+    # written here the way the script's other branch builds its shape: torch.jit.script(SphereSDF(n=2<<5)) (:63)
+    start = SphereSDF(n=2 << 5, device=device)
+    with torch.no_grad():
+        start.radii.abs_().add_(0.05)
+    torch.jit.save(torch.jit.script(start), sdf_path)
+    try:
+        config.set_precision("f16"); config.set_train_precision("f16")
+        Rs, Ts, exp_imgs, exp_masks, xyzs = test_colocate_resources(k, SIZE, dist=DIST, device=device, root=root)
+        Rs, Ts, exp_imgs, exp_masks = Rs[:6], Ts[:6], exp_imgs[:6], exp_masks[:6]        # six of the 144 views are enough here
+        sdf = torch.jit.load(sdf_path)
+        density_field = SDF(sdf=sdf)
+        density_field.max_steps = 64
+        learned_bsdf = ComposeSpatialVarying([
+            *[NeuralBSDF() for _ in range(2)],
+            Diffuse(preprocess=nn.Softplus()).random(),
+            Conductor(activation=nn.Softplus(), device=device).random(),
+        ])
+        integrator = Direct()
+        lights = PointLights(device=device, scale=5)
+        occ_mlp = SkipConnMLP(in_size=5, out=1, device=device).to(device)
+        opt = torch.optim.AdamW([
+            {"params": density_field.parameters(), "lr": 8e-5},
+            {"params": learned_bsdf.parameters(), "lr": 8e-5},
+            {"params": lights.intensity_parameters(), "lr": 8e-5},
+            {"params": occ_mlp.parameters(), "lr": 8e-5},
+        ], lr=8e-5, weight_decay=0)
+
+        seen_hits = []
+
+        def extra_loss(mi, got, exp, mask):
+            raw_n = getattr(mi, "raw_normals", None)
+            loss = 0
+            if raw_n is not None:
+                seen_hits.append(raw_n.shape[0])
+                loss = loss + eikonal_loss(raw_n)
+            raw_w = getattr(mi, "normalized_weights", None)
+            if raw_w is not None:
+                loss = loss + 1e-2 * raw_w.std(dim=-1).mean()
+            return loss
+
+        def light_update(cam, light):
+            light.location = cam.get_camera_center() * 1.05
+        ops.profile_collect()
+        losses = train_sample(density_field, bsdf=learned_bsdf, integrator=integrator, lights=lights, Rs=Rs, Ts=Ts,
+                              exp_imgs=exp_imgs, exp_masks=exp_masks, opt=opt, size=SIZE, crop_size=SIZE, save_freq=7500,
+                              valid_freq=2, max_valid_size=SIZE, iters=3, N=2, extra_loss=extra_loss,
+                              uv_select=lambda _, crop_size: rand_uv(SIZE, SIZE, crop_size), light_update=light_update,
+                              name_fn=lambda i: str(tmp_path / "outputs" / ("train_%06d.png" % i)),
+                              valid_name_fn=lambda i: str(tmp_path / "outputs" / ("valid_%06d.png" % i)),
+                              silent=True, really_silent=True, w_isect=occ_mlp)
+        counts = {k2: c for k2, (_, c) in ops.profile_collect().items() if c}
+        assert len(losses) >= 1 and all(np.isfinite(losses))
+        assert counts.get("sdf_march_tc", 0) >= 3 and "sdf_march_f32" not in counts, counts
+        assert seen_hits and min(seen_hits) > 0, seen_hits
+        # the learned occlusion is in the graph (it only scales the light where the shadow ray is blocked, scene.py:301-318: with
+        # the light next to the camera that is almost nowhere, so its gradient is a tensor of zeros rather than a change)
+        assert occ_mlp.out.weight.grad is not None and torch.isfinite(occ_mlp.out.weight.grad).all()
+        assert counts.get("sdf_shadow_tc", 0) >= 1, counts
+        torch.jit.save(density_field.sdf, sdf_path)
+        torch.save(learned_bsdf, str(tmp_path / "models" / ("col_%s_bsdf.pt" % k)))
+        ops.profile_collect()
+        stats = test(density_field, integrator=integrator, bsdf=learned_bsdf, lights=lights, Rs=Rs, Ts=Ts, exp_imgs=exp_imgs,
+                     size=SIZE, light_update=light_update,
+                     name_fn=lambda i: str(tmp_path / "outputs" / ("col_final_%03d.png" % i)), w_isect=True)
+        counts = {k2: c for k2, (_, c) in ops.profile_collect().items() if c}
+        assert isinstance(stats, dict) and all(np.isfinite(np.asarray(v, np.float64)).all() for v in stats.values())
+        assert counts.get("sdf_march_tc", 0) == len(Rs), counts                       # one row block per view
+        reloaded = SDF(sdf=torch.jit.load(sdf_path))
+        assert isinstance(reloaded._impl, SphereSDF)
+        for (ka, a), (kb, b) in zip(sdf.state_dict().items(), reloaded.sdf.state_dict().items()):
+            assert ka == kb and torch.equal(a.cpu(), b.cpu())
+    finally:
+        config.set_precision("f32"); config.set_train_precision("f32")
