@@ -200,3 +200,174 @@ def test_colocate_script_flow(tmp_path):
             assert ka == kb and torch.equal(a.cpu(), b.cpu())
     finally:
         config.set_precision("f32"); config.set_train_precision("f32")
+
+
+def test_dtu_script_flow(tmp_path):
+    """scripts/dtu.py:88-200 on this package at toy size: `SDF(sdf=torch.jit.load(path, device))`, the BSDF and the lights read
+    back with `torch.load` and `setattr(bsdf, "act", nn.Sigmoid())` on the children, the three-group AdamW, `train_dtu` with the
+    eikonal extra loss and a validation render, the three save calls, `test_dtu`."""
+    import torch
+    import torch.nn as nn
+    import scenes
+    from neural_raytracing_b200 import config, ops
+    from neural_raytracing_b200.pathtracer.bsdf import ComposeSpatialVarying, Diffuse, NeuralBSDF
+    from neural_raytracing_b200.pathtracer.integrators import Direct
+    from neural_raytracing_b200.pathtracer.lights import LightField
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    from neural_raytracing_b200.pathtracer.training_utils import test_dtu, train_dtu
+    from neural_raytracing_b200.pathtracer.utils import eikonal_loss, rand_uv
+    device, SIZE, dataset = "cuda", 16, 65
+    random.seed(2); np.random.seed(2); torch.manual_seed(2)
+    os.makedirs(tmp_path / "models"); os.makedirs(tmp_path / "outputs")
+    m = lambda name: str(tmp_path / "models" / ("dtu_%d_%s.pt" % (dataset, name)))      # noqa: E731
+    # what an earlier run left behind (dtu.py:159-170), written with the same calls
+    start = SphereSDF(n=2 << 5, device=device)
+    with torch.no_grad():
+        start.radii.abs_().add_(0.05)
+    torch.jit.save(torch.jit.script(start), m("sdf"))
+    torch.save(ComposeSpatialVarying([NeuralBSDF() for _ in range(10)] +
+                                     [Diffuse(preprocess=torch.sigmoid).random() for _ in range(6)]), m("bsdf"))
+    torch.save(LightField(), m("lights"))
+    poses, intrinsics = scenes.dtu_cameras(4, device=device)
+    poses = [p for p in poses]
+    g = torch.Generator().manual_seed(0)
+    exp_imgs = [torch.rand(SIZE, SIZE, 3, generator=g).to(device) for _ in range(4)]
+    exp_masks = [(torch.rand(SIZE, SIZE, generator=g) > 0.4).float().to(device) for _ in range(4)]
+    try:
+        config.set_precision("f16"); config.set_train_precision("f16")
+        integrator = Direct()
+        shape = torch.jit.load(m("sdf"), device)
+        density_field = SDF(sdf=shape)
+        density_field.max_steps = 64
+        learned_bsdf = torch.load(m("bsdf"), weights_only=False)
+        for bsdf in learned_bsdf.bsdfs:
+            setattr(bsdf, "act", nn.Sigmoid())
+        lights = torch.load(m("lights"), weights_only=False)
+        torch.jit.save(density_field.sdf, str(tmp_path / "models" / "tmp.pt"))
+        torch.save(learned_bsdf, str(tmp_path / "models" / "tmp.pt"))
+        torch.save(lights, str(tmp_path / "models" / "tmp.pt"))
+        opt = torch.optim.AdamW([
+            {"params": density_field.parameters(), "lr": 8e-5},
+            {"params": learned_bsdf.parameters(), "lr": 8e-5},
+            {"params": lights.parameters(), "lr": 8e-5},
+        ], lr=8e-5, weight_decay=0)
+
+        def extra_loss(mi, got, exp, mask):
+            raw_n = getattr(mi, "raw_normals", None)
+            loss = 0
+            if raw_n is not None:
+                loss = loss + eikonal_loss(raw_n)
+            return loss
+        before = {k: v.detach().clone() for k, v in shape.state_dict().items()}
+        ops.profile_collect()
+        losses = train_dtu(density_field, bsdf=learned_bsdf, integrator=integrator, lights=lights, poses=poses,
+                           intrinsics=intrinsics, exp_imgs=exp_imgs, exp_masks=exp_masks, opt=opt, size=SIZE, crop_size=SIZE,
+                           save_freq=5000, valid_freq=2, max_valid_size=SIZE, N=2, iters=3, extra_loss=extra_loss,
+                           uv_select=lambda _, crop_size: rand_uv(SIZE, SIZE, crop_size), silent=True,
+                           name_fn=lambda i: str(tmp_path / "outputs" / ("train_dtu_%06d.png" % i)),
+                           valid_name_fn=lambda i: str(tmp_path / "outputs" / ("valid_dtu_%06d.png" % i)))
+        counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+        assert len(losses) == 3 and all(np.isfinite(losses))
+        assert counts.get("sdf_march_tc", 0) >= 3 and counts.get("mlp_tc_wgrad", 0) >= 3 and "sdf_march_f32" not in counts, counts
+        assert any(not torch.equal(v, before[k]) for k, v in shape.state_dict().items())
+        torch.jit.save(density_field.sdf, m("sdf"))
+        torch.save(learned_bsdf, m("bsdf"))
+        torch.save(lights, m("lights"))
+        stats = test_dtu(density_field, integrator=integrator, bsdf=learned_bsdf, lights=lights, poses=poses[:2],
+                         intrinsics=intrinsics[:2], exp_imgs=exp_imgs[:2], exp_masks=exp_masks[:2], size=SIZE,
+                         name_fn=lambda i: str(tmp_path / "outputs" / ("dtu_test_%03d.png" % i)))
+        assert isinstance(stats, dict) and all(np.isfinite(np.asarray(v, np.float64)).all() for v in stats.values())
+        back = torch.load(m("bsdf"), weights_only=False)
+        assert isinstance(back.bsdfs[0].act, nn.Sigmoid) and len(back.bsdfs) == 16
+    finally:
+        config.set_precision("f32"); config.set_train_precision("f32")
+
+
+@pytest.mark.parametrize("envmap", [False, True])
+def test_nerfle_script_flow(tmp_path, envmap):
+    """scripts/nerfle.py:36-200 on this package at toy size: NeRFLE(envmap=...) under NeRFReproduce, the script's own training
+    loop (pathtrace_sample on a crop + F.mse_loss + AdamW, the light following the camera), its validation render (one library
+    call per frame, rays generated on the device), `torch.save(nerfle, ...)` of the whole module, `test(...)`."""
+    import torch
+    import torch.nn.functional as F
+    import neural_raytracing_b200.pathtracer as pt
+    from neural_raytracing_b200 import config, ops
+    from neural_raytracing_b200.pathtracer.integrators import NeRFReproduce
+    from neural_raytracing_b200.pathtracer.lights import PointLights
+    from neural_raytracing_b200.pathtracer.shapes.nerf import NeRFLE
+    from neural_raytracing_b200.pathtracer.training_utils import test
+    from neural_raytracing_b200.pathtracer.utils import LossSampler, rand_uv
+    from neural_raytracing_b200.renderer import OpenGLPerspectiveCameras, look_at_view_transform
+    device, SIZE, DIST, crop_size, N = "cuda", 16, 1.0, 8, 2
+    random.seed(3); np.random.seed(3); torch.manual_seed(3)
+    os.makedirs(tmp_path / "models"); os.makedirs(tmp_path / "outputs")
+    Rs, Ts, exp_imgs = [], [], []
+    g = torch.Generator().manual_seed(1)
+    for elev in torch.linspace(0, 45, 2, device=device):
+        for azim in torch.linspace(-90, 90, 2, device=device):
+            R, T = look_at_view_transform(dist=DIST, elev=elev, azim=azim, device=device)
+            Rs.append(R); Ts.append(T)
+            exp_imgs.append(torch.rand(SIZE, SIZE, 3, generator=g).to(device))
+    try:
+        config.set_precision("f16"); config.set_train_precision("f16")
+        nerfle = NeRFLE(envmap=envmap, device=device)
+        with torch.no_grad():
+            nerfle.first.out.bias[0] = 0.8      # positive density at the start (a fresh model can be born with relu(sigma) = 0
+            #                                     everywhere: a black image and no gradient, in the reference as well)
+        integrator = NeRFReproduce()
+        lights = PointLights(device=device, scale=10)
+        opt = torch.optim.AdamW([{"params": nerfle.parameters(), "lr": 8e-5}], lr=8e-5, weight_decay=0)
+
+        def light_update(cam, light):
+            light.location = cam.get_camera_center() * 1.05
+        before = nerfle.first.init.weight.detach().clone()
+        selector = LossSampler(len(exp_imgs))
+        losses = []
+        ops.profile_collect()
+        for i in range(3):                                                  # nerfle.py:88-118
+            idxs = selector.sample(n=N)
+            R = torch.cat([Rs[j] for j in idxs], dim=0)
+            T = torch.cat([Ts[j] for j in idxs], dim=0)
+            exp = torch.stack([exp_imgs[j] for j in idxs])
+            cameras = OpenGLPerspectiveCameras(device=device, R=R, T=T)
+            light_update(cameras, lights)
+            opt.zero_grad()
+            (u, v) = rand_uv(SIZE, SIZE, crop_size)
+            got, mi = pt.pathtrace_sample(nerfle, size=SIZE, chunk_size=SIZE, bundle_size=1, crop_size=crop_size, bsdf=None,
+                                          integrator=integrator, cameras=cameras, lights=lights, device=device, uv=(u, v),
+                                          addition=lambda mi: mi, squeeze_first=False, silent=True)
+            exp = exp[:, u:u + crop_size, v:v + crop_size]
+            loss = F.mse_loss(got, exp)
+            assert not loss.isnan()
+            loss.backward()
+            opt.step()
+            losses.append(loss.detach().item())
+        counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+        assert all(np.isfinite(losses)) and not torch.equal(nerfle.first.init.weight.detach(), before)
+        assert counts.get("mlp_tc_train_fwd", 0) >= 3 and counts.get("mlp_tc_wgrad", 0) >= 3, counts     # tensor-core training kernels
+        with torch.no_grad():                                               # nerfle.py:125-136
+            cameras = OpenGLPerspectiveCameras(device=device, R=Rs[0], T=Ts[0])
+            light_update(cameras, lights)
+            ops.profile_collect()
+            validate, _ = pt.pathtrace(nerfle, size=SIZE, chunk_size=min(SIZE, 8), bundle_size=1, bsdf=None,
+                                       integrator=integrator, cameras=cameras, lights=lights, device=device, silent=True)
+            counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+        assert tuple(validate.shape) == (SIZE, SIZE, 3) and torch.isfinite(validate).all()
+        assert counts.get("camera_rays") == 1 and counts.get("mlp_tc_nerf_first") == 1, counts            # one call per frame
+        path = str(tmp_path / "models" / ("nerfle_%s.pt" % ("envmap" if envmap else "ptl")))
+        torch.save(nerfle, path)                                            # nerfle.py:160-161
+        again = torch.load(path, weights_only=False)
+        assert again.envmap == envmap
+        with torch.no_grad():
+            random.seed(7)                       # each forward draws its far plane from `random` (nerf.py:178): same draw for both
+            v2, _ = pt.pathtrace(again, size=SIZE, chunk_size=SIZE, bundle_size=1, bsdf=None, integrator=integrator,
+                                 cameras=cameras, lights=lights, device=device, silent=True, with_noise=False)
+            random.seed(7)
+            v1, _ = pt.pathtrace(nerfle, size=SIZE, chunk_size=SIZE, bundle_size=1, bsdf=None, integrator=integrator,
+                                 cameras=cameras, lights=lights, device=device, silent=True, with_noise=False)
+        assert torch.equal(v1, v2)
+        stats = test(nerfle, integrator=integrator, bsdf=None, lights=lights, Rs=Rs, Ts=Ts, exp_imgs=exp_imgs, size=SIZE,
+                     light_update=light_update, name_fn=lambda i: str(tmp_path / "outputs" / ("test_%03d.png" % i)))
+        assert isinstance(stats, dict) and all(np.isfinite(np.asarray(v, np.float64)).all() for v in stats.values())
+    finally:
+        config.set_precision("f32"); config.set_train_precision("f32")
