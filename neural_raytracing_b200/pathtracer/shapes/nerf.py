@@ -108,6 +108,15 @@ class NeRFLE(nn.Module):
             return code.reshape(code.shape[0], -1)
         return lights.location
 
+    @staticmethod
+    def _code_rows(code, n_views):
+        """One light-code row per view: a single light broadcasts over the views as it does in nerf.py:199-201 (`expand`)."""
+        if code.shape[0] == 1 and n_views > 1:
+            return code.expand(n_views, code.shape[-1])
+        if code.shape[0] != n_views:
+            raise ValueError("light code has %d rows for %d views" % (code.shape[0], n_views))
+        return code
+
     def _view_index(self, rays):
         """[R] int32: which view (light code row) each ray belongs to; cached per batch shape."""
         key = (rays.shape[0], rays[0].numel() // 6, rays.device)
@@ -127,7 +136,7 @@ class NeRFLE(nn.Module):
         -> rgb [n_views, nx, ny, bundle, 3]."""
         device = cam.device
         ts = self._sample_ts(device)
-        code = self._light_code(lights, device)
+        code = self._code_rows(self._light_code(lights, device), cam.n_views)
         prec = config.precision if self.first.precision() != "f32" and self.second.precision() != "f32" else "f32"
         return ops.nerfle_render_camera(self.first.packed(), self.second.packed(), cam, ts, code.detach().float(),
                                         prec=prec)
@@ -136,7 +145,7 @@ class NeRFLE(nn.Module):
         r_o, r_d = rays.split([3, 3], dim=-1)
         device = r_o.device
         ts = self._sample_ts(device)
-        code = self._light_code(lights, device)
+        code = self._code_rows(self._light_code(lights, device), rays.shape[0])
         if rays.is_cuda and not self._needs_grad(rays):
             # fused render: rays in, rgb out
             view = self._view_index(rays)

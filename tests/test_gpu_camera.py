@@ -240,3 +240,28 @@ def test_render_camera_equals_render_of_generated_rays(prec):
     ops.nerfle_render_camera_host(first, second, desc, ts.pin_memory(), code, host, prec=prec)
     dev = ops.nerfle_render_camera(first, second, desc, ts.cuda(), code, prec=prec)
     assert torch.equal(host, dev.cpu())
+
+
+def test_single_light_broadcasts_over_views():
+    """nerf.py:199-201 expands the light code over the batch: ONE light for several views is legal in the reference (`expand`).
+    The fused paths index the code by view, so a single row is broadcast first -- from rays and from a camera."""
+    import torch
+    from neural_raytracing_b200.pathtracer.lights import PointLights
+    real_random = random.random
+    try:
+        n, _two_lights = _golden_nerfle()
+        cam = _nerf_cam(n=3, size=16)
+        one = PointLights(device="cuda", location=torch.tensor([[0.4, 1.0, 0.3]], device="cuda"), scale=10)
+        three = PointLights(device="cuda", location=torch.tensor([[0.4, 1.0, 0.3]] * 3, device="cuda"), scale=10)
+        rays = cam.sample_positions(_window_positions(0, 0, 16, 16), _Sampler(), size=16, N=3)
+        with torch.no_grad():
+            a, b = n(rays, one), n(rays, three)
+            desc = cam.device_desc(16, nx=16, ny=16)
+            c, d = n.render_camera(desc, one), n.render_camera(desc, three)
+        assert tuple(a.shape) == (3, 16, 16, 1, 3) and torch.equal(a, b) and torch.equal(c, d) and torch.equal(a, c)
+        assert (a[0] - a[1]).abs().max().item() > 0
+        two = PointLights(device="cuda", location=torch.tensor([[0.4, 1.0, 0.3]] * 2, device="cuda"), scale=10)
+        with pytest.raises(ValueError):
+            n(rays, two)
+    finally:
+        random.random = real_random
