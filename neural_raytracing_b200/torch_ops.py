@@ -302,5 +302,42 @@ def _(rays, ts, light_code, params1, basis1, arch1, params2, basis2, arch2, prec
     return rays.new_empty((rays.reshape(-1, 6).shape[0], 3))
 
 
-OPERATORS = ["mlp_forward", "mlp_backward", "mlp_forward_train_tc", "mlp_backward_tc", "composite", "composite_backward", "mlp_value_jac", "mlp_value_jac_backward",
+# ---- a21 / f4: ray generators and the camera-driven render -------------------------------------------------------
+def _cam(kind: int, a: Tensor, b: Optional[Tensor], focal: float, size: float, x0: int, y0: int, nx: int, ny: int, bundle: int,
+         positions: Optional[Tensor], jitter: float, jitter_seed: int) -> "ops.CameraDesc":
+    return ops.CameraDesc(int(kind), a, b, focal=focal, size=size, x0=x0, y0=y0, nx=nx, ny=ny, bundle=bundle,
+                          positions=positions, jitter=jitter, jitter_seed=jitter_seed)
+
+
+@torch.library.custom_op(NS + "::camera_rays", mutates_args=())
+def camera_rays(kind: int, a: Tensor, b: Optional[Tensor], focal: float, size: float, x0: int, y0: int, nx: int, ny: int,
+                bundle: int, positions: Optional[Tensor], jitter: float, jitter_seed: int) -> Tensor:
+    """sample_positions of NeRFCamera (kind 0) / DTUCamera (1) / FoVPerspectiveCameras (2) for a pixel window or explicit
+    positions (cameras.py:23-54, 132-192; renderer/cameras.py:539-575) -> rays [n_views, nx, ny, bundle, 6]."""
+    return ops.camera_rays(_cam(kind, a, b, focal, size, x0, y0, nx, ny, bundle, positions, jitter, jitter_seed))
+
+
+@camera_rays.register_fake
+def _(kind, a, b, focal, size, x0, y0, nx, ny, bundle, positions, jitter, jitter_seed):
+    return a.new_empty((a.shape[0], nx, ny, bundle, 6))
+
+
+@torch.library.custom_op(NS + "::nerfle_render_camera", mutates_args=())
+def nerfle_render_camera(kind: int, a: Tensor, b: Optional[Tensor], focal: float, size: float, x0: int, y0: int, nx: int,
+                         ny: int, bundle: int, jitter: float, jitter_seed: int, ts: Tensor, light_code: Tensor,
+                         params1: Tensor, basis1: Tensor, arch1: List[int], params2: Tensor, basis2: Tensor,
+                         arch2: List[int], prec: int) -> Tensor:
+    """The frame of a NeRFLE from its camera in one call, rays generated on the device inside the library (f4; what pathtrace
+    + NeRFReproduce compute, main.py:57-88 + nerf.py:175-214) -> rgb [n_views, nx, ny, bundle, 3] (gradient-free)."""
+    cam = _cam(kind, a, b, focal, size, x0, y0, nx, ny, bundle, None, jitter, jitter_seed)
+    return ops.nerfle_render_camera(_mlp(params1, basis1, arch1), _mlp(params2, basis2, arch2), cam, ts, light_code, prec=prec)
+
+
+@nerfle_render_camera.register_fake
+def _(kind, a, b, focal, size, x0, y0, nx, ny, bundle, jitter, jitter_seed, ts, light_code, params1, basis1, arch1, params2,
+      basis2, arch2, prec):
+    return a.new_empty((a.shape[0], nx, ny, bundle, 3))
+
+
+OPERATORS = ["camera_rays", "nerfle_render_camera", "mlp_forward", "mlp_backward", "mlp_forward_train_tc", "mlp_backward_tc", "composite", "composite_backward", "mlp_value_jac", "mlp_value_jac_backward",
              "sdf_eval", "sdf_sphere_trace", "sdf_shadow_test", "sdf_min_scan", "nerfle_render"]

@@ -143,3 +143,26 @@ def test_opcheck_accepts_the_registrations():
     rgb = torch.rand(16, 40, 3, device="cuda", requires_grad=True)
     torch.library.opcheck(torch.ops.nrt_b200.composite.default, (sig, rgb, torch.linspace(0.1, 2, 16, device="cuda")),
                           test_utils=("test_schema", "test_faketensor", "test_autograd_registration"))
+
+
+def test_camera_operators_equal_the_ctypes_layer():
+    """torch.ops.nrt_b200.camera_rays / nerfle_render_camera (registered, with fake implementations) == ops.camera_rays /
+    ops.nerfle_render_camera on the same camera."""
+    import torch
+    from neural_raytracing_b200 import ops, torch_ops  # noqa: F401
+    w1, w2 = helpers.nerfle_weights(False)
+    m1, m2 = helpers.cuda_mlp(w1), helpers.cuda_mlp(w2)
+    c2w, focal = synth.nerf_cameras(2, 16, device="cuda")
+    desc = ops.CameraDesc(ops.CAM_NERF, c2w, None, focal=focal, size=16, x0=1, y0=2, nx=9, ny=7)
+    rays = torch.ops.nrt_b200.camera_rays(ops.CAM_NERF, c2w, None, float(focal), 16.0, 1, 2, 9, 7, 1, None, 0.0, 0)
+    assert torch.equal(rays, ops.camera_rays(desc))
+    ts = torch.linspace(0, 2.05, 64, device="cuda")
+    code = torch.tensor([[0.4, 1.0, 0.3], [-0.8, 0.5, 0.6]], device="cuda")
+    a1 = [w1["in_size"], 0, w1["freqs"], w1["hidden"], w1["num_layers"], w1["skip"], w1["out"], ops.ACT_LEAKY_RELU]
+    a2 = [w2["in_size"], 0, w2["freqs"], w2["hidden"], w2["num_layers"], w2["skip"], w2["out"], ops.ACT_LEAKY_RELU]
+    img = torch.ops.nrt_b200.nerfle_render_camera(ops.CAM_NERF, c2w, None, float(focal), 16.0, 1, 2, 9, 7, 1, 0.0, 0, ts, code,
+                                                  m1.params, m1.basis, a1, m2.params, m2.basis, a2, ops.PREC_F16)
+    assert torch.equal(img, ops.nerfle_render_camera(m1, m2, desc, ts, code, prec="f16"))
+    torch.library.opcheck(torch.ops.nrt_b200.camera_rays.default,
+                          (ops.CAM_NERF, c2w, None, float(focal), 16.0, 1, 2, 9, 7, 1, None, 0.0, 0),
+                          test_utils=("test_schema", "test_faketensor"))

@@ -45,6 +45,15 @@ def test_fake_implementations_propagate_shapes():
         assert tuple(d.shape) == (77,) and h.dtype == torch.bool
         i, pos, mv = torch.ops.nrt_b200.sdf_min_scan(rays, c, r, t, sp, sb, sarch, 0.017, 128, ops.PREC_F32)
         assert i.dtype == torch.int32 and tuple(pos.shape) == (77, 3) and tuple(mv.shape) == (77,)
+        c2w = torch.empty(2, 4, 4, device="cuda")
+        cr = torch.ops.nrt_b200.camera_rays(ops.CAM_NERF, c2w, None, 20.0, 16.0, 3, 2, 10, 6, 1, None, 0.0, 0)
+        assert tuple(cr.shape) == (2, 10, 6, 1, 6)
+        a1, a2 = [3, 0, 16, 128, 5, 3, 65, 0], [70, 0, 16, 64, 8, 3, 3, 0]
+        img = torch.ops.nrt_b200.nerfle_render_camera(ops.CAM_NERF, c2w, None, 20.0, 16.0, 0, 0, 16, 16, 1, 0.0, 0, ts,
+                                                      torch.empty(2, 3, device="cuda"), torch.empty(_nparams(a1), device="cuda"),
+                                                      torch.empty(3, 16, device="cuda"), a1, torch.empty(_nparams(a2), device="cuda"),
+                                                      torch.empty(70, 16, device="cuda"), a2, ops.PREC_F16)
+        assert tuple(img.shape) == (2, 16, 16, 1, 3)
         v, j, a = torch.ops.nrt_b200.mlp_value_jac(torch.empty(9, 3, device="cuda"), sp, sb, sarch)
         assert tuple(v.shape) == (9, 1) and tuple(j.shape) == (9, 1, 3) and tuple(a.shape) == (9 * 128, 36)
 
