@@ -194,6 +194,11 @@ class SDF:
         self._impl = model
         if isinstance(model, torch.jit.ScriptModule):
             from ..checkpoint import adopt_script_sphere_sdf
+            first = next(model.parameters(), None)
+            if first is not None and self.device.type == "cuda" and first.device.type == "cpu" and torch.cuda.is_available():
+                # colocate.py:65 loads its archive without a device argument; one written from CPU tensors
+                # (checkpoint.save_sdf_archive) then sits on the host while the rays are on the GPU: move it to the shape's device
+                model.to(self.device)
             adopted = adopt_script_sphere_sdf(model)
             if adopted is not None:
                 self._impl = adopted

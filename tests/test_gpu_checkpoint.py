@@ -70,3 +70,24 @@ def test_script_archive_held_by_sdf_runs_on_the_fused_kernels(tmp_path):
     ((it3.raw_normals.norm(dim=-1) - 1) ** 2).mean().backward()
     grads = [p.grad for p in shape.parameters()]
     assert all(gr is not None for gr in grads) and sum(float(gr.abs().sum()) for gr in grads) > 0
+
+
+def test_cpu_archive_loaded_without_a_device_is_moved_to_the_shape_device(tmp_path):
+    """colocate.py:65 `sdf = torch.jit.load(path)` (no device): an archive written from CPU tensors lands on the host; SDF
+    (device="cuda" by default) moves it next to the rays before adopting it."""
+    import torch
+    from neural_raytracing_b200.pathtracer import checkpoint
+    from neural_raytracing_b200.pathtracer.shapes.sdfs import SDF, SphereSDF
+    g = helpers.golden("sdf")
+    path = str(tmp_path / "col_sdf.pt")
+    checkpoint.save_sdf_archive(_sphere_sdf_from(helpers.golden_sdf_weights()), path)
+    sdf = torch.jit.load(path)
+    assert next(sdf.parameters()).device.type == "cpu"
+    field = SDF(sdf=sdf)
+    field.max_steps = 64
+    assert next(sdf.parameters()).is_cuda and isinstance(field._impl, SphereSDF) and field._fused() is not None
+    random.random = lambda: float(g["fixed_random"])
+    rays = torch.from_numpy(g["rays"]).cuda().reshape(1, -1, 1, 1, 6)
+    with torch.no_grad():
+        it, active = field.intersect(rays)
+    assert int((active.reshape(-1).cpu().numpy() != g["hit"].astype(bool)).sum()) <= 2
