@@ -67,10 +67,10 @@ def _row_block(width, height, rays_per_pixel, chunk_size, addition, device):
     budget = config.max_tile_rays
     if budget <= 0 or torch.is_grad_enabled() or addition is not nothing or not str(device).startswith("cuda"):
         return 0
-    rows = max(1, budget // max(1, height * rays_per_pixel))
-    if rows * height <= chunk_size * chunk_size:
-        return 0
-    return min(rows, width)
+    rows = min(width, budget // max(1, height * rays_per_pixel))
+    if rows < 1 or rows * height <= chunk_size * chunk_size:
+        return 0                                         # one row is over the budget, or the caller's tile is at least as large
+    return rows
 
 
 def pathtrace(shapes, lights, cameras, integrator, bsdf=None, size=512, width=None, height=None, chunk_size=32,
