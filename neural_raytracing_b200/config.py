@@ -22,6 +22,15 @@ TC_NETS = {
     (2, 64, 16, 32, 5, 3, 3, 0),    # PlainNeRF.second
 }
 
+def tc_instantiated(key):
+    """Whether the tensor-core (gradient-free) path evaluates a network of this shape: the shapes above, plus
+    ComposeSpatialVarying.sp_var_fn for ANY number of bases up to 16 (the 4- and the 16-output instantiations serve the narrower
+    ones; training kernels exist for 4 / 8 / 16 only, other counts train on the fp32 kernels)."""
+    if key in TC_NETS:
+        return True
+    return tuple(key[:6]) == (3, 0, 128, 256, 16, 3) and 1 <= key[6] <= 16 and key[7] == 0
+
+
 # arithmetic of the differentiable (training) MLP evaluations:
 #   "f32"  : fused fp32 forward/backward kernels (default; gradients agree with float64 autograd to ~1e-6)
 #   "f16"  : tcgen05 forward-with-saved-tiles + fused dgrad chain + wgrad kernel, fp16 operands with an automatic

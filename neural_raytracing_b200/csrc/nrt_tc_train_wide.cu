@@ -474,7 +474,7 @@ static bool matches_wt(const MlpDev& d) {
 template <class NET, int FMT>
 static int wide_train_forward(const nrt_mlp_t* m, int out_act, const float* x, int64_t M, float* out, const TrainWs& ws, cudaStream_t st) {
   using W = Wide<NET>;
-  IoPlainWide<NET::IN, NET::OUT> io{x, out, out_act};
+  IoPlainWide<NET::IN, NET::OUT> io{x, out, out_act, 0};
   SaveTiles sv{ws.acts, ws.enc_raw, ws.enc_act, ws.masks, ws.ntiles};
   const size_t bytes = (size_t)W::SMEM_BYTES + 1024;
   const int grid = (int)std::min<int64_t>(ws.ntiles, (int64_t)nrt_sm_count());

@@ -23,11 +23,18 @@ static bool matches_w(const MlpDev& d) {
          d.skip == NET::SKIP && d.out == NET::OUT && d.act == NET::ACT;
 }
 
+// every field but the output width (the sp_var family: one instantiation serves every basis count up to its own)
+template <class NET>
+static bool matches_w_upto(const MlpDev& d, int out_lo) {
+  return d.in_size == NET::IN && d.latent == NET::LAT && d.freqs == NET::F && d.hidden == NET::H && d.L == NET::L &&
+         d.skip == NET::SKIP && d.out >= out_lo && d.out <= NET::OUT && d.act == NET::ACT;
+}
+
 template <class NET, int FMT, bool SAVE>
 static int launch_wide(const nrt_mlp_t* m, int out_act, const float* x, int64_t M, float* out, float* acts, cudaStream_t st) {
   using SVP = typename std::conditional<SAVE, SaveF32, NoSave>::type;
   using W = Wide<NET>;
-  IoPlainWide<NET::IN, NET::OUT> io{x, out, out_act};
+  IoPlainWide<NET::IN, NET::OUT> io{x, out, out_act, m->out_size == NET::OUT ? 0 : m->out_size};
   const size_t bytes = (size_t)W::SMEM_BYTES + 1024;
   const int64_t ntiles = (M + 127) / 128;
   const int grid = (int)std::min<int64_t>(ntiles, (int64_t)nrt_sm_count());
@@ -62,6 +69,10 @@ int nrt_mlp_forward_tc_wide(const nrt_mlp_t* m, const MlpDev& d, int prec, int o
   if (matches_w<NetSpVar8>(d)) return forward_wide<NetSpVar8>(m, prec, out_act, x, M, out, acts, st);
   if (matches_w<NetSpVar16>(d)) return forward_wide<NetSpVar16>(m, prec, out_act, x, M, out, acts, st);
   if (matches_w<NetLightField>(d)) return forward_wide<NetLightField>(m, prec, out_act, x, M, out, acts, st);
+  // any other basis count of ComposeSpatialVarying.sp_var_fn up to 16: the next wider instantiation (same blob layout within
+  // 1..4 and within 5..16; the missing output rows are zero in the blob and are not stored)
+  if (matches_w_upto<NetSpVar4>(d, 1)) return forward_wide<NetSpVar4>(m, prec, out_act, x, M, out, acts, st);
+  if (matches_w_upto<NetSpVar16>(d, 5)) return forward_wide<NetSpVar16>(m, prec, out_act, x, M, out, acts, st);
   *handled = false;
   return NRT_OK;
 }

@@ -317,18 +317,23 @@ k_mlp_wide_tc(const uint8_t* __restrict__ blob, IO io, int64_t M, SV sv = SV{}) 
 template <int IN, int OUT>
 struct IoPlainWide {
   const float* x; float* out; int out_act;
+  // number of output columns of the network that is evaluated, when it is narrower than the instantiation's OUT (a
+  // ComposeSpatialVarying with, say, 10 bases runs on the 16-output instantiation: the blob layout of out = 5..16 is the same,
+  // the pack kernel zero-fills the missing rows); 0 = OUT
+  int out_cols;
   __device__ __forceinline__ void load(int64_t m, float* v) const {
 #pragma unroll
     for (int j = 0; j < IN; ++j) v[j] = __ldg(x + m * IN + j);
   }
   __device__ __forceinline__ void store(int64_t m, const float* o) const {
+    const int nc = out_cols > 0 ? out_cols : OUT;
 #pragma unroll
     for (int j = 0; j < OUT; ++j) {
       float v = o[j];
       if (out_act == NRT_OUT_SIGMOID) v = 1.0f / (1.0f + __expf(-v));
       else if (out_act == NRT_OUT_SOFTPLUS) v = v > 20.0f ? v : __logf(1.0f + __expf(v));
       else if (out_act == NRT_OUT_TANH) v = tanhf(v);
-      out[m * OUT + j] = v;
+      if (j < nc) out[m * nc + j] = v;
     }
   }
 };

@@ -134,7 +134,7 @@ class SkipConnMLP(nn.Module):
         m = self
         key = (m.in_size, m.latent_size, m.basis_p.shape[-1], m.init.out_features, len(m.layers), m.skip,
                m.out.out_features, _activation_id(m.activation))
-        return config.precision if key in config.TC_NETS else "f32"
+        return config.precision if config.tc_instantiated(key) else "f32"
 
     def train_precision(self):
         """Arithmetic of the differentiable evaluation (config.train_precision where the tensor-core training

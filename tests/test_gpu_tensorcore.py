@@ -76,6 +76,10 @@ WIDE_CASES = {
     "light_field": dict(seed=52, in_size=3, out=3, num_layers=10, hidden=256, freqs=16, sigma=32.0),
     "sp_var8": dict(seed=53, in_size=3, out=8, num_layers=16, hidden=256, freqs=128, sigma=128.0),     # nerf_synthetic.py
     "sp_var16": dict(seed=54, in_size=3, out=16, num_layers=16, hidden=256, freqs=128, sigma=128.0),   # dtu.py
+    # other basis counts run on the next wider instantiation (dtu.py:101-103 in its commented form builds 10 bases)
+    "sp_var10": dict(seed=55, in_size=3, out=10, num_layers=16, hidden=256, freqs=128, sigma=128.0),
+    "sp_var3": dict(seed=56, in_size=3, out=3, num_layers=16, hidden=256, freqs=128, sigma=128.0),
+    "sp_var5": dict(seed=57, in_size=3, out=5, num_layers=16, hidden=256, freqs=128, sigma=128.0),
 }
 
 

@@ -59,3 +59,43 @@ def test_vis_integrator_matches_reference(scene, kind, key, prec):
     finally:
         config.set_precision("f32")
         random.random = real_random
+
+
+def test_odd_basis_count_stays_on_the_tensor_cores():
+    """A spatially varying BSDF with a basis count other than 4 / 8 / 16 (dtu.py:101-103 in its commented form builds 10
+    NeuralBSDF): under set_precision("f16") the weight network runs on the next wider tensor-core instantiation, not on the fp32
+    kernels, and the weight map equals the fp32 render."""
+    import torch
+    import neural_raytracing_b200.pathtracer as P
+    from neural_raytracing_b200 import config, ops
+    from neural_raytracing_b200.pathtracer.bsdf import ComposeSpatialVarying, NeuralBSDF
+    from neural_raytracing_b200.pathtracer.cameras import NeRFCamera
+    from neural_raytracing_b200.pathtracer.integrators import BasisBRDF
+    g = helpers.golden("vis")
+    real_random = random.random
+    random.random = lambda: float(g["fixed_random"])
+    try:
+        torch.manual_seed(5)
+        shape, _sphere, _bsdf, lights, _integ, _w = scenes.build_pipeline(P, "dtu", device="cuda")
+        bsdf = ComposeSpatialVarying([NeuralBSDF(device="cuda") for _ in range(10)], device="cuda")
+        with torch.no_grad():
+            for q in bsdf.sp_var_fn.parameters():
+                q.normal_(0, 0.05)
+        c2w, focal = synth.nerf_cameras(1, 16, device="cuda")
+        cam = NeRFCamera(cam_to_world=c2w, focal=focal, device="cuda")
+        imgs = {}
+        for prec in ("f32", "f16"):
+            config.set_precision(prec)
+            ops.profile_collect()
+            with torch.no_grad():
+                imgs[prec], _ = P.pathtrace(shape, size=16, chunk_size=16, bundle_size=1, bsdf=bsdf, integrator=BasisBRDF(bsdf),
+                                            lights=lights, cameras=cam, device="cuda", silent=True, background=0, with_noise=False)
+            counts = {k: c for k, (_, c) in ops.profile_collect().items() if c}
+            if prec == "f16":
+                assert counts.get("mlp_tc_wide", 0) >= 1 and "mlp_fwd_f32" not in counts, counts
+        assert tuple(imgs["f16"].shape) == (16, 16, 10) and imgs["f32"].abs().sum().item() > 0
+        err = (imgs["f16"] - imgs["f32"]).abs().amax(dim=-1)
+        assert (err < 2e-3).float().mean().item() >= 0.98             # grazing rays may hit on one side only
+    finally:
+        config.set_precision("f32")
+        random.random = real_random
